@@ -1,0 +1,33 @@
+// Library-level entry points of libdrn_sm100.so (include/drn_b200.h): version, error text, device check.
+#include "common.cuh"
+
+namespace drn {
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+}  // namespace drn
+
+using namespace drn;
+
+extern "C" int drn_version(void) { return DRN_VERSION; }
+
+extern "C" const char* drn_last_error(void) { return err_buf(); }
+
+extern "C" int drn_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaGetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10) return fail(DRN_EARCH, "device %d is sm_%d%d; libdrn_sm100 needs a B200 (sm_100a)", dev, prop.major, prop.minor);
+  return 0;
+}
+
+extern "C" int drn_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}

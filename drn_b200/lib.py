@@ -1,0 +1,71 @@
+"""ctypes binding of libdrn_sm100.so (C ABI: include/drn_b200.h).
+
+The library is built in-tree by `__graft_entry__.build()` / `make -C drn_b200/csrc`.  There is no fallback: if the
+shared object is missing, or a call fails, a RuntimeError carrying `drn_last_error()` is raised.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdrn_sm100.so")
+
+MAX_TAPS = 4
+GEMM_ROWS, GEMM_WGRAD = 0, 2
+OUT_STORE, OUT_ADD, OUT_ATOMIC = 0, 1, 2
+
+
+class Planes(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("plane_stride", C.c_int64),
+                ("B", C.c_int32), ("T", C.c_int32), ("P", C.c_int32), ("C", C.c_int32)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("form", C.c_int32), ("b_mn", C.c_int32),
+        ("a", Planes), ("b", Planes),
+        ("B", C.c_int32), ("T", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("M", C.c_int32),
+        ("ntaps", C.c_int32),
+        ("tap_shift", C.c_int32 * MAX_TAPS), ("tap_par", C.c_int32 * MAX_TAPS), ("tap_w", C.c_int32 * MAX_TAPS),
+        ("a_c0", C.c_int32), ("b_c0", C.c_int32),
+        ("nprod", C.c_int32), ("split_k", C.c_int32),
+        ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_col0", C.c_int32), ("out_mode", C.c_int32),
+        ("out_tap_stride", C.c_int64),
+        ("out_T", C.c_int32), ("out_t_mul", C.c_int32), ("out_t_add", C.c_int32),
+        ("bias", C.c_void_p),
+        ("rowscale", C.c_void_p), ("rowscale_ld", C.c_int32),
+        ("out2", C.c_void_p), ("out2_ld", C.c_int64),
+        ("outp", C.c_void_p), ("outp_ld", C.c_int64), ("outp_col0", C.c_int32), ("outp_plane_stride", C.c_int64),
+        ("engine", C.c_int32),
+        ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32), ("dbg_kadv", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared object once.  Raises if it has not been built (no CPU / torch fallback exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError("libdrn_sm100.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "or `make -C drn_b200/csrc` (expected at %s)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        lib.drn_last_error.restype = C.c_char_p
+        lib.drn_version.restype = C.c_int
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError("libdrn_sm100 %s failed (%d): %s" % (what, rc, load().drn_last_error().decode()))
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,53 @@
+"""Python launchers for the kernels of libdrn_sm100.so.  Thin: argument marshalling only, no math."""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from .planes import Planes
+
+# numeric mode of the tensor-core contraction: 3 = split-BF16 parity mode (default), 1 = single BF16 pass, 4 = + lo*lo
+NPROD = 3
+ENGINE = 0  # 0 = tcgen05 (product), 1 = fp32 CUDA-core checker (tests only)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def gemm(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=0, nprod=None, split_k=1,
+         out=None, out_ld=None, out_col0=0, out_mode=L.OUT_STORE, out_tap_stride=0, out_T=None, out_t_mul=1,
+         out_t_add=0, bias=None, rowscale=None, out2=None, outp=None, outp_col0=0, engine=None, dbg=(0, 0, 0)):
+    """a, b: L.Planes descriptors.  taps: sequence of (shift, parity, weight_tap).  See include/drn_b200.h."""
+    g = L.GemmDesc()
+    g.form, g.b_mn = form, b_mn
+    g.a, g.b = a, b
+    g.B, g.T, g.N, g.K, g.M = B, T, N, K, M
+    g.ntaps = len(taps)
+    for i, (sh, par, w) in enumerate(taps):
+        g.tap_shift[i], g.tap_par[i], g.tap_w[i] = sh, par, w
+    g.a_c0, g.b_c0 = a_c0, b_c0
+    g.nprod = NPROD if nprod is None else nprod
+    g.split_k = split_k
+    if out is not None:
+        g.out = out.data_ptr()
+        g.out_ld = out_ld if out_ld is not None else out.shape[-1]
+    g.out_col0, g.out_mode, g.out_tap_stride = out_col0, out_mode, out_tap_stride
+    g.out_T = T if out_T is None else out_T
+    g.out_t_mul, g.out_t_add = out_t_mul, out_t_add
+    if bias is not None:
+        g.bias = bias.data_ptr()
+    if rowscale is not None:
+        g.rowscale = rowscale.data_ptr()
+        g.rowscale_ld = rowscale.shape[-1]
+    if out2 is not None:
+        g.out2 = out2.data_ptr()
+        g.out2_ld = out2.shape[-1]
+    if outp is not None:
+        g.outp = outp.data.data_ptr()
+        g.outp_ld = outp.C
+        g.outp_col0 = outp_col0
+        g.outp_plane_stride = outp.plane_stride
+    g.engine = ENGINE if engine is None else engine
+    g.dbg_lbo, g.dbg_sbo, g.dbg_kadv = dbg
+    L.check(L.load().drn_gemm(C.byref(g), L.stream_ptr()), "drn_gemm")

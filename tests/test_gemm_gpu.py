@@ -1,0 +1,148 @@
+"""drn_gemm (tcgen05 split-BF16 contraction) against a torch fp64 reference of the same operands, and against the
+library's fp32 CUDA-core checker engine.  Shapes cover every layer form of the path: linear, k3 conv stride 1 / 2,
+data gradients (MN-major weights, parity-split outputs), weight gradients (MN-major both, split-K), ragged tiles."""
+import pytest
+import torch
+
+from drn_b200 import lib as L
+from drn_b200 import ops
+from drn_b200.planes import Planes
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def ref_rows(a, w, taps, stride_par, B, T, N, K, b_mn, a_c0=0):
+    """a: Planes [B,Ta,C]; w: Planes [ntapsW, rows, cols].  Returns fp64 [B,T,N]."""
+    A = a.to_float().double()
+    W = w.to_float().double()
+    P = stride_par
+    Ta = A.shape[1] // P
+    A = A.view(B, Ta, P, -1)
+    out = torch.zeros(B, T, N, dtype=torch.float64, device=DEV)
+    for (sh, par, wt) in taps:
+        src = torch.zeros(B, T, K, dtype=torch.float64, device=DEV)
+        lo, hi = max(0, -sh), min(T, Ta - sh)
+        if hi > lo:
+            src[:, lo:hi] = A[:, lo + sh:hi + sh, par, a_c0:a_c0 + K]
+        Wt = W[wt, :K, :N] if b_mn else W[wt, :N, :K].t()
+        out += src @ Wt
+    return out
+
+
+def run_rows(B, T, Cin, N, taps, P=1, b_mn=0, engine=0, nprod=3, seed=0, a_c0=0, K=None, dbg=(0, 0, 0)):
+    K = K or Cin
+    a = Planes.from_float(_rand(B, T * P, Cin, seed=seed))
+    ntw = max(t[2] for t in taps) + 1
+    w = Planes.from_float(_rand(ntw, K if b_mn else N, N if b_mn else K, seed=seed + 1, scale=K ** -0.5))
+    out = torch.full((B, T, N), float("nan"), device=DEV)
+    ops.gemm(L.GEMM_ROWS, a.desc(P), w.desc(), B, T, N, K=K, taps=taps, b_mn=b_mn, a_c0=a_c0, nprod=nprod, out=out,
+             engine=engine, dbg=dbg)
+    torch.cuda.synchronize()
+    ref = ref_rows(a, w, taps, P, B, T, N, K, b_mn, a_c0)
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    return err, out, ref
+
+
+K3 = ((-1, 0, 0), (0, 0, 1), (1, 0, 2))
+K3S2 = ((-1, 1, 0), (0, 0, 1), (0, 1, 2))  # input viewed [T/2][2]: row 2t+r-1
+
+
+@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("case", [
+    dict(B=2, T=256, Cin=128, N=128, taps=((0, 0, 0),)),
+    dict(B=2, T=256, Cin=256, N=256, taps=K3),
+    dict(B=3, T=128, Cin=192, N=512, taps=K3),
+    dict(B=5, T=64, Cin=128, N=256, taps=K3),            # 2 samples per 128-row tile, ragged batch
+    dict(B=4, T=32, Cin=64, N=128, taps=K3),
+    dict(B=3, T=8, Cin=64, N=64, taps=K3),
+    dict(B=2, T=96, Cin=64, N=1000, taps=K3),            # ragged T and N
+    dict(B=2, T=128, Cin=128, N=256, taps=K3S2, P=2),    # stride-2 conv through the parity view
+    dict(B=2, T=16, Cin=128, N=512, taps=K3S2, P=2),
+    dict(B=2, T=256, Cin=256, N=128, taps=K3, b_mn=1),   # data gradient: weights [tap][K][N]
+    dict(B=2, T=64, Cin=512, N=4352, taps=K3, b_mn=1),
+    dict(B=2, T=256, Cin=320, N=128, taps=((0, 0, 0),), a_c0=64, K=256),
+])
+def test_rows(case, engine):
+    err, _, _ = run_rows(engine=engine, **case)
+    assert err < 2e-5, err
+
+
+def test_rows_single_pass_is_bf16_accurate():
+    err, _, _ = run_rows(2, 256, 256, 256, K3, nprod=1)
+    assert 1e-5 < err < 2e-2, err
+
+
+def run_wgrad(B, T, Co, Ci, taps, P=1, engine=0, split_k=1, seed=0, dbg=(0, 0, 0)):
+    dy = Planes.from_float(_rand(B, T, Co, seed=seed))
+    x = Planes.from_float(_rand(B, T * P, Ci, seed=seed + 1))
+    ntap = len(taps)
+    out = torch.zeros(ntap, Co, Ci, device=DEV)
+    ops.gemm(L.GEMM_WGRAD, dy.desc(), x.desc(P), B, T, Ci, M=Co, taps=taps, out=out, out_ld=Ci,
+             out_tap_stride=Co * Ci, out_mode=L.OUT_ATOMIC if split_k > 1 else L.OUT_STORE, split_k=split_k,
+             engine=engine, dbg=dbg)
+    torch.cuda.synchronize()
+    DY = dy.to_float().double()
+    X = x.to_float().double().view(B, T, P, Ci)
+    ref = torch.zeros(ntap, Co, Ci, dtype=torch.float64, device=DEV)
+    for (sh, par, wt) in taps:
+        src = torch.zeros(B, T, Ci, dtype=torch.float64, device=DEV)
+        lo, hi = max(0, -sh), min(T, T - sh)
+        src[:, lo:hi] = X[:, lo + sh:hi + sh, par]
+        ref[wt] = torch.einsum("bto,btc->oc", DY, src)
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    return err
+
+
+@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("case", [
+    dict(B=2, T=256, Co=128, Ci=128, taps=((0, 0, 0),)),
+    dict(B=2, T=128, Co=256, Ci=320, taps=K3),
+    dict(B=5, T=32, Co=192, Ci=256, taps=K3),
+    dict(B=3, T=8, Co=64, Ci=64, taps=K3),
+    dict(B=2, T=64, Co=512, Ci=256, taps=K3S2, P=2),
+    dict(B=4, T=96, Co=128, Ci=128, taps=K3),
+])
+def test_wgrad(case, engine):
+    err = run_wgrad(engine=engine, **case)
+    assert err < 2e-5, err
+
+
+def test_wgrad_split_k():
+    err = run_wgrad(8, 128, 256, 256, K3, split_k=4)
+    assert err < 2e-5, err
+
+
+def test_epilogue_options():
+    B, T, Cin, N = 2, 128, 128, 256
+    a = Planes.from_float(_rand(B, T, Cin, seed=3))
+    w = Planes.from_float(_rand(1, N, Cin, seed=4, scale=Cin ** -0.5))
+    bias = _rand(N, seed=5)
+    q = _rand(B, N, seed=6)
+    wide = torch.zeros(B, T, N + 64, device=DEV)
+    pre = torch.empty(B, T, N, device=DEV)
+    pl = Planes.zeros(B, T, N + 64, DEV)
+    ops.gemm(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, out=wide, out_ld=N + 64, out_col0=32, bias=bias, rowscale=q,
+             out2=pre, outp=pl, outp_col0=64)
+    ref_pre = ref_rows(a, w, ((0, 0, 0),), 1, B, T, N, Cin, 0) + bias.double()
+    ref = ref_pre * q.double()[:, None, :]
+    s = ref.abs().max().item()
+    assert (pre.double() - ref_pre).abs().max().item() / s < 2e-5
+    assert (wide[:, :, 32:32 + N].double() - ref).abs().max().item() / s < 2e-5
+    assert wide[:, :, :32].abs().max().item() == 0 and wide[:, :, 32 + N:].abs().max().item() == 0
+    assert (pl.to_float()[:, :, 64:].double() - ref).abs().max().item() / s < 3e-5
+    # accumulate mode
+    ops.gemm(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, out=wide, out_ld=N + 64, out_col0=32, bias=bias, rowscale=q,
+             out_mode=L.OUT_ADD)
+    assert (wide[:, :, 32:32 + N].double() - 2 * ref).abs().max().item() / s < 4e-5
+    # parity-strided output rows (stride-2 data gradient writes every other time step)
+    out = torch.zeros(B, 2 * T, N, device=DEV)
+    ops.gemm(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, out=out, out_T=2 * T, out_t_mul=2, out_t_add=1)
+    ref0 = ref_rows(a, w, ((0, 0, 0),), 1, B, T, N, Cin, 0)
+    assert (out[:, 1::2].double() - ref0).abs().max().item() / s < 2e-5
+    assert out[:, 0::2].abs().max().item() == 0
