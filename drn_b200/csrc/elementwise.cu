@@ -1,0 +1,540 @@
+// HBM-bound kernels of the path: plane splitting / weight packing, train-mode BatchNorm (+ReLU, +FPN upsample-add,
+// +query gate) forward and backward, gate reductions.  All are coalesced 16-byte-vectorised streaming kernels; the
+// per-channel reductions use per-thread fp32 partials -> shared-memory tree -> one fp64 atomic per channel per CTA.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace drn {
+
+constexpr int EW_THREADS = 256;
+
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+// 8 bf16 hi + 8 bf16 lo -> 8 floats
+__device__ __forceinline__ void load8_planes(const __nv_bfloat16* hi, long long plane_stride, float* v) {
+  const uint4 h = *reinterpret_cast<const uint4*>(hi);
+  const uint4 l = *reinterpret_cast<const uint4*>(hi + plane_stride);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+    v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8_planes(__nv_bfloat16* hi, long long plane_stride, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[2 * i], h0, l0);
+    split_bf16(v[2 * i + 1], h1, l1);
+    h[i] = pack_bf16x2(h0, h1);
+    l[i] = pack_bf16x2(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(hi) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(hi + plane_stride) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// ---- split fp32 rows into planes ---------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) split_planes_kernel(const float* __restrict__ src, long long rows, int C8,
+                                                                  long long src_ld, __nv_bfloat16* __restrict__ dst,
+                                                                  long long dst_ld, int dst_col0, long long plane_stride) {
+  const long long total = rows * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C8;
+    const int c = static_cast<int>(i % C8) * 8;
+    float v[8];
+    load8(src + r * src_ld + c, v);
+    store8_planes(dst + r * dst_ld + dst_col0 + c, plane_stride, v);
+  }
+}
+
+// ---- conv weight [O][C][k] fp32 -> planes [k][Ototal][C] ----------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const float* __restrict__ w, int O, int C, int k,
+                                                                      __nv_bfloat16* __restrict__ dst, int Ototal, int o0,
+                                                                      long long plane_stride) {
+  const long long total = static_cast<long long>(O) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i / C), c = static_cast<int>(i % C);
+    for (int r = 0; r < k; ++r) {
+      __nv_bfloat16 h, l;
+      split_bf16(w[i * k + r], h, l);
+      const long long d = (static_cast<long long>(r) * Ototal + o0 + o) * C + c;
+      dst[d] = h;
+      dst[d + plane_stride] = l;
+    }
+  }
+}
+
+// ---- weight-gradient workspace [k][Ototal][C] -> grad [O][C][k] ---------------------------------
+__global__ void __launch_bounds__(EW_THREADS) unpack_conv_wgrad_kernel(const float* __restrict__ ws, int O, int C, int k,
+                                                                       int Ototal, int o0, float* __restrict__ grad,
+                                                                       int accumulate) {
+  const long long total = static_cast<long long>(O) * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i / C), c = static_cast<int>(i % C);
+    for (int r = 0; r < k; ++r) {
+      const float v = ws[(static_cast<long long>(r) * Ototal + o0 + o) * C + c];
+      if (accumulate) grad[i * k + r] += v;
+      else grad[i * k + r] = v;
+    }
+  }
+}
+
+// ---- position feature (model/main_model.py:53-55): Linear(3 -> Cp) of (s, e, e-s), written as planes ----------------
+__global__ void __launch_bounds__(EW_THREADS) pos_feature_kernel(const double* __restrict__ pse, const float* __restrict__ Wp,
+                                                                 const float* __restrict__ bp, long long rows, int Cp,
+                                                                 __nv_bfloat16* __restrict__ dst, long long dst_ld,
+                                                                 int dst_col0, long long plane_stride,
+                                                                 float* __restrict__ pos_in) {
+  const long long total = rows * Cp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / Cp;
+    const int c = static_cast<int>(i % Cp);
+    const double s = pse[2 * r], e = pse[2 * r + 1];
+    const float f0 = static_cast<float>(s), f1 = static_cast<float>(e), f2 = static_cast<float>(e - s);
+    if (c == 0 && pos_in) {
+      pos_in[3 * r] = f0;
+      pos_in[3 * r + 1] = f1;
+      pos_in[3 * r + 2] = f2;
+    }
+    float v = bp[c];
+    v = fmaf(f0, Wp[3 * c], v);
+    v = fmaf(f1, Wp[3 * c + 1], v);
+    v = fmaf(f2, Wp[3 * c + 2], v);
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    __nv_bfloat16* d = dst + r * dst_ld + dst_col0 + c;
+    d[0] = h;
+    d[plane_stride] = l;
+  }
+}
+
+// ---- column statistics: block = 32 x 8 threads, 128 columns x ROWS_PER_BLOCK rows -------------------------------------
+constexpr int STAT_ROWS = 64;
+
+template <int MODE>  // 0: sum y, sum y^2 ; 1: BN backward sums (sum g, sum g*xhat) with g = relu-masked da
+__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ y, const float* __restrict__ da,
+                                                        long long rows, int C, const float* __restrict__ coef,
+                                                        double* __restrict__ sums) {
+  __shared__ float red[2][8][128];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 128 + tx * 4;
+  const long long r0 = static_cast<long long>(blockIdx.y) * STAT_ROWS;
+  float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+  if (c < C) {
+    float sc[4], sh[4], mu[4], is[4];
+    if (MODE == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sc[j] = coef[c + j];
+        sh[j] = coef[C + c + j];
+        mu[j] = coef[2 * C + c + j];
+        is[j] = coef[3 * C + c + j];
+      }
+    }
+    for (int i = ty; i < STAT_ROWS; i += 8) {
+      const long long r = r0 + i;
+      if (r >= rows) break;
+      const float4 v4 = *reinterpret_cast<const float4*>(y + r * C + c);
+      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s0[j] += v[j];
+          s1[j] = fmaf(v[j], v[j], s1[j]);
+        }
+      } else {
+        const float4 g4 = *reinterpret_cast<const float4*>(da + r * C + c);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gm = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+          s0[j] += gm;
+          s1[j] = fmaf(gm, (v[j] - mu[j]) * is[j], s1[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][ty][tx * 4 + j] = s0[j];
+    red[1][ty][tx * 4 + j] = s1[j];
+  }
+  __syncthreads();
+  const int t = ty * 32 + tx;  // 256 threads: 2 x 128 outputs
+  const int which = t >> 7, col = t & 127;
+  if (blockIdx.x * 128 + col < C) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += static_cast<double>(red[which][i][col]);
+    atomicAdd(sums + static_cast<long long>(which) * C + blockIdx.x * 128 + col, acc);
+  }
+}
+
+// ---- BN finalize: batch statistics -> (scale, shift, mean, invstd) + running-stat update (torch BatchNorm1d semantics)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int sums_stride, long long n, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ nbt, float momentum, float eps, int training,
+                                   float* __restrict__ coef, int coef_stride) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt) nbt[0] += 1;
+  if (c >= C) return;
+  double mean, var;
+  if (training) {
+    mean = sums[c] / static_cast<double>(n);
+    var = sums[sums_stride + c] / static_cast<double>(n) - mean * mean;
+    if (var < 0) var = 0;
+    const double unbiased = (n > 1) ? var * static_cast<double>(n) / static_cast<double>(n - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float scale = gamma[c] * invstd;
+  coef[c] = scale;
+  coef[coef_stride + c] = beta[c] - static_cast<float>(mean) * scale;
+  coef[2 * coef_stride + c] = static_cast<float>(mean);
+  coef[3 * coef_stride + c] = invstd;
+}
+
+// ---- BN apply + ReLU (+ nearest x2 upsample add, + query gate) -> planes ---------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) bn_relu_apply_kernel(const float* __restrict__ y, int B, int T, int C,
+                                                                   const float* __restrict__ coef,
+                                                                   const __nv_bfloat16* __restrict__ up, long long up_ps,
+                                                                   const float* __restrict__ gate,
+                                                                   __nv_bfloat16* __restrict__ out_a, long long a_ps,
+                                                                   __nv_bfloat16* __restrict__ out_qa, long long qa_ps) {
+  const int C8 = C >> 3;
+  const long long total = static_cast<long long>(B) * T * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / C8;
+    const int c = static_cast<int>(i % C8) * 8;
+    const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
+    float v[8], sc[8], sh[8];
+    load8(y + row * C + c, v);
+    load8(coef + c, sc);
+    load8(coef + C + c, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+    if (up) {
+      float u[8];
+      load8_planes(up + (static_cast<long long>(b) * (T >> 1) + (t >> 1)) * C + c, up_ps, u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += u[j];
+    }
+    if (out_a) store8_planes(out_a + row * C + c, a_ps, v);
+    if (out_qa) {
+      float q[8];
+      load8(gate + static_cast<long long>(b) * C + c, q);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] *= v[j];
+      store8_planes(out_qa + row * C + c, qa_ps, q);
+    }
+  }
+}
+
+// ---- BN backward apply: dy = scale * (g - mean(g) - xhat * mean(g*xhat)) -> planes ------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ y,
+                                                                  long long rows, int C, const float* __restrict__ coef,
+                                                                  const double* __restrict__ sums,
+                                                                  __nv_bfloat16* __restrict__ dy, long long dy_ps) {
+  const int C8 = C >> 3;
+  const long long total = rows * C8;
+  const float inv_n = 1.f / static_cast<float>(rows);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / C8;
+    const int c = static_cast<int>(i % C8) * 8;
+    float v[8], g[8], sc[8], sh[8], mu[8], is[8];
+    load8(y + row * C + c, v);
+    load8(da + row * C + c, g);
+    load8(coef + c, sc);
+    load8(coef + C + c, sh);
+    load8(coef + 2 * C + c, mu);
+    load8(coef + 3 * C + c, is);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mg = static_cast<float>(sums[c + j]) * inv_n;
+      const float mgx = static_cast<float>(sums[C + c + j]) * inv_n;
+      const float gm = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+      const float xh = (v[j] - mu[j]) * is[j];
+      v[j] = sc[j] * (gm - mg - xh * mgx);
+    }
+    store8_planes(dy + row * C + c, dy_ps, v);
+  }
+}
+
+__global__ void bn_bwd_param_kernel(const double* __restrict__ sums, int sums_stride, int C, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] += static_cast<float>(sums[c]);
+  dgamma[c] += static_cast<float>(sums[sums_stride + c]);
+}
+
+// ---- FPN backward of nearest x2 upsample: dst[b,j,:] += src[b,2j,:] + src[b,2j+1,:] ------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) pair_sum_add_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                                  long long rows_half, int C) {
+  const int C4 = C >> 2;
+  const long long total = rows_half * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C4;
+    const int c = static_cast<int>(i % C4) * 4;
+    float4 d = *reinterpret_cast<const float4*>(dst + r * C + c);
+    const float4 a = *reinterpret_cast<const float4*>(src + (2 * r) * C + c);
+    const float4 b = *reinterpret_cast<const float4*>(src + (2 * r + 1) * C + c);
+    d.x += a.x + b.x; d.y += a.y + b.y; d.z += a.z + b.z; d.w += a.w + b.w;
+    *reinterpret_cast<float4*>(dst + r * C + c) = d;
+  }
+}
+
+// ---- gate gradient: dq[b,c] (+)= sum_t g[b,t,c] * a[b,t,c]; block = 32x8 threads, 128 columns of one sample -----------
+// A_PLANES: a is a planes tensor (hi+lo) else fp32.  Optionally also writes dP planes = q[b,c]*g and column sums of dP.
+template <bool A_PLANES>
+__global__ void __launch_bounds__(256) gate_reduce_kernel(const float* __restrict__ g, long long g_ld,
+                                                          const void* __restrict__ a, long long a_ld, long long a_ps, int T,
+                                                          int C, int t_chunk, float* __restrict__ dq,
+                                                          const float* __restrict__ q, __nv_bfloat16* __restrict__ dp,
+                                                          long long dp_ps, float* __restrict__ dbias) {
+  __shared__ float red[2][8][128];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 128 + tx * 4;
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.y * t_chunk;
+  float s[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0};
+  if (c < C) {
+    float qv[4] = {0, 0, 0, 0};
+    if (dp) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qv[j] = q[static_cast<long long>(b) * C + c + j];
+    }
+    for (int i = ty; i < t_chunk; i += 8) {
+      const int t = t0 + i;
+      if (t >= T) break;
+      const long long row = static_cast<long long>(b) * T + t;
+      const float4 g4 = *reinterpret_cast<const float4*>(g + row * g_ld + c);
+      const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+      float av[4];
+      if (A_PLANES) {
+        const __nv_bfloat16* ah = static_cast<const __nv_bfloat16*>(a) + row * a_ld + c;
+        const uint2 h = *reinterpret_cast<const uint2*>(ah);
+        const uint2 l = *reinterpret_cast<const uint2*>(ah + a_ps);
+        av[0] = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+        av[1] = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+        av[2] = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+        av[3] = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+      } else {
+        const float4 a4 = *reinterpret_cast<const float4*>(static_cast<const float*>(a) + row * a_ld + c);
+        av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] = fmaf(gv[j], av[j], s[j]);
+      if (dp) {
+        float pv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pv[j] = gv[j] * qv[j];
+          sb[j] += pv[j];
+        }
+        __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+        split_bf16(pv[0], h0, l0); split_bf16(pv[1], h1, l1); split_bf16(pv[2], h2, l2); split_bf16(pv[3], h3, l3);
+        __nv_bfloat16* d = dp + row * C + c;
+        *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        *reinterpret_cast<uint2*>(d + dp_ps) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[0][ty][tx * 4 + j] = s[j];
+    red[1][ty][tx * 4 + j] = sb[j];
+  }
+  __syncthreads();
+  const int t = ty * 32 + tx;
+  const int which = t >> 7, col = t & 127;
+  const int cc = blockIdx.x * 128 + col;
+  if (cc < C) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += red[which][i][col];
+    if (which == 0) atomicAdd(dq + static_cast<long long>(b) * C + cc, acc);
+    else if (dbias) atomicAdd(dbias + cc, acc);
+  }
+}
+
+// ---- position-feature backward: dWp[c][j] += sum_rows dpos[row,c]*pos_in[row,j], dbp[c] += sum_rows dpos[row,c] ----------
+__global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ dx, long long dx_ld, int col0,
+                                                      const float* __restrict__ pos_in, long long rows, int Cp,
+                                                      int rows_per_block, float* __restrict__ dWp, float* __restrict__ dbp) {
+  const int c = threadIdx.x;  // Cp <= 256 threads
+  if (c >= Cp) return;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  float a0 = 0, a1 = 0, a2 = 0, ab = 0;
+  for (int i = 0; i < rows_per_block; ++i) {
+    const long long r = r0 + i;
+    if (r >= rows) break;
+    const float g = dx[r * dx_ld + col0 + c];
+    a0 = fmaf(g, pos_in[3 * r], a0);
+    a1 = fmaf(g, pos_in[3 * r + 1], a1);
+    a2 = fmaf(g, pos_in[3 * r + 2], a2);
+    ab += g;
+  }
+  atomicAdd(dWp + 3 * c, a0);
+  atomicAdd(dWp + 3 * c + 1, a1);
+  atomicAdd(dWp + 3 * c + 2, a2);
+  atomicAdd(dbp + c, ab);
+}
+
+// ---- column sums (bias gradients of the small Linear layers): out[c] += sum_rows x[row,c] ------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld,
+                                                     float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) acc += x[r * ld + c];
+  atomicAdd(out + c, acc);
+}
+
+static inline int ew_grid(long long total) {
+  long long g = (total + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace drn
+
+using namespace drn;
+
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int drn_split_planes(const float* src, int64_t rows, int C, int64_t src_ld, void* dst, int64_t dst_ld,
+                                int dst_col0, int64_t dst_plane_stride, void* stream) {
+  if (C % 8 || src_ld % 4 || dst_ld % 8 || dst_col0 % 8 || dst_plane_stride % 8) return fail(DRN_EINVAL, "drn_split_planes: alignment (C=%d)", C);
+  if (rows <= 0) return 0;
+  split_planes_kernel<<<ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream)>>>(src, rows, C / 8, src_ld, static_cast<__nv_bfloat16*>(dst),
+                                                                              dst_ld, dst_col0, dst_plane_stride);
+  return check_launch("split_planes");
+}
+
+extern "C" int drn_pack_conv_weight(const float* w, int O, int C, int k, void* dst, int Ototal, int o0, int64_t plane_stride,
+                                    void* stream) {
+  pack_conv_weight_kernel<<<ew_grid(static_cast<long long>(O) * C), EW_THREADS, 0, ST(stream)>>>(
+      w, O, C, k, static_cast<__nv_bfloat16*>(dst), Ototal, o0, plane_stride);
+  return check_launch("pack_conv_weight");
+}
+
+extern "C" int drn_unpack_conv_wgrad(const float* ws, int O, int C, int k, int Ototal, int o0, float* grad, int accumulate,
+                                     void* stream) {
+  unpack_conv_wgrad_kernel<<<ew_grid(static_cast<long long>(O) * C), EW_THREADS, 0, ST(stream)>>>(ws, O, C, k, Ototal, o0, grad,
+                                                                                                   accumulate);
+  return check_launch("unpack_conv_wgrad");
+}
+
+extern "C" int drn_pos_feature(const double* pse, const float* Wp, const float* bp, int64_t rows, int Cp, void* dst,
+                               int64_t dst_ld, int dst_col0, int64_t plane_stride, float* pos_in, void* stream) {
+  pos_feature_kernel<<<ew_grid(rows * Cp), EW_THREADS, 0, ST(stream)>>>(pse, Wp, bp, rows, Cp, static_cast<__nv_bfloat16*>(dst),
+                                                                        dst_ld, dst_col0, plane_stride, pos_in);
+  return check_launch("pos_feature");
+}
+
+extern "C" int drn_bn_stats(const float* y, int64_t rows, int C, double* sums, void* stream) {
+  if (C % 4) return fail(DRN_EINVAL, "drn_bn_stats: C %% 4");
+  dim3 grid(ceil_div(C, 128), static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS));
+  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, nullptr, rows, C, nullptr, sums);
+  return check_launch("bn_stats");
+}
+
+extern "C" int drn_bn_finalize(const double* sums, int sums_stride, int64_t n, int C, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps, int training,
+                               float* coef, int coef_stride, void* stream) {
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(sums, sums_stride, n, C, gamma, beta, running_mean, running_var,
+                                                               reinterpret_cast<long long*>(nbt), momentum, eps, training, coef,
+                                                               coef_stride);
+  return check_launch("bn_finalize");
+}
+
+extern "C" int drn_bn_relu_apply(const float* y, int B, int T, int C, const float* coef, const void* up, int64_t up_plane_stride,
+                                 const float* gate, void* out_a, int64_t a_plane_stride, void* out_qa, int64_t qa_plane_stride,
+                                 void* stream) {
+  if (C % 8) return fail(DRN_EINVAL, "drn_bn_relu_apply: C %% 8");
+  if (up && (T % 2)) return fail(DRN_EINVAL, "drn_bn_relu_apply: upsample-add needs even T");
+  if (out_qa && !gate) return fail(DRN_EINVAL, "drn_bn_relu_apply: gated output without gate");
+  bn_relu_apply_kernel<<<ew_grid(static_cast<long long>(B) * T * (C / 8)), EW_THREADS, 0, ST(stream)>>>(
+      y, B, T, C, coef, static_cast<const __nv_bfloat16*>(up), up_plane_stride, gate, static_cast<__nv_bfloat16*>(out_a),
+      a_plane_stride, static_cast<__nv_bfloat16*>(out_qa), qa_plane_stride);
+  return check_launch("bn_relu_apply");
+}
+
+extern "C" int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, const float* coef, double* sums,
+                                 void* stream) {
+  if (C % 4) return fail(DRN_EINVAL, "drn_bn_bwd_reduce: C %% 4");
+  dim3 grid(ceil_div(C, 128), static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS));
+  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, da, rows, C, coef, sums);
+  return check_launch("bn_bwd_reduce");
+}
+
+extern "C" int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const double* sums,
+                                void* dy, int64_t dy_plane_stride, void* stream) {
+  if (C % 8) return fail(DRN_EINVAL, "drn_bn_bwd_apply: C %% 8");
+  bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream)>>>(da, y, rows, C, coef, sums,
+                                                                              static_cast<__nv_bfloat16*>(dy), dy_plane_stride);
+  return check_launch("bn_bwd_apply");
+}
+
+extern "C" int drn_bn_bwd_param(const double* sums, int sums_stride, int C, float* dgamma, float* dbeta, void* stream) {
+  bn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(sums, sums_stride, C, dgamma, dbeta);
+  return check_launch("bn_bwd_param");
+}
+
+extern "C" int drn_pair_sum_add(float* dst, const float* src, int64_t rows_half, int C, void* stream) {
+  if (C % 4) return fail(DRN_EINVAL, "drn_pair_sum_add: C %% 4");
+  pair_sum_add_kernel<<<ew_grid(rows_half * (C / 4)), EW_THREADS, 0, ST(stream)>>>(dst, src, rows_half, C);
+  return check_launch("pair_sum_add");
+}
+
+extern "C" int drn_gate_reduce(const float* g, int64_t g_ld, const void* a, int64_t a_ld, int64_t a_plane_stride, int a_is_planes,
+                               int B, int T, int C, float* dq, const float* q, void* dp, int64_t dp_plane_stride, float* dbias,
+                               void* stream) {
+  if (C % 4 || g_ld % 4 || a_ld % 4) return fail(DRN_EINVAL, "drn_gate_reduce: alignment");
+  const int t_chunk = 64;
+  dim3 grid(ceil_div(C, 128), ceil_div(T, t_chunk), B);
+  if (a_is_planes)
+    gate_reduce_kernel<true><<<grid, dim3(32, 8), 0, ST(stream)>>>(g, g_ld, a, a_ld, a_plane_stride, T, C, t_chunk, dq, q,
+                                                                  static_cast<__nv_bfloat16*>(dp), dp_plane_stride, dbias);
+  else
+    gate_reduce_kernel<false><<<grid, dim3(32, 8), 0, ST(stream)>>>(g, g_ld, a, a_ld, a_plane_stride, T, C, t_chunk, dq, q,
+                                                                   static_cast<__nv_bfloat16*>(dp), dp_plane_stride, dbias);
+  return check_launch("gate_reduce");
+}
+
+extern "C" int drn_pos_bwd(const float* dx, int64_t dx_ld, int col0, const float* pos_in, int64_t rows, int Cp, float* dWp,
+                           float* dbp, void* stream) {
+  if (Cp > 256) return fail(DRN_EINVAL, "drn_pos_bwd: Cp > 256");
+  const int rpb = 64;
+  pos_bwd_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, 0, ST(stream)>>>(dx, dx_ld, col0, pos_in, rows, Cp, rpb, dWp,
+                                                                                       dbp);
+  return check_launch("pos_bwd");
+}
+
+extern "C" int drn_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream) {
+  dim3 grid(ceil_div(C, 256), static_cast<unsigned>(rows < 64 ? rows : 64));
+  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(x, rows, C, ld, out);
+  return check_launch("colsum");
+}

@@ -1,0 +1,386 @@
+// FCOS head projections (the N = 1 / 2 / 1 skinny convs of model/fcos.py:41-69, on CUDA cores), closed-form target
+// assignment (model/loss.py:90-127), sigmoid focal loss (model/layers/sigmoid_focal_loss.py:40-52, stable log-sigmoid),
+// IoU regression loss (model/layers/iou_loss.py:5-24), the stage-2/3 IoU-score branch (model/loss.py:168-198) and
+// all of their backward passes.  One thread per location; scalars are reduced block-wise and accumulated in fp64.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace drn {
+
+constexpr int MAX_LEVELS = 4;
+
+struct LevelGeom {
+  int nlevels;
+  int B;
+  int T[MAX_LEVELS];      // locations per sample on each level
+  int off[MAX_LEVELS];    // cumulative locations per sample before this level
+  float stride[MAX_LEVELS];
+  float lo[MAX_LEVELS], hi[MAX_LEVELS];  // size-of-interest bands (model/loss.py:47-51)
+  int P;                  // total locations per sample
+};
+
+// ---- skinny conv forward: out[b,t,o] = bias[o] + sum_r sum_c W[o][c][r] * X[b, t+r-pad, c0+c]; one warp per (b,t) ------
+template <int NOUT, int K>
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ps, int x_ld, int c0,
+                                                         int Cw, int B, int T, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * T) return;
+  const int b = warp / T, t = warp % T;
+  constexpr int PAD = (K - 1) / 2;
+  float acc[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) acc[o] = 0.f;
+#pragma unroll
+  for (int r = 0; r < K; ++r) {
+    const int ts = t + r - PAD;
+    if (ts < 0 || ts >= T) continue;
+    const __nv_bfloat16* row = x + (static_cast<long long>(b) * T + ts) * x_ld + c0;
+    for (int c = lane * 8; c < Cw; c += 256) {
+      const uint4 h = *reinterpret_cast<const uint4*>(row + c);
+      const uint4 l = *reinterpret_cast<const uint4*>(row + c + x_ps);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(hw[i] << 16) + __uint_as_float(lw[i] << 16);
+        v[2 * i + 1] = __uint_as_float(hw[i] & 0xffff0000u) + __uint_as_float(lw[i] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[o] = fmaf(v[j], __ldg(W + (static_cast<long long>(o) * Cw + c + j) * K + r), acc[o]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    const float s = warp_sum(acc[o]);
+    if (lane == 0) out[static_cast<long long>(warp) * NOUT + o] = s + bias[o];
+  }
+}
+
+// ---- skinny conv backward: dX[b,t,c0+c] = sum_o sum_r d[b,t+pad-r,o] W[o][c][r];  dW[o][c][r] += sum X[b,t,c] d[b,t+pad-r,o]
+// one thread per channel, a block walks a chunk of rows.
+template <int NOUT, int K>
+__global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict__ d, const __nv_bfloat16* __restrict__ x,
+                                                         long long x_ps, int x_ld, int c0, int Cw, int B, int T,
+                                                         const float* __restrict__ W, int rows_per_block,
+                                                         float* __restrict__ dx, int dx_ld, int dx_accumulate,
+                                                         float* __restrict__ dW) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cw) return;
+  constexpr int PAD = (K - 1) / 2;
+  float w[NOUT][K], gw[NOUT][K];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      w[o][r] = W[(static_cast<long long>(o) * Cw + c) * K + r];
+      gw[o][r] = 0.f;
+    }
+  const long long rows = static_cast<long long>(B) * T;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  for (int i = 0; i < rows_per_block; ++i) {
+    const long long row = r0 + i;
+    if (row >= rows) break;
+    const int t = static_cast<int>(row % T);
+    const __nv_bfloat16* xp = x + row * x_ld + c0 + c;
+    const float xv = __bfloat162float(xp[0]) + __bfloat162float(xp[x_ps]);
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int td = t + PAD - r;
+      if (td < 0 || td >= T) continue;
+#pragma unroll
+      for (int o = 0; o < NOUT; ++o) {
+        const float e = __ldg(d + (row + PAD - r) * NOUT + o);
+        g = fmaf(e, w[o][r], g);
+        gw[o][r] = fmaf(e, xv, gw[o][r]);
+      }
+    }
+    float* dp = dx + row * dx_ld + c0 + c;
+    if (dx_accumulate) *dp += g;
+    else *dp = g;
+  }
+  if (dW) {
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+      for (int r = 0; r < K; ++r) atomicAdd(dW + (static_cast<long long>(o) * Cw + c) * K + r, gw[o][r]);
+  }
+}
+
+// ---- loss ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
+
+struct LocInfo {
+  int lvl, b, t;
+  float loc;
+};
+__device__ __forceinline__ LocInfo locate(const LevelGeom& g, long long i) {
+  LocInfo r;
+  r.lvl = 0;
+#pragma unroll
+  for (int l = 1; l < MAX_LEVELS; ++l)
+    if (l < g.nlevels && i >= static_cast<long long>(g.B) * g.off[l]) r.lvl = l;
+  const long long j = i - static_cast<long long>(g.B) * g.off[r.lvl];
+  r.b = static_cast<int>(j / g.T[r.lvl]);
+  r.t = static_cast<int>(j % g.T[r.lvl]);
+  r.loc = g.stride[r.lvl] * r.t + g.stride[r.lvl] * 0.5f;  // model/fcos.py:204-211
+  return r;
+}
+
+struct IouBranch {
+  float tiou, dt_dpl, dt_dpr;  // tIoU of the decoded prediction vs GT and its derivative w.r.t. the (left,right) distances
+};
+// model/loss.py:176-187 + segment_tiou (241-256).  `first` = first location of the sample in level-major order, the only
+// one the reference clamps to [0,1] (the loss.py:180-181 quirk).
+__device__ __forceinline__ IouBranch iou_branch(float loc, float pl, float pr, float gs, float ge, bool first) {
+  float ps = (loc - pl) * (1.f / 32.f), pe = (loc + pr) * (1.f / 32.f);
+  float cs = 1.f, ce = 1.f;  // clamp pass-through
+  if (first) {
+    if (ps < 0.f || ps > 1.f) cs = 0.f;
+    if (pe < 0.f || pe > 1.f) ce = 0.f;
+    ps = fminf(fmaxf(ps, 0.f), 1.f);
+    pe = fminf(fmaxf(pe, 0.f), 1.f);
+  }
+  const float iraw = fminf(pe, ge) - fmaxf(ps, gs);
+  const float uraw = fmaxf(pe, ge) - fminf(ps, gs);
+  const float inter = fmaxf(iraw, 0.f), uni = fmaxf(uraw, 0.f);
+  const float den = uni + 1e-6f;
+  IouBranch r;
+  r.tiou = inter / den;
+  const float ia = iraw > 0.f ? 1.f : 0.f, ua = uraw > 0.f ? 1.f : 0.f;
+  const float di_dpe = ia * (pe < ge ? 1.f : 0.f), di_dps = -ia * (ps > gs ? 1.f : 0.f);
+  const float du_dpe = ua * (pe > ge ? 1.f : 0.f), du_dps = -ua * (ps < gs ? 1.f : 0.f);
+  const float dt_dpe = (di_dpe * den - inter * du_dpe) / (den * den);
+  const float dt_dps = (di_dps * den - inter * du_dps) / (den * den);
+  r.dt_dpl = dt_dps * cs * (-1.f / 32.f);
+  r.dt_dpr = dt_dpe * ce * (1.f / 32.f);
+  return r;
+}
+
+// acc: [0] focal sum, [1] n_pos, [2] sum of -log IoU over positives, [3] smooth-L1 sum, [4] IoU-branch count
+__global__ void __launch_bounds__(256) fcos_loss_fwd_kernel(LevelGeom g, const float* __restrict__ cls_raw,
+                                                            const float* __restrict__ box_raw, const float* __restrict__ iou_raw,
+                                                            const float* __restrict__ scales, const float* __restrict__ gt,
+                                                            float gamma, float alpha, int iou_branch_on,
+                                                            float* __restrict__ bbox_out, double* __restrict__ acc) {
+  __shared__ double red[5][8];
+  const long long total = static_cast<long long>(g.B) * g.P;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  double v[5] = {0, 0, 0, 0, 0};
+  if (i < total) {
+    const LocInfo L = locate(g, i);
+    const float s = scales[L.lvl];
+    const float pl = expf(box_raw[2 * i] * s), pr = expf(box_raw[2 * i + 1] * s);
+    bbox_out[2 * i] = pl;
+    bbox_out[2 * i + 1] = pr;
+    const float gs = gt[2 * L.b], ge = gt[2 * L.b + 1];
+    const float tl = L.loc - gs * 32.f, tr = ge * 32.f - L.loc;
+    const float m = fmaxf(tl, tr);
+    const bool pos = (fminf(tl, tr) > 0.f) && (m >= g.lo[L.lvl]) && (m <= g.hi[L.lvl]);
+    const float x = cls_raw[i];
+    const float p = 1.f / (1.f + expf(-x));
+    if (pos) {
+      v[0] = -alpha * powf(1.f - p, gamma) * log_sigmoid(x);
+      v[1] = 1.0;
+      const float inter = fminf(pl, tl) + fminf(pr, tr);
+      const float uni = tl + tr + pl + pr - inter;
+      v[2] = -logf((inter + 1e-8f) / (uni + 1e-8f));
+    } else {
+      v[0] = -(1.f - alpha) * powf(p, gamma) * log_sigmoid(-x);
+    }
+    if (iou_branch_on) {
+      const IouBranch ib = iou_branch(L.loc, pl, pr, gs, ge, L.lvl == 0 && L.t == 0);
+      if (ib.tiou > 0.9f) {
+        const float d = 1.f / (1.f + expf(-iou_raw[i])) - ib.tiou;
+        const float ad = fabsf(d);
+        v[3] = ad < 1.f ? 0.5f * d * d : ad - 0.5f;
+        v[4] = 1.0;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) red[k][warp] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    if (s != 0.0) atomicAdd(acc + threadIdx.x, s);
+  }
+}
+
+// losses: [0] loss_cls, [1] loss_reg, [2] loss_iou, [3] n_pos, [4] IoU-branch count
+__global__ void fcos_loss_finalize_kernel(const double* __restrict__ acc, int B, float* __restrict__ losses) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double npos = acc[1], cnt = acc[4];
+  losses[0] = static_cast<float>(acc[0] / (npos + B));          // model/loss.py:210-213
+  losses[1] = npos > 0 ? static_cast<float>(acc[2] / npos) : 0.f;  // loss.py:215-231
+  losses[2] = cnt > 0 ? static_cast<float>(acc[3] / cnt) : 0.f;    // loss.py:189-197
+  losses[3] = static_cast<float>(npos);
+  losses[4] = static_cast<float>(cnt);
+}
+
+// upstream: [0] d loss_cls, [1] d loss_reg, [2] d loss_iou.  Outputs gradients w.r.t. the raw conv outputs.
+// pgrad: [0] d cls_logits.bias, [1..2] d bbox_pred.bias, [3] d iou_scores.3.bias, [4..4+nlevels) d scales
+__global__ void __launch_bounds__(256) fcos_loss_bwd_kernel(LevelGeom g, const float* __restrict__ cls_raw,
+                                                            const float* __restrict__ box_raw, const float* __restrict__ iou_raw,
+                                                            const float* __restrict__ scales, const float* __restrict__ gt,
+                                                            float gamma, float alpha, int iou_branch_on,
+                                                            const double* __restrict__ acc, const float* __restrict__ upstream,
+                                                            float* __restrict__ dcls, float* __restrict__ dbox,
+                                                            float* __restrict__ diou, float* __restrict__ pgrad) {
+  __shared__ float red[4 + MAX_LEVELS][8];
+  const long long total = static_cast<long long>(g.B) * g.P;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  float pg[4 + MAX_LEVELS];
+#pragma unroll
+  for (int k = 0; k < 4 + MAX_LEVELS; ++k) pg[k] = 0.f;
+  if (i < total) {
+    const LocInfo L = locate(g, i);
+    const float npos = static_cast<float>(acc[1]), cnt = static_cast<float>(acc[4]);
+    const float g_cls = upstream[0] / (npos + g.B);
+    const float g_reg = npos > 0.f ? upstream[1] / npos : 0.f;
+    const float g_iou = (iou_branch_on && cnt > 0.f) ? upstream[2] / cnt : 0.f;
+    const float s = scales[L.lvl];
+    const float r0 = box_raw[2 * i], r1 = box_raw[2 * i + 1];
+    const float pl = expf(r0 * s), pr = expf(r1 * s);
+    const float gs = gt[2 * L.b], ge = gt[2 * L.b + 1];
+    const float tl = L.loc - gs * 32.f, tr = ge * 32.f - L.loc;
+    const float m = fmaxf(tl, tr);
+    const bool pos = (fminf(tl, tr) > 0.f) && (m >= g.lo[L.lvl]) && (m <= g.hi[L.lvl]);
+    const float x = cls_raw[i];
+    const float p = 1.f / (1.f + expf(-x));
+    float dx, dpl = 0.f, dpr = 0.f, du = 0.f;
+    if (pos) {
+      dx = -alpha * powf(1.f - p, gamma) * ((1.f - p) - gamma * p * log_sigmoid(x));
+      const float il = pl < tl ? 1.f : 0.f, ir = pr < tr ? 1.f : 0.f;
+      const float inter = fminf(pl, tl) + fminf(pr, tr);
+      const float uni = tl + tr + pl + pr - inter;
+      dpl = g_reg * (-il / (inter + 1e-8f) + (1.f - il) / (uni + 1e-8f));
+      dpr = g_reg * (-ir / (inter + 1e-8f) + (1.f - ir) / (uni + 1e-8f));
+    } else {
+      dx = -(1.f - alpha) * powf(p, gamma) * (gamma * (1.f - p) * log_sigmoid(-x) - p);
+    }
+    dx *= g_cls;
+    if (g_iou != 0.f) {
+      const IouBranch ib = iou_branch(L.loc, pl, pr, gs, ge, L.lvl == 0 && L.t == 0);
+      if (ib.tiou > 0.9f) {
+        const float sg = 1.f / (1.f + expf(-iou_raw[i]));
+        const float d = sg - ib.tiou;
+        const float dl = (fabsf(d) < 1.f ? d : (d > 0.f ? 1.f : -1.f)) * g_iou;
+        du = dl * sg * (1.f - sg);
+        dpl -= dl * ib.dt_dpl;
+        dpr -= dl * ib.dt_dpr;
+      }
+    }
+    const float d0 = dpl * pl * s, d1 = dpr * pr * s;  // through exp(scale * raw), model/fcos.py:98-100
+    dcls[i] = dx;
+    dbox[2 * i] = d0;
+    dbox[2 * i + 1] = d1;
+    diou[i] = du;
+    pg[0] = dx;
+    pg[1] = d0;
+    pg[2] = d1;
+    pg[3] = du;
+    const float ds = dpl * pl * r0 + dpr * pr * r1;
+#pragma unroll
+    for (int l = 0; l < MAX_LEVELS; ++l)
+      if (l == L.lvl) pg[4 + l] = ds;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 4 + MAX_LEVELS; ++k) {
+    const float sm = warp_sum(pg[k]);
+    if (lane == 0) red[k][warp] = sm;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 + g.nlevels) {
+    float sm = 0;
+    for (int w = 0; w < 8; ++w) sm += red[threadIdx.x][w];
+    if (sm != 0.f) atomicAdd(pgrad + threadIdx.x, sm);
+  }
+}
+
+}  // namespace drn
+
+using namespace drn;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+static int make_geom(LevelGeom* g, int nlevels, int B, const int* T, const float* strides) {
+  if (nlevels < 1 || nlevels > 3) return fail(DRN_EINVAL, "fcos: the reference defines size bands for exactly 3 levels (got %d)", nlevels);
+  const float lo[3] = {-1.f, 5.6f, 11.f}, hi[3] = {6.f, 11.f, 100000000.f};  // model/loss.py:47-51
+  g->nlevels = nlevels;
+  g->B = B;
+  int off = 0;
+  for (int l = 0; l < nlevels; ++l) {
+    g->T[l] = T[l];
+    g->off[l] = off;
+    off += T[l];
+    g->stride[l] = strides[l];
+    g->lo[l] = lo[l];
+    g->hi[l] = hi[l];
+  }
+  g->P = off;
+  return 0;
+}
+
+extern "C" int drn_skinny_conv_fwd(const void* x, int64_t x_plane_stride, int x_ld, int c0, int Cw, int B, int T, int nout, int k,
+                                   const float* W, const float* bias, float* out, void* stream) {
+  if (Cw % 8 || x_ld % 8 || c0 % 8) return fail(DRN_EINVAL, "drn_skinny_conv_fwd: alignment");
+  const long long warps = static_cast<long long>(B) * T;
+  const unsigned grid = static_cast<unsigned>((warps * 32 + 255) / 256);
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  if (nout == 1 && k == 3) skinny_fwd_kernel<1, 3><<<grid, 256, 0, ST(stream)>>>(xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
+  else if (nout == 2 && k == 3) skinny_fwd_kernel<2, 3><<<grid, 256, 0, ST(stream)>>>(xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
+  else if (nout == 1 && k == 1) skinny_fwd_kernel<1, 1><<<grid, 256, 0, ST(stream)>>>(xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
+  else return fail(DRN_EINVAL, "drn_skinny_conv_fwd: unsupported (nout=%d,k=%d)", nout, k);
+  return check_launch("skinny_conv_fwd");
+}
+
+extern "C" int drn_skinny_conv_bwd(const float* d, const void* x, int64_t x_plane_stride, int x_ld, int c0, int Cw, int B, int T,
+                                   int nout, int k, const float* W, float* dx, int dx_ld, int dx_accumulate, float* dW,
+                                   void* stream) {
+  const int rpb = 64;
+  dim3 grid(ceil_div(Cw, 256), static_cast<unsigned>((static_cast<long long>(B) * T + rpb - 1) / rpb));
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+  if (nout == 1 && k == 3) skinny_bwd_kernel<1, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
+  else if (nout == 2 && k == 3) skinny_bwd_kernel<2, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
+  else if (nout == 1 && k == 1) skinny_bwd_kernel<1, 1><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
+  else return fail(DRN_EINVAL, "drn_skinny_conv_bwd: unsupported (nout=%d,k=%d)", nout, k);
+  return check_launch("skinny_conv_bwd");
+}
+
+extern "C" int drn_fcos_loss_fwd(int nlevels, int B, const int* T, const float* strides, const float* cls_raw, const float* box_raw,
+                                 const float* iou_raw, const float* scales, const float* gt, float gamma, float alpha,
+                                 int iou_branch_on, float* bbox_out, double* acc, float* losses, void* stream) {
+  LevelGeom g;
+  int rc = make_geom(&g, nlevels, B, T, strides);
+  if (rc) return rc;
+  cudaError_t e = cudaMemsetAsync(acc, 0, 8 * sizeof(double), ST(stream));
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "memset: %s", cudaGetErrorString(e));
+  const long long total = static_cast<long long>(B) * g.P;
+  fcos_loss_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ST(stream)>>>(g, cls_raw, box_raw, iou_raw, scales, gt, gamma,
+                                                                                         alpha, iou_branch_on, bbox_out, acc);
+  fcos_loss_finalize_kernel<<<1, 32, 0, ST(stream)>>>(acc, B, losses);
+  return check_launch("fcos_loss_fwd");
+}
+
+extern "C" int drn_fcos_loss_bwd(int nlevels, int B, const int* T, const float* strides, const float* cls_raw, const float* box_raw,
+                                 const float* iou_raw, const float* scales, const float* gt, float gamma, float alpha,
+                                 int iou_branch_on, const double* acc, const float* upstream, float* dcls, float* dbox, float* diou,
+                                 float* pgrad, void* stream) {
+  LevelGeom g;
+  int rc = make_geom(&g, nlevels, B, T, strides);
+  if (rc) return rc;
+  const long long total = static_cast<long long>(B) * g.P;
+  fcos_loss_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ST(stream)>>>(
+      g, cls_raw, box_raw, iou_raw, scales, gt, gamma, alpha, iou_branch_on, acc, upstream, dcls, dbox, diou, pgrad);
+  return check_launch("fcos_loss_bwd");
+}

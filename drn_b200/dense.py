@@ -1,0 +1,429 @@
+"""Host-side schedule of the DRN dense-regression path on libdrn_sm100 kernels.
+
+`DensePath` owns the device buffers for one (B, T) shape and enqueues, on the current CUDA stream, the forward
+(model/main_model.py:48-74 after the query encoder: gates, position feature, prop_fc, backbone, FPN, FCOS head, losses)
+and the hand-derived backward of the same graph.  Python here only marshals pointers: every FLOP and every byte is
+moved by a kernel of the C-ABI library (include/drn_b200.h).  Layouts are channels-last; tensor-core operands are
+split-BF16 planes (drn_b200/planes.py).
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+from . import ops
+from .planes import Planes
+
+K1 = ((0, 0, 0),)
+K3 = ((-1, 0, 0), (0, 0, 1), (1, 0, 2))            # (time shift, parity, weight tap) of a k3/s1/p1 conv
+K3S2 = ((-1, 1, 0), (0, 0, 1), (0, 1, 2))           # k3/s2/p1 on the [T/2][2] parity view: input row 2t+r-1
+K3_DGRAD = ((1, 0, 0), (0, 0, 1), (-1, 0, 2))       # dX[u] = sum_r dY[u+1-r] W_r
+S2_DGRAD = (((0, 0, 1),), ((1, 0, 0), (0, 0, 2)))   # per output parity u = 2j+p
+BN_MOMENTUM, BN_EPS = 0.1, 1e-5
+SM_COUNT = 148
+
+
+def _lib():
+    return L.load()
+
+
+def _st():
+    return L.stream_ptr()
+
+
+def _vp(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class ConvBN:
+    """Buffers of one conv -> BatchNorm(train) -> ReLU application (one level of a shared head block = one ConvBN)."""
+
+    def __init__(self, prefix, cin, cout, k, stride, B, t_in, dev, bn_parts=None):
+        self.prefix, self.cin, self.cout, self.k, self.stride = prefix, cin, cout, k, stride
+        self.t_in, self.t_out = t_in, t_in // stride
+        self.rows = B * self.t_out
+        self.y = torch.empty(B, self.t_out, cout, device=dev)
+        self.coef = torch.empty(4, cout, device=dev)
+        self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+        self.bsums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+        self.dy = Planes.empty(B, self.t_out, cout, dev)
+        # bn_parts: [(param prefix, channel offset, channels)] -- the fused cls|bbox tower has two BatchNorm modules
+        self.bn_parts = bn_parts or [(prefix + ".1", 0, cout)]
+
+
+class DensePath:
+    def __init__(self, cfg, B, T, device):
+        assert T % 4 == 0, "T must be a multiple of 4 (two stride-2 levels)"
+        self.cfg, self.B, self.T, self.dev = cfg, B, T, device
+        D = cfg[cfg["feature_type"]]["feature_dim"]
+        c1, F = cfg["first_output_dim"], cfg["fpn_feature_dim"]
+        self.D, self.C0, self.c = D, D + 256, (c1, 2 * c1, 4 * c1)
+        self.F = F
+        self.Tl = (T, T // 2, T // 4)
+        self.P = sum(self.Tl)
+        self.strides = [float(s) for s in cfg["fpn_stride"]]
+        dev = device
+        e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+        z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
+        # inputs / gates
+        self.f_pl = Planes.empty(B, T, D, dev)
+        self.cmd_pl = [Planes.empty(1, B, 1024, dev) for _ in range(3)]
+        self.qdim = (D, c1, 2 * c1)
+        self.q = [e(B, n) for n in self.qdim]
+        self.dq = [z(B, n) for n in self.qdim]
+        self.dq_pl = [Planes.empty(1, B, n, dev) for n in self.qdim]
+        self.dcmd = [e(B, 1024) for _ in range(3)]
+        self.pos_in = e(B * T, 3)
+        self.Pre = e(B, T, D)                       # prop_fc output before gating
+        self.X0 = Planes.empty(B, T, self.C0, dev)  # [q0 * prop_fc(f) | position feature]
+        self.dX0 = e(B, T, self.C0)
+        self.dP_pl = Planes.empty(B, T, D, dev)
+        # backbone
+        self.conv = [ConvBN("backbone_net.forward_conv0", self.C0, c1, 3, 1, B, T, dev),
+                     ConvBN("backbone_net.forward_conv1", c1, 2 * c1, 3, 2, B, T, dev),
+                     ConvBN("backbone_net.forward_conv2", 2 * c1, 4 * c1, 3, 2, B, T // 2, dev)]
+        self.Cact = [Planes.empty(B, self.Tl[i], self.c[i], dev) for i in range(3)]
+        self.QC = [Planes.empty(B, self.Tl[i], self.c[i], dev) for i in range(2)]
+        self.dC = [e(B, self.Tl[i], self.c[i]) for i in range(3)]
+        self.dQC = [e(B, self.Tl[i], self.c[i]) for i in range(2)]
+        # FPN
+        self.inner = [ConvBN("fpn.fpn_inner%d" % (i + 1), self.c[i], F, 1, 1, B, self.Tl[i], dev) for i in range(3)]
+        self.layer = [ConvBN("fpn.fpn_layer%d" % (i + 1), F, F, 3, 1, B, self.Tl[i], dev) for i in range(3)]
+        self.I = [Planes.empty(B, self.Tl[i], F, dev) for i in range(3)]
+        self.Pf = [Planes.empty(B, self.Tl[i], F, dev) for i in range(3)]
+        self.dI = [e(B, self.Tl[i], F) for i in range(3)]
+        self.dPf = [e(B, self.Tl[i], F) for i in range(3)]
+        # head (weights shared across levels, statistics per level)
+        h = "fcos.head."
+        self.tower = [ConvBN(h + "towers", F, 2 * F, 3, 1, B, self.Tl[i], dev,
+                             bn_parts=[(h + "cls_tower.1", 0, F), (h + "bbox_tower.1", F, F)]) for i in range(3)]
+        self.mix = [ConvBN(h + "mix_fc", 2 * F, F, 1, 1, B, self.Tl[i], dev) for i in range(3)]
+        self.iouc = [ConvBN(h + "iou_scores", F, F // 2, 3, 1, B, self.Tl[i], dev) for i in range(3)]
+        self.TW = [Planes.empty(B, self.Tl[i], 2 * F, dev) for i in range(3)]
+        self.MX = [Planes.empty(B, self.Tl[i], F, dev) for i in range(3)]
+        self.HI = [Planes.empty(B, self.Tl[i], F // 2, dev) for i in range(3)]
+        self.dTW = [e(B, self.Tl[i], 2 * F) for i in range(3)]
+        self.dMX = [e(B, self.Tl[i], F) for i in range(3)]
+        self.dHI = [e(B, self.Tl[i], F // 2) for i in range(3)]
+        n = B * self.P
+        self.cls_raw, self.box_raw, self.iou_raw = e(n), e(n, 2), e(n)
+        self.bbox = e(n, 2)
+        self.dcls, self.dbox, self.diou = e(n), e(n, 2), e(n)
+        self.acc = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.losses = z(8)
+        self.pgrad = z(8)
+        self.upstream = z(3)
+        self.gt = e(B, 2)
+        self.Tl_c = (C.c_int * 3)(*self.Tl)
+        self.strides_c = (C.c_float * 3)(*self.strides)
+        self.lvl_off = [B * sum(self.Tl[:i]) for i in range(3)]
+        # packed weights (planes) and weight-gradient workspaces
+        self.wp = {
+            "prop_fc": Planes.empty(1, D, D, dev),
+            "conv0": Planes.empty(3, c1, self.C0, dev), "conv1": Planes.empty(3, 2 * c1, c1, dev),
+            "conv2": Planes.empty(3, 4 * c1, 2 * c1, dev),
+            "towers": Planes.empty(3, 2 * F, F, dev), "mix": Planes.empty(1, F, 2 * F, dev),
+            "iouc": Planes.empty(3, F // 2, F, dev),
+        }
+        for i in range(3):
+            self.wp["inner%d" % i] = Planes.empty(1, F, self.c[i], dev)
+            self.wp["layer%d" % i] = Planes.empty(3, F, F, dev)
+            self.wp["q%d" % i] = Planes.empty(1, self.qdim[i], 1024, dev)
+        self.tower_bias = e(2 * F)
+        ws_shapes = {"conv0": (3, c1, self.C0), "conv1": (3, 2 * c1, c1), "conv2": (3, 4 * c1, 2 * c1),
+                     "towers": (3, 2 * F, F), "iouc": (3, F // 2, F)}
+        for i in range(3):
+            ws_shapes["layer%d" % i] = (3, F, F)
+        tot = sum(a * b * c for a, b, c in ws_shapes.values())
+        self.ws_flat = z(tot)
+        self.ws, o = {}, 0
+        for k, s in ws_shapes.items():
+            m = s[0] * s[1] * s[2]
+            self.ws[k] = self.ws_flat[o:o + m].view(*s)
+            o += m
+        self.iou_branch_on = not cfg["is_first_stage"]
+        self.gamma = float(cfg["fcos_loss_gamma"][0] if isinstance(cfg["fcos_loss_gamma"], (list, tuple)) else cfg["fcos_loss_gamma"])
+        self.alpha = float(cfg["fcos_loss_alpha"][0] if isinstance(cfg["fcos_loss_alpha"], (list, tuple)) else cfg["fcos_loss_alpha"])
+        self.launches = self.launches_fwd = self.launches_bwd = 0
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # small launch helpers
+    # ---------------------------------------------------------------------------------------------------------------
+    def _chk(self, rc, what):
+        self.launches += 1
+        L.check(rc, what)
+
+    def _gemm(self, *a, **k):
+        self.launches += 1
+        ops.gemm(*a, **k)
+
+    def _split(self, src2d, dst, dst_col0=0):
+        rows, Cn = src2d.shape
+        self._chk(_lib().drn_split_planes(_vp(src2d), C.c_int64(rows), Cn, C.c_int64(src2d.stride(0)), _vp(dst.data),
+                                          C.c_int64(dst.C), dst_col0, C.c_int64(dst.plane_stride), _st()), "split_planes")
+
+    def _pack(self, w, dst, o0=0):
+        O, Cn = w.shape[0], w.shape[1]
+        k = w.shape[2] if w.dim() == 3 else 1
+        self._chk(_lib().drn_pack_conv_weight(_vp(w), O, Cn, k, _vp(dst.data), dst.T, o0, C.c_int64(dst.plane_stride), _st()),
+                  "pack_conv_weight")
+
+    def _unpack(self, ws, grad, o0=0):
+        O, Cn, k = grad.shape
+        self._chk(_lib().drn_unpack_conv_wgrad(_vp(ws), O, Cn, k, ws.shape[1], o0, _vp(grad), 0, _st()), "unpack_conv_wgrad")
+
+    def pack_weights(self, p):
+        """fp32 parameters -> tap-major split-BF16 planes (once per forward: the optimizer changes them every step)."""
+        h = "fcos.head."
+        self._pack(p["prop_fc.weight"], self.wp["prop_fc"])
+        for i in range(3):
+            self._pack(p["backbone_net.forward_conv%d.0.weight" % i], self.wp["conv%d" % i])
+            self._pack(p["fpn.fpn_inner%d.0.weight" % (i + 1)], self.wp["inner%d" % i])
+            self._pack(p["fpn.fpn_layer%d.0.weight" % (i + 1)], self.wp["layer%d" % i])
+            self._pack(p["qInput%d.weight" % i], self.wp["q%d" % i])
+        self._pack(p[h + "cls_tower.0.weight"], self.wp["towers"], 0)
+        self._pack(p[h + "bbox_tower.0.weight"], self.wp["towers"], self.F)
+        self._pack(p[h + "mix_fc.0.weight"], self.wp["mix"])
+        self._pack(p[h + "iou_scores.0.weight"], self.wp["iouc"])
+        torch.cat([p[h + "cls_tower.0.bias"], p[h + "bbox_tower.0.bias"]], out=self.tower_bias)
+
+    def _bn_fwd(self, blk, p, training):
+        lib = _lib()
+        if training:
+            blk.sums.zero_()
+            self._chk(lib.drn_bn_stats(_vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.sums), _st()), "bn_stats")
+        for (pre, c0, n) in blk.bn_parts:
+            self._chk(lib.drn_bn_finalize(
+                C.c_void_p(blk.sums.data_ptr() + 8 * c0), blk.cout, C.c_int64(blk.rows), n,
+                _vp(p[pre + ".weight"]), _vp(p[pre + ".bias"]), _vp(p[pre + ".running_mean"]), _vp(p[pre + ".running_var"]),
+                _vp(p[pre + ".num_batches_tracked"]), C.c_float(BN_MOMENTUM), C.c_float(BN_EPS), 1 if training else 0,
+                C.c_void_p(blk.coef.data_ptr() + 4 * c0), blk.cout, _st()), "bn_finalize")
+
+    def _apply(self, blk, out_a, up=None, gate=None, out_qa=None):
+        self._chk(_lib().drn_bn_relu_apply(
+            _vp(blk.y), self.B, blk.t_out, blk.cout, _vp(blk.coef),
+            _vp(up.data) if up is not None else None, C.c_int64(up.plane_stride if up is not None else 0),
+            _vp(gate), _vp(out_a.data) if out_a is not None else None,
+            C.c_int64(out_a.plane_stride if out_a is not None else 0),
+            _vp(out_qa.data) if out_qa is not None else None, C.c_int64(out_qa.plane_stride if out_qa is not None else 0),
+            _st()), "bn_relu_apply")
+
+    def _conv(self, blk, a_pl, w_pl, bias=None):
+        par = blk.stride
+        taps = K1 if blk.k == 1 else (K3 if blk.stride == 1 else K3S2)
+        self._gemm(L.GEMM_ROWS, a_pl.desc(par), w_pl.desc(), self.B, blk.t_out, blk.cout, K=blk.cin, taps=taps,
+                   out=blk.y, bias=bias)
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # forward
+    # ---------------------------------------------------------------------------------------------------------------
+    def forward(self, p, cmds, feats, pse, gt, training):
+        """p: name -> parameter/buffer tensor (fp32 on device); cmds: 3 x [B,1024] fp32 query commands;
+        feats [B,T,D] fp32, pse [B,T,2] f64, gt [B,2] f32.  Fills self.losses / raw head outputs."""
+        lib, B, T = _lib(), self.B, self.T
+        h = "fcos.head."
+        self.launches = 0
+        self.pack_weights(p)
+        self.gt.copy_(gt)
+        # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50)
+        for i in range(3):
+            self._split(cmds[i], self.cmd_pl[i])
+            self._gemm(L.GEMM_ROWS, self.cmd_pl[i].desc(), self.wp["q%d" % i].desc(), 1, B, self.qdim[i], K=1024,
+                       out=self.q[i], bias=p["qInput%d.bias" % i])
+        # position feature -> X0[:, :, D:] (main_model.py:53-55, backbone.py:31-32)
+        self._chk(lib.drn_pos_feature(_vp(pse), _vp(p["position_transform.weight"]), _vp(p["position_transform.bias"]),
+                                      C.c_int64(B * T), 256, _vp(self.X0.data), C.c_int64(self.C0), self.D,
+                                      C.c_int64(self.X0.plane_stride), _vp(self.pos_in), _st()), "pos_feature")
+        # prop_fc with the level-0 gate fused in the epilogue -> X0[:, :, :D] (main_model.py:59, backbone.py:28-30)
+        self._split(feats.view(B * T, self.D), self.f_pl)
+        self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
+                   out2=self.Pre, rowscale=self.q[0], outp=self.X0)
+        # backbone (backbone.py:27-34)
+        src = self.X0
+        for i in range(3):
+            blk = self.conv[i]
+            self._conv(blk, src, self.wp["conv%d" % i])
+            self._bn_fwd(blk, p, training)
+            if i < 2:
+                self._apply(blk, self.Cact[i], gate=self.q[i + 1], out_qa=self.QC[i])
+                src = self.QC[i]
+            else:
+                self._apply(blk, self.Cact[i])
+        # FPN top-down (FPN.py:54-69); BN update order inner3, layer3, inner2, layer2, inner1, layer1
+        for i in (2, 1, 0):
+            self._conv(self.inner[i], self.Cact[i], self.wp["inner%d" % i])
+            self._bn_fwd(self.inner[i], p, training)
+            self._apply(self.inner[i], self.I[i], up=self.I[i + 1] if i < 2 else None)
+            self._conv(self.layer[i], self.I[i], self.wp["layer%d" % i])
+            self._bn_fwd(self.layer[i], p, training)
+            self._apply(self.layer[i], self.Pf[i])
+        # head (fcos.py:93-102), levels ascending, BN order cls_tower, bbox_tower, mix_fc, iou_scores
+        for l in range(3):
+            Tl = self.Tl[l]
+            o = self.lvl_off[l]
+            self._conv(self.tower[l], self.Pf[l], self.wp["towers"], bias=self.tower_bias)
+            self._bn_fwd(self.tower[l], p, training)
+            self._apply(self.tower[l], self.TW[l])
+            self._conv(self.mix[l], self.TW[l], self.wp["mix"], bias=p[h + "mix_fc.0.bias"])
+            self._bn_fwd(self.mix[l], p, training)
+            self._apply(self.mix[l], self.MX[l])
+            self._conv(self.iouc[l], self.MX[l], self.wp["iouc"], bias=p[h + "iou_scores.0.bias"])
+            self._bn_fwd(self.iouc[l], p, training)
+            self._apply(self.iouc[l], self.HI[l])
+            tw, hi = self.TW[l], self.HI[l]
+            self._chk(lib.drn_skinny_conv_fwd(_vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, self.F, B, Tl, 1, 3,
+                                              _vp(p[h + "cls_logits.weight"]), _vp(p[h + "cls_logits.bias"]),
+                                              _vp(self.cls_raw[o:]), _st()), "cls_logits")
+            self._chk(lib.drn_skinny_conv_fwd(_vp(tw.data), C.c_int64(tw.plane_stride), tw.C, self.F, self.F, B, Tl, 2, 3,
+                                              _vp(p[h + "bbox_pred.weight"]), _vp(p[h + "bbox_pred.bias"]),
+                                              _vp(self.box_raw[o:]), _st()), "bbox_pred")
+            self._chk(lib.drn_skinny_conv_fwd(_vp(hi.data), C.c_int64(hi.plane_stride), hi.C, 0, self.F // 2, B, Tl, 1, 1,
+                                              _vp(p[h + "iou_scores.3.weight"]), _vp(p[h + "iou_scores.3.bias"]),
+                                              _vp(self.iou_raw[o:]), _st()), "iou_scores.3")
+        self.scales = torch.cat([p[h + "scales.%d.scale" % l] for l in range(3)])
+        self._chk(lib.drn_fcos_loss_fwd(3, B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.box_raw), _vp(self.iou_raw),
+                                        _vp(self.scales), _vp(self.gt), C.c_float(self.gamma), C.c_float(self.alpha),
+                                        1 if self.iou_branch_on else 0, _vp(self.bbox), _vp(self.acc), _vp(self.losses), _st()),
+                  "fcos_loss_fwd")
+        self.launches += 1  # finalize kernel inside drn_fcos_loss_fwd
+        self.launches_fwd = self.launches
+
+    # ---------------------------------------------------------------------------------------------------------------
+    # backward
+    # ---------------------------------------------------------------------------------------------------------------
+    def _bn_bwd(self, blk, da, grads):
+        lib = _lib()
+        blk.bsums.zero_()
+        self._chk(lib.drn_bn_bwd_reduce(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), _vp(blk.bsums), _st()),
+                  "bn_bwd_reduce")
+        self._chk(lib.drn_bn_bwd_apply(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), _vp(blk.bsums),
+                                       _vp(blk.dy.data), C.c_int64(blk.dy.plane_stride), _st()), "bn_bwd_apply")
+        for (pre, c0, n) in blk.bn_parts:
+            if (pre + ".weight") in grads:
+                self._chk(lib.drn_bn_bwd_param(C.c_void_p(blk.bsums.data_ptr() + 8 * c0), blk.cout, n,
+                                               _vp(grads[pre + ".weight"]), _vp(grads[pre + ".bias"]), _st()), "bn_bwd_param")
+
+    def _wgrad(self, blk, x_pl, out, accumulate=False):
+        """out: [k][cout][cin] fp32 (workspace, or the gradient itself when k == 1)."""
+        taps = K1 if blk.k == 1 else (K3 if blk.stride == 1 else K3S2)
+        tiles = -(-blk.cout // 128) * -(-blk.cin // (256 if blk.cin > 128 else 128)) * blk.k
+        kblocks = max(1, blk.rows // 64)
+        split = 1
+        if tiles < SM_COUNT:
+            split = max(1, min(kblocks, (2 * SM_COUNT) // tiles, 16))
+        mode = L.OUT_ATOMIC if (split > 1 or accumulate) else L.OUT_STORE
+        self._gemm(L.GEMM_WGRAD, blk.dy.desc(), x_pl.desc(blk.stride), self.B, blk.t_out, blk.cin, M=blk.cout, taps=taps,
+                   out=out, out_ld=blk.cin, out_tap_stride=blk.cout * blk.cin, out_mode=mode, split_k=split)
+
+    def _dgrad(self, blk, w_pl, out, mode=L.OUT_STORE, rowscale=None, out2=None):
+        if blk.stride == 1:
+            taps = K1 if blk.k == 1 else K3_DGRAD
+            self._gemm(L.GEMM_ROWS, blk.dy.desc(), w_pl.desc(), self.B, blk.t_out, blk.cin, K=blk.cout, taps=taps, b_mn=1,
+                       out=out, out_mode=mode, rowscale=rowscale, out2=out2)
+        else:
+            for par in (0, 1):
+                self._gemm(L.GEMM_ROWS, blk.dy.desc(), w_pl.desc(), self.B, blk.t_out, blk.cin, K=blk.cout, taps=S2_DGRAD[par],
+                           b_mn=1, out=out, out_mode=mode, rowscale=rowscale, out2=out2, out_T=blk.t_in, out_t_mul=2,
+                           out_t_add=par)
+
+    def backward(self, p, grads, upstream, need_cmd_grad=True):
+        """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
+        upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou).  Returns d cmds (3 x [B,1024])."""
+        lib, B = _lib(), self.B
+        h = "fcos.head."
+        F = self.F
+        self.launches = 0
+        iou_on = self.iou_branch_on and (h + "mix_fc.0.weight") in grads
+        self.ws_flat.zero_()
+        self.pgrad.zero_()
+        for t in self.dq:
+            t.zero_()
+        self._chk(lib.drn_fcos_loss_bwd(3, B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.box_raw), _vp(self.iou_raw),
+                                        _vp(self.scales), _vp(self.gt), C.c_float(self.gamma), C.c_float(self.alpha),
+                                        1 if self.iou_branch_on else 0, _vp(self.acc), _vp(upstream), _vp(self.dcls),
+                                        _vp(self.dbox), _vp(self.diou), _vp(self.pgrad), _st()), "fcos_loss_bwd")
+        for l in range(3):
+            Tl, o = self.Tl[l], self.lvl_off[l]
+            tw, hi = self.TW[l], self.HI[l]
+            if iou_on:
+                self._chk(lib.drn_skinny_conv_bwd(_vp(self.diou[o:]), _vp(hi.data), C.c_int64(hi.plane_stride), hi.C, 0, F // 2,
+                                                  B, Tl, 1, 1, _vp(p[h + "iou_scores.3.weight"]), _vp(self.dHI[l]), F // 2, 0,
+                                                  _vp(grads[h + "iou_scores.3.weight"]), _st()), "iou3_bwd")
+                self._bn_bwd(self.iouc[l], self.dHI[l], grads)
+                self._wgrad(self.iouc[l], self.MX[l], self.ws["iouc"], accumulate=True)
+                self._dgrad(self.iouc[l], self.wp["iouc"], self.dMX[l])
+                self._bn_bwd(self.mix[l], self.dMX[l], grads)
+                self._wgrad(self.mix[l], tw, grads[h + "mix_fc.0.weight"], accumulate=True)
+            self._chk(lib.drn_skinny_conv_bwd(_vp(self.dcls[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, F, B, Tl, 1, 3,
+                                              _vp(p[h + "cls_logits.weight"]), _vp(self.dTW[l]), 2 * F, 0,
+                                              _vp(grads[h + "cls_logits.weight"]), _st()), "cls_logits_bwd")
+            self._chk(lib.drn_skinny_conv_bwd(_vp(self.dbox[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, F, F, B, Tl, 2, 3,
+                                              _vp(p[h + "bbox_pred.weight"]), _vp(self.dTW[l]), 2 * F, 0,
+                                              _vp(grads[h + "bbox_pred.weight"]), _st()), "bbox_pred_bwd")
+            if iou_on:
+                self._dgrad(self.mix[l], self.wp["mix"], self.dTW[l], mode=L.OUT_ADD)
+            self._bn_bwd(self.tower[l], self.dTW[l], grads)
+            self._wgrad(self.tower[l], self.Pf[l], self.ws["towers"], accumulate=True)
+            self._dgrad(self.tower[l], self.wp["towers"], self.dPf[l])
+        # FPN
+        for i in range(3):
+            self._bn_bwd(self.layer[i], self.dPf[i], grads)
+            self._wgrad(self.layer[i], self.I[i], self.ws["layer%d" % i])
+            self._dgrad(self.layer[i], self.wp["layer%d" % i], self.dI[i])
+            if i > 0:
+                self._chk(lib.drn_pair_sum_add(_vp(self.dI[i]), _vp(self.dI[i - 1]), C.c_int64(B * self.Tl[i]), F, _st()),
+                          "pair_sum_add")
+        for i in range(3):
+            self._bn_bwd(self.inner[i], self.dI[i], grads)
+            self._wgrad(self.inner[i], self.Cact[i], grads["fpn.fpn_inner%d.0.weight" % (i + 1)].view(1, F, self.c[i]))
+            self._dgrad(self.inner[i], self.wp["inner%d" % i], self.dC[i])
+        # backbone
+        for i in (2, 1):
+            blk = self.conv[i]
+            self._bn_bwd(blk, self.dC[i], grads)
+            self._wgrad(blk, self.QC[i - 1], self.ws["conv%d" % i])
+            self._dgrad(blk, self.wp["conv%d" % i], self.dC[i - 1], mode=L.OUT_ADD, rowscale=self.q[i], out2=self.dQC[i - 1])
+            a = self.Cact[i - 1]
+            self._chk(lib.drn_gate_reduce(_vp(self.dQC[i - 1]), C.c_int64(a.C), _vp(a.data), C.c_int64(a.C),
+                                          C.c_int64(a.plane_stride), 1, B, self.Tl[i - 1], a.C, _vp(self.dq[i]), None, None,
+                                          C.c_int64(0), None, _st()), "gate_reduce")
+        blk = self.conv[0]
+        self._bn_bwd(blk, self.dC[0], grads)
+        self._wgrad(blk, self.X0, self.ws["conv0"])
+        self._dgrad(blk, self.wp["conv0"], self.dX0)
+        self._chk(lib.drn_gate_reduce(_vp(self.dX0), C.c_int64(self.C0), _vp(self.Pre), C.c_int64(self.D), C.c_int64(0), 0, B,
+                                      self.T, self.D, _vp(self.dq[0]), _vp(self.q[0]), _vp(self.dP_pl.data),
+                                      C.c_int64(self.dP_pl.plane_stride), _vp(grads["prop_fc.bias"]), _st()), "gate0_bwd")
+        self._chk(lib.drn_pos_bwd(_vp(self.dX0), C.c_int64(self.C0), self.D, _vp(self.pos_in), C.c_int64(B * self.T), 256,
+                                  _vp(grads["position_transform.weight"]), _vp(grads["position_transform.bias"]), _st()),
+                  "pos_bwd")
+        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D] (the largest contraction of the backward pass)
+        self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
+                   out_ld=self.D, out_tap_stride=0)
+        # gates
+        for i in range(3):
+            n = self.qdim[i]
+            self._split(self.dq[i], self.dq_pl[i])
+            self._gemm(L.GEMM_WGRAD, self.dq_pl[i].desc(), self.cmd_pl[i].desc(), 1, B, 1024, M=n,
+                       out=grads["qInput%d.weight" % i], out_ld=1024, out_tap_stride=0)
+            self._chk(lib.drn_colsum(_vp(self.dq[i]), C.c_int64(B), n, C.c_int64(n), _vp(grads["qInput%d.bias" % i]), _st()),
+                      "colsum")
+            if need_cmd_grad:
+                self._gemm(L.GEMM_ROWS, self.dq_pl[i].desc(), self.wp["q%d" % i].desc(), 1, B, 1024, K=n, b_mn=1, out=self.dcmd[i])
+        # tap-major workspaces -> parameter layout [O][C][k]
+        for i in range(3):
+            self._unpack(self.ws["conv%d" % i], grads["backbone_net.forward_conv%d.0.weight" % i])
+            self._unpack(self.ws["layer%d" % i], grads["fpn.fpn_layer%d.0.weight" % (i + 1)])
+        self._unpack(self.ws["towers"], grads[h + "cls_tower.0.weight"], 0)
+        self._unpack(self.ws["towers"], grads[h + "bbox_tower.0.weight"], F)
+        if iou_on:
+            self._unpack(self.ws["iouc"], grads[h + "iou_scores.0.weight"])
+        # scalar parameter gradients gathered by the loss kernel
+        grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
+        grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])
+        if iou_on:
+            grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
+        for l in range(3):
+            grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
+        self.launches_bwd = self.launches
+        return self.dcmd

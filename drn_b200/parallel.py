@@ -1,0 +1,48 @@
+"""Data parallelism for the DRN dense-regression path: one process per GPU, full replica per rank, the batch sharded
+across ranks, ONE exchange step per iteration -- an NCCL all-reduce (sum, then 1/world) of the fp32 gradients over
+NVLink/NVSwitch.  BatchNorm statistics and the loss normalisers stay per replica, which is what the
+reference's own (nominal) multi-GPU mode, nn.DataParallel at main.py:99, computes.
+
+The dense path produces all of its gradients in one flat buffer (model/main_model.py:_DenseFn.backward); that buffer is
+all-reduced in place as soon as the hand-written backward has filled it, i.e. before autograd continues into the query
+encoder, whose (small) gradients are all-reduced in `finish_gradient_sync()` after `loss.backward()`.
+"""
+import torch
+import torch.distributed as dist
+from torch import nn
+
+
+class DataParallelDRN(nn.Module):
+    def __init__(self, module, process_group=None):
+        super().__init__()
+        self.module = module
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        # replica 0's parameters and buffers win, as with nn.DataParallel
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t, 0, group=process_group)
+        module._dp_hook = self._reduce_dense
+
+    def _reduce_dense(self, flat):
+        if self.world > 1:
+            dist.all_reduce(flat, group=self.group)
+            flat.mul_(1.0 / self.world)
+
+    def forward(self, *a, **k):
+        return self.module(*a, **k)
+
+    def finish_gradient_sync(self):
+        """All-reduce the gradients autograd produced outside the dense path (query encoder)."""
+        if self.world == 1:
+            return
+        grads = [p.grad for n, p in self.module.named_parameters() if n.startswith("query_encoder.") and p.grad is not None]
+        if not grads:
+            return
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat, group=self.group)
+        flat.mul_(1.0 / self.world)
+        o = 0
+        for g in grads:
+            g.copy_(flat[o:o + g.numel()].view_as(g))
+            o += g.numel()

@@ -104,6 +104,66 @@ typedef struct {
 
 int drn_gemm(const drn_gemm_t* g, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * HBM-bound kernels (drn_b200/csrc/elementwise.cu).  "planes" arguments are the hi plane pointer of a
+ * split-plane tensor plus the element stride to its lo plane.
+ * ---------------------------------------------------------------------------------------------- */
+/* fp32 rows [rows][C] (leading dim src_ld) -> planes at column dst_col0 of a [rows][dst_ld] planes tensor.
+ * Used for the C3D clip features (input of prop_fc, model/main_model.py:59) and small host-side vectors. */
+int drn_split_planes(const float* src, int64_t rows, int C, int64_t src_ld, void* dst, int64_t dst_ld, int dst_col0,
+                     int64_t dst_plane_stride, void* stream);
+/* nn.Conv1d / nn.Linear weight [O][C][k] fp32 -> planes [k][Ototal][C] at row offset o0 (tap-major operand of drn_gemm). */
+int drn_pack_conv_weight(const float* w, int O, int C, int k, void* dst, int Ototal, int o0, int64_t plane_stride, void* stream);
+/* weight-gradient workspace [k][Ototal][C] fp32 -> parameter gradient [O][C][k] (= or +=). */
+int drn_unpack_conv_wgrad(const float* ws, int O, int C, int k, int Ototal, int o0, float* grad, int accumulate, void* stream);
+/* position feature, model/main_model.py:53-55: planes[row, dst_col0 + c] = Wp[c] . (s, e, e-s) + bp[c]; pos_in[row][3] saved for backward. */
+int drn_pos_feature(const double* pse, const float* Wp, const float* bp, int64_t rows, int Cp, void* dst, int64_t dst_ld,
+                    int dst_col0, int64_t plane_stride, float* pos_in, void* stream);
+int drn_pos_bwd(const float* dx, int64_t dx_ld, int col0, const float* pos_in, int64_t rows, int Cp, float* dWp, float* dbp, void* stream);
+
+/* Train-mode BatchNorm1d + ReLU (model/basic_blocks.py:22-30, model/fcos.py:31-38) on a conv output y [rows][C] fp32:
+ *   drn_bn_stats      sums[0][c] += sum y, sums[1][c] += sum y^2 (fp64; caller zeroes sums)
+ *   drn_bn_finalize   coef[0..3][c] = scale, shift, mean, invstd; updates running_mean/var (momentum, unbiased var) and
+ *                     num_batches_tracked when training, else uses the running statistics (eval)
+ *   drn_bn_relu_apply a = relu(y*scale+shift) [+ nearest-x2 upsample of `up` (FPN top-down add, model/FPN.py:63-68)]
+ *                     -> planes out_a; optional planes out_qa = gate[b][c] * a (query gating, model/backbone.py:28-30)
+ *   backward: drn_bn_bwd_reduce (sums[0] = sum g, sums[1] = sum g*xhat, g = da masked by the ReLU),
+ *             drn_bn_bwd_apply (dy planes), drn_bn_bwd_param (dgamma += sums[1], dbeta += sums[0]). */
+int drn_bn_stats(const float* y, int64_t rows, int C, double* sums, void* stream);
+int drn_bn_finalize(const double* sums, int sums_stride, int64_t n, int C, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, float eps,
+                    int training, float* coef, int coef_stride, void* stream);
+int drn_bn_relu_apply(const float* y, int B, int T, int C, const float* coef, const void* up, int64_t up_plane_stride,
+                      const float* gate, void* out_a, int64_t a_plane_stride, void* out_qa, int64_t qa_plane_stride, void* stream);
+int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, const float* coef, double* sums, void* stream);
+int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const double* sums, void* dy,
+                     int64_t dy_plane_stride, void* stream);
+int drn_bn_bwd_param(const double* sums, int sums_stride, int C, float* dgamma, float* dbeta, void* stream);
+/* backward of the FPN nearest-x2 upsample: dst[b][j] += src[b][2j] + src[b][2j+1]. */
+int drn_pair_sum_add(float* dst, const float* src, int64_t rows_half, int C, void* stream);
+/* backward of the query gate x = q[b][c] * a[b][t][c]: dq[b][c] += sum_t g*a; optionally dp planes = q*g and dbias[c] += sum q*g
+ * (level 0: a = prop_fc output, dp = gradient w.r.t. it, dbias = d prop_fc.bias). */
+int drn_gate_reduce(const float* g, int64_t g_ld, const void* a, int64_t a_ld, int64_t a_plane_stride, int a_is_planes, int B,
+                    int T, int C, float* dq, const float* q, void* dp, int64_t dp_plane_stride, float* dbias, void* stream);
+int drn_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * FCOS head projections and losses (drn_b200/csrc/head.cu).
+ * ---------------------------------------------------------------------------------------------- */
+/* cls_logits / bbox_pred / iou_scores.3 (model/fcos.py:41-69): out[b][t][o] = bias[o] + sum_r sum_c W[o][c][r] x[b][t+r-(k-1)/2][c0+c]. */
+int drn_skinny_conv_fwd(const void* x, int64_t x_plane_stride, int x_ld, int c0, int Cw, int B, int T, int nout, int k,
+                        const float* W, const float* bias, float* out, void* stream);
+int drn_skinny_conv_bwd(const float* d, const void* x, int64_t x_plane_stride, int x_ld, int c0, int Cw, int B, int T, int nout,
+                        int k, const float* W, float* dx, int dx_ld, int dx_accumulate, float* dW, void* stream);
+/* FCOSLossComputation.__call__ (model/loss.py:134-239) on raw head outputs in the reference's flatten order
+ * (level-major, then sample, then t).  losses = {loss_cls, loss_reg, loss_iou, n_pos, n_iou}; acc = 8 doubles of scratch kept for backward. */
+int drn_fcos_loss_fwd(int nlevels, int B, const int* T, const float* strides, const float* cls_raw, const float* box_raw,
+                      const float* iou_raw, const float* scales, const float* gt, float gamma, float alpha, int iou_branch_on,
+                      float* bbox_out, double* acc, float* losses, void* stream);
+int drn_fcos_loss_bwd(int nlevels, int B, const int* T, const float* strides, const float* cls_raw, const float* box_raw,
+                      const float* iou_raw, const float* scales, const float* gt, float gamma, float alpha, int iou_branch_on,
+                      const double* acc, const float* upstream, float* dcls, float* dbox, float* diou, float* pgrad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,130 @@
+"""`mainModel`: the drop-in boundary of the DRN dense-regression path (reference model/main_model.py:13-81).
+
+Same constructor signature, attribute tree, state_dict keys/shapes and `forward(query_tokens, query_length,
+props_features, props_start_end, gt_start_end, props_num, num_frames) -> (box_lists | None, loss_dict)` as the reference,
+so the reference's main.py (19, 89-99, 124-140, 218-243) runs against it unchanged.  Everything after the query encoder
+is executed by hand-written sm_100a kernels (drn_b200.dense.DensePath -> libdrn_sm100.so); gradients arrive in
+`param.grad` through one autograd.Function whose backward is the hand-derived backward schedule.  There is no CPU or
+torch-op fallback: calling forward without a B200 raises.
+"""
+import torch
+import torch.nn as nn
+
+from drn_b200.dense import DensePath
+from model.inference import postprocess
+from model.language_module import QueryEncoder
+from model.modules import FPN, Backbone, FCOSModule
+
+
+class _DenseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, path, training, feats, pse, gt, c0, c1, c2, *params):
+        p = model._tensor_dict()
+        path.forward(p, (c0.contiguous(), c1.contiguous(), c2.contiguous()), feats, pse, gt, training)
+        ctx.model, ctx.path = model, path
+        ctx.need_cmd = c0.requires_grad or c1.requires_grad or c2.requires_grad
+        ctx.nparams = len(params)
+        return path.losses[:3].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        model, path = ctx.model, ctx.path
+        names = model._trainable_names
+        assert len(names) == ctx.nparams
+        p = model._tensor_dict()
+        sizes = [p[n].numel() for n in names]
+        flat = torch.zeros(sum(sizes), device=g.device, dtype=torch.float32)
+        grads, o = {}, 0
+        for n, s in zip(names, sizes):
+            grads[n] = flat[o:o + s].view_as(p[n])
+            o += s
+        dcmd = path.backward(p, grads, g.contiguous().float(), need_cmd_grad=ctx.need_cmd)
+        if model._dp_hook is not None:  # data parallel: all-reduce the flat gradient buffer (drn_b200/parallel.py)
+            model._dp_hook(flat)
+        dc = tuple(d.clone() for d in dcmd) if ctx.need_cmd else (None, None, None)
+        return (None, None, None, None, None, None) + dc + tuple(grads[n] for n in names)
+
+
+class mainModel(nn.Module):
+    def __init__(self, vocab_size, dataset_configs, hidden_dim=512, embed_dim=300, bidirection=True,
+                 graph_node_features=1024):
+        super().__init__()
+        cfg = dict(vars(dataset_configs))
+        self.cfg = cfg
+        self.first_output_dim = cfg["first_output_dim"]
+        self.fpn_feature_dim = cfg["fpn_feature_dim"]
+        self.feature_dim = cfg[cfg["feature_type"]]["feature_dim"]
+        c1 = self.first_output_dim
+        if (c1, self.fpn_feature_dim) != (256, 512):
+            raise NotImplementedError("channel plan 256/512/1024 -> 512 of the reference config is assumed by the FPN "
+                                      "(model/main_model.py:29 hard-codes [256, 512, 1024])")
+        self.query_encoder = QueryEncoder(vocab_size, hidden_dim, embed_dim, cfg["lstm_layers"], bidirection)
+        channels_list = [(self.feature_dim + 256, c1, 3, 1), (c1, c1 * 2, 3, 2), (c1 * 2, c1 * 4, 3, 2)]
+        self.backbone_net = Backbone(channels_list)
+        self.fpn = FPN([256, 512, 1024], 512)
+        self.fcos = FCOSModule(cfg, self.fpn_feature_dim)
+        self.prop_fc = nn.Linear(self.feature_dim, self.feature_dim)
+        self.position_transform = nn.Linear(3, 256)
+        for t in range(len(channels_list)):
+            setattr(self, "qInput%d" % t, nn.Linear(1024, channels_list[t - 1][1] if t > 0 else self.feature_dim))
+        self._paths = {}
+        self._trainable_names = []
+        self._dp_hook = None
+
+    # ---- parameter plumbing ---------------------------------------------------------------------------------------
+    def _tensor_dict(self):
+        d = {k: v for k, v in self.named_parameters()}
+        d.update({k: v for k, v in self.named_buffers()})
+        return d
+
+    def _dense_trainable(self):
+        names, tensors = [], []
+        for k, v in self.named_parameters():
+            if k.startswith("query_encoder.") or k.startswith("fcos.head.centerness"):
+                continue
+            if v.requires_grad:
+                names.append(k)
+                tensors.append(v)
+        return names, tensors
+
+    def _path(self, B, T, device):
+        key = (B, T, device.index, bool(self.cfg["is_first_stage"]))
+        if key not in self._paths:
+            self._paths[key] = DensePath(self.cfg, B, T, device)
+        return self._paths[key]
+
+    # ---- forward -------------------------------------------------------------------------------------------------
+    def forward(self, query_tokens, query_length, props_features, props_start_end, gt_start_end, props_num, num_frames):
+        dev = self.prop_fc.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("mainModel runs on a B200 through libdrn_sm100.so only (no CPU / torch fallback): call .cuda()")
+        tokens = query_tokens.to(dev)
+        feats = props_features.to(dev, dtype=torch.float32).contiguous()
+        pse = props_start_end.to(dev, dtype=torch.float64).contiguous()
+        gt = gt_start_end.to(dev).float().contiguous()  # `.float()` as at main_model.py:74
+        B, T = feats.shape[0], feats.shape[1]
+        cmds = self.query_encoder(tokens, query_length)
+        path = self._path(B, T, dev)
+        names, tensors = self._dense_trainable()
+        self._trainable_names = names
+        training = self.training
+        if torch.is_grad_enabled() and (tensors or any(c.requires_grad for c in cmds)):
+            losses = _DenseFn.apply(self, path, training, feats, pse, gt, cmds[0], cmds[1], cmds[2], *tensors)
+        else:
+            with torch.no_grad():
+                path.forward(self._tensor_dict(), tuple(c.contiguous() for c in cmds), feats, pse, gt, training)
+                losses = path.losses[:3].clone()
+        loss_dict = {"loss_cls": losses[0], "loss_reg": losses[1]}
+        if self.cfg["is_first_stage"]:
+            loss_dict["loss_iou"] = torch.zeros(1, device=dev)  # torch.FloatTensor([0]).cuda(), loss.py:239
+        elif int(path.losses[4].item()) == 0:
+            loss_dict["loss_iou"] = torch.tensor([0], device=dev)  # integer constant, loss.py:194-195
+        else:
+            loss_dict["loss_iou"] = losses[2]
+        if training:
+            return None, loss_dict
+        boxes = postprocess(path.cls_raw.cpu(), path.bbox.cpu(), path.iou_raw.cpu(), path.Tl, path.strides, self.cfg, B)
+        for d in boxes:
+            for k in ("detections", "scores", "locations"):
+                d[k] = d[k].to(dev)
+        return boxes, loss_dict
