@@ -57,37 +57,55 @@ __global__ void __launch_bounds__(EW_THREADS) split_planes_kernel(const float* _
   }
 }
 
-// ---- conv weight [O][C][k] fp32 -> planes [k][Ototal][C] ----------------------------------------
-__global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const float* __restrict__ w, int O, int C, int k,
-                                                                      __nv_bfloat16* __restrict__ dst, int Ototal, int o0,
-                                                                      long long plane_stride) {
-  const long long total = static_cast<long long>(O) * C;
+// ---- conv / linear weights [O][C][k] fp32 -> tap-major planes [k][Ototal][C]; one launch packs a whole table ------------
+constexpr int PACK_MAX_ITEMS = 24;
+struct PackItem {
+  const float* w;
+  __nv_bfloat16* dst;
+  float* grad;  // unpack only
+  int O, C, k, Ototal, o0;
+  long long plane_stride;
+};
+struct PackTable {
+  int n;
+  PackItem it[PACK_MAX_ITEMS];
+};
+
+__global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const PackTable tab) {
+  const PackItem& e = tab.it[blockIdx.y];
+  const long long total = static_cast<long long>(e.O) * e.C;
+  if (e.k == 1) {  // nn.Linear / 1x1 conv: straight split, 8 elements per thread
+    const long long total8 = total >> 3;  // C % 8 == 0
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      float v[8];
+      load8(e.w + i * 8, v);
+      const long long o = (i * 8) / e.C, c = (i * 8) % e.C;
+      store8_planes(e.dst + (e.o0 + o) * e.C + c, e.plane_stride, v);
+    }
+    return;
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int o = static_cast<int>(i / C), c = static_cast<int>(i % C);
-    for (int r = 0; r < k; ++r) {
+    const int o = static_cast<int>(i / e.C), c = static_cast<int>(i % e.C);
+    for (int r = 0; r < e.k; ++r) {
       __nv_bfloat16 h, l;
-      split_bf16(w[i * k + r], h, l);
-      const long long d = (static_cast<long long>(r) * Ototal + o0 + o) * C + c;
-      dst[d] = h;
-      dst[d + plane_stride] = l;
+      split_bf16(e.w[i * e.k + r], h, l);
+      const long long d = (static_cast<long long>(r) * e.Ototal + e.o0 + o) * e.C + c;
+      e.dst[d] = h;
+      e.dst[d + e.plane_stride] = l;
     }
   }
 }
 
-// ---- weight-gradient workspace [k][Ototal][C] -> grad [O][C][k] ---------------------------------
-__global__ void __launch_bounds__(EW_THREADS) unpack_conv_wgrad_kernel(const float* __restrict__ ws, int O, int C, int k,
-                                                                       int Ototal, int o0, float* __restrict__ grad,
-                                                                       int accumulate) {
-  const long long total = static_cast<long long>(O) * C;
+// ---- weight-gradient workspaces [k][Ototal][C] -> parameter gradients [O][C][k] ---------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) unpack_conv_wgrad_kernel(const PackTable tab) {
+  const PackItem& e = tab.it[blockIdx.y];
+  const long long total = static_cast<long long>(e.O) * e.C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int o = static_cast<int>(i / C), c = static_cast<int>(i % C);
-    for (int r = 0; r < k; ++r) {
-      const float v = ws[(static_cast<long long>(r) * Ototal + o0 + o) * C + c];
-      if (accumulate) grad[i * k + r] += v;
-      else grad[i * k + r] = v;
-    }
+    const int o = static_cast<int>(i / e.C), c = static_cast<int>(i % e.C);
+    for (int r = 0; r < e.k; ++r) e.grad[i * e.k + r] = e.w[(static_cast<long long>(r) * e.Ototal + e.o0 + o) * e.C + c];
   }
 }
 
@@ -122,13 +140,41 @@ __global__ void __launch_bounds__(EW_THREADS) pos_feature_kernel(const double* _
 }
 
 // ---- column statistics: block = 32 x 8 threads, 128 columns x ROWS_PER_BLOCK rows -------------------------------------
+// The LAST block to finish (device-wide counter) finalises: MODE 0 -> BatchNorm coefficients + running statistics,
+// MODE 1 -> mean(g), mean(g*xhat) + dgamma/dbeta accumulation.  It also re-zeroes the fp64 sums and the counter, so
+// no memset / finalize launches are needed between uses.
 constexpr int STAT_ROWS = 64;
+constexpr int BN_MAX_PARTS = 2;
+
+struct BnParts {  // the fused cls|bbox tower output carries two BatchNorm modules side by side
+  int nparts;
+  int c0[BN_MAX_PARTS], n[BN_MAX_PARTS];
+  const float* gamma[BN_MAX_PARTS];
+  const float* beta[BN_MAX_PARTS];
+  float* running_mean[BN_MAX_PARTS];
+  float* running_var[BN_MAX_PARTS];
+  long long* nbt[BN_MAX_PARTS];
+  float* dgamma[BN_MAX_PARTS];
+  float* dbeta[BN_MAX_PARTS];
+};
+
+__device__ __forceinline__ void bn_coef_from_stats(double mean, double var, float gamma, float beta, float eps, int c, int C,
+                                                   float* coef) {
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float scale = gamma * invstd;
+  coef[c] = scale;
+  coef[C + c] = beta - static_cast<float>(mean) * scale;
+  coef[2 * C + c] = static_cast<float>(mean);
+  coef[3 * C + c] = invstd;
+}
 
 template <int MODE>  // 0: sum y, sum y^2 ; 1: BN backward sums (sum g, sum g*xhat) with g = relu-masked da
 __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ y, const float* __restrict__ da,
-                                                        long long rows, int C, const float* __restrict__ coef,
-                                                        double* __restrict__ sums) {
+                                                        long long rows, int C, float* __restrict__ coef,
+                                                        double* __restrict__ sums, unsigned* __restrict__ counter,
+                                                        BnParts parts, float momentum, float eps, float* __restrict__ bcoef) {
   __shared__ float red[2][8][128];
+  __shared__ bool is_last;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 128 + tx * 4;
   const long long r0 = static_cast<long long>(blockIdx.y) * STAT_ROWS;
@@ -181,35 +227,51 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
     for (int i = 0; i < 8; ++i) acc += static_cast<double>(red[which][i][col]);
     atomicAdd(sums + static_cast<long long>(which) * C + blockIdx.x * 128 + col, acc);
   }
+  // ---- last block finalises ----
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    is_last = (atomicAdd(counter, 1u) == total - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const double n = static_cast<double>(rows);
+  for (int p = 0; p < parts.nparts; ++p) {
+    for (int i = t; i < parts.n[p]; i += 256) {
+      const int cc = parts.c0[p] + i;
+      const double a0 = __ldcg(sums + cc), a1 = __ldcg(sums + C + cc);
+      sums[cc] = 0.0;
+      sums[C + cc] = 0.0;
+      if (MODE == 0) {
+        const double mean = a0 / n;
+        double var = a1 / n - mean * mean;
+        if (var < 0) var = 0;
+        const double unbiased = (rows > 1) ? var * n / (n - 1.0) : var;
+        parts.running_mean[p][i] = (1.f - momentum) * parts.running_mean[p][i] + momentum * static_cast<float>(mean);
+        parts.running_var[p][i] = (1.f - momentum) * parts.running_var[p][i] + momentum * static_cast<float>(unbiased);
+        bn_coef_from_stats(mean, var, parts.gamma[p][i], parts.beta[p][i], eps, cc, C, coef);
+      } else {
+        bcoef[cc] = static_cast<float>(a0 / n);
+        bcoef[C + cc] = static_cast<float>(a1 / n);
+        if (parts.dgamma[p]) {
+          parts.dbeta[p][i] += static_cast<float>(a0);
+          parts.dgamma[p][i] += static_cast<float>(a1);
+        }
+      }
+    }
+    if (MODE == 0 && t == 0 && parts.nbt[p]) parts.nbt[p][0] += 1;
+  }
+  if (t == 0) *counter = 0u;
 }
 
-// ---- BN finalize: batch statistics -> (scale, shift, mean, invstd) + running-stat update (torch BatchNorm1d semantics)
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int sums_stride, long long n, int C,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   long long* __restrict__ nbt, float momentum, float eps, int training,
-                                   float* __restrict__ coef, int coef_stride) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && training && nbt) nbt[0] += 1;
-  if (c >= C) return;
-  double mean, var;
-  if (training) {
-    mean = sums[c] / static_cast<double>(n);
-    var = sums[sums_stride + c] / static_cast<double>(n) - mean * mean;
-    if (var < 0) var = 0;
-    const double unbiased = (n > 1) ? var * static_cast<double>(n) / static_cast<double>(n - 1) : var;
-    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
-  } else {
-    mean = running_mean[c];
-    var = running_var[c];
-  }
-  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-  const float scale = gamma[c] * invstd;
-  coef[c] = scale;
-  coef[coef_stride + c] = beta[c] - static_cast<float>(mean) * scale;
-  coef[2 * coef_stride + c] = static_cast<float>(mean);
-  coef[3 * coef_stride + c] = invstd;
+// ---- eval-mode BN: coefficients from the running statistics ----------------------------------------------------------------
+__global__ void bn_eval_coef_kernel(int C, BnParts parts, float eps, float* __restrict__ coef) {
+  for (int p = 0; p < parts.nparts; ++p)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < parts.n[p]; i += gridDim.x * blockDim.x)
+      bn_coef_from_stats(parts.running_mean[p][i], parts.running_var[p][i], parts.gamma[p][i], parts.beta[p][i], eps,
+                         parts.c0[p] + i, C, coef);
 }
 
 // ---- BN apply + ReLU (+ nearest x2 upsample add, + query gate) -> planes ---------------------------------------------
@@ -252,40 +314,31 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_apply_kernel(const float* 
 // ---- BN backward apply: dy = scale * (g - mean(g) - xhat * mean(g*xhat)) -> planes ------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ y,
                                                                   long long rows, int C, const float* __restrict__ coef,
-                                                                  const double* __restrict__ sums,
+                                                                  const float* __restrict__ bcoef,
                                                                   __nv_bfloat16* __restrict__ dy, long long dy_ps) {
   const int C8 = C >> 3;
   const long long total = rows * C8;
-  const float inv_n = 1.f / static_cast<float>(rows);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = i / C8;
     const int c = static_cast<int>(i % C8) * 8;
-    float v[8], g[8], sc[8], sh[8], mu[8], is[8];
+    float v[8], g[8], sc[8], sh[8], mu[8], is[8], mg[8], mgx[8];
     load8(y + row * C + c, v);
     load8(da + row * C + c, g);
     load8(coef + c, sc);
     load8(coef + C + c, sh);
     load8(coef + 2 * C + c, mu);
     load8(coef + 3 * C + c, is);
+    load8(bcoef + c, mg);
+    load8(bcoef + C + c, mgx);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float mg = static_cast<float>(sums[c + j]) * inv_n;
-      const float mgx = static_cast<float>(sums[C + c + j]) * inv_n;
       const float gm = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
       const float xh = (v[j] - mu[j]) * is[j];
-      v[j] = sc[j] * (gm - mg - xh * mgx);
+      v[j] = sc[j] * (gm - mg[j] - xh * mgx[j]);
     }
     store8_planes(dy + row * C + c, dy_ps, v);
   }
-}
-
-__global__ void bn_bwd_param_kernel(const double* __restrict__ sums, int sums_stride, int C, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  dbeta[c] += static_cast<float>(sums[c]);
-  dgamma[c] += static_cast<float>(sums[sums_stride + c]);
 }
 
 // ---- FPN backward of nearest x2 upsample: dst[b,j,:] += src[b,2j,:] + src[b,2j+1,:] ------------------------------------
@@ -433,18 +486,31 @@ extern "C" int drn_split_planes(const float* src, int64_t rows, int C, int64_t s
   return check_launch("split_planes");
 }
 
-extern "C" int drn_pack_conv_weight(const float* w, int O, int C, int k, void* dst, int Ototal, int o0, int64_t plane_stride,
-                                    void* stream) {
-  pack_conv_weight_kernel<<<ew_grid(static_cast<long long>(O) * C), EW_THREADS, 0, ST(stream)>>>(
-      w, O, C, k, static_cast<__nv_bfloat16*>(dst), Ototal, o0, plane_stride);
-  return check_launch("pack_conv_weight");
+static int fill_table(PackTable* t, int n, const drn_pack_item_t* items) {
+  if (n < 1 || n > PACK_MAX_ITEMS) return fail(DRN_EINVAL, "pack table: 1..%d items (got %d)", PACK_MAX_ITEMS, n);
+  t->n = n;
+  for (int i = 0; i < n; ++i) {
+    if (items[i].C % 8) return fail(DRN_EINVAL, "pack table: C %% 8 (item %d, C=%d)", i, items[i].C);
+    t->it[i] = PackItem{items[i].src, static_cast<__nv_bfloat16*>(items[i].planes), items[i].grad, items[i].O, items[i].C,
+                        items[i].k, items[i].Ototal, items[i].o0, items[i].plane_stride};
+  }
+  return 0;
 }
 
-extern "C" int drn_unpack_conv_wgrad(const float* ws, int O, int C, int k, int Ototal, int o0, float* grad, int accumulate,
-                                     void* stream) {
-  unpack_conv_wgrad_kernel<<<ew_grid(static_cast<long long>(O) * C), EW_THREADS, 0, ST(stream)>>>(ws, O, C, k, Ototal, o0, grad,
-                                                                                                   accumulate);
-  return check_launch("unpack_conv_wgrad");
+extern "C" int drn_pack_conv_weights(int n, const drn_pack_item_t* items, void* stream) {
+  PackTable t;
+  int rc = fill_table(&t, n, items);
+  if (rc) return rc;
+  pack_conv_weight_kernel<<<dim3(148, n), EW_THREADS, 0, ST(stream)>>>(t);
+  return check_launch("pack_conv_weights");
+}
+
+extern "C" int drn_unpack_conv_wgrads(int n, const drn_pack_item_t* items, void* stream) {
+  PackTable t;
+  int rc = fill_table(&t, n, items);
+  if (rc) return rc;
+  unpack_conv_wgrad_kernel<<<dim3(74, n), EW_THREADS, 0, ST(stream)>>>(t);
+  return check_launch("unpack_conv_wgrads");
 }
 
 extern "C" int drn_pos_feature(const double* pse, const float* Wp, const float* bp, int64_t rows, int Cp, void* dst,
@@ -454,20 +520,36 @@ extern "C" int drn_pos_feature(const double* pse, const float* Wp, const float* 
   return check_launch("pos_feature");
 }
 
-extern "C" int drn_bn_stats(const float* y, int64_t rows, int C, double* sums, void* stream) {
-  if (C % 4) return fail(DRN_EINVAL, "drn_bn_stats: C %% 4");
-  dim3 grid(ceil_div(C, 128), static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS));
-  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, nullptr, rows, C, nullptr, sums);
-  return check_launch("bn_stats");
+static int fill_parts(BnParts* bp, int nparts, const drn_bn_part_t* parts) {
+  if (nparts < 1 || nparts > BN_MAX_PARTS) return fail(DRN_EINVAL, "BatchNorm: 1..%d parameter parts supported (got %d)", BN_MAX_PARTS, nparts);
+  bp->nparts = nparts;
+  for (int i = 0; i < nparts; ++i) {
+    bp->c0[i] = parts[i].c0;
+    bp->n[i] = parts[i].n;
+    bp->gamma[i] = parts[i].gamma;
+    bp->beta[i] = parts[i].beta;
+    bp->running_mean[i] = parts[i].running_mean;
+    bp->running_var[i] = parts[i].running_var;
+    bp->nbt[i] = reinterpret_cast<long long*>(parts[i].num_batches_tracked);
+    bp->dgamma[i] = parts[i].dgamma;
+    bp->dbeta[i] = parts[i].dbeta;
+  }
+  return 0;
 }
 
-extern "C" int drn_bn_finalize(const double* sums, int sums_stride, int64_t n, int C, const float* gamma, const float* beta,
-                               float* running_mean, float* running_var, int64_t* nbt, float momentum, float eps, int training,
-                               float* coef, int coef_stride, void* stream) {
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(sums, sums_stride, n, C, gamma, beta, running_mean, running_var,
-                                                               reinterpret_cast<long long*>(nbt), momentum, eps, training, coef,
-                                                               coef_stride);
-  return check_launch("bn_finalize");
+extern "C" int drn_bn_stats(const float* y, int64_t rows, int C, int nparts, const drn_bn_part_t* parts, float momentum, float eps,
+                            int training, float* coef, double* sums, unsigned* counter, void* stream) {
+  if (C % 4) return fail(DRN_EINVAL, "drn_bn_stats: C %% 4");
+  BnParts bp;
+  int rc = fill_parts(&bp, nparts, parts);
+  if (rc) return rc;
+  if (!training) {
+    bn_eval_coef_kernel<<<ceil_div(C, 256), 256, 0, ST(stream)>>>(C, bp, eps, coef);
+    return check_launch("bn_eval_coef");
+  }
+  dim3 grid(ceil_div(C, 128), static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS));
+  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, nullptr, rows, C, coef, sums, counter, bp, momentum, eps, nullptr);
+  return check_launch("bn_stats");
 }
 
 extern "C" int drn_bn_relu_apply(const float* y, int B, int T, int C, const float* coef, const void* up, int64_t up_plane_stride,
@@ -482,25 +564,23 @@ extern "C" int drn_bn_relu_apply(const float* y, int B, int T, int C, const floa
   return check_launch("bn_relu_apply");
 }
 
-extern "C" int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, const float* coef, double* sums,
-                                 void* stream) {
+extern "C" int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, float* coef, int nparts,
+                                 const drn_bn_part_t* parts, double* sums, unsigned* counter, float* bcoef, void* stream) {
   if (C % 4) return fail(DRN_EINVAL, "drn_bn_bwd_reduce: C %% 4");
+  BnParts bp;
+  int rc = fill_parts(&bp, nparts, parts);
+  if (rc) return rc;
   dim3 grid(ceil_div(C, 128), static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS));
-  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, da, rows, C, coef, sums);
+  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, da, rows, C, coef, sums, counter, bp, 0.f, 0.f, bcoef);
   return check_launch("bn_bwd_reduce");
 }
 
-extern "C" int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const double* sums,
+extern "C" int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const float* bcoef,
                                 void* dy, int64_t dy_plane_stride, void* stream) {
   if (C % 8) return fail(DRN_EINVAL, "drn_bn_bwd_apply: C %% 8");
-  bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream)>>>(da, y, rows, C, coef, sums,
+  bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream)>>>(da, y, rows, C, coef, bcoef,
                                                                               static_cast<__nv_bfloat16*>(dy), dy_plane_stride);
   return check_launch("bn_bwd_apply");
-}
-
-extern "C" int drn_bn_bwd_param(const double* sums, int sums_stride, int C, float* dgamma, float* dbeta, void* stream) {
-  bn_bwd_param_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(sums, sums_stride, C, dgamma, dbeta);
-  return check_launch("bn_bwd_param");
 }
 
 extern "C" int drn_pair_sum_add(float* dst, const float* src, int64_t rows_half, int C, void* stream) {

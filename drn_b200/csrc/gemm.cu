@@ -11,143 +11,9 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"
 
 namespace drn {
-
-struct PlanesView {
-  const __nv_bfloat16* ptr;
-  long long plane_stride;
-  int B, T, P, C;
-};
-
-struct GemmKParams {
-  int form, b_mn;
-  int B, T, N, K, M;
-  int Rm, Bbm, tiles_per_sample;                // ROWS: M-tile = Rm time slots x Bbm samples (=128 rows)
-  int Rk, Bbk, kblocks_per_sample, num_kblocks;  // WGRAD: K-block = Rk time slots x Bbk samples (=64 rows)
-  int ntaps;
-  int tap_shift[DRN_MAX_TAPS], tap_par[DRN_MAX_TAPS], tap_w[DRN_MAX_TAPS];
-  int a_c0, b_c0;
-  int nprod, split_k;
-  float* out;
-  long long out_ld;
-  int out_col0, out_mode;
-  long long out_tap_stride;
-  int out_T, out_t_mul, out_t_add;
-  const float* bias;
-  const float* rowscale;
-  int rowscale_ld;
-  float* out2;
-  long long out2_ld;
-  __nv_bfloat16* outp;
-  long long outp_ld;
-  int outp_col0;
-  long long outp_plane_stride;
-  int vec_ok;
-  PlanesView a, b;
-  int dbg_lbo, dbg_sbo, dbg_kadv;
-};
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;               // 64 bf16 = one 128-byte swizzle row
-constexpr uint32_t A_PLANE = BLOCK_M * 128;  // bytes of one A plane tile
-constexpr int GEMM_THREADS = 192;
-
-template <int BLOCK_N>
-struct TileCfg {
-  static constexpr uint32_t B_PLANE = BLOCK_N * 128;
-  static constexpr uint32_t STAGE = 2 * A_PLANE + 2 * B_PLANE;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 2 : 3;
-  static constexpr uint32_t SMEM = STAGES * STAGE + 1024;
-};
-
-// ------------------------------------------------------------------------------------------------
-// Epilogue for one 32-column chunk held in registers (one row per thread).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, bool valid, long long orow, int bb,
-                                               int ncol0, float* out_base) {
-  if (!valid) return;
-  const int nleft = p.N - ncol0;
-  const bool full = nleft >= 32;
-  const int cnt = full ? 32 : nleft;
-  if (p.bias) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < cnt) v[j] += __ldg(p.bias + ncol0 + j);
-  }
-  if (p.out2) {
-    float* o2 = p.out2 + orow * p.out2_ld + ncol0;
-    if (full && p.vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o2 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < cnt) o2[j] = v[j];
-    }
-  }
-  if (p.rowscale) {
-    const float* rs = p.rowscale + static_cast<long long>(bb) * p.rowscale_ld + ncol0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < cnt) v[j] *= __ldg(rs + j);
-  }
-  if (out_base) {
-    float* o = out_base + orow * p.out_ld + p.out_col0 + ncol0;
-    if (p.out_mode == DRN_OUT_ATOMIC) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < cnt) atomicAdd(o + j, v[j]);
-    } else if (full && p.vec_ok) {
-      if (p.out_mode == DRN_OUT_ADD) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 t = *reinterpret_cast<const float4*>(o + j);
-          t.x += v[j]; t.y += v[j + 1]; t.z += v[j + 2]; t.w += v[j + 3];
-          *reinterpret_cast<float4*>(o + j) = t;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < cnt) o[j] = (p.out_mode == DRN_OUT_ADD) ? o[j] + v[j] : v[j];
-    }
-  }
-  if (p.outp) {
-    __nv_bfloat16* oh = p.outp + orow * p.outp_ld + p.outp_col0 + ncol0;
-    __nv_bfloat16* ol = oh + p.outp_plane_stride;
-    if (full && p.vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[j + 2 * q], h0, l0);
-          split_bf16(v[j + 2 * q + 1], h1, l1);
-          h[q] = pack_bf16x2(h0, h1);
-          l[q] = pack_bf16x2(l0, l1);
-        }
-        *reinterpret_cast<uint4*>(oh + j) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(ol + j) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (j < cnt) {
-          __nv_bfloat16 h0, l0;
-          split_bf16(v[j], h0, l0);
-          oh[j] = h0;
-          ol[j] = l0;
-        }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // tcgen05 kernel: one 128 x BLOCK_N output tile per CTA.

@@ -61,24 +61,26 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const __nv_bfloat16* __
 }
 
 // ---- skinny conv backward: dX[b,t,c0+c] = sum_o sum_r d[b,t+pad-r,o] W[o][c][r];  dW[o][c][r] += sum X[b,t,c] d[b,t+pad-r,o]
-// one thread per channel, a block walks a chunk of rows.
+// one thread per channel PAIR (4-byte plane loads, 8-byte stores), a block walks a chunk of rows.
 template <int NOUT, int K>
 __global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict__ d, const __nv_bfloat16* __restrict__ x,
                                                          long long x_ps, int x_ld, int c0, int Cw, int B, int T,
                                                          const float* __restrict__ W, int rows_per_block,
                                                          float* __restrict__ dx, int dx_ld, int dx_accumulate,
                                                          float* __restrict__ dW) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
   if (c >= Cw) return;
   constexpr int PAD = (K - 1) / 2;
-  float w[NOUT][K], gw[NOUT][K];
+  float w[2][NOUT][K], gw[2][NOUT][K];
 #pragma unroll
-  for (int o = 0; o < NOUT; ++o)
+  for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int r = 0; r < K; ++r) {
-      w[o][r] = W[(static_cast<long long>(o) * Cw + c) * K + r];
-      gw[o][r] = 0.f;
-    }
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        w[h][o][r] = W[(static_cast<long long>(o) * Cw + c + h) * K + r];
+        gw[h][o][r] = 0.f;
+      }
   const long long rows = static_cast<long long>(B) * T;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   for (int i = 0; i < rows_per_block; ++i) {
@@ -86,8 +88,10 @@ __global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict
     if (row >= rows) break;
     const int t = static_cast<int>(row % T);
     const __nv_bfloat16* xp = x + row * x_ld + c0 + c;
-    const float xv = __bfloat162float(xp[0]) + __bfloat162float(xp[x_ps]);
-    float g = 0.f;
+    const uint32_t xh = *reinterpret_cast<const uint32_t*>(xp), xl = *reinterpret_cast<const uint32_t*>(xp + x_ps);
+    const float xv[2] = {__uint_as_float(xh << 16) + __uint_as_float(xl << 16),
+                         __uint_as_float(xh & 0xffff0000u) + __uint_as_float(xl & 0xffff0000u)};
+    float g[2] = {0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < K; ++r) {
       const int td = t + PAD - r;
@@ -95,19 +99,28 @@ __global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict
 #pragma unroll
       for (int o = 0; o < NOUT; ++o) {
         const float e = __ldg(d + (row + PAD - r) * NOUT + o);
-        g = fmaf(e, w[o][r], g);
-        gw[o][r] = fmaf(e, xv, gw[o][r]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          g[h] = fmaf(e, w[h][o][r], g[h]);
+          gw[h][o][r] = fmaf(e, xv[h], gw[h][o][r]);
+        }
       }
     }
-    float* dp = dx + row * dx_ld + c0 + c;
-    if (dx_accumulate) *dp += g;
-    else *dp = g;
+    float2* dp = reinterpret_cast<float2*>(dx + row * dx_ld + c0 + c);
+    if (dx_accumulate) {
+      const float2 old = *dp;
+      *dp = make_float2(old.x + g[0], old.y + g[1]);
+    } else {
+      *dp = make_float2(g[0], g[1]);
+    }
   }
   if (dW) {
 #pragma unroll
-    for (int o = 0; o < NOUT; ++o)
+    for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int r = 0; r < K; ++r) atomicAdd(dW + (static_cast<long long>(o) * Cw + c) * K + r, gw[o][r]);
+      for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+        for (int r = 0; r < K; ++r) atomicAdd(dW + (static_cast<long long>(o) * Cw + c + h) * K + r, gw[h][o][r]);
   }
 }
 
@@ -347,8 +360,9 @@ extern "C" int drn_skinny_conv_fwd(const void* x, int64_t x_plane_stride, int x_
 extern "C" int drn_skinny_conv_bwd(const float* d, const void* x, int64_t x_plane_stride, int x_ld, int c0, int Cw, int B, int T,
                                    int nout, int k, const float* W, float* dx, int dx_ld, int dx_accumulate, float* dW,
                                    void* stream) {
-  const int rpb = 64;
-  dim3 grid(ceil_div(Cw, 256), static_cast<unsigned>((static_cast<long long>(B) * T + rpb - 1) / rpb));
+  if (Cw % 2 || c0 % 2 || dx_ld % 2 || x_ld % 2) return fail(DRN_EINVAL, "drn_skinny_conv_bwd: alignment");
+  const int rpb = 16;
+  dim3 grid(ceil_div(Cw, 512), static_cast<unsigned>((static_cast<long long>(B) * T + rpb - 1) / rpb));
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   if (nout == 1 && k == 3) skinny_bwd_kernel<1, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
   else if (nout == 2 && k == 3) skinny_bwd_kernel<2, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);

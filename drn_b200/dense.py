@@ -44,8 +44,9 @@ class ConvBN:
         self.rows = B * self.t_out
         self.y = torch.empty(B, self.t_out, cout, device=dev)
         self.coef = torch.empty(4, cout, device=dev)
-        self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
-        self.bsums = torch.zeros(2, cout, dtype=torch.float64, device=dev)
+        self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)   # kept zero between uses by the kernels
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.bcoef = torch.empty(2, cout, device=dev)
         self.dy = Planes.empty(B, self.t_out, cout, dev)
         # bn_parts: [(param prefix, channel offset, channels)] -- the fused cls|bbox tower has two BatchNorm modules
         self.bn_parts = bn_parts or [(prefix + ".1", 0, cout)]
@@ -114,6 +115,9 @@ class DensePath:
         self.pgrad = z(8)
         self.upstream = z(3)
         self.gt = e(B, 2)
+        self.scales = e(3)
+        self.graphs = {}
+        self.launches_stage = 0
         self.Tl_c = (C.c_int * 3)(*self.Tl)
         self.strides_c = (C.c_float * 3)(*self.strides)
         self.lvl_off = [B * sum(self.Tl[:i]) for i in range(3)]
@@ -162,42 +166,55 @@ class DensePath:
         self._chk(_lib().drn_split_planes(_vp(src2d), C.c_int64(rows), Cn, C.c_int64(src2d.stride(0)), _vp(dst.data),
                                           C.c_int64(dst.C), dst_col0, C.c_int64(dst.plane_stride), _st()), "split_planes")
 
-    def _pack(self, w, dst, o0=0):
-        O, Cn = w.shape[0], w.shape[1]
-        k = w.shape[2] if w.dim() == 3 else 1
-        self._chk(_lib().drn_pack_conv_weight(_vp(w), O, Cn, k, _vp(dst.data), dst.T, o0, C.c_int64(dst.plane_stride), _st()),
-                  "pack_conv_weight")
-
-    def _unpack(self, ws, grad, o0=0):
-        O, Cn, k = grad.shape
-        self._chk(_lib().drn_unpack_conv_wgrad(_vp(ws), O, Cn, k, ws.shape[1], o0, _vp(grad), 0, _st()), "unpack_conv_wgrad")
+    @staticmethod
+    def _pack_item(w, dst, o0=0, grad=None, ws=None):
+        """weight w [O][C][k] <-> tap-major planes `dst` (pack) or fp32 workspace `ws` -> `grad` (unpack)."""
+        t = grad if grad is not None else w
+        O, Cn = t.shape[0], t.shape[1]
+        k = t.shape[2] if t.dim() == 3 else 1
+        it = L.PackItem()
+        if grad is None:
+            it.src, it.planes, it.Ototal, it.plane_stride = w.data_ptr(), dst.data.data_ptr(), dst.T, dst.plane_stride
+        else:
+            it.src, it.grad, it.Ototal = ws.data_ptr(), grad.data_ptr(), ws.shape[1]
+        it.O, it.C, it.k, it.o0 = O, Cn, k, o0
+        return it
 
     def pack_weights(self, p):
         """fp32 parameters -> tap-major split-BF16 planes (once per forward: the optimizer changes them every step)."""
         h = "fcos.head."
-        self._pack(p["prop_fc.weight"], self.wp["prop_fc"])
+        items = [self._pack_item(p["prop_fc.weight"], self.wp["prop_fc"])]
         for i in range(3):
-            self._pack(p["backbone_net.forward_conv%d.0.weight" % i], self.wp["conv%d" % i])
-            self._pack(p["fpn.fpn_inner%d.0.weight" % (i + 1)], self.wp["inner%d" % i])
-            self._pack(p["fpn.fpn_layer%d.0.weight" % (i + 1)], self.wp["layer%d" % i])
-            self._pack(p["qInput%d.weight" % i], self.wp["q%d" % i])
-        self._pack(p[h + "cls_tower.0.weight"], self.wp["towers"], 0)
-        self._pack(p[h + "bbox_tower.0.weight"], self.wp["towers"], self.F)
-        self._pack(p[h + "mix_fc.0.weight"], self.wp["mix"])
-        self._pack(p[h + "iou_scores.0.weight"], self.wp["iouc"])
+            items.append(self._pack_item(p["backbone_net.forward_conv%d.0.weight" % i], self.wp["conv%d" % i]))
+            items.append(self._pack_item(p["fpn.fpn_inner%d.0.weight" % (i + 1)], self.wp["inner%d" % i]))
+            items.append(self._pack_item(p["fpn.fpn_layer%d.0.weight" % (i + 1)], self.wp["layer%d" % i]))
+            items.append(self._pack_item(p["qInput%d.weight" % i], self.wp["q%d" % i]))
+        items.append(self._pack_item(p[h + "cls_tower.0.weight"], self.wp["towers"], 0))
+        items.append(self._pack_item(p[h + "bbox_tower.0.weight"], self.wp["towers"], self.F))
+        items.append(self._pack_item(p[h + "mix_fc.0.weight"], self.wp["mix"]))
+        items.append(self._pack_item(p[h + "iou_scores.0.weight"], self.wp["iouc"]))
+        arr = (L.PackItem * len(items))(*items)
+        self._chk(_lib().drn_pack_conv_weights(len(items), arr, _st()), "pack_conv_weights")
         torch.cat([p[h + "cls_tower.0.bias"], p[h + "bbox_tower.0.bias"]], out=self.tower_bias)
 
+    @staticmethod
+    def _bn_parts(blk, p, grads=None):
+        arr = (L.BnPart * len(blk.bn_parts))()
+        for i, (pre, c0, n) in enumerate(blk.bn_parts):
+            a = arr[i]
+            a.c0, a.n = c0, n
+            a.gamma, a.beta = p[pre + ".weight"].data_ptr(), p[pre + ".bias"].data_ptr()
+            a.running_mean, a.running_var = p[pre + ".running_mean"].data_ptr(), p[pre + ".running_var"].data_ptr()
+            a.num_batches_tracked = p[pre + ".num_batches_tracked"].data_ptr()
+            if grads is not None and (pre + ".weight") in grads:
+                a.dgamma, a.dbeta = grads[pre + ".weight"].data_ptr(), grads[pre + ".bias"].data_ptr()
+        return arr
+
     def _bn_fwd(self, blk, p, training):
-        lib = _lib()
-        if training:
-            blk.sums.zero_()
-            self._chk(lib.drn_bn_stats(_vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.sums), _st()), "bn_stats")
-        for (pre, c0, n) in blk.bn_parts:
-            self._chk(lib.drn_bn_finalize(
-                C.c_void_p(blk.sums.data_ptr() + 8 * c0), blk.cout, C.c_int64(blk.rows), n,
-                _vp(p[pre + ".weight"]), _vp(p[pre + ".bias"]), _vp(p[pre + ".running_mean"]), _vp(p[pre + ".running_var"]),
-                _vp(p[pre + ".num_batches_tracked"]), C.c_float(BN_MOMENTUM), C.c_float(BN_EPS), 1 if training else 0,
-                C.c_void_p(blk.coef.data_ptr() + 4 * c0), blk.cout, _st()), "bn_finalize")
+        parts = self._bn_parts(blk, p)
+        self._chk(_lib().drn_bn_stats(_vp(blk.y), C.c_int64(blk.rows), blk.cout, len(blk.bn_parts), parts,
+                                      C.c_float(BN_MOMENTUM), C.c_float(BN_EPS), 1 if training else 0, _vp(blk.coef),
+                                      _vp(blk.sums), _vp(blk.counter), _st()), "bn_stats")
 
     def _apply(self, blk, out_a, up=None, gate=None, out_qa=None):
         self._chk(_lib().drn_bn_relu_apply(
@@ -217,25 +234,38 @@ class DensePath:
     # ---------------------------------------------------------------------------------------------------------------
     # forward
     # ---------------------------------------------------------------------------------------------------------------
-    def forward(self, p, cmds, feats, pse, gt, training):
-        """p: name -> parameter/buffer tensor (fp32 on device); cmds: 3 x [B,1024] fp32 query commands;
-        feats [B,T,D] fp32, pse [B,T,2] f64, gt [B,2] f32.  Fills self.losses / raw head outputs."""
+    def stage_inputs(self, p, cmds, feats, pse, gt):
+        """Eager part of the forward: reads the caller's tensors and fills the static operand buffers (split planes of the
+        clip features and query commands, position feature, GT).  Everything after this runs on library-owned buffers only,
+        so it can be replayed from a CUDA graph."""
         lib, B, T = _lib(), self.B, self.T
-        h = "fcos.head."
         self.launches = 0
-        self.pack_weights(p)
         self.gt.copy_(gt)
-        # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50)
         for i in range(3):
             self._split(cmds[i], self.cmd_pl[i])
-            self._gemm(L.GEMM_ROWS, self.cmd_pl[i].desc(), self.wp["q%d" % i].desc(), 1, B, self.qdim[i], K=1024,
-                       out=self.q[i], bias=p["qInput%d.bias" % i])
         # position feature -> X0[:, :, D:] (main_model.py:53-55, backbone.py:31-32)
         self._chk(lib.drn_pos_feature(_vp(pse), _vp(p["position_transform.weight"]), _vp(p["position_transform.bias"]),
                                       C.c_int64(B * T), 256, _vp(self.X0.data), C.c_int64(self.C0), self.D,
                                       C.c_int64(self.X0.plane_stride), _vp(self.pos_in), _st()), "pos_feature")
-        # prop_fc with the level-0 gate fused in the epilogue -> X0[:, :, :D] (main_model.py:59, backbone.py:28-30)
         self._split(feats.view(B * T, self.D), self.f_pl)
+        self.launches_stage = self.launches
+
+    def forward(self, p, cmds, feats, pse, gt, training):
+        """p: name -> parameter/buffer tensor (fp32 on device); cmds: 3 x [B,1024] fp32 query commands;
+        feats [B,T,D] fp32, pse [B,T,2] f64, gt [B,2] f32.  Fills self.losses / raw head outputs."""
+        self.stage_inputs(p, cmds, feats, pse, gt)
+        self.forward_core(p, training)
+
+    def forward_core(self, p, training):
+        lib, B, T = _lib(), self.B, self.T
+        h = "fcos.head."
+        self.launches = self.launches_stage
+        self.pack_weights(p)
+        # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50)
+        for i in range(3):
+            self._gemm(L.GEMM_ROWS, self.cmd_pl[i].desc(), self.wp["q%d" % i].desc(), 1, B, self.qdim[i], K=1024,
+                       out=self.q[i], bias=p["qInput%d.bias" % i])
+        # prop_fc with the level-0 gate fused in the epilogue -> X0[:, :, :D] (main_model.py:59, backbone.py:28-30)
         self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
                    out2=self.Pre, rowscale=self.q[0], outp=self.X0)
         # backbone (backbone.py:27-34)
@@ -280,7 +310,7 @@ class DensePath:
             self._chk(lib.drn_skinny_conv_fwd(_vp(hi.data), C.c_int64(hi.plane_stride), hi.C, 0, self.F // 2, B, Tl, 1, 1,
                                               _vp(p[h + "iou_scores.3.weight"]), _vp(p[h + "iou_scores.3.bias"]),
                                               _vp(self.iou_raw[o:]), _st()), "iou_scores.3")
-        self.scales = torch.cat([p[h + "scales.%d.scale" % l] for l in range(3)])
+        torch.cat([p[h + "scales.%d.scale" % l] for l in range(3)], out=self.scales)
         self._chk(lib.drn_fcos_loss_fwd(3, B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.box_raw), _vp(self.iou_raw),
                                         _vp(self.scales), _vp(self.gt), C.c_float(self.gamma), C.c_float(self.alpha),
                                         1 if self.iou_branch_on else 0, _vp(self.bbox), _vp(self.acc), _vp(self.losses), _st()),
@@ -291,17 +321,13 @@ class DensePath:
     # ---------------------------------------------------------------------------------------------------------------
     # backward
     # ---------------------------------------------------------------------------------------------------------------
-    def _bn_bwd(self, blk, da, grads):
+    def _bn_bwd(self, blk, da, p, grads):
         lib = _lib()
-        blk.bsums.zero_()
-        self._chk(lib.drn_bn_bwd_reduce(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), _vp(blk.bsums), _st()),
-                  "bn_bwd_reduce")
-        self._chk(lib.drn_bn_bwd_apply(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), _vp(blk.bsums),
+        parts = self._bn_parts(blk, p, grads)
+        self._chk(lib.drn_bn_bwd_reduce(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), len(blk.bn_parts),
+                                        parts, _vp(blk.sums), _vp(blk.counter), _vp(blk.bcoef), _st()), "bn_bwd_reduce")
+        self._chk(lib.drn_bn_bwd_apply(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), _vp(blk.bcoef),
                                        _vp(blk.dy.data), C.c_int64(blk.dy.plane_stride), _st()), "bn_bwd_apply")
-        for (pre, c0, n) in blk.bn_parts:
-            if (pre + ".weight") in grads:
-                self._chk(lib.drn_bn_bwd_param(C.c_void_p(blk.bsums.data_ptr() + 8 * c0), blk.cout, n,
-                                               _vp(grads[pre + ".weight"]), _vp(grads[pre + ".bias"]), _st()), "bn_bwd_param")
 
     def _wgrad(self, blk, x_pl, out, accumulate=False):
         """out: [k][cout][cin] fp32 (workspace, or the gradient itself when k == 1)."""
@@ -349,10 +375,10 @@ class DensePath:
                 self._chk(lib.drn_skinny_conv_bwd(_vp(self.diou[o:]), _vp(hi.data), C.c_int64(hi.plane_stride), hi.C, 0, F // 2,
                                                   B, Tl, 1, 1, _vp(p[h + "iou_scores.3.weight"]), _vp(self.dHI[l]), F // 2, 0,
                                                   _vp(grads[h + "iou_scores.3.weight"]), _st()), "iou3_bwd")
-                self._bn_bwd(self.iouc[l], self.dHI[l], grads)
+                self._bn_bwd(self.iouc[l], self.dHI[l], p, grads)
                 self._wgrad(self.iouc[l], self.MX[l], self.ws["iouc"], accumulate=True)
                 self._dgrad(self.iouc[l], self.wp["iouc"], self.dMX[l])
-                self._bn_bwd(self.mix[l], self.dMX[l], grads)
+                self._bn_bwd(self.mix[l], self.dMX[l], p, grads)
                 self._wgrad(self.mix[l], tw, grads[h + "mix_fc.0.weight"], accumulate=True)
             self._chk(lib.drn_skinny_conv_bwd(_vp(self.dcls[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, F, B, Tl, 1, 3,
                                               _vp(p[h + "cls_logits.weight"]), _vp(self.dTW[l]), 2 * F, 0,
@@ -362,25 +388,25 @@ class DensePath:
                                               _vp(grads[h + "bbox_pred.weight"]), _st()), "bbox_pred_bwd")
             if iou_on:
                 self._dgrad(self.mix[l], self.wp["mix"], self.dTW[l], mode=L.OUT_ADD)
-            self._bn_bwd(self.tower[l], self.dTW[l], grads)
+            self._bn_bwd(self.tower[l], self.dTW[l], p, grads)
             self._wgrad(self.tower[l], self.Pf[l], self.ws["towers"], accumulate=True)
             self._dgrad(self.tower[l], self.wp["towers"], self.dPf[l])
         # FPN
         for i in range(3):
-            self._bn_bwd(self.layer[i], self.dPf[i], grads)
+            self._bn_bwd(self.layer[i], self.dPf[i], p, grads)
             self._wgrad(self.layer[i], self.I[i], self.ws["layer%d" % i])
             self._dgrad(self.layer[i], self.wp["layer%d" % i], self.dI[i])
             if i > 0:
                 self._chk(lib.drn_pair_sum_add(_vp(self.dI[i]), _vp(self.dI[i - 1]), C.c_int64(B * self.Tl[i]), F, _st()),
                           "pair_sum_add")
         for i in range(3):
-            self._bn_bwd(self.inner[i], self.dI[i], grads)
+            self._bn_bwd(self.inner[i], self.dI[i], p, grads)
             self._wgrad(self.inner[i], self.Cact[i], grads["fpn.fpn_inner%d.0.weight" % (i + 1)].view(1, F, self.c[i]))
             self._dgrad(self.inner[i], self.wp["inner%d" % i], self.dC[i])
         # backbone
         for i in (2, 1):
             blk = self.conv[i]
-            self._bn_bwd(blk, self.dC[i], grads)
+            self._bn_bwd(blk, self.dC[i], p, grads)
             self._wgrad(blk, self.QC[i - 1], self.ws["conv%d" % i])
             self._dgrad(blk, self.wp["conv%d" % i], self.dC[i - 1], mode=L.OUT_ADD, rowscale=self.q[i], out2=self.dQC[i - 1])
             a = self.Cact[i - 1]
@@ -388,7 +414,7 @@ class DensePath:
                                           C.c_int64(a.plane_stride), 1, B, self.Tl[i - 1], a.C, _vp(self.dq[i]), None, None,
                                           C.c_int64(0), None, _st()), "gate_reduce")
         blk = self.conv[0]
-        self._bn_bwd(blk, self.dC[0], grads)
+        self._bn_bwd(blk, self.dC[0], p, grads)
         self._wgrad(blk, self.X0, self.ws["conv0"])
         self._dgrad(blk, self.wp["conv0"], self.dX0)
         self._chk(lib.drn_gate_reduce(_vp(self.dX0), C.c_int64(self.C0), _vp(self.Pre), C.c_int64(self.D), C.c_int64(0), 0, B,
@@ -410,14 +436,17 @@ class DensePath:
                       "colsum")
             if need_cmd_grad:
                 self._gemm(L.GEMM_ROWS, self.dq_pl[i].desc(), self.wp["q%d" % i].desc(), 1, B, 1024, K=n, b_mn=1, out=self.dcmd[i])
-        # tap-major workspaces -> parameter layout [O][C][k]
+        # tap-major workspaces -> parameter layout [O][C][k], one launch
+        items = []
         for i in range(3):
-            self._unpack(self.ws["conv%d" % i], grads["backbone_net.forward_conv%d.0.weight" % i])
-            self._unpack(self.ws["layer%d" % i], grads["fpn.fpn_layer%d.0.weight" % (i + 1)])
-        self._unpack(self.ws["towers"], grads[h + "cls_tower.0.weight"], 0)
-        self._unpack(self.ws["towers"], grads[h + "bbox_tower.0.weight"], F)
+            items.append(self._pack_item(None, None, 0, grads["backbone_net.forward_conv%d.0.weight" % i], self.ws["conv%d" % i]))
+            items.append(self._pack_item(None, None, 0, grads["fpn.fpn_layer%d.0.weight" % (i + 1)], self.ws["layer%d" % i]))
+        items.append(self._pack_item(None, None, 0, grads[h + "cls_tower.0.weight"], self.ws["towers"]))
+        items.append(self._pack_item(None, None, F, grads[h + "bbox_tower.0.weight"], self.ws["towers"]))
         if iou_on:
-            self._unpack(self.ws["iouc"], grads[h + "iou_scores.0.weight"])
+            items.append(self._pack_item(None, None, 0, grads[h + "iou_scores.0.weight"], self.ws["iouc"]))
+        arr = (L.PackItem * len(items))(*items)
+        self._chk(lib.drn_unpack_conv_wgrads(len(items), arr, _st()), "unpack_conv_wgrads")
         # scalar parameter gradients gathered by the loss kernel
         grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
         grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])

@@ -40,6 +40,18 @@ class GemmDesc(C.Structure):
     ]
 
 
+class BnPart(C.Structure):
+    _fields_ = [("c0", C.c_int32), ("n", C.c_int32), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p),
+                ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
+
+
+class PackItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("planes", C.c_void_p), ("grad", C.c_void_p),
+                ("O", C.c_int32), ("C", C.c_int32), ("k", C.c_int32), ("Ototal", C.c_int32), ("o0", C.c_int32),
+                ("plane_stride", C.c_int64)]
+
+
 _lib = None
 
 

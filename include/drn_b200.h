@@ -112,33 +112,49 @@ int drn_gemm(const drn_gemm_t* g, void* stream);
  * Used for the C3D clip features (input of prop_fc, model/main_model.py:59) and small host-side vectors. */
 int drn_split_planes(const float* src, int64_t rows, int C, int64_t src_ld, void* dst, int64_t dst_ld, int dst_col0,
                      int64_t dst_plane_stride, void* stream);
-/* nn.Conv1d / nn.Linear weight [O][C][k] fp32 -> planes [k][Ototal][C] at row offset o0 (tap-major operand of drn_gemm). */
-int drn_pack_conv_weight(const float* w, int O, int C, int k, void* dst, int Ototal, int o0, int64_t plane_stride, void* stream);
-/* weight-gradient workspace [k][Ototal][C] fp32 -> parameter gradient [O][C][k] (= or +=). */
-int drn_unpack_conv_wgrad(const float* ws, int O, int C, int k, int Ototal, int o0, float* grad, int accumulate, void* stream);
+/* Table-driven weight packing, ONE launch for all layers.  Item: nn.Conv1d / nn.Linear weight `src` [O][C][k] fp32 ->
+ * planes [k][Ototal][C] at row offset o0 (tap-major operand of drn_gemm).  drn_unpack_conv_wgrads goes the other way for
+ * weight gradients: workspace `src` [k][Ototal][C] fp32 -> parameter gradient `grad` [O][C][k]. */
+typedef struct {
+  const float* src;
+  void* planes;   /* pack: destination hi plane */
+  float* grad;    /* unpack: destination */
+  int32_t O, C, k, Ototal, o0;
+  int64_t plane_stride;
+} drn_pack_item_t;
+int drn_pack_conv_weights(int n, const drn_pack_item_t* items, void* stream);
+int drn_unpack_conv_wgrads(int n, const drn_pack_item_t* items, void* stream);
 /* position feature, model/main_model.py:53-55: planes[row, dst_col0 + c] = Wp[c] . (s, e, e-s) + bp[c]; pos_in[row][3] saved for backward. */
 int drn_pos_feature(const double* pse, const float* Wp, const float* bp, int64_t rows, int Cp, void* dst, int64_t dst_ld,
                     int dst_col0, int64_t plane_stride, float* pos_in, void* stream);
 int drn_pos_bwd(const float* dx, int64_t dx_ld, int col0, const float* pos_in, int64_t rows, int Cp, float* dWp, float* dbp, void* stream);
 
-/* Train-mode BatchNorm1d + ReLU (model/basic_blocks.py:22-30, model/fcos.py:31-38) on a conv output y [rows][C] fp32:
- *   drn_bn_stats      sums[0][c] += sum y, sums[1][c] += sum y^2 (fp64; caller zeroes sums)
- *   drn_bn_finalize   coef[0..3][c] = scale, shift, mean, invstd; updates running_mean/var (momentum, unbiased var) and
- *                     num_batches_tracked when training, else uses the running statistics (eval)
+/* Train-mode BatchNorm1d + ReLU (model/basic_blocks.py:22-30, model/fcos.py:31-38) on a conv output y [rows][C] fp32.
+ * A BatchNorm "part" names the parameters of one nn.BatchNorm1d covering channels [c0, c0+n) of y (the fused cls|bbox tower
+ * output carries two modules side by side).
+ *   drn_bn_stats      training: per-channel sum / sum of squares (fp64 atomics); the last CTA to finish writes
+ *                     coef[0..3][c] = scale, shift, mean, invstd, updates running_mean/var (momentum, unbiased variance) and
+ *                     num_batches_tracked, and re-zeroes `sums` and `counter` (both must be zero before the first use).
+ *                     eval (training = 0): coef from the running statistics.
  *   drn_bn_relu_apply a = relu(y*scale+shift) [+ nearest-x2 upsample of `up` (FPN top-down add, model/FPN.py:63-68)]
  *                     -> planes out_a; optional planes out_qa = gate[b][c] * a (query gating, model/backbone.py:28-30)
- *   backward: drn_bn_bwd_reduce (sums[0] = sum g, sums[1] = sum g*xhat, g = da masked by the ReLU),
- *             drn_bn_bwd_apply (dy planes), drn_bn_bwd_param (dgamma += sums[1], dbeta += sums[0]). */
-int drn_bn_stats(const float* y, int64_t rows, int C, double* sums, void* stream);
-int drn_bn_finalize(const double* sums, int sums_stride, int64_t n, int C, const float* gamma, const float* beta,
-                    float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, float eps,
-                    int training, float* coef, int coef_stride, void* stream);
+ *   drn_bn_bwd_reduce sums of g and g*xhat (g = da masked by the ReLU); last CTA writes bcoef[0..1][c] = mean(g), mean(g*xhat),
+ *                     accumulates dgamma / dbeta of each part (when non-null) and re-zeroes sums / counter.
+ *   drn_bn_bwd_apply  dy planes = scale * (g - mean(g) - xhat * mean(g*xhat)). */
+typedef struct {
+  int32_t c0, n;
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; int64_t* num_batches_tracked;
+  float* dgamma; float* dbeta; /* backward only; may be null (frozen parameters) */
+} drn_bn_part_t;
+int drn_bn_stats(const float* y, int64_t rows, int C, int nparts, const drn_bn_part_t* parts, float momentum, float eps,
+                 int training, float* coef, double* sums, unsigned* counter, void* stream);
 int drn_bn_relu_apply(const float* y, int B, int T, int C, const float* coef, const void* up, int64_t up_plane_stride,
                       const float* gate, void* out_a, int64_t a_plane_stride, void* out_qa, int64_t qa_plane_stride, void* stream);
-int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, const float* coef, double* sums, void* stream);
-int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const double* sums, void* dy,
+int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, float* coef, int nparts, const drn_bn_part_t* parts,
+                      double* sums, unsigned* counter, float* bcoef, void* stream);
+int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const float* bcoef, void* dy,
                      int64_t dy_plane_stride, void* stream);
-int drn_bn_bwd_param(const double* sums, int sums_stride, int C, float* dgamma, float* dbeta, void* stream);
 /* backward of the FPN nearest-x2 upsample: dst[b][j] += src[b][2j] + src[b][2j+1]. */
 int drn_pair_sum_add(float* dst, const float* src, int64_t rows_half, int C, void* stream);
 /* backward of the query gate x = q[b][c] * a[b][t][c]: dq[b][c] += sum_t g*a; optionally dp planes = q*g and dbias[c] += sum q*g

@@ -7,6 +7,8 @@ is executed by hand-written sm_100a kernels (drn_b200.dense.DensePath -> libdrn_
 `param.grad` through one autograd.Function whose backward is the hand-derived backward schedule.  There is no CPU or
 torch-op fallback: calling forward without a B200 raises.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -16,11 +18,64 @@ from model.language_module import QueryEncoder
 from model.modules import FPN, Backbone, FCOSModule
 
 
+def _sig(p):
+    return hash(tuple(t.data_ptr() for t in p.values()))
+
+
+def _run_forward_core(path, p, training, use_graphs):
+    """The replayable part of the forward.  First call for a (mode, parameter-storage) signature runs eagerly and records a
+    CUDA graph of the same launch sequence; later calls replay it (~150 kernel launches -> one graph launch)."""
+    if not use_graphs:
+        path.forward_core(p, training)
+        return
+    key = ("fwd", training, _sig(p))
+    g = path.graphs.get(key)
+    if g is None:
+        path.forward_core(p, training)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            path.forward_core(p, training)
+        path.graphs[key] = g
+    else:
+        g.replay()
+
+
+def _run_backward(path, p, names, upstream, need_cmd, use_graphs):
+    key = ("bwd", _sig(p), tuple(names), need_cmd)
+    ent = path.graphs.get(key)
+    if ent is None:
+        sizes = [p[n].numel() for n in names]
+        flat = torch.zeros(sum(sizes), device=upstream.device, dtype=torch.float32)
+        grads, o = {}, 0
+        for n, sz in zip(names, sizes):
+            grads[n] = flat[o:o + sz].view_as(p[n])
+            o += sz
+        path.upstream.copy_(upstream)
+        path.backward(p, grads, path.upstream, need_cmd_grad=need_cmd)
+        g = None
+        if use_graphs:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                flat.zero_()
+                path.backward(p, grads, path.upstream, need_cmd_grad=need_cmd)
+        path.graphs[key] = (g, flat, grads)
+    else:
+        g, flat, grads = ent
+        path.upstream.copy_(upstream)
+        if g is not None:
+            g.replay()
+        else:
+            flat.zero_()
+            path.backward(p, grads, path.upstream, need_cmd_grad=need_cmd)
+    return flat, grads
+
+
 class _DenseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, path, training, feats, pse, gt, c0, c1, c2, *params):
         p = model._tensor_dict()
-        path.forward(p, (c0.contiguous(), c1.contiguous(), c2.contiguous()), feats, pse, gt, training)
+        path.stage_inputs(p, (c0.contiguous(), c1.contiguous(), c2.contiguous()), feats, pse, gt)
+        _run_forward_core(path, p, training, model.use_graphs)
         ctx.model, ctx.path = model, path
         ctx.need_cmd = c0.requires_grad or c1.requires_grad or c2.requires_grad
         ctx.nparams = len(params)
@@ -32,16 +87,12 @@ class _DenseFn(torch.autograd.Function):
         names = model._trainable_names
         assert len(names) == ctx.nparams
         p = model._tensor_dict()
-        sizes = [p[n].numel() for n in names]
-        flat = torch.zeros(sum(sizes), device=g.device, dtype=torch.float32)
-        grads, o = {}, 0
-        for n, s in zip(names, sizes):
-            grads[n] = flat[o:o + s].view_as(p[n])
-            o += s
-        dcmd = path.backward(p, grads, g.contiguous().float(), need_cmd_grad=ctx.need_cmd)
+        # gradients are produced in ONE flat static buffer (graph-replayable, and the unit of the data-parallel all-reduce);
+        # autograd copies the returned views into param.grad, so the buffer can be reused by the next step.
+        flat, grads = _run_backward(path, p, names, g.contiguous().float(), ctx.need_cmd, model.use_graphs)
         if model._dp_hook is not None:  # data parallel: all-reduce the flat gradient buffer (drn_b200/parallel.py)
             model._dp_hook(flat)
-        dc = tuple(d.clone() for d in dcmd) if ctx.need_cmd else (None, None, None)
+        dc = tuple(d.clone() for d in path.dcmd) if ctx.need_cmd else (None, None, None)
         return (None, None, None, None, None, None) + dc + tuple(grads[n] for n in names)
 
 
@@ -70,6 +121,8 @@ class mainModel(nn.Module):
         self._paths = {}
         self._trainable_names = []
         self._dp_hook = None
+        # CUDA graphs over the dense path (static shapes, library-owned buffers); DRN_NO_GRAPHS=1 launches kernel by kernel
+        self.use_graphs = os.environ.get("DRN_NO_GRAPHS", "0") != "1"
 
     # ---- parameter plumbing ---------------------------------------------------------------------------------------
     def _tensor_dict(self):
@@ -112,7 +165,9 @@ class mainModel(nn.Module):
             losses = _DenseFn.apply(self, path, training, feats, pse, gt, cmds[0], cmds[1], cmds[2], *tensors)
         else:
             with torch.no_grad():
-                path.forward(self._tensor_dict(), tuple(c.contiguous() for c in cmds), feats, pse, gt, training)
+                p = self._tensor_dict()
+                path.stage_inputs(p, tuple(c.contiguous() for c in cmds), feats, pse, gt)
+                _run_forward_core(path, p, training, self.use_graphs)
                 losses = path.losses[:3].clone()
         loss_dict = {"loss_cls": losses[0], "loss_reg": losses[1]}
         if self.cfg["is_first_stage"]:

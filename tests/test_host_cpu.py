@@ -1,0 +1,149 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/drn_b200.h declares, the ctypes mirrors match
+the C structs, the drop-in model keeps the reference's state_dict contract and refuses to run without a GPU, the tap
+tables of the host schedule describe the reference convolutions, and the host-side post-processing matches the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from drn_b200 import dense
+from drn_b200 import lib as L
+from drn_b200 import spec as spec_mod
+from drn_b200 import synthetic as S
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(REPO, "include", "drn_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(drn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libdrn_sm100.so does not export %s" % n
+    assert lib.drn_version() == 100
+
+
+def test_ctypes_structs_match_c_layout():
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "drn_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(drn_planes_t), sizeof(drn_gemm_t), offsetof(drn_gemm_t, b), offsetof(drn_gemm_t, tap_w),
+         offsetof(drn_gemm_t, out_tap_stride), offsetof(drn_gemm_t, outp_plane_stride), offsetof(drn_gemm_t, dbg_kadv),
+         sizeof(drn_bn_part_t), offsetof(drn_bn_part_t, dbeta), sizeof(drn_pack_item_t), offsetof(drn_pack_item_t, plane_stride));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(d, "t")
+        subprocess.run(["gcc", "-I", os.path.join(REPO, "include"), c, "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    G = L.GemmDesc
+    mine = [ctypes.sizeof(L.Planes), ctypes.sizeof(G), G.b.offset, G.tap_w.offset, G.out_tap_stride.offset,
+            G.outp_plane_stride.offset, G.dbg_kadv.offset, ctypes.sizeof(L.BnPart), L.BnPart.dbeta.offset,
+            ctypes.sizeof(L.PackItem), L.PackItem.plane_stride.offset]
+    assert [int(x) for x in out] == mine
+
+
+def test_model_state_dict_contract_and_no_cpu_fallback():
+    from model.main_model import mainModel
+    m = mainModel(1301, S.config_namespace(stage=1))
+    sd = m.state_dict()
+    sp = spec_mod.state_dict_spec(S.default_config(stage=1))
+    assert [k for k, _ in sp] == list(sd.keys())
+    assert all(tuple(sd[k].shape) == tuple(s) for k, s in sp)
+    m.load_state_dict(S.synth_state_dict(sp))
+    assert sum(p.numel() for p in m.parameters()) == 45511378
+    # attributes the reference's main.py touches (main.py:94, 126-133)
+    assert m.query_encoder.embedding.weight.shape == (1302, 300)
+    assert len(list(m.fcos.head.iou_scores.parameters())) == 6 and len(list(m.fcos.head.mix_fc.parameters())) == 4
+    b = S.synth_batch(2, 32)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(b["query_tokens"], b["query_length"], b["props_features"], b["props_start_end"], b["gt_start_end"], None, None)
+    with pytest.raises(RuntimeError):
+        m.backbone_net(torch.zeros(1))
+
+
+def _emulate_rows(x, w, taps, par, t_out):
+    """drn_gemm ROWS semantics in torch: x [B,T_in,C] viewed [B,T_in/par,par,C]; w [tap][N][K]."""
+    B, Tin, Cn = x.shape
+    xv = x.view(B, Tin // par, par, Cn)
+    out = torch.zeros(B, t_out, w.shape[1])
+    for sh, p, wt in taps:
+        for t in range(t_out):
+            ts = t + sh
+            if 0 <= ts < Tin // par:
+                out[:, t] += xv[:, ts, p] @ w[wt].t()
+    return out
+
+
+def test_tap_tables_are_the_reference_convolutions():
+    torch.manual_seed(0)
+    B, T, Ci, Co = 2, 16, 5, 7
+    x = torch.randn(B, T, Ci)
+    w = torch.randn(Co, Ci, 3)
+    wt = w.permute(2, 0, 1).contiguous()  # tap-major [k][O][C] as drn_pack_conv_weight stores it
+    for stride, taps in ((1, dense.K3), (2, dense.K3S2)):
+        ref = F.conv1d(x.permute(0, 2, 1), w, stride=stride, padding=1).permute(0, 2, 1)
+        got = _emulate_rows(x, wt, taps, stride, T // stride)
+        assert torch.allclose(got, ref, atol=1e-5)
+    # data gradients: stride 1, and stride 2 through the two output parities
+    dy = torch.randn(B, T, Co)
+    xx = x.clone().requires_grad_(True)
+    F.conv1d(xx.permute(0, 2, 1), w, stride=1, padding=1).permute(0, 2, 1).mul(dy).sum().backward()
+    wdg = w.permute(2, 1, 0).contiguous()  # [k][C][O]: "N" = C_in rows, "K" = C_out
+    got = _emulate_rows(dy, wdg, dense.K3_DGRAD, 1, T)
+    assert torch.allclose(got, xx.grad, atol=1e-5)
+    dy2 = torch.randn(B, T // 2, Co)
+    xx = x.clone().requires_grad_(True)
+    F.conv1d(xx.permute(0, 2, 1), w, stride=2, padding=1).permute(0, 2, 1).mul(dy2).sum().backward()
+    got = torch.zeros(B, T, Ci)
+    for par in (0, 1):
+        got[:, par::2] = _emulate_rows(dy2, wdg, dense.S2_DGRAD[par], 1, T // 2)
+    assert torch.allclose(got, xx.grad, atol=1e-5)
+
+
+def test_postprocess_matches_oracle():
+    from model.inference import postprocess
+    from oracle import drn_oracle as O
+    torch.manual_seed(1)
+    for first in (True, False):
+        cfg = S.default_config(stage=1 if first else 3)
+        B, T = 3, 64
+        Tl = (T, T // 2, T // 4)
+        logits = [torch.randn(B, 1, t) * 2 - 1 for t in Tl]
+        bbox = [torch.rand(B, 2, t) * 8 for t in Tl]
+        iou = [torch.randn(B, 1, t) for t in Tl]
+        logits[0][2] = -20.0  # sample 2: nothing passes on level 0
+        locs = O.compute_locations(T, cfg["fpn_stride"])
+        ref = O.postprocess(locs, logits, bbox, iou, cfg)
+        cls_raw = torch.cat([x.permute(0, 2, 1).reshape(-1) for x in logits])
+        box = torch.cat([x.permute(0, 2, 1).reshape(-1, 2) for x in bbox])
+        iou_raw = torch.cat([x.permute(0, 2, 1).reshape(-1) for x in iou])
+        got = postprocess(cls_raw, box, iou_raw, Tl, cfg["fpn_stride"], cfg, B)
+        for g, r in zip(got, ref):
+            assert g["detections"].shape == r["detections"].shape
+            og = torch.argsort(g["scores"] + g["detections"][:, 0] * 1e-3)
+            orf = torch.argsort(r["scores"] + r["detections"][:, 0] * 1e-3)
+            assert torch.allclose(g["detections"][og], r["detections"][orf], atol=1e-6)
+            assert torch.allclose(g["scores"][og], r["scores"][orf], atol=1e-6)
+            assert g["level"] == r["level"]
+    # nothing anywhere -> the reference's fallback detection (inference.py:192-197)
+    cfg = S.default_config(stage=1)
+    n = 1 * (64 + 32 + 16)
+    got = postprocess(torch.full((n,), -20.0), torch.ones(n, 2), torch.zeros(n), (64, 32, 16), cfg["fpn_stride"], cfg, 1)
+    assert got[0]["detections"].tolist() == [[0.0, 1.0]] and got[0]["level"] == [[-1]]

@@ -1,0 +1,62 @@
+"""Host-side logic of the data-parallel wrapper on CPU: 2 ranks, gloo, 127.0.0.1.  Checks the rank-0 broadcast of
+parameters/buffers, the averaged all-reduce of the dense path's flat gradient buffer and of the query-encoder gradients."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Toy(nn.Module):
+    def __init__(self, rank):
+        super().__init__()
+        self.query_encoder = nn.Linear(4, 3)
+        self.prop_fc = nn.Linear(3, 2)
+        self.register_buffer("running", torch.full((2,), float(rank)))
+        with torch.no_grad():
+            for p in self.parameters():
+                p.fill_(float(rank) + 1.0)
+        self._dp_hook = None
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from drn_b200.parallel import DataParallelDRN
+    toy = _Toy(rank)
+    dp = DataParallelDRN(toy)
+    ok = all(bool((p == 1.0).all()) for p in toy.parameters()) and bool((toy.running == 0.0).all())  # replica 0 wins
+    flat = torch.arange(6, dtype=torch.float32) * (rank + 1)
+    toy._dp_hook(flat)  # what _DenseFn.backward calls on the dense gradient buffer
+    ok = ok and torch.allclose(flat, torch.arange(6, dtype=torch.float32) * 1.5)
+    for p in toy.query_encoder.parameters():
+        p.grad = torch.full_like(p, float(rank))
+    toy.prop_fc.weight.grad = torch.full_like(toy.prop_fc.weight, 7.0)  # dense grads are NOT touched by finish_gradient_sync
+    dp.finish_gradient_sync()
+    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 0.5)) for p in toy.query_encoder.parameters())
+    ok = ok and bool((toy.prop_fc.weight.grad == 7.0).all())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_wrapper_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
