@@ -354,6 +354,9 @@ static int launch_tc(const GemmKParams& kp, const CUtensorMap& ma, const CUtenso
   return check_launch("gemm_tc_kernel");
 }
 
+int launch_pair(const GemmKParams& kp, const CUtensorMap& ma, const CUtensorMap& mb, int num_tiles, int n_tiles, int m_tiles,
+                int sm_count, cudaStream_t st);  // gemm2.cu
+
 }  // namespace drn
 
 using namespace drn;
@@ -412,24 +415,50 @@ extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
     return check_launch("gemm_simt_kernel");
   }
 
-  const int block_n = (g->N > 128) ? 256 : 128;
-  CUtensorMap ma, mb;
-  dim3 grid;
-  int rc;
+  // ---- engine selection: 0 = auto, 2 = persistent CTA-pair kernel (gemm2.cu), 3 = one-tile-per-CTA kernel -------------
   if (!wgrad) {
     if (g->T >= 128) { kp.Rm = 128; kp.Bbm = 1; }
     else { kp.Rm = pow2_ceil(g->T); kp.Bbm = 128 / kp.Rm; }
     kp.tiles_per_sample = ceil_div(g->T, kp.Rm);
-    const int m_tiles = (kp.Bbm == 1) ? g->B * kp.tiles_per_sample : ceil_div(g->B, kp.Bbm);
-    if ((rc = make_map(&ma, g->a, kp.Rm, kp.Bbm)) != 0) return rc;
-    if ((rc = make_map(&mb, g->b, g->b_mn ? 64 : block_n, 1)) != 0) return rc;
-    grid = dim3(m_tiles, ceil_div(g->N, block_n), 1);
   } else {
     if (g->T >= 64) { kp.Rk = 64; kp.Bbk = 1; }
     else { kp.Rk = pow2_ceil(g->T); kp.Bbk = 64 / kp.Rk; }
     kp.kblocks_per_sample = ceil_div(g->T, kp.Rk);
     kp.num_kblocks = (kp.Bbk == 1) ? g->B * kp.kblocks_per_sample : ceil_div(g->B, kp.Bbk);
     if (kp.split_k > kp.num_kblocks) kp.split_k = kp.num_kblocks;
+  }
+  const int m_sub = wgrad ? ceil_div(g->M, BLOCK_M) : ((kp.Bbm == 1) ? g->B * kp.tiles_per_sample : ceil_div(g->B, kp.Bbm));
+  const int pair_n_tiles = ceil_div(g->N, 256);
+  const int pair_m_tiles = ceil_div(m_sub, 2);
+  const int pair_tiles = pair_m_tiles * pair_n_tiles * (wgrad ? g->ntaps * kp.split_k : 1);
+  static int sm_count = 0;
+  if (!sm_count) {
+    sm_count = drn_sm_count();
+    if (sm_count <= 0) sm_count = 148;
+  }
+  bool use_pair = (g->engine == 2) || (g->engine == 0 && pair_tiles >= sm_count / 4);
+  if (g->engine == 3) use_pair = false;
+  if (g->dbg_lbo || g->dbg_sbo || g->dbg_kadv) use_pair = false;
+
+  CUtensorMap ma, mb;
+  int rc;
+  if (use_pair) {
+    if (!wgrad) {
+      if ((rc = make_map(&ma, g->a, kp.Rm, kp.Bbm)) != 0) return rc;
+      if ((rc = make_map(&mb, g->b, g->b_mn ? 64 : 128, 1)) != 0) return rc;
+    } else {
+      if ((rc = make_map(&ma, g->a, kp.Rk, kp.Bbk)) != 0) return rc;
+      if ((rc = make_map(&mb, g->b, kp.Rk, kp.Bbk)) != 0) return rc;
+    }
+    return launch_pair(kp, ma, mb, pair_tiles, pair_n_tiles, pair_m_tiles, sm_count, st);
+  }
+  const int block_n = (g->N > 128) ? 256 : 128;
+  dim3 grid;
+  if (!wgrad) {
+    if ((rc = make_map(&ma, g->a, kp.Rm, kp.Bbm)) != 0) return rc;
+    if ((rc = make_map(&mb, g->b, g->b_mn ? 64 : block_n, 1)) != 0) return rc;
+    grid = dim3(m_sub, ceil_div(g->N, block_n), 1);
+  } else {
     if ((rc = make_map(&ma, g->a, kp.Rk, kp.Bbk)) != 0) return rc;
     if ((rc = make_map(&mb, g->b, kp.Rk, kp.Bbk)) != 0) return rc;
     grid = dim3(ceil_div(g->M, BLOCK_M), ceil_div(g->N, block_n), g->ntaps * kp.split_k);

@@ -1,0 +1,266 @@
+// drn_gemm, engine 0 for large problems: PERSISTENT kernel on CTA PAIRS (tcgen05 cta_group::2).
+//
+//   * one cluster of 2 CTAs per SM pair (74 pairs on a B200) walks 256 x 256 output tiles; each CTA stages its own 128 rows
+//     of A and its own 128 columns of B (hi and lo planes) by TMA, the leader CTA's single MMA thread issues
+//     256 x 256 x 16 UMMAs that read both CTAs' shared memory, so every staged byte feeds twice the math of the 1-CTA kernel
+//     (64 KB per 1536 tensor cycles and CTA instead of 96 KB) -- this is what lifts the smem-capacity/latency bound that kept
+//     the one-tile-per-CTA kernel (gemm.cu) at ~40 % tensor-pipe utilisation;
+//   * 3-stage TMA->MMA pipeline that runs across tile boundaries;
+//   * the fp32 accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i (TMEM -> registers ->
+//     global, bias / gate / split-plane outputs) overlaps the MMAs of tile i+1.
+// Operand forms, tensor maps and epilogue semantics are those of gemm.cu (include/drn_b200.h).
+#include <cuda.h>
+
+#include "gemm_common.cuh"
+
+namespace drn {
+
+constexpr int P2_STAGES = 3;
+constexpr uint32_t P2_HALF = 128 * 128;                 // one plane of one operand half: 128 rows x 128 B
+constexpr uint32_t P2_STAGE = 4 * P2_HALF;              // A hi, A lo, B hi, B lo
+constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + 1024;
+constexpr int P2_THREADS = 192;
+constexpr int P2_TILE = 256;
+
+struct PairTile {
+  int b0, t0;     // ROWS: first (sample, time slot) of this CTA's 128 rows
+  int m0;         // WGRAD: first A channel (= output row) of this CTA
+  int nb;         // first column of B staged by this CTA
+  int n0;         // first output column of the pair's tile
+  int tap;        // WGRAD: tap handled by this tile
+  int it_begin, nk;
+};
+
+__device__ __forceinline__ PairTile decode_tile(const GemmKParams& p, int tile, int rank, int n_tiles, int m_tiles) {
+  PairTile t{};
+  const bool wgrad = (p.form == DRN_GEMM_WGRAD);
+  const int nt = tile % n_tiles;
+  int rest = tile / n_tiles;
+  t.n0 = nt * P2_TILE;
+  t.nb = t.n0 + rank * 128;
+  if (!wgrad) {
+    const int ms = 2 * rest + rank;  // 128-row sub-tile of this CTA
+    if (p.Bbm == 1) {
+      t.b0 = ms / p.tiles_per_sample;
+      t.t0 = (ms % p.tiles_per_sample) * p.Rm;
+    } else {
+      t.b0 = ms * p.Bbm;
+      t.t0 = 0;
+    }
+    t.it_begin = 0;
+    t.nk = p.ntaps * (p.K / BLOCK_K);
+  } else {
+    const int mt = rest % m_tiles;
+    const int z = rest / m_tiles;
+    t.m0 = mt * P2_TILE + rank * 128;
+    t.tap = z / p.split_k;
+    const int split = z % p.split_k;
+    t.it_begin = static_cast<int>(static_cast<long long>(p.num_kblocks) * split / p.split_k);
+    t.nk = static_cast<int>(static_cast<long long>(p.num_kblocks) * (split + 1) / p.split_k) - t.it_begin;
+  }
+  return t;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tma_a,
+                 const __grid_constant__ CUtensorMap tma_b, int num_tiles, int n_tiles, int m_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[P2_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[P2_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_holder;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const bool wgrad = (p.form == DRN_GEMM_WGRAD);
+  const bool a_mn = wgrad;
+  const bool b_mn = wgrad || (p.b_mn != 0);
+  const int nplanes = (p.nprod == 1) ? 1 : 2;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int kpt = wgrad ? 1 : p.K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < P2_STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(smem_u32(&tmem_base_holder), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer (one thread per CTA; completion is signalled on the LEADER's full barrier) =====
+    if (lane == 0) {
+      const uint32_t tx = 2u * nplanes * 2u * P2_HALF;  // both CTAs' bytes land on the leader's barrier
+      int g = 0;                                        // global k-iteration counter (pipeline runs across tiles)
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const PairTile t = decode_tile(p, tile, rank, n_tiles, m_tiles);
+        for (int i = 0; i < t.nk; ++i, ++g) {
+          const int s = g % P2_STAGES;
+          const uint32_t ph = (g / P2_STAGES) & 1;
+          mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(smem_u32(&full_bar[s]), tx);
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+          const uint32_t sa = smem_base + s * P2_STAGE;
+          const uint32_t sb = sa + 2 * P2_HALF;
+          const int it = t.it_begin + i;
+          if (!wgrad) {
+            const int tap = it / kpt, kb = it % kpt;
+            for (int pl = 0; pl < nplanes; ++pl) {
+              tma_load_5d_pair(sa + pl * P2_HALF, &tma_a, fb, p.a_c0 + kb * BLOCK_K, p.tap_par[tap], t.t0 + p.tap_shift[tap],
+                               t.b0, pl);
+              if (!b_mn) {
+                tma_load_5d_pair(sb + pl * P2_HALF, &tma_b, fb, p.b_c0 + kb * BLOCK_K, 0, t.nb, p.tap_w[tap], pl);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                  tma_load_5d_pair(sb + pl * P2_HALF + j * 8192, &tma_b, fb, p.b_c0 + t.nb + j * 64, 0, kb * BLOCK_K,
+                                   p.tap_w[tap], pl);
+              }
+            }
+          } else {
+            int bk, tk;
+            if (p.Bbk == 1) {
+              bk = it / p.kblocks_per_sample;
+              tk = (it % p.kblocks_per_sample) * p.Rk;
+            } else {
+              bk = it * p.Bbk;
+              tk = 0;
+            }
+            for (int pl = 0; pl < nplanes; ++pl) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                tma_load_5d_pair(sa + pl * P2_HALF + j * 8192, &tma_a, fb, p.a_c0 + t.m0 + j * 64, 0, tk, bk, pl);
+                tma_load_5d_pair(sb + pl * P2_HALF + j * 8192, &tma_b, fb, p.b_c0 + t.nb + j * 64, p.tap_par[t.tap],
+                                 tk + p.tap_shift[t.tap], bk, pl);
+              }
+            }
+          }
+        }
+      }
+      // drain: every commit multicast to this CTA's empty barriers must have landed before the CTA may exit
+      for (int d = 0; d < P2_STAGES && d < g; ++d) {
+        const int gi = g - 1 - d;
+        mbar_wait(smem_u32(&empty_bar[gi % P2_STAGES]), (gi / P2_STAGES) & 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA =====
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(P2_TILE, P2_TILE, a_mn, b_mn);
+      const uint32_t a_lbo = a_mn ? 8192u : 0u, a_kadv = a_mn ? 2048u : 32u;
+      const uint32_t b_lbo = b_mn ? 8192u : 0u, b_kadv = b_mn ? 2048u : 32u;
+      int g = 0, lt = 0;  // lt counts the tiles that actually use an accumulator stage
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const PairTile t = decode_tile(p, tile, rank, n_tiles, m_tiles);
+        if (t.nk <= 0) continue;
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        ++lt;
+        mbar_wait(smem_u32(&tmem_empty_bar[as]), aph ^ 1);  // both CTAs' epilogues drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * P2_TILE;
+        uint32_t accumulate = 0;
+        for (int i = 0; i < t.nk; ++i, ++g) {
+          const int s = g % P2_STAGES;
+          const uint32_t ph = (g / P2_STAGES) & 1;
+          mbar_wait(smem_u32(&full_bar[s]), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * P2_STAGE;
+          const uint32_t sb = sa + 2 * P2_HALF;
+          for (int prod = 0; prod < p.nprod; ++prod) {
+            const uint32_t pa = (prod >> 1) & 1, pb = prod & 1;  // (hi,hi) (hi,lo) (lo,hi) (lo,lo)
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t ad = umma_smem_desc(sa + pa * P2_HALF + k * a_kadv, a_lbo, 1024u);
+              const uint64_t bd = umma_smem_desc(sb + pb * P2_HALF + k * b_kadv, b_lbo, 1024u);
+              umma_bf16_pair(d_tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit_pair(smem_u32(&empty_bar[s]));  // frees this stage in BOTH CTAs
+        }
+        umma_commit_pair(smem_u32(&tmem_full_bar[as]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 2..5 (both CTAs): TMEM lane quarter = warp % 4 =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int lt = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const PairTile t = decode_tile(p, tile, rank, n_tiles, m_tiles);
+      if (t.nk <= 0) continue;
+      const int as = lt & 1;
+      const uint32_t aph = (lt >> 1) & 1;
+      ++lt;
+      mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
+      tc_fence_after();
+      bool valid;
+      long long orow;
+      int bb = 0;
+      float* out_base = p.out;
+      if (!wgrad) {
+        bb = t.b0 + row / p.Rm;
+        const int tt = t.t0 + row % p.Rm;
+        valid = (bb < p.B) && (tt < p.T);
+        orow = static_cast<long long>(bb) * p.out_T + static_cast<long long>(tt) * p.out_t_mul + p.out_t_add;
+      } else {
+        valid = (t.m0 + row) < p.M;
+        orow = t.m0 + row;
+        if (out_base) out_base += p.tap_w[t.tap] * p.out_tap_stride;
+      }
+      const uint32_t taddr = tmem_base + as * P2_TILE + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < P2_TILE; c0 += 32) {
+        if (t.n0 + c0 >= p.N) break;
+        float v[32];
+        tmem_ld_32x32(taddr + c0, v);
+        tmem_ld_wait();
+        epilogue_chunk(p, v, valid, orow, bb, t.n0 + c0, out_base);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+int launch_pair(const GemmKParams& kp, const CUtensorMap& ma, const CUtensorMap& mb, int num_tiles, int n_tiles, int m_tiles,
+                int sm_count, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(gemm_pair): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  int clusters = sm_count / 2;
+  if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters < 1) clusters = 1;
+  gemm_pair_kernel<<<2 * clusters, P2_THREADS, P2_SMEM, st>>>(kp, ma, mb, num_tiles, n_tiles, m_tiles);
+  return check_launch("gemm_pair_kernel");
+}
+
+}  // namespace drn

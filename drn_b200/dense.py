@@ -332,11 +332,11 @@ class DensePath:
     def _wgrad(self, blk, x_pl, out, accumulate=False):
         """out: [k][cout][cin] fp32 (workspace, or the gradient itself when k == 1)."""
         taps = K1 if blk.k == 1 else (K3 if blk.stride == 1 else K3S2)
-        tiles = -(-blk.cout // 128) * -(-blk.cin // (256 if blk.cin > 128 else 128)) * blk.k
+        tiles = -(-blk.cout // 256) * -(-blk.cin // 256) * blk.k   # 256 x 256 tiles of the CTA-pair kernel
         kblocks = max(1, blk.rows // 64)
         split = 1
-        if tiles < SM_COUNT:
-            split = max(1, min(kblocks, (2 * SM_COUNT) // tiles, 16))
+        if tiles < SM_COUNT // 2:
+            split = max(1, min(kblocks // 4, SM_COUNT // tiles, 16))
         mode = L.OUT_ATOMIC if (split > 1 or accumulate) else L.OUT_STORE
         self._gemm(L.GEMM_WGRAD, blk.dy.desc(), x_pl.desc(blk.stride), self.B, blk.t_out, blk.cin, M=blk.cout, taps=taps,
                    out=out, out_ld=blk.cin, out_tap_stride=blk.cout * blk.cin, out_mode=mode, split_k=split)

@@ -53,7 +53,7 @@ K3 = ((-1, 0, 0), (0, 0, 1), (1, 0, 2))
 K3S2 = ((-1, 1, 0), (0, 0, 1), (0, 1, 2))  # input viewed [T/2][2]: row 2t+r-1
 
 
-@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("engine", [1, 3, 2])  # fp32 checker, one-tile-per-CTA tcgen05, persistent CTA-pair tcgen05
 @pytest.mark.parametrize("case", [
     dict(B=2, T=256, Cin=128, N=128, taps=((0, 0, 0),)),
     dict(B=2, T=256, Cin=256, N=256, taps=K3),
@@ -99,7 +99,7 @@ def run_wgrad(B, T, Co, Ci, taps, P=1, engine=0, split_k=1, seed=0, dbg=(0, 0, 0
     return err
 
 
-@pytest.mark.parametrize("engine", [1, 0])
+@pytest.mark.parametrize("engine", [1, 3, 2])  # fp32 checker, one-tile-per-CTA tcgen05, persistent CTA-pair tcgen05
 @pytest.mark.parametrize("case", [
     dict(B=2, T=256, Co=128, Ci=128, taps=((0, 0, 0),)),
     dict(B=2, T=128, Co=256, Ci=320, taps=K3),
@@ -113,12 +113,24 @@ def test_wgrad(case, engine):
     assert err < 2e-5, err
 
 
-def test_wgrad_split_k():
-    err = run_wgrad(8, 128, 256, 256, K3, split_k=4)
+@pytest.mark.parametrize("engine", [3, 2])
+def test_wgrad_split_k(engine):
+    err = run_wgrad(8, 128, 256, 256, K3, split_k=4, engine=engine)
     assert err < 2e-5, err
 
 
-def test_epilogue_options():
+@pytest.mark.parametrize("engine", [3, 2])
+def test_many_tiles_persistent(engine):
+    """More tiles than SM pairs: the persistent kernel walks several tiles per cluster (TMEM double buffering, pipeline
+    state carried across tiles)."""
+    err, _, _ = run_rows(16, 256, 128, 2048, K3, engine=engine)
+    assert err < 2e-5, err
+    err = run_wgrad(16, 256, 1024, 1536, K3, engine=engine)
+    assert err < 2e-5, err
+
+
+@pytest.mark.parametrize("engine", [3, 2])
+def test_epilogue_options(engine):
     B, T, Cin, N = 2, 128, 128, 256
     a = Planes.from_float(_rand(B, T, Cin, seed=3))
     w = Planes.from_float(_rand(1, N, Cin, seed=4, scale=Cin ** -0.5))
@@ -128,7 +140,7 @@ def test_epilogue_options():
     pre = torch.empty(B, T, N, device=DEV)
     pl = Planes.zeros(B, T, N + 64, DEV)
     ops.gemm(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, out=wide, out_ld=N + 64, out_col0=32, bias=bias, rowscale=q,
-             out2=pre, outp=pl, outp_col0=64)
+             out2=pre, outp=pl, outp_col0=64, engine=engine)
     ref_pre = ref_rows(a, w, ((0, 0, 0),), 1, B, T, N, Cin, 0) + bias.double()
     ref = ref_pre * q.double()[:, None, :]
     s = ref.abs().max().item()
@@ -138,11 +150,11 @@ def test_epilogue_options():
     assert (pl.to_float()[:, :, 64:].double() - ref).abs().max().item() / s < 3e-5
     # accumulate mode
     ops.gemm(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, out=wide, out_ld=N + 64, out_col0=32, bias=bias, rowscale=q,
-             out_mode=L.OUT_ADD)
+             out_mode=L.OUT_ADD, engine=engine)
     assert (wide[:, :, 32:32 + N].double() - 2 * ref).abs().max().item() / s < 4e-5
     # parity-strided output rows (stride-2 data gradient writes every other time step)
     out = torch.zeros(B, 2 * T, N, device=DEV)
-    ops.gemm(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, out=out, out_T=2 * T, out_t_mul=2, out_t_add=1)
+    ops.gemm(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, out=out, out_T=2 * T, out_t_mul=2, out_t_add=1, engine=engine)
     ref0 = ref_rows(a, w, ((0, 0, 0),), 1, B, T, N, Cin, 0)
     assert (out[:, 1::2].double() - ref0).abs().max().item() / s < 2e-5
     assert out[:, 0::2].abs().max().item() == 0
