@@ -14,8 +14,8 @@ tail -c 1000 gpurun_out/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches rc=$?"
-# full capture of the dominant kernel: 4th gemm_tc launch of a step = prop_fc forward
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 3 -c 1 -o gpurun_out/prof_propfc \
+# full capture of the dominant kernel: gemm_pair launch #5 = prop_fc forward of the 2nd warm-up step
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_pair_kernel -s 4 -c 1 -o gpurun_out/prof_propfc \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 echo "ncu full rc=$?"
 ls -la gpurun_out
