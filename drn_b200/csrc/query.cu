@@ -1,0 +1,674 @@
+// Query encoder of the DRN path (reference model/language_module.py:27-62, model/ops.py:16-25,74-85), forward and
+// hand-derived backward, plus the small fp32 CUDA-core contraction (drn_sgemm) it and the query gates are built from.
+//
+// The encoder is 0.6 % of the path's FLOPs but, as ~300 library launches (cuDNN RNN + cuBLAS + ATen), it was 27 % of the
+// step.  Here it is ~20 launches forward and ~45 backward, all graph-capturable, all exact fp32 FMA arithmetic:
+//   embedding gather -> input projection (one contraction for all time steps) -> L recurrent steps of a masked
+//   ("packed") BiLSTM, one launch per step for both directions -> q_vector gather -> qInput / qInput0..2 -> attention
+//   over the words (mask -1e30, softmax) -> the three command vectors; backward = the same chain reversed (BPTT).
+// Layouts: R = B*L rows (b-major); xg / G / dG [R][2 dirs][4 gates i,f,g,o][H]; Hout [R][2H]; Cst [R][2][H].
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace drn {
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Small fp32 contraction: C[m][n] (=|+=) sum_k A(m,k) * B(k,n) (+ bias[n] + bias2[n]) with arbitrary element strides, so the
+// same kernel serves x W^T (Linear forward), dy W (data gradient) and dy^T x (weight gradient).  64(32) x 64 x 16 tiles,
+// 256 threads, 4(2) x 4 outputs per thread; split-K over blockIdx.z with atomic accumulation.
+// ------------------------------------------------------------------------------------------------------------------------
+struct SgemmP {
+  const float* A;
+  long long sam, sak;
+  const float* B;
+  long long sbk, sbn;
+  float* C;
+  long long ldc;
+  int M, N, K;
+  const float* bias;
+  const float* bias2;
+  int relu, atomic, kchunk;
+};
+
+template <int BM>
+__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
+  constexpr int BN = 64, BK = 16, TM = BM / 16;
+  __shared__ float As[BK][BM + 1];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int kbeg = blockIdx.z * p.kchunk;
+  const int kend = min(p.K, kbeg + p.kchunk);
+  float acc[TM][4];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_kfast = (p.sak == 1);
+  const bool b_nfast = (p.sbn == 1);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+    for (int e = 0; e < (BM * BK) / 256; ++e) {
+      const int idx = tid + e * 256;
+      int m, k;
+      if (a_kfast) { k = idx % BK; m = idx / BK; }
+      else { m = idx % BM; k = idx / BM; }
+      const int gm = m0 + m, gk = k0 + k;
+      As[k][m] = (gm < p.M && gk < kend) ? __ldg(p.A + gm * p.sam + gk * p.sak) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < (BN * BK) / 256; ++e) {
+      const int idx = tid + e * 256;
+      int n, k;
+      if (b_nfast) { n = idx % BN; k = idx / BN; }
+      else { k = idx % BK; n = idx / BK; }
+      const int gn = n0 + n, gk = k0 + k;
+      Bs[k][n] = (gn < p.N && gk < kend) ? __ldg(p.B + gk * p.sbk + gn * p.sbn) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float a[TM];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        acc[i][0] = fmaf(a[i], b4.x, acc[i][0]);
+        acc[i][1] = fmaf(a[i], b4.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], b4.z, acc[i][2]);
+        acc[i][3] = fmaf(a[i], b4.w, acc[i][3]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gm = m0 + ty * TM + i;
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= p.N) continue;
+      float v = acc[i][j];
+      if (blockIdx.z == 0) {
+        if (p.bias) v += __ldg(p.bias + gn);
+        if (p.bias2) v += __ldg(p.bias2 + gn);
+      }
+      float* o = p.C + gm * p.ldc + gn;
+      if (p.atomic) atomicAdd(o, v);
+      else *o = p.relu ? fmaxf(v, 0.f) : v;
+    }
+  }
+}
+
+// accumulate = 0: C is overwritten; 1: C += (C must hold valid data, e.g. a zeroed gradient buffer)
+static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
+                 float* C, long long ldc, int M, int N, int K, const float* bias, const float* bias2, int relu, int accumulate,
+                 bool allow_split = true) {
+  if (M < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "drn_sgemm: empty problem (%d,%d,%d)", M, N, K);
+  if (relu && accumulate) return fail(DRN_EINVAL, "drn_sgemm: relu cannot be combined with accumulation");
+  const int bm = (M <= 32) ? 32 : 64;
+  const int tiles = ceil_div(M, bm) * ceil_div(N, 64);
+  int splits = 1;
+  if (!relu && allow_split && tiles < 148) {  // fill the 148 SMs by splitting the contraction
+    splits = min(ceil_div(296, tiles), ceil_div(K, 64));
+    if (splits < 1) splits = 1;
+  }
+  int kchunk = ceil_div(ceil_div(K, splits), 16) * 16;
+  splits = ceil_div(K, kchunk);
+  SgemmP p{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, bias2, relu, (splits > 1 || accumulate) ? 1 : 0, kchunk};
+  if (splits > 1 && !accumulate) {
+    cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, st);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_sgemm memset: %s", cudaGetErrorString(e));
+  }
+  dim3 grid(ceil_div(M, bm), ceil_div(N, 64), splits);
+  if (bm == 32) sgemm_kernel<32><<<grid, 256, 0, st>>>(p);
+  else sgemm_kernel<64><<<grid, 256, 0, st>>>(p);
+  return check_launch("sgemm");
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Deterministic small-batch nn.Linear forward: out[b][n] = act(bias[n] + sum_k x[b][k] W[n][k]).  The forward of the path must
+// be run-to-run reproducible (train-mode BatchNorm amplifies 1e-7 input noise ~100x into the early-layer gradients), so the
+// contraction is split over the 8 warps of a CTA and reduced in a fixed order -- no atomics.  CTA = 32 samples x 8 outputs;
+// lane = sample, W row segments live in registers and are broadcast with shuffles.
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr int LIN_NT = 8;
+__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W,
+                                                           long long ldw, const float* __restrict__ bias, float* __restrict__ out,
+                                                           long long ldo, int Bn, int N, int K, int relu) {
+  __shared__ float xs[8][32][33];
+  __shared__ float red[8][LIN_NT][32];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n0 = blockIdx.x * LIN_NT, b0 = blockIdx.y * 32;
+  const int kper = ((K + 7) / 8 + 31) / 32 * 32;  // K slice per warp, multiple of 32
+  const int kbeg = w * kper, kend = min(K, kbeg + kper);
+  float acc[LIN_NT];
+#pragma unroll
+  for (int j = 0; j < LIN_NT; ++j) acc[j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
+    const int k = k0 + lane;
+    float wr[LIN_NT];
+#pragma unroll
+    for (int j = 0; j < LIN_NT; ++j) wr[j] = (n0 + j < N && k < kend) ? __ldg(W + (n0 + j) * ldw + k) : 0.f;
+    for (int b = 0; b < 32; ++b) xs[w][lane][b] = (b0 + b < Bn && k < kend) ? __ldg(x + (b0 + b) * ldx + k) : 0.f;
+    __syncwarp();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const float xv = xs[w][kk][lane];
+#pragma unroll
+      for (int j = 0; j < LIN_NT; ++j) acc[j] = fmaf(xv, __shfl_sync(0xffffffffu, wr[j], kk), acc[j]);
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < LIN_NT; ++j) red[w][j][lane] = acc[j];
+  __syncthreads();
+  const int j = tid >> 5, b = tid & 31;  // 256 threads = 8 outputs x 32 samples
+  if (n0 + j < N && b0 + b < Bn) {
+    float v = bias ? __ldg(bias + n0 + j) : 0.f;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += red[ww][j][b];
+    out[(b0 + b) * ldo + n0 + j] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+static int linear_small(cudaStream_t st, const float* x, long long ldx, const float* W, long long ldw, const float* bias,
+                        float* out, long long ldo, int Bn, int N, int K, int relu) {
+  if (Bn < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "drn_linear_fwd: empty problem (%d,%d,%d)", Bn, N, K);
+  linear_small_kernel<<<dim3(ceil_div(N, LIN_NT), ceil_div(Bn, 32)), 256, 0, st>>>(x, ldx, W, ldw, bias, out, ldo, Bn, N, K, relu);
+  return check_launch("linear_small");
+}
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Query encoder device view
+// ------------------------------------------------------------------------------------------------------------------------
+struct QeDev {
+  int B, L, H, E, tok_ld, BC;  // BC = ceil(B / 32) sample chunks
+  const long long* tokens;
+  const long long* lengths;
+  const float* w_hh[2];
+  float *Ebuf, *xg, *G, *Cst, *Hout, *Hprev, *v, *hid, *c3, *alpha;
+  float *dH, *dc3, *dhid, *dhid_pre, *dv, *dG, *dcarry, *part, *dE;
+  unsigned* cnt;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- embedding gather (language_module.py:41) / scatter-add of its gradient (row 0 = padding_idx gets none) ------------
+__global__ void __launch_bounds__(256) qe_embed_kernel(QeDev q, const float* __restrict__ emb) {
+  const int r = blockIdx.x;
+  const int b = r / q.L, t = r % q.L;
+  const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
+  for (int e = threadIdx.x; e < q.E; e += blockDim.x) q.Ebuf[static_cast<long long>(r) * q.E + e] = emb[tok * q.E + e];
+}
+__global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __restrict__ g_emb) {
+  const int r = blockIdx.x;
+  const int b = r / q.L, t = r % q.L;
+  const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
+  if (tok == 0 || t >= q.lengths[b]) return;
+  for (int e = threadIdx.x; e < q.E; e += blockDim.x) atomicAdd(g_emb + tok * q.E + e, q.dE[static_cast<long long>(r) * q.E + e]);
+}
+
+// ---- one recurrent step, both directions (language_module.py:42-46; torch.nn.LSTM gate order i,f,g,o) -----------------
+// grid (H/8, 2, BC); warp = one hidden unit (its 4 gate rows of W_hh), lane = sample.  Packed-sequence semantics: a sample
+// is live at time t iff t < length; the reverse direction starts at t = length-1 from the zero state, which falls out of
+// Hout/Cst being zero at every non-live position.
+__global__ void __launch_bounds__(256) lstm_fwd_step_kernel(QeDev q, int s) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = q.H, L = q.L;
+  float* ws = smem;                 // [32][H]   rows (unit w, gate g) -> w*4+g
+  float* hs = smem + 32 * H;        // [H][33]   previous hidden state, transposed
+  const int ug = blockIdx.x, dir = blockIdx.y, b0 = blockIdx.z * 32;
+  const int t = dir == 0 ? s : L - 1 - s;
+  const int tp = dir == 0 ? t - 1 : t + 1;
+  const bool tp_ok = (tp >= 0 && tp < L);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* W = q.w_hh[dir];
+  for (int idx = tid; idx < 32 * (H / 4); idx += 256) {
+    const int row = idx / (H / 4), k4 = idx % (H / 4);
+    const int unit = ug * 8 + (row >> 2), g = row & 3;
+    reinterpret_cast<float4*>(ws)[row * (H / 4) + k4] =
+        __ldg(reinterpret_cast<const float4*>(W + (static_cast<long long>(g) * H + unit) * H) + k4);
+  }
+  for (int idx = tid; idx < 32 * H; idx += 256) {
+    const int b = idx / H, k = idx % H;
+    float hv = 0.f;
+    if (tp_ok && b0 + b < q.B) hv = q.Hout[(static_cast<long long>(b0 + b) * L + tp) * 2 * H + dir * H + k];
+    hs[k * 33 + b] = hv;
+    if (ug == 0 && b0 + b < q.B) q.Hprev[(static_cast<long long>(dir) * q.B * L + static_cast<long long>(b0 + b) * L + t) * H + k] = hv;
+  }
+  __syncthreads();
+  const int b = b0 + lane;
+  const int unit = ug * 8 + w;
+  const bool inb = b < q.B;
+  const long long r = static_cast<long long>(inb ? b : 0) * L + t;
+  float acc[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) acc[g] = inb ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
+  const float* wr = ws + (w * 4) * H;
+#pragma unroll 2
+  for (int k = 0; k < H; k += 4) {
+    const float h0 = hs[(k + 0) * 33 + lane], h1 = hs[(k + 1) * 33 + lane], h2 = hs[(k + 2) * 33 + lane],
+                h3 = hs[(k + 3) * 33 + lane];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 wv = *reinterpret_cast<const float4*>(wr + g * H + k);
+      acc[g] = fmaf(h0, wv.x, acc[g]);
+      acc[g] = fmaf(h1, wv.y, acc[g]);
+      acc[g] = fmaf(h2, wv.z, acc[g]);
+      acc[g] = fmaf(h3, wv.w, acc[g]);
+    }
+  }
+  if (!inb) return;
+  const bool live = t < q.lengths[b];
+  float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
+  if (live) {
+    gi = sigmoidf_(acc[0]);
+    gf = sigmoidf_(acc[1]);
+    gg = tanhf(acc[2]);
+    go = sigmoidf_(acc[3]);
+    const float cp = tp_ok ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+    c = gf * cp + gi * gg;
+    h = go * tanhf(c);
+  }
+  float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+  G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
+  q.Cst[(r * 2 + dir) * H + unit] = c;
+  q.Hout[r * 2 * H + dir * H + unit] = h;
+}
+
+// ---- one BPTT step, both directions -------------------------------------------------------------------------------------
+// grid (H/32, nq, 2*BC).  Phase A: the CTA (unit group ug, quarter jq of the 4H gate rows) forms its part of
+//   dh_rec[b][u] = sum_j dG_next[b][j] * W_hh[j][u]   (lane = unit u, 32 accumulators = samples), writes it to `part`;
+// the LAST of the nq CTAs of a unit group (device counter, no spinning) sums the parts and does the cell backward
+// (Phase B), producing dG at this time step and the carried dc.  nq = 1 on the first step (no recurrent gradient yet).
+constexpr int BWD_JQ = 4;
+__global__ void __launch_bounds__(256) lstm_bwd_step_kernel(QeDev q, int s, int nq) {
+  extern __shared__ __align__(16) float smem[];
+  const int H = q.H, L = q.L;
+  const int ug = blockIdx.x, jq = blockIdx.y, dir = blockIdx.z / q.BC, bc = blockIdx.z % q.BC, b0 = bc * 32;
+  const int t = dir == 0 ? L - 1 - s : s;
+  const int tn = dir == 0 ? t + 1 : t - 1;  // time step processed by the previous launch of this pass
+  const int tp = dir == 0 ? t - 1 : t + 1;  // recurrence predecessor (source of c_prev)
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int UG = H / 32;
+  const long long slot = (static_cast<long long>(dir) * q.BC + bc) * UG + ug;
+  float* part = q.part + slot * BWD_JQ * 1024;
+  __shared__ bool is_last;
+  if (nq > 1) {
+    float* dgs = smem;               // [H][36]  dG_next of this quarter, transposed (j, b)
+    float* red = smem + H * 36;      // [8][32][33]
+    for (int idx = tid; idx < 32 * H; idx += 256) {
+      const int b = idx / H, j = idx % H;
+      float v = 0.f;
+      if (b0 + b < q.B) v = q.dG[((static_cast<long long>(b0 + b) * L + tn) * 2 + dir) * 4 * H + jq * H + j];
+      dgs[j * 36 + b] = v;
+    }
+    __syncthreads();
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    const int jw = H / 8;  // rows per warp
+    const float* W = q.w_hh[dir] + (static_cast<long long>(jq) * H + w * jw) * H + ug * 32 + lane;
+#pragma unroll 2
+    for (int j = 0; j < jw; ++j) {
+      const float wv = __ldg(W + static_cast<long long>(j) * H);
+      const float4* d4 = reinterpret_cast<const float4*>(dgs + (w * jw + j) * 36);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 d = d4[i];
+        acc[4 * i + 0] = fmaf(d.x, wv, acc[4 * i + 0]);
+        acc[4 * i + 1] = fmaf(d.y, wv, acc[4 * i + 1]);
+        acc[4 * i + 2] = fmaf(d.z, wv, acc[4 * i + 2]);
+        acc[4 * i + 3] = fmaf(d.w, wv, acc[4 * i + 3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) red[(w * 32 + i) * 33 + lane] = acc[i];
+    __syncthreads();
+    for (int idx = tid; idx < 1024; idx += 256) {
+      const int b = idx >> 5, u = idx & 31;
+      float sum = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) sum += red[(ww * 32 + b) * 33 + u];
+      part[jq * 1024 + idx] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(q.cnt + slot, 1u) == static_cast<unsigned>(nq - 1));
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+  }
+  for (int idx = tid; idx < 1024; idx += 256) {
+    const int bl = idx >> 5, u = idx & 31;
+    const int b = b0 + bl, unit = ug * 32 + u;
+    if (b >= q.B) continue;
+    float dhrec = 0.f;
+    if (nq > 1) {
+#pragma unroll
+      for (int qq = 0; qq < BWD_JQ; ++qq) dhrec += __ldcg(part + qq * 1024 + idx);
+    }
+    const long long r = static_cast<long long>(b) * L + t;
+    const bool live = t < q.lengths[b];
+    float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, carry = 0.f;
+    if (live) {
+      const float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+      const float gi = G[0], gf = G[H], gg = G[2 * H], go = G[3 * H];
+      const float c = q.Cst[(r * 2 + dir) * H + unit];
+      const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+      const float dh = q.dH[r * 2 * H + dir * H + unit] + dhrec;
+      const float tc = tanhf(c);
+      float dc = dh * go * (1.f - tc * tc);
+      if (s > 0) dc += q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit];
+      d_i = dc * gg * gi * (1.f - gi);
+      d_f = dc * cp * gf * (1.f - gf);
+      d_g = dc * gi * (1.f - gg * gg);
+      d_o = dh * tc * go * (1.f - go);
+      carry = dc * gf;
+    }
+    float* dG = q.dG + ((r * 2 + dir) * 4) * H + unit;
+    dG[0] = d_i; dG[H] = d_f; dG[2 * H] = d_g; dG[3 * H] = d_o;
+    q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit] = carry;
+  }
+  if (tid == 0 && nq > 1) q.cnt[slot] = 0u;
+}
+
+// ---- q_vector = [H[b,0] | H[b,len-1]] (language_module.py:50-55) and the scatter of its gradient ------------------------
+__global__ void __launch_bounds__(256) qe_vgather_kernel(QeDev q) {
+  const int b = blockIdx.x, D = 2 * q.H;
+  const long long last = q.lengths[b] - 1;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    q.v[static_cast<long long>(b) * 2 * D + d] = q.Hout[(static_cast<long long>(b) * q.L) * D + d];
+    q.v[static_cast<long long>(b) * 2 * D + D + d] = q.Hout[(static_cast<long long>(b) * q.L + last) * D + d];
+  }
+}
+__global__ void __launch_bounds__(256) qe_vscatter_kernel(QeDev q) {
+  const int b = blockIdx.x, D = 2 * q.H;
+  const long long last = q.lengths[b] - 1;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    q.dH[(static_cast<long long>(b) * q.L) * D + d] += q.dv[static_cast<long long>(b) * 2 * D + d];
+    q.dH[(static_cast<long long>(b) * q.L + last) * D + d] += q.dv[static_cast<long long>(b) * 2 * D + D + d];
+  }
+}
+// ReLU backward from the activation itself (relu(x) > 0 <=> x > 0)
+__global__ void relu_mask_kernel(const float* __restrict__ g, const float* __restrict__ act, float* __restrict__ y, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = act[i] > 0.f ? g[i] : 0.f;
+}
+
+// ---- attention over the words (language_module.py:27-36): grid (B, 3) --------------------------------------------------
+constexpr int QE_MAX_L = 64;
+__global__ void __launch_bounds__(256) qe_attn_fwd_kernel(QeDev q, const float* __restrict__ wa, const float* __restrict__ ba,
+                                                          float* cmd0, float* cmd1, float* cmd2) {
+  extern __shared__ __align__(16) float smem[];
+  const int D = 2 * q.H, L = q.L;
+  float* wc = smem;       // [D]
+  float* raw = smem + D;  // [L]
+  const int b = blockIdx.x, t = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* c = q.c3 + (static_cast<long long>(t) * q.B + b) * D;
+  const float* Hb = q.Hout + static_cast<long long>(b) * L * D;
+  const int len = static_cast<int>(q.lengths[b]);
+  for (int d = tid; d < D; d += 256) wc[d] = c[d] * wa[d];
+  __syncthreads();
+  for (int j = w; j < L; j += 8) {
+    float sdot = 0.f;
+    for (int d = lane; d < D; d += 32) sdot = fmaf(wc[d], Hb[static_cast<long long>(j) * D + d], sdot);
+    sdot = warp_sum(sdot);
+    if (lane == 0) raw[j] = (j < len) ? sdot + ba[0] : -1e30f;  // ops.py:74-85
+  }
+  __syncthreads();
+  if (w == 0) {
+    float m = -INFINITY;
+    for (int j = lane; j < L; j += 32) m = fmaxf(m, raw[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float e = expf(raw[j] - m);
+      raw[j] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int j = lane; j < L; j += 32) {
+      const float a = raw[j] / sum;
+      raw[j] = a;
+      q.alpha[(static_cast<long long>(t) * q.B + b) * L + j] = a;
+    }
+  }
+  __syncthreads();
+  float* cmd = (t == 0 ? cmd0 : (t == 1 ? cmd1 : cmd2)) + static_cast<long long>(b) * D;
+  for (int d = tid; d < D; d += 256) {
+    float acc = 0.f;
+    for (int j = 0; j < L; ++j) acc = fmaf(raw[j], Hb[static_cast<long long>(j) * D + d], acc);
+    cmd[d] = acc;
+  }
+}
+
+// grid (B): writes dH[b] (all L rows), dc3[t][b], accumulates d cmd_inter2logits
+__global__ void __launch_bounds__(256) qe_attn_bwd_kernel(QeDev q, const float* __restrict__ wa, const float* dcmd0,
+                                                          const float* dcmd1, const float* dcmd2, float* __restrict__ g_wa,
+                                                          float* __restrict__ g_ba) {
+  __shared__ float da[QE_MAX_L], dr[QE_MAX_L], al[QE_MAX_L];
+  __shared__ float sdot_s;
+  const int D = 2 * q.H, L = q.L;
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* Hb = q.Hout + static_cast<long long>(b) * L * D;
+  float* dHb = q.dH + static_cast<long long>(b) * L * D;
+  float dba = 0.f;
+  for (int t = 0; t < 3; ++t) {
+    const float* dcmd = (t == 0 ? dcmd0 : (t == 1 ? dcmd1 : dcmd2)) + static_cast<long long>(b) * D;
+    const float* c = q.c3 + (static_cast<long long>(t) * q.B + b) * D;
+    const float* alpha = q.alpha + (static_cast<long long>(t) * q.B + b) * L;
+    for (int j = w; j < L; j += 8) {
+      float sdot = 0.f;
+      for (int d = lane; d < D; d += 32) sdot = fmaf(dcmd[d], Hb[static_cast<long long>(j) * D + d], sdot);
+      sdot = warp_sum(sdot);
+      if (lane == 0) {
+        da[j] = sdot;
+        al[j] = alpha[j];
+      }
+    }
+    __syncthreads();
+    if (w == 0) {
+      float sdot = 0.f;
+      for (int j = lane; j < L; j += 32) sdot = fmaf(al[j], da[j], sdot);
+      sdot = warp_sum(sdot);
+      if (lane == 0) sdot_s = sdot;
+    }
+    __syncthreads();
+    if (tid < L) dr[tid] = al[tid] * (da[tid] - sdot_s);  // softmax backward; 0 at masked positions (alpha = 0)
+    __syncthreads();
+    if (tid == 0)
+      for (int j = 0; j < L; ++j) dba += dr[j];
+    for (int d = tid; d < D; d += 256) {
+      const float wad = wa[d], cd = c[d], dcd = dcmd[d];
+      float hsum = 0.f;
+      for (int j = 0; j < L; ++j) {
+        const float hv = Hb[static_cast<long long>(j) * D + d];
+        hsum = fmaf(dr[j], hv, hsum);
+        const float g = al[j] * dcd + dr[j] * wad * cd;
+        if (t == 0) dHb[static_cast<long long>(j) * D + d] = g;
+        else dHb[static_cast<long long>(j) * D + d] += g;
+      }
+      q.dc3[(static_cast<long long>(t) * q.B + b) * D + d] = wad * hsum;
+      if (g_wa) atomicAdd(g_wa + d, cd * hsum);
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && g_ba) atomicAdd(g_ba, dba);
+}
+
+__global__ void colsum_rows_kernel(const float* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (long long r = blockIdx.y; r < rows; r += gridDim.y) acc += x[r * ld + c];
+  atomicAdd(out + c, acc);
+}
+static int colsum(cudaStream_t st, const float* x, long long rows, int C, long long ld, float* out) {
+  dim3 grid(ceil_div(C, 256), static_cast<unsigned>(rows < 32 ? rows : 32));
+  colsum_rows_kernel<<<grid, 256, 0, st>>>(x, rows, C, ld, out);
+  return check_launch("qe colsum");
+}
+
+// ---- workspace carving ------------------------------------------------------------------------------------------------
+static size_t carve(const drn_qe_t* a, QeDev* q) {
+  const size_t B = a->B, L = a->L, H = a->H, E = a->E, R = B * L;
+  const size_t BC = (B + 31) / 32;
+  size_t off = 0;
+  char* base = static_cast<char*>(a->workspace);
+  auto take = [&](size_t nfloat) -> float* {
+    float* p = q ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += ((nfloat * sizeof(float) + 255) / 256) * 256;
+    return p;
+  };
+  float* Ebuf = take(R * E);
+  float* xg = take(R * 8 * H);
+  float* G = take(R * 8 * H);
+  float* Cst = take(R * 2 * H);
+  float* Hout = take(R * 2 * H);
+  float* Hprev = take(2 * R * H);
+  float* v = take(B * 4 * H);
+  float* hid = take(B * H);
+  float* c3 = take(3 * B * 2 * H);
+  float* alpha = take(3 * B * L);
+  float* dH = take(R * 2 * H);
+  float* dc3 = take(3 * B * 2 * H);
+  float* dhid = take(B * H);
+  float* dhid_pre = take(B * H);
+  float* dv = take(B * 4 * H);
+  float* dG = take(R * 8 * H);
+  float* dcarry = take(2 * B * H);
+  float* part = take(2 * BC * (H / 32) * BWD_JQ * 1024);
+  float* dE = take(R * E);
+  float* cnt = take(2 * BC * (H / 32));
+  if (q) {
+    q->Ebuf = Ebuf; q->xg = xg; q->G = G; q->Cst = Cst; q->Hout = Hout; q->Hprev = Hprev; q->v = v;
+    q->hid = hid; q->c3 = c3; q->alpha = alpha; q->dH = dH; q->dc3 = dc3; q->dhid = dhid; q->dhid_pre = dhid_pre; q->dv = dv;
+    q->dG = dG; q->dcarry = dcarry; q->part = part; q->dE = dE; q->cnt = reinterpret_cast<unsigned*>(cnt);
+  }
+  return off;
+}
+
+static int make_dev(const drn_qe_t* a, QeDev* q, const char* who) {
+  if (!a) return fail(DRN_EINVAL, "%s: null descriptor", who);
+  if (a->B < 1 || a->L < 1 || a->L > QE_MAX_L) return fail(DRN_EINVAL, "%s: need B >= 1 and 1 <= L <= %d (B=%d, L=%d)", who, QE_MAX_L, a->B, a->L);
+  if (a->H < 32 || a->H % 32 || a->H > 512) return fail(DRN_EINVAL, "%s: hidden size must be a multiple of 32, <= 512 (H=%d)", who, a->H);
+  if (a->E < 1 || a->tok_ld < a->L) return fail(DRN_EINVAL, "%s: bad embedding width / token stride", who);
+  const size_t need = carve(a, nullptr);
+  if (!a->workspace || a->workspace_bytes < need)
+    return fail(DRN_EINVAL, "%s: workspace too small (%zu < %zu bytes)", who, a->workspace_bytes, need);
+  q->B = a->B; q->L = a->L; q->H = a->H; q->E = a->E; q->tok_ld = a->tok_ld; q->BC = (a->B + 31) / 32;
+  q->tokens = reinterpret_cast<const long long*>(a->tokens);
+  q->lengths = reinterpret_cast<const long long*>(a->lengths);
+  q->w_hh[0] = a->w_hh[0];
+  q->w_hh[1] = a->w_hh[1];
+  carve(a, q);
+  return 0;
+}
+
+static int set_smem(const void* fn, size_t bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+}  // namespace drn
+
+using namespace drn;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+extern "C" int drn_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc,
+                         int M, int N, int K, const float* bias, int relu, int accumulate, void* stream) {
+  return sgemm(ST(stream), A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, nullptr, relu, accumulate);
+}
+
+extern "C" int drn_linear_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* out, int64_t ldo,
+                              int B, int N, int K, int relu, void* stream) {
+  return linear_small(ST(stream), x, ldx, W, ldw, bias, out, ldo, B, N, K, relu);
+}
+
+extern "C" size_t drn_qe_workspace_bytes(int B, int L, int H, int E) {
+  drn_qe_t a{};
+  a.B = B; a.L = L; a.H = H; a.E = E;
+  return carve(&a, nullptr);
+}
+
+extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
+  QeDev q;
+  TRY(make_dev(a, &q, "drn_qe_forward"));
+  cudaStream_t st = ST(stream);
+  const int B = q.B, L = q.L, H = q.H, E = q.E, R = B * L, D = 2 * H;
+  cudaError_t e = cudaMemsetAsync(q.cnt, 0, sizeof(unsigned) * 2 * q.BC * (H / 32), st);
+  if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_qe_forward memset: %s", cudaGetErrorString(e));
+  qe_embed_kernel<<<R, 256, 0, st>>>(q, a->emb);
+  TRY(check_launch("qe_embed"));
+  for (int dir = 0; dir < 2; ++dir)  // xg = E W_ih^T + b_ih + b_hh, all time steps at once
+    TRY(sgemm(st, q.Ebuf, E, 1, a->w_ih[dir], 1, E, q.xg + dir * 4 * H, 8 * H, R, 4 * H, E, a->b_ih[dir], a->b_hh[dir], 0, 0,
+              false));  // forward: no split-K atomics, run-to-run reproducible
+  const size_t smem_f = (32 * H + H * 33) * sizeof(float);
+  TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_step_kernel), smem_f, "lstm_fwd_step"));
+  for (int s = 0; s < L; ++s) {
+    lstm_fwd_step_kernel<<<dim3(H / 8, 2, q.BC), 256, smem_f, st>>>(q, s);
+    TRY(check_launch("lstm_fwd_step"));
+  }
+  qe_vgather_kernel<<<B, 256, 0, st>>>(q);
+  TRY(check_launch("qe_vgather"));
+  TRY(linear_small(st, q.v, 4 * H, a->w1, 4 * H, a->b1, q.hid, H, B, H, 4 * H, 1));
+  for (int t = 0; t < 3; ++t)
+    TRY(linear_small(st, q.hid, H, a->w2[t], H, a->b2[t], q.c3 + static_cast<long long>(t) * B * D, D, B, D, H, 0));
+  qe_attn_fwd_kernel<<<dim3(B, 3), 256, (D + L) * sizeof(float), st>>>(q, a->wa, a->ba, a->cmd[0], a->cmd[1], a->cmd[2]);
+  return check_launch("qe_attn_fwd");
+}
+
+extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
+  QeDev q;
+  TRY(make_dev(a, &q, "drn_qe_backward"));
+  cudaStream_t st = ST(stream);
+  const int B = q.B, L = q.L, H = q.H, E = q.E, R = B * L, D = 2 * H;
+  if (!a->dcmd[0] || !a->dcmd[1] || !a->dcmd[2]) return fail(DRN_EINVAL, "drn_qe_backward: dcmd missing");
+  qe_attn_bwd_kernel<<<B, 256, 0, st>>>(q, a->wa, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_wa, a->g_ba);
+  TRY(check_launch("qe_attn_bwd"));
+  for (int t = 0; t < 3; ++t) {
+    const float* dc = q.dc3 + static_cast<long long>(t) * B * D;
+    TRY(sgemm(st, dc, D, 1, a->w2[t], H, 1, q.dhid, H, B, H, D, nullptr, nullptr, 0, t > 0));
+    if (a->g_w2[t]) TRY(sgemm(st, dc, 1, D, q.hid, H, 1, a->g_w2[t], H, D, H, B, nullptr, nullptr, 0, 1));
+    if (a->g_b2[t]) TRY(colsum(st, dc, B, D, D, a->g_b2[t]));
+  }
+  relu_mask_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(q.dhid, q.hid, q.dhid_pre, B * H);
+  TRY(check_launch("qe relu_mask"));
+  TRY(sgemm(st, q.dhid_pre, H, 1, a->w1, 4 * H, 1, q.dv, 4 * H, B, 4 * H, H, nullptr, nullptr, 0, 0));
+  if (a->g_w1) TRY(sgemm(st, q.dhid_pre, 1, H, q.v, 4 * H, 1, a->g_w1, 4 * H, H, 4 * H, B, nullptr, nullptr, 0, 1));
+  if (a->g_b1) TRY(colsum(st, q.dhid_pre, B, H, H, a->g_b1));
+  qe_vscatter_kernel<<<B, 256, 0, st>>>(q);
+  TRY(check_launch("qe_vscatter"));
+  const size_t smem_b = (H * 36 + 8 * 32 * 33) * sizeof(float);
+  TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_step_kernel), smem_b, "lstm_bwd_step"));
+  for (int s = 0; s < L; ++s) {
+    const int nq = s == 0 ? 1 : BWD_JQ;
+    lstm_bwd_step_kernel<<<dim3(H / 32, nq, 2 * q.BC), 256, smem_b, st>>>(q, s, nq);
+    TRY(check_launch("lstm_bwd_step"));
+  }
+  for (int dir = 0; dir < 2; ++dir) {
+    const float* dG = q.dG + dir * 4 * H;  // [R] rows of stride 8H
+    if (a->g_w_ih[dir]) TRY(sgemm(st, dG, 1, 8 * H, q.Ebuf, E, 1, a->g_w_ih[dir], E, 4 * H, E, R, nullptr, nullptr, 0, 1));
+    if (a->g_w_hh[dir])
+      TRY(sgemm(st, dG, 1, 8 * H, q.Hprev + static_cast<long long>(dir) * R * H, H, 1, a->g_w_hh[dir], H, 4 * H, H, R, nullptr,
+                nullptr, 0, 1));
+    if (a->g_b_ih[dir]) TRY(colsum(st, dG, R, 4 * H, 8 * H, a->g_b_ih[dir]));
+    if (a->g_b_hh[dir]) TRY(colsum(st, dG, R, 4 * H, 8 * H, a->g_b_hh[dir]));
+  }
+  if (a->g_emb) {
+    for (int dir = 0; dir < 2; ++dir)
+      TRY(sgemm(st, q.dG + dir * 4 * H, 8 * H, 1, a->w_ih[dir], E, 1, q.dE, E, R, E, 4 * H, nullptr, nullptr, 0, dir > 0));
+    qe_embed_bwd_kernel<<<R, 256, 0, st>>>(q, a->g_emb);
+    TRY(check_launch("qe_embed_bwd"));
+  }
+  return 0;
+}

@@ -53,9 +53,10 @@ class ConvBN:
 
 
 class DensePath:
-    def __init__(self, cfg, B, T, device):
+    def __init__(self, cfg, B, T, device, L=10, qe_hidden=512, qe_embed=300):
         assert T % 4 == 0, "T must be a multiple of 4 (two stride-2 levels)"
         self.cfg, self.B, self.T, self.dev = cfg, B, T, device
+        self.L, self.qe_H, self.qe_E = L, qe_hidden, qe_embed
         D = cfg[cfg["feature_type"]]["feature_dim"]
         c1, F = cfg["first_output_dim"], cfg["fpn_feature_dim"]
         self.D, self.C0, self.c = D, D + 256, (c1, 2 * c1, 4 * c1)
@@ -68,12 +69,16 @@ class DensePath:
         z = lambda *s: torch.zeros(*s, device=dev)  # noqa: E731
         # inputs / gates
         self.f_pl = Planes.empty(B, T, D, dev)
-        self.cmd_pl = [Planes.empty(1, B, 1024, dev) for _ in range(3)]
+        # query encoder (drn_qe_forward / drn_qe_backward): static token / length buffers, commands, workspace
+        self.tokens = torch.zeros(B, L, dtype=torch.int64, device=dev)
+        self.lengths = torch.ones(B, dtype=torch.int64, device=dev)
+        self.cmd_dim = 2 * qe_hidden
+        self.cmd = [e(B, self.cmd_dim) for _ in range(3)]
+        self.dcmd = [e(B, self.cmd_dim) for _ in range(3)]
+        self.qe_ws = torch.zeros(int(_lib().drn_qe_workspace_bytes(B, L, qe_hidden, qe_embed)), dtype=torch.uint8, device=dev)
         self.qdim = (D, c1, 2 * c1)
         self.q = [e(B, n) for n in self.qdim]
         self.dq = [z(B, n) for n in self.qdim]
-        self.dq_pl = [Planes.empty(1, B, n, dev) for n in self.qdim]
-        self.dcmd = [e(B, 1024) for _ in range(3)]
         self.pos_in = e(B * T, 3)
         self.Pre = e(B, T, D)                       # prop_fc output before gating
         self.X0 = Planes.empty(B, T, self.C0, dev)  # [q0 * prop_fc(f) | position feature]
@@ -132,7 +137,6 @@ class DensePath:
         for i in range(3):
             self.wp["inner%d" % i] = Planes.empty(1, F, self.c[i], dev)
             self.wp["layer%d" % i] = Planes.empty(3, F, F, dev)
-            self.wp["q%d" % i] = Planes.empty(1, self.qdim[i], 1024, dev)
         self.tower_bias = e(2 * F)
         ws_shapes = {"conv0": (3, c1, self.C0), "conv1": (3, 2 * c1, c1), "conv2": (3, 4 * c1, 2 * c1),
                      "towers": (3, 2 * F, F), "iouc": (3, F // 2, F)}
@@ -161,6 +165,32 @@ class DensePath:
         self.launches += 1
         ops.gemm(*a, **k)
 
+    def _sgemm(self, A, sam, sak, Bm, sbk, sbn, Cm, ldc, M, N, K, bias=None, relu=0, accumulate=0):
+        self._chk(_lib().drn_sgemm(_vp(A), C.c_int64(sam), C.c_int64(sak), _vp(Bm), C.c_int64(sbk), C.c_int64(sbn), _vp(Cm),
+                                   C.c_int64(ldc), M, N, K, _vp(bias), relu, accumulate, _st()), "sgemm")
+
+    def _qe_desc(self, p, grads=None):
+        """drn_qe_t for this path (reference model/language_module.py:9-62 parameter names)."""
+        q = L.Qe()
+        q.B, q.L, q.H, q.E, q.tok_ld = self.B, self.L, self.qe_H, self.qe_E, self.L
+        q.tokens, q.lengths = self.tokens.data_ptr(), self.lengths.data_ptr()
+        pre = "query_encoder."
+        g = (lambda n: grads[pre + n].data_ptr() if (pre + n) in grads else None) if grads is not None else (lambda n: None)
+        q.emb, q.g_emb = p[pre + "embedding.weight"].data_ptr(), g("embedding.weight")
+        for d, suf in enumerate(("", "_reverse")):
+            for f, n in (("w_ih", "weight_ih_l0"), ("w_hh", "weight_hh_l0"), ("b_ih", "bias_ih_l0"), ("b_hh", "bias_hh_l0")):
+                getattr(q, f)[d] = p[pre + "biLSTM." + n + suf].data_ptr()
+                getattr(q, "g_" + f)[d] = g("biLSTM." + n + suf)
+        q.w1, q.b1, q.g_w1, q.g_b1 = p[pre + "qInput.weight"].data_ptr(), p[pre + "qInput.bias"].data_ptr(), g("qInput.weight"), g("qInput.bias")
+        for t in range(3):
+            q.w2[t], q.b2[t] = p[pre + "qInput%d.weight" % t].data_ptr(), p[pre + "qInput%d.bias" % t].data_ptr()
+            q.g_w2[t], q.g_b2[t] = g("qInput%d.weight" % t), g("qInput%d.bias" % t)
+            q.cmd[t], q.dcmd[t] = self.cmd[t].data_ptr(), self.dcmd[t].data_ptr()
+        q.wa, q.ba = p[pre + "cmd_inter2logits.weight"].data_ptr(), p[pre + "cmd_inter2logits.bias"].data_ptr()
+        q.g_wa, q.g_ba = g("cmd_inter2logits.weight"), g("cmd_inter2logits.bias")
+        q.workspace, q.workspace_bytes = self.qe_ws.data_ptr(), self.qe_ws.numel()
+        return q
+
     def _split(self, src2d, dst, dst_col0=0):
         rows, Cn = src2d.shape
         self._chk(_lib().drn_split_planes(_vp(src2d), C.c_int64(rows), Cn, C.c_int64(src2d.stride(0)), _vp(dst.data),
@@ -188,7 +218,6 @@ class DensePath:
             items.append(self._pack_item(p["backbone_net.forward_conv%d.0.weight" % i], self.wp["conv%d" % i]))
             items.append(self._pack_item(p["fpn.fpn_inner%d.0.weight" % (i + 1)], self.wp["inner%d" % i]))
             items.append(self._pack_item(p["fpn.fpn_layer%d.0.weight" % (i + 1)], self.wp["layer%d" % i]))
-            items.append(self._pack_item(p["qInput%d.weight" % i], self.wp["q%d" % i]))
         items.append(self._pack_item(p[h + "cls_tower.0.weight"], self.wp["towers"], 0))
         items.append(self._pack_item(p[h + "bbox_tower.0.weight"], self.wp["towers"], self.F))
         items.append(self._pack_item(p[h + "mix_fc.0.weight"], self.wp["mix"]))
@@ -234,15 +263,15 @@ class DensePath:
     # ---------------------------------------------------------------------------------------------------------------
     # forward
     # ---------------------------------------------------------------------------------------------------------------
-    def stage_inputs(self, p, cmds, feats, pse, gt):
-        """Eager part of the forward: reads the caller's tensors and fills the static operand buffers (split planes of the
-        clip features and query commands, position feature, GT).  Everything after this runs on library-owned buffers only,
-        so it can be replayed from a CUDA graph."""
+    def stage_inputs(self, p, tokens, lengths, feats, pse, gt):
+        """Eager part of the forward: reads the caller's tensors and fills the static operand buffers (query tokens and
+        lengths, split planes of the clip features, position feature, GT).  Everything after this runs on library-owned
+        buffers only, so it can be replayed from a CUDA graph."""
         lib, B, T = _lib(), self.B, self.T
         self.launches = 0
         self.gt.copy_(gt)
-        for i in range(3):
-            self._split(cmds[i], self.cmd_pl[i])
+        self.tokens.copy_(tokens)
+        self.lengths.copy_(lengths)
         # position feature -> X0[:, :, D:] (main_model.py:53-55, backbone.py:31-32)
         self._chk(lib.drn_pos_feature(_vp(pse), _vp(p["position_transform.weight"]), _vp(p["position_transform.bias"]),
                                       C.c_int64(B * T), 256, _vp(self.X0.data), C.c_int64(self.C0), self.D,
@@ -250,10 +279,10 @@ class DensePath:
         self._split(feats.view(B * T, self.D), self.f_pl)
         self.launches_stage = self.launches
 
-    def forward(self, p, cmds, feats, pse, gt, training):
-        """p: name -> parameter/buffer tensor (fp32 on device); cmds: 3 x [B,1024] fp32 query commands;
+    def forward(self, p, tokens, lengths, feats, pse, gt, training):
+        """p: name -> parameter/buffer tensor (fp32 on device); tokens [B,L] i64, lengths [B] i64 (device);
         feats [B,T,D] fp32, pse [B,T,2] f64, gt [B,2] f32.  Fills self.losses / raw head outputs."""
-        self.stage_inputs(p, cmds, feats, pse, gt)
+        self.stage_inputs(p, tokens, lengths, feats, pse, gt)
         self.forward_core(p, training)
 
     def forward_core(self, p, training):
@@ -261,10 +290,15 @@ class DensePath:
         h = "fcos.head."
         self.launches = self.launches_stage
         self.pack_weights(p)
-        # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50)
+        # query encoder -> three command vectors (model/main_model.py:47, language_module.py:38-62)
+        self._chk(lib.drn_qe_forward(C.byref(self._qe_desc(p)), _st()), "qe_forward")
+        self.launches += 9 + self.L  # launches enqueued inside drn_qe_forward
+        # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50): exact fp32 on CUDA cores (M = B rows only)
+        K = self.cmd_dim
         for i in range(3):
-            self._gemm(L.GEMM_ROWS, self.cmd_pl[i].desc(), self.wp["q%d" % i].desc(), 1, B, self.qdim[i], K=1024,
-                       out=self.q[i], bias=p["qInput%d.bias" % i])
+            n = self.qdim[i]
+            self._chk(lib.drn_linear_fwd(_vp(self.cmd[i]), C.c_int64(K), _vp(p["qInput%d.weight" % i]), C.c_int64(K),
+                                         _vp(p["qInput%d.bias" % i]), _vp(self.q[i]), C.c_int64(n), B, n, K, 0, _st()), "gate")
         # prop_fc with the level-0 gate fused in the epilogue -> X0[:, :, :D] (main_model.py:59, backbone.py:28-30)
         self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
                    out2=self.Pre, rowscale=self.q[0], outp=self.X0)
@@ -352,9 +386,9 @@ class DensePath:
                            b_mn=1, out=out, out_mode=mode, rowscale=rowscale, out2=out2, out_T=blk.t_in, out_t_mul=2,
                            out_t_add=par)
 
-    def backward(self, p, grads, upstream, need_cmd_grad=True):
+    def backward(self, p, grads, upstream):
         """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
-        upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou).  Returns d cmds (3 x [B,1024])."""
+        upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou)."""
         lib, B = _lib(), self.B
         h = "fcos.head."
         F = self.F
@@ -426,16 +460,17 @@ class DensePath:
         # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D] (the largest contraction of the backward pass)
         self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
                    out_ld=self.D, out_tap_stride=0)
-        # gates
+        # gates: dW = dq^T cmd, db = colsum(dq), dcmd = dq W
+        K = self.cmd_dim
         for i in range(3):
             n = self.qdim[i]
-            self._split(self.dq[i], self.dq_pl[i])
-            self._gemm(L.GEMM_WGRAD, self.dq_pl[i].desc(), self.cmd_pl[i].desc(), 1, B, 1024, M=n,
-                       out=grads["qInput%d.weight" % i], out_ld=1024, out_tap_stride=0)
+            self._sgemm(self.dq[i], 1, n, self.cmd[i], K, 1, grads["qInput%d.weight" % i], K, n, K, B, accumulate=1)
             self._chk(lib.drn_colsum(_vp(self.dq[i]), C.c_int64(B), n, C.c_int64(n), _vp(grads["qInput%d.bias" % i]), _st()),
                       "colsum")
-            if need_cmd_grad:
-                self._gemm(L.GEMM_ROWS, self.dq_pl[i].desc(), self.wp["q%d" % i].desc(), 1, B, 1024, K=n, b_mn=1, out=self.dcmd[i])
+            self._sgemm(self.dq[i], n, 1, p["qInput%d.weight" % i], K, 1, self.dcmd[i], K, B, K, n)
+        # query encoder backward (BPTT), gradients accumulated into the zeroed buffers
+        self._chk(lib.drn_qe_backward(C.byref(self._qe_desc(p, grads)), _st()), "qe_backward")
+        self.launches += 30 + self.L
         # tap-major workspaces -> parameter layout [O][C][k], one launch
         items = []
         for i in range(3):
@@ -455,4 +490,3 @@ class DensePath:
         for l in range(3):
             grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
         self.launches_bwd = self.launches
-        return self.dcmd

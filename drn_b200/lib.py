@@ -52,6 +52,27 @@ class PackItem(C.Structure):
                 ("plane_stride", C.c_int64)]
 
 
+class Qe(C.Structure):
+    """drn_qe_t (include/drn_b200.h): query encoder parameters, gradients, outputs and workspace."""
+    _fields_ = [
+        ("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("E", C.c_int32), ("tok_ld", C.c_int32),
+        ("tokens", C.c_void_p), ("lengths", C.c_void_p),
+        ("emb", C.c_void_p),
+        ("w_ih", C.c_void_p * 2), ("w_hh", C.c_void_p * 2), ("b_ih", C.c_void_p * 2), ("b_hh", C.c_void_p * 2),
+        ("w1", C.c_void_p), ("b1", C.c_void_p),
+        ("w2", C.c_void_p * 3), ("b2", C.c_void_p * 3),
+        ("wa", C.c_void_p), ("ba", C.c_void_p),
+        ("cmd", C.c_void_p * 3),
+        ("dcmd", C.c_void_p * 3),
+        ("g_emb", C.c_void_p),
+        ("g_w_ih", C.c_void_p * 2), ("g_w_hh", C.c_void_p * 2), ("g_b_ih", C.c_void_p * 2), ("g_b_hh", C.c_void_p * 2),
+        ("g_w1", C.c_void_p), ("g_b1", C.c_void_p),
+        ("g_w2", C.c_void_p * 3), ("g_b2", C.c_void_p * 3),
+        ("g_wa", C.c_void_p), ("g_ba", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lib = None
 
 
@@ -65,6 +86,7 @@ def load():
         lib = C.CDLL(LIB_PATH)
         lib.drn_last_error.restype = C.c_char_p
         lib.drn_version.restype = C.c_int
+        lib.drn_qe_workspace_bytes.restype = C.c_size_t
         _lib = lib
     return _lib
 

@@ -3,9 +3,10 @@ across ranks, ONE exchange step per iteration -- an NCCL all-reduce (sum, then 1
 NVLink/NVSwitch.  BatchNorm statistics and the loss normalisers stay per replica, which is what the
 reference's own (nominal) multi-GPU mode, nn.DataParallel at main.py:99, computes.
 
-The dense path produces all of its gradients in one flat buffer (model/main_model.py:_DenseFn.backward); that buffer is
-all-reduced in place as soon as the hand-written backward has filled it, i.e. before autograd continues into the query
-encoder, whose (small) gradients are all-reduced in `finish_gradient_sync()` after `loss.backward()`.
+The path (query encoder included) produces all of its gradients in one flat buffer (model/main_model.py:
+_DenseFn.backward); that buffer is all-reduced in place as soon as the hand-written backward has filled it.  Gradients
+that autograd produced outside that buffer (none for the reference model; kept for wrapped modules that add their own
+parameters) are all-reduced in `finish_gradient_sync()` after `loss.backward()`.
 """
 import torch
 import torch.distributed as dist
@@ -33,10 +34,11 @@ class DataParallelDRN(nn.Module):
         return self.module(*a, **k)
 
     def finish_gradient_sync(self):
-        """All-reduce the gradients autograd produced outside the dense path (query encoder)."""
+        """All-reduce the gradients autograd produced outside the flat buffer of the path."""
         if self.world == 1:
             return
-        grads = [p.grad for n, p in self.module.named_parameters() if n.startswith("query_encoder.") and p.grad is not None]
+        inside = set(getattr(self.module, "_trainable_names", ()))
+        grads = [p.grad for n, p in self.module.named_parameters() if n not in inside and p.grad is not None]
         if not grads:
             return
         flat = torch.cat([g.reshape(-1) for g in grads])

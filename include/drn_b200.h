@@ -180,6 +180,48 @@ int drn_fcos_loss_bwd(int nlevels, int B, const int* T, const float* strides, co
                       const float* iou_raw, const float* scales, const float* gt, float gamma, float alpha, int iou_branch_on,
                       const double* acc, const float* upstream, float* dcls, float* dbox, float* diou, float* pgrad, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Query encoder (drn_b200/csrc/query.cu): model/language_module.py:27-62 (QueryEncoder.forward +
+ * extract_textual_command) with model/ops.py:16-25,74-85, forward and backward, exact fp32 FMA arithmetic.
+ * ---------------------------------------------------------------------------------------------- */
+/* Small fp32 contraction on CUDA cores: C[m][n] (= | +=) sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]), optional ReLU.
+ * accumulate = 1 adds into C.  Serves nn.Linear forward (x W^T), data gradient (dy W) and weight gradient (dy^T x) of the
+ * query encoder's projections and of the gates qInput0-2 (model/main_model.py:36-40,49-50) -- M is the batch (<= a few hundred). */
+int drn_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc, int M,
+              int N, int K, const float* bias, int relu, int accumulate, void* stream);
+
+/* Deterministic (fixed reduction order, no atomics) small-batch nn.Linear forward out[b][n] = act(bias[n] + sum_k x[b][k] W[n][k]):
+ * query_encoder.qInput / qInput0-2 (model/language_module.py:57-58,30-31) and the gates qInput0-2 (model/main_model.py:49-50). */
+int drn_linear_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* out, int64_t ldo, int B,
+                   int N, int K, int relu, void* stream);
+
+typedef struct {
+  int32_t B, L;            /* batch, padded query length = number of token columns processed (<= 64) */
+  int32_t H, E;            /* LSTM hidden size per direction (512), embedding width (300) */
+  int32_t tok_ld;          /* row stride of `tokens` (>= L) */
+  const int64_t* tokens;   /* [B][tok_ld] device; 0 = padding */
+  const int64_t* lengths;  /* [B] device; 1 <= length <= L (any order: no sorting requirement) */
+  /* parameters, torch layouts (state_dict names under query_encoder.) */
+  const float* emb;                          /* embedding.weight [V][E] */
+  const float* w_ih[2]; const float* w_hh[2]; /* biLSTM.weight_{ih,hh}_l0{,_reverse} [4H][E], [4H][H] */
+  const float* b_ih[2]; const float* b_hh[2]; /* biLSTM.bias_* [4H] */
+  const float* w1; const float* b1;           /* qInput [H][4H], [H] */
+  const float* w2[3]; const float* b2[3];     /* qInput0..2 [2H][H], [2H] */
+  const float* wa; const float* ba;           /* cmd_inter2logits [1][2H], [1] */
+  /* forward output: the three command vectors [B][2H] */
+  float* cmd[3];
+  /* backward input d cmd [B][2H] and gradient destinations (ACCUMULATED into; null = parameter frozen) */
+  const float* dcmd[3];
+  float* g_emb; float* g_w_ih[2]; float* g_w_hh[2]; float* g_b_ih[2]; float* g_b_hh[2];
+  float* g_w1; float* g_b1; float* g_w2[3]; float* g_b2[3]; float* g_wa; float* g_ba;
+  /* scratch that carries the forward state to the backward call: drn_qe_workspace_bytes(B, L, H, E) bytes */
+  void* workspace; size_t workspace_bytes;
+} drn_qe_t;
+
+size_t drn_qe_workspace_bytes(int B, int L, int H, int E);
+int drn_qe_forward(const drn_qe_t* q, void* stream);
+int drn_qe_backward(const drn_qe_t* q, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

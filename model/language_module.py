@@ -1,17 +1,17 @@
-"""Query encoder (reference model/language_module.py:9-62, model/ops.py:16-25,74-85).
+"""Query encoder parameter container (reference model/language_module.py:9-62, model/ops.py:16-25).
 
-0.6 % of the path's FLOPs, latency-bound.  The module keeps the reference's parameter
-names (including the never-called `textualAttention`, 6.3 M parameters that live in every checkpoint).
+Holds the parameters under the reference's names (including the never-called `textualAttention`, 6.3 M parameters
+that live in every checkpoint) with the reference's initialisers.  The math -- embedding, packed BiLSTM, the three
+attention "commands" (language_module.py:27-62), forward and backward -- runs in drn_qe_forward / drn_qe_backward
+(drn_b200/csrc/query.cu) as part of the path's CUDA-graph; there is no torch forward.
 """
 import numpy as np
-import torch
 import torch.nn as nn
-import torch.nn.functional as F
-from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
 
-# The parity contract of the path is fp32 (1e-3 on outputs AND gradients).  cuDNN's RNN otherwise runs in TF32, whose
-# 1e-4 error in the three query commands is amplified ~100x by the train-mode BatchNorm backward of the dense path.
-torch.backends.cudnn.allow_tf32 = False
+
+def _no_forward(self, *a, **k):
+    raise RuntimeError("parameter container: the query encoder runs in libdrn_sm100 (drn_qe_forward), "
+                       "there is no torch forward / CPU fallback")
 
 
 class XavierLinear(nn.Linear):
@@ -23,6 +23,7 @@ class XavierLinear(nn.Linear):
         nn.init.uniform_(self.weight, -bound, bound)
         if self.bias is not None:
             nn.init.constant_(self.bias, 0.0)
+    forward = _no_forward
 
 
 class TextualAttention(nn.Module):
@@ -33,11 +34,15 @@ class TextualAttention(nn.Module):
         self.W1 = nn.Linear(hidden_dim, 1)
         self.W2 = nn.Linear(hidden_dim * 2, hidden_dim)
         self.W3 = nn.Linear(hidden_dim * 2, hidden_dim * 2)
+    forward = _no_forward
 
 
 class QueryEncoder(nn.Module):
     def __init__(self, vocab_size, hidden_dim=512, embed_dim=300, num_layers=1, bidirection=True):
         super().__init__()
+        if num_layers != 1 or not bidirection:
+            raise NotImplementedError("the B200 query-encoder kernels implement the reference configuration: one "
+                                      "bidirectional LSTM layer (default_config.yaml lstm_layers: 1, main.py:89-90)")
         self.hidden_dim, self.embed_dim = hidden_dim, embed_dim
         self.embedding = nn.Embedding(vocab_size + 1, embed_dim, padding_idx=0)
         self.biLSTM = nn.LSTM(embed_dim, hidden_dim, num_layers, dropout=0.0, batch_first=True, bidirectional=bidirection)
@@ -46,25 +51,4 @@ class QueryEncoder(nn.Module):
         for t in range(3):
             setattr(self, "qInput%d" % t, XavierLinear(hidden_dim, hidden_dim * 2))
         self.cmd_inter2logits = XavierLinear(hidden_dim * 2, 1)
-
-    def forward(self, query_tokens, query_length):
-        """tokens [B,L] int64 (device), lengths [B] int64 sorted descending -> 3 x [B, 2*hidden]."""
-        lengths_cpu = query_length.detach().to("cpu")
-        emb = self.embedding(query_tokens)
-        packed = pack_padded_sequence(emb, lengths_cpu, batch_first=True)
-        self.biLSTM.flatten_parameters()
-        out, _ = self.biLSTM(packed)
-        out, _ = pad_packed_sequence(out, batch_first=True)  # [B, Lmax, 2H], zero after each length
-        B, Lm = out.shape[0], out.shape[1]
-        lengths = query_length.to(out.device)
-        last = out[torch.arange(B, device=out.device), lengths - 1]
-        q_vector = torch.cat((out[:, 0], last), dim=-1)
-        hid = F.relu(self.qInput(q_vector))
-        mask = torch.arange(Lm, device=out.device)[None, :] >= lengths[:, None]
-        cmds = []
-        for t in range(3):
-            q_cmd = getattr(self, "qInput%d" % t)(hid)
-            raw = self.cmd_inter2logits(q_cmd[:, None, :] * out).squeeze(-1)
-            att = F.softmax(raw.masked_fill(mask, -1e30), dim=-1)
-            cmds.append(torch.bmm(att[:, None, :], out).squeeze(1))
-        return cmds
+    forward = _no_forward

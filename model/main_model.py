@@ -2,7 +2,7 @@
 
 Same constructor signature, attribute tree, state_dict keys/shapes and `forward(query_tokens, query_length,
 props_features, props_start_end, gt_start_end, props_num, num_frames) -> (box_lists | None, loss_dict)` as the reference,
-so the reference's main.py (19, 89-99, 124-140, 218-243) runs against it unchanged.  Everything after the query encoder
+so the reference's main.py (19, 89-99, 124-140, 218-243) runs against it unchanged.  Everything, query encoder included,
 is executed by hand-written sm_100a kernels (drn_b200.dense.DensePath -> libdrn_sm100.so); gradients arrive in
 `param.grad` through one autograd.Function whose backward is the hand-derived backward schedule.  There is no CPU or
 torch-op fallback: calling forward without a B200 raises.
@@ -40,8 +40,8 @@ def _run_forward_core(path, p, training, use_graphs):
         g.replay()
 
 
-def _run_backward(path, p, names, upstream, need_cmd, use_graphs):
-    key = ("bwd", _sig(p), tuple(names), need_cmd)
+def _run_backward(path, p, names, upstream, use_graphs):
+    key = ("bwd", _sig(p), tuple(names))
     ent = path.graphs.get(key)
     if ent is None:
         sizes = [p[n].numel() for n in names]
@@ -51,13 +51,13 @@ def _run_backward(path, p, names, upstream, need_cmd, use_graphs):
             grads[n] = flat[o:o + sz].view_as(p[n])
             o += sz
         path.upstream.copy_(upstream)
-        path.backward(p, grads, path.upstream, need_cmd_grad=need_cmd)
+        path.backward(p, grads, path.upstream)
         g = None
         if use_graphs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 flat.zero_()
-                path.backward(p, grads, path.upstream, need_cmd_grad=need_cmd)
+                path.backward(p, grads, path.upstream)
         path.graphs[key] = (g, flat, grads)
     else:
         g, flat, grads = ent
@@ -66,18 +66,17 @@ def _run_backward(path, p, names, upstream, need_cmd, use_graphs):
             g.replay()
         else:
             flat.zero_()
-            path.backward(p, grads, path.upstream, need_cmd_grad=need_cmd)
+            path.backward(p, grads, path.upstream)
     return flat, grads
 
 
 class _DenseFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, path, training, feats, pse, gt, c0, c1, c2, *params):
+    def forward(ctx, model, path, training, tokens, lengths, feats, pse, gt, *params):
         p = model._tensor_dict()
-        path.stage_inputs(p, (c0.contiguous(), c1.contiguous(), c2.contiguous()), feats, pse, gt)
+        path.stage_inputs(p, tokens, lengths, feats, pse, gt)
         _run_forward_core(path, p, training, model.use_graphs)
         ctx.model, ctx.path = model, path
-        ctx.need_cmd = c0.requires_grad or c1.requires_grad or c2.requires_grad
         ctx.nparams = len(params)
         return path.losses[:3].clone()
 
@@ -89,11 +88,10 @@ class _DenseFn(torch.autograd.Function):
         p = model._tensor_dict()
         # gradients are produced in ONE flat static buffer (graph-replayable, and the unit of the data-parallel all-reduce);
         # autograd copies the returned views into param.grad, so the buffer can be reused by the next step.
-        flat, grads = _run_backward(path, p, names, g.contiguous().float(), ctx.need_cmd, model.use_graphs)
+        flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs)
         if model._dp_hook is not None:  # data parallel: all-reduce the flat gradient buffer (drn_b200/parallel.py)
             model._dp_hook(flat)
-        dc = tuple(d.clone() for d in path.dcmd) if ctx.need_cmd else (None, None, None)
-        return (None, None, None, None, None, None) + dc + tuple(grads[n] for n in names)
+        return (None,) * 8 + tuple(grads[n] for n in names)
 
 
 class mainModel(nn.Module):
@@ -133,17 +131,18 @@ class mainModel(nn.Module):
     def _dense_trainable(self):
         names, tensors = [], []
         for k, v in self.named_parameters():
-            if k.startswith("query_encoder.") or k.startswith("fcos.head.centerness"):
-                continue
+            if k.startswith("query_encoder.textualAttention") or k.startswith("fcos.head.centerness"):
+                continue  # built by the reference, never called: no gradient (language_module.py:17, fcos.py:53-56,97)
             if v.requires_grad:
                 names.append(k)
                 tensors.append(v)
         return names, tensors
 
-    def _path(self, B, T, device):
-        key = (B, T, device.index, bool(self.cfg["is_first_stage"]))
+    def _path(self, B, T, L, device):
+        key = (B, T, L, device.index, bool(self.cfg["is_first_stage"]))
         if key not in self._paths:
-            self._paths[key] = DensePath(self.cfg, B, T, device)
+            qe = self.query_encoder
+            self._paths[key] = DensePath(self.cfg, B, T, device, L=L, qe_hidden=qe.hidden_dim, qe_embed=qe.embed_dim)
         return self._paths[key]
 
     # ---- forward -------------------------------------------------------------------------------------------------
@@ -151,22 +150,22 @@ class mainModel(nn.Module):
         dev = self.prop_fc.weight.device
         if dev.type != "cuda":
             raise RuntimeError("mainModel runs on a B200 through libdrn_sm100.so only (no CPU / torch fallback): call .cuda()")
-        tokens = query_tokens.to(dev)
+        tokens = torch.as_tensor(query_tokens).to(dev, dtype=torch.int64).contiguous()
+        lengths = torch.as_tensor(query_length).to(dev, dtype=torch.int64).contiguous()
         feats = props_features.to(dev, dtype=torch.float32).contiguous()
         pse = props_start_end.to(dev, dtype=torch.float64).contiguous()
         gt = gt_start_end.to(dev).float().contiguous()  # `.float()` as at main_model.py:74
         B, T = feats.shape[0], feats.shape[1]
-        cmds = self.query_encoder(tokens, query_length)
-        path = self._path(B, T, dev)
+        path = self._path(B, T, tokens.shape[1], dev)
         names, tensors = self._dense_trainable()
         self._trainable_names = names
         training = self.training
-        if torch.is_grad_enabled() and (tensors or any(c.requires_grad for c in cmds)):
-            losses = _DenseFn.apply(self, path, training, feats, pse, gt, cmds[0], cmds[1], cmds[2], *tensors)
+        if torch.is_grad_enabled() and tensors:
+            losses = _DenseFn.apply(self, path, training, tokens, lengths, feats, pse, gt, *tensors)
         else:
             with torch.no_grad():
                 p = self._tensor_dict()
-                path.stage_inputs(p, tuple(c.contiguous() for c in cmds), feats, pse, gt)
+                path.stage_inputs(p, tokens, lengths, feats, pse, gt)
                 _run_forward_core(path, p, training, self.use_graphs)
                 losses = path.losses[:3].clone()
         loss_dict = {"loss_cls": losses[0], "loss_reg": losses[1]}

@@ -1,5 +1,5 @@
 """Host-side logic of the data-parallel wrapper on CPU: 2 ranks, gloo, 127.0.0.1.  Checks the rank-0 broadcast of
-parameters/buffers, the averaged all-reduce of the dense path's flat gradient buffer and of the query-encoder gradients."""
+parameters/buffers, the averaged all-reduce of the dense path's flat gradient buffer and of gradients produced outside that buffer."""
 import os
 import socket
 
@@ -27,6 +27,7 @@ class _Toy(nn.Module):
             for p in self.parameters():
                 p.fill_(float(rank) + 1.0)
         self._dp_hook = None
+        self._trainable_names = ["prop_fc.weight", "prop_fc.bias"]  # produced in the flat buffer of the path
 
 
 def _worker(rank, world, port, q):
