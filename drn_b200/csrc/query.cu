@@ -47,26 +47,52 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (p.sak == 1);
   const bool b_nfast = (p.sbn == 1);
-  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+  constexpr int AE = (BM * BK) / 256, BE = (BN * BK) / 256;
+  float areg[AE], breg[BE];
+  // global -> registers for the tile starting at k0 (issued one tile ahead of the math: software pipelining)
+  auto fetch = [&](int k0) {
 #pragma unroll
-    for (int e = 0; e < (BM * BK) / 256; ++e) {
+    for (int e = 0; e < AE; ++e) {
       const int idx = tid + e * 256;
       int m, k;
       if (a_kfast) { k = idx % BK; m = idx / BK; }
       else { m = idx % BM; k = idx / BM; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < p.M && gk < kend) ? __ldg(p.A + gm * p.sam + gk * p.sak) : 0.f;
+      areg[e] = (gm < p.M && gk < kend) ? __ldg(p.A + gm * p.sam + gk * p.sak) : 0.f;
     }
 #pragma unroll
-    for (int e = 0; e < (BN * BK) / 256; ++e) {
+    for (int e = 0; e < BE; ++e) {
       const int idx = tid + e * 256;
       int n, k;
       if (b_nfast) { n = idx % BN; k = idx / BN; }
       else { k = idx % BK; n = idx / BK; }
       const int gn = n0 + n, gk = k0 + k;
-      Bs[k][n] = (gn < p.N && gk < kend) ? __ldg(p.B + gk * p.sbk + gn * p.sbn) : 0.f;
+      breg[e] = (gn < p.N && gk < kend) ? __ldg(p.B + gk * p.sbk + gn * p.sbn) : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int e = 0; e < AE; ++e) {
+      const int idx = tid + e * 256;
+      int m, k;
+      if (a_kfast) { k = idx % BK; m = idx / BK; }
+      else { m = idx % BM; k = idx / BM; }
+      As[k][m] = areg[e];
+    }
+#pragma unroll
+    for (int e = 0; e < BE; ++e) {
+      const int idx = tid + e * 256;
+      int n, k;
+      if (b_nfast) { n = idx % BN; k = idx / BN; }
+      else { k = idx % BK; n = idx / BK; }
+      Bs[k][n] = breg[e];
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    stash();
     __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
@@ -135,49 +161,72 @@ static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, 
 // contraction is split over the 8 warps of a CTA and reduced in a fixed order -- no atomics.  CTA = 32 samples x 8 outputs;
 // lane = sample, W row segments live in registers and are broadcast with shuffles.
 // ------------------------------------------------------------------------------------------------------------------------
-constexpr int LIN_NT = 8;
-__global__ void __launch_bounds__(256) linear_small_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ W,
-                                                           long long ldw, const float* __restrict__ bias, float* __restrict__ out,
-                                                           long long ldo, int Bn, int N, int K, int relu) {
-  __shared__ float xs[8][32][33];
-  __shared__ float red[8][LIN_NT][32];
+constexpr int LIN_NT = 8, LIN_WARPS = 16;
+__global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const float* __restrict__ x, long long ldx,
+                                                                      const float* __restrict__ W, long long ldw,
+                                                                      const float* __restrict__ bias, float* __restrict__ out,
+                                                                      long long ldo, int Bn, int N, int K, int relu) {
+  extern __shared__ __align__(16) float lin_smem[];
+  float (*xs)[32][33] = reinterpret_cast<float (*)[32][33]>(lin_smem);              // [LIN_WARPS][32][33]
+  float (*red)[LIN_NT][32] = reinterpret_cast<float (*)[LIN_NT][32]>(lin_smem);     // reused after the main loop
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int n0 = blockIdx.x * LIN_NT, b0 = blockIdx.y * 32;
-  const int kper = ((K + 7) / 8 + 31) / 32 * 32;  // K slice per warp, multiple of 32
+  const int kper = ((K + LIN_WARPS - 1) / LIN_WARPS + 31) / 32 * 32;  // K slice per warp, multiple of 32
   const int kbeg = w * kper, kend = min(K, kbeg + kper);
   float acc[LIN_NT];
 #pragma unroll
   for (int j = 0; j < LIN_NT; ++j) acc[j] = 0.f;
-  for (int k0 = kbeg; k0 < kend; k0 += 32) {
+  float wr[LIN_NT], xr[32];
+  auto fetch = [&](int k0) {
     const int k = k0 + lane;
-    float wr[LIN_NT];
 #pragma unroll
     for (int j = 0; j < LIN_NT; ++j) wr[j] = (n0 + j < N && k < kend) ? __ldg(W + (n0 + j) * ldw + k) : 0.f;
-    for (int b = 0; b < 32; ++b) xs[w][lane][b] = (b0 + b < Bn && k < kend) ? __ldg(x + (b0 + b) * ldx + k) : 0.f;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) xr[b] = (b0 + b < Bn && k < kend) ? __ldg(x + (b0 + b) * ldx + k) : 0.f;
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += 32) {
+    float wc[LIN_NT];
+#pragma unroll
+    for (int j = 0; j < LIN_NT; ++j) wc[j] = wr[j];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) xs[w][lane][b] = xr[b];
     __syncwarp();
+    if (k0 + 32 < kend) fetch(k0 + 32);
 #pragma unroll 8
     for (int kk = 0; kk < 32; ++kk) {
       const float xv = xs[w][kk][lane];
 #pragma unroll
-      for (int j = 0; j < LIN_NT; ++j) acc[j] = fmaf(xv, __shfl_sync(0xffffffffu, wr[j], kk), acc[j]);
+      for (int j = 0; j < LIN_NT; ++j) acc[j] = fmaf(xv, __shfl_sync(0xffffffffu, wc[j], kk), acc[j]);
     }
     __syncwarp();
   }
+  __syncthreads();
 #pragma unroll
   for (int j = 0; j < LIN_NT; ++j) red[w][j][lane] = acc[j];
   __syncthreads();
-  const int j = tid >> 5, b = tid & 31;  // 256 threads = 8 outputs x 32 samples
-  if (n0 + j < N && b0 + b < Bn) {
-    float v = bias ? __ldg(bias + n0 + j) : 0.f;
+  if (tid < LIN_NT * 32) {
+    const int j = tid >> 5, b = tid & 31;
+    if (n0 + j < N && b0 + b < Bn) {
+      float v = bias ? __ldg(bias + n0 + j) : 0.f;
 #pragma unroll
-    for (int ww = 0; ww < 8; ++ww) v += red[ww][j][b];
-    out[(b0 + b) * ldo + n0 + j] = relu ? fmaxf(v, 0.f) : v;
+      for (int ww = 0; ww < LIN_WARPS; ++ww) v += red[ww][j][b];
+      out[(b0 + b) * ldo + n0 + j] = relu ? fmaxf(v, 0.f) : v;
+    }
   }
 }
 static int linear_small(cudaStream_t st, const float* x, long long ldx, const float* W, long long ldw, const float* bias,
                         float* out, long long ldo, int Bn, int N, int K, int relu) {
   if (Bn < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "drn_linear_fwd: empty problem (%d,%d,%d)", Bn, N, K);
-  linear_small_kernel<<<dim3(ceil_div(N, LIN_NT), ceil_div(Bn, 32)), 256, 0, st>>>(x, ldx, W, ldw, bias, out, ldo, Bn, N, K, relu);
+  constexpr size_t smem = LIN_WARPS * 32 * 33 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(linear_small): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  linear_small_kernel<<<dim3(ceil_div(N, LIN_NT), ceil_div(Bn, 32)), LIN_WARPS * 32, smem, st>>>(x, ldx, W, ldw, bias, out, ldo, Bn, N,
+                                                                                               K, relu);
   return check_launch("linear_small");
 }
 
@@ -190,7 +239,7 @@ struct QeDev {
   const long long* lengths;
   const float* w_hh[2];
   float *Ebuf, *xg, *G, *Cst, *Hout, *Hprev, *v, *hid, *c3, *alpha;
-  float *dH, *dc3, *dhid, *dhid_pre, *dv, *dG, *dcarry, *part, *dE;
+  float *dH, *dc3, *dhid, *dhid_pre, *dv, *dG, *dcarry, *part, *dE, *HT, *dGT, *dr;
   unsigned* cnt;
 };
 
@@ -211,35 +260,42 @@ __global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __res
   for (int e = threadIdx.x; e < q.E; e += blockDim.x) atomicAdd(g_emb + tok * q.E + e, q.dE[static_cast<long long>(r) * q.E + e]);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ---- one recurrent step, both directions (language_module.py:42-46; torch.nn.LSTM gate order i,f,g,o) -----------------
 // grid (H/8, 2, BC); warp = one hidden unit (its 4 gate rows of W_hh), lane = sample.  Packed-sequence semantics: a sample
 // is live at time t iff t < length; the reverse direction starts at t = length-1 from the zero state, which falls out of
-// Hout/Cst being zero at every non-live position.
+// the state being zero at every non-live position.  The hidden state is also kept TRANSPOSED ([unit][32 samples],
+// double-buffered over steps) so that the next step stages it, like its 64 KB slice of W_hh, with straight 16-byte
+// cp.async copies -- no per-element transposition, all loads in flight at once.
 __global__ void __launch_bounds__(256) lstm_fwd_step_kernel(QeDev q, int s) {
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
   float* ws = smem;                 // [32][H]   rows (unit w, gate g) -> w*4+g
-  float* hs = smem + 32 * H;        // [H][33]   previous hidden state, transposed
-  const int ug = blockIdx.x, dir = blockIdx.y, b0 = blockIdx.z * 32;
+  float* hs = smem + 32 * H;        // [H][32]   previous hidden state of this sample chunk, unit-major
+  const int ug = blockIdx.x, dir = blockIdx.y, bc = blockIdx.z, b0 = bc * 32;
   const int t = dir == 0 ? s : L - 1 - s;
   const int tp = dir == 0 ? t - 1 : t + 1;
-  const bool tp_ok = (tp >= 0 && tp < L);
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const float* W = q.w_hh[dir];
-  for (int idx = tid; idx < 32 * (H / 4); idx += 256) {
-    const int row = idx / (H / 4), k4 = idx % (H / 4);
-    const int unit = ug * 8 + (row >> 2), g = row & 3;
-    reinterpret_cast<float4*>(ws)[row * (H / 4) + k4] =
-        __ldg(reinterpret_cast<const float4*>(W + (static_cast<long long>(g) * H + unit) * H) + k4);
+  const long long ht_sz = 2LL * q.BC * H * 32;
+  if (s > 0) {
+    const float* W = q.w_hh[dir];
+    const float* hprev = q.HT + ((s - 1) & 1) * ht_sz + (static_cast<long long>(dir) * q.BC + bc) * H * 32;
+    const int c4 = H / 4;  // 16-byte chunks per W row
+    for (int idx = tid; idx < 32 * c4; idx += 256) {
+      const int row = idx / c4, k4 = idx % c4;
+      const int unit = ug * 8 + (row >> 2), g = row & 3;
+      cp_async16(ws + row * H + k4 * 4, W + (static_cast<long long>(g) * H + unit) * H + k4 * 4);
+    }
+    for (int idx = tid; idx < H * 8; idx += 256) cp_async16(hs + idx * 4, hprev + idx * 4);
+    cp_async_wait_all();
+    __syncthreads();
   }
-  for (int idx = tid; idx < 32 * H; idx += 256) {
-    const int b = idx / H, k = idx % H;
-    float hv = 0.f;
-    if (tp_ok && b0 + b < q.B) hv = q.Hout[(static_cast<long long>(b0 + b) * L + tp) * 2 * H + dir * H + k];
-    hs[k * 33 + b] = hv;
-    if (ug == 0 && b0 + b < q.B) q.Hprev[(static_cast<long long>(dir) * q.B * L + static_cast<long long>(b0 + b) * L + t) * H + k] = hv;
-  }
-  __syncthreads();
   const int b = b0 + lane;
   const int unit = ug * 8 + w;
   const bool inb = b < q.B;
@@ -247,36 +303,56 @@ __global__ void __launch_bounds__(256) lstm_fwd_step_kernel(QeDev q, int s) {
   float acc[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) acc[g] = inb ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
-  const float* wr = ws + (w * 4) * H;
+  if (s > 0) {
+    const float* wr = ws + (w * 4) * H;
 #pragma unroll 2
-  for (int k = 0; k < H; k += 4) {
-    const float h0 = hs[(k + 0) * 33 + lane], h1 = hs[(k + 1) * 33 + lane], h2 = hs[(k + 2) * 33 + lane],
-                h3 = hs[(k + 3) * 33 + lane];
+    for (int k = 0; k < H; k += 4) {
+      const float h0 = hs[(k + 0) * 32 + lane], h1 = hs[(k + 1) * 32 + lane], h2 = hs[(k + 2) * 32 + lane],
+                  h3 = hs[(k + 3) * 32 + lane];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const float4 wv = *reinterpret_cast<const float4*>(wr + g * H + k);
-      acc[g] = fmaf(h0, wv.x, acc[g]);
-      acc[g] = fmaf(h1, wv.y, acc[g]);
-      acc[g] = fmaf(h2, wv.z, acc[g]);
-      acc[g] = fmaf(h3, wv.w, acc[g]);
+      for (int g = 0; g < 4; ++g) {
+        const float4 wv = *reinterpret_cast<const float4*>(wr + g * H + k);
+        acc[g] = fmaf(h0, wv.x, acc[g]);
+        acc[g] = fmaf(h1, wv.y, acc[g]);
+        acc[g] = fmaf(h2, wv.z, acc[g]);
+        acc[g] = fmaf(h3, wv.w, acc[g]);
+      }
     }
   }
-  if (!inb) return;
-  const bool live = t < q.lengths[b];
+  const bool live = inb && t < q.lengths[b];
   float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
   if (live) {
     gi = sigmoidf_(acc[0]);
     gf = sigmoidf_(acc[1]);
     gg = tanhf(acc[2]);
     go = sigmoidf_(acc[3]);
-    const float cp = tp_ok ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+    const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
     c = gf * cp + gi * gg;
     h = go * tanhf(c);
   }
+  q.HT[(s & 1) * ht_sz + ((static_cast<long long>(dir) * q.BC + bc) * H + unit) * 32 + lane] = h;
+  if (!inb) return;
   float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
   G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
   q.Cst[(r * 2 + dir) * H + unit] = c;
   q.Hout[r * 2 * H + dir * H + unit] = h;
+}
+
+// Hprev[dir][b][t] = hidden state the recurrence consumed at step t (operand of the W_hh weight gradient)
+__global__ void __launch_bounds__(256) qe_hprev_kernel(QeDev q) {
+  const int H = q.H, L = q.L;
+  const long long total = 2LL * q.B * L * (H / 4);
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+    const int k4 = static_cast<int>(i % (H / 4));
+    const long long rr = i / (H / 4);
+    const int t = static_cast<int>(rr % L);
+    const long long db = rr / L;
+    const int b = static_cast<int>(db % q.B), dir = static_cast<int>(db / q.B);
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tp >= 0 && tp < L) v = *reinterpret_cast<const float4*>(q.Hout + (static_cast<long long>(b) * L + tp) * 2 * H + dir * H + k4 * 4);
+    *reinterpret_cast<float4*>(q.Hprev + ((static_cast<long long>(dir) * q.B + b) * L + t) * H + k4 * 4) = v;
+  }
 }
 
 // ---- one BPTT step, both directions -------------------------------------------------------------------------------------
@@ -284,38 +360,41 @@ __global__ void __launch_bounds__(256) lstm_fwd_step_kernel(QeDev q, int s) {
 //   dh_rec[b][u] = sum_j dG_next[b][j] * W_hh[j][u]   (lane = unit u, 32 accumulators = samples), writes it to `part`;
 // the LAST of the nq CTAs of a unit group (device counter, no spinning) sums the parts and does the cell backward
 // (Phase B), producing dG at this time step and the carried dc.  nq = 1 on the first step (no recurrent gradient yet).
+// dG is also kept transposed ([gate row][32 samples], double-buffered) so Phase A stages both operands with cp.async.
 constexpr int BWD_JQ = 4;
 __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(QeDev q, int s, int nq) {
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
   const int ug = blockIdx.x, jq = blockIdx.y, dir = blockIdx.z / q.BC, bc = blockIdx.z % q.BC, b0 = bc * 32;
   const int t = dir == 0 ? L - 1 - s : s;
-  const int tn = dir == 0 ? t + 1 : t - 1;  // time step processed by the previous launch of this pass
   const int tp = dir == 0 ? t - 1 : t + 1;  // recurrence predecessor (source of c_prev)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int UG = H / 32;
   const long long slot = (static_cast<long long>(dir) * q.BC + bc) * UG + ug;
+  const long long gt_sz = 2LL * q.BC * 4 * H * 32;
   float* part = q.part + slot * BWD_JQ * 1024;
+  float* dgs = smem;               // [H][32]  dG_next rows of this quarter, (gate row j, sample b)
+  float* wsm = smem + H * 32;      // [H][32]  W_hh[jq*H + j][ug*32 + u]
+  float* red = smem + 2 * H * 32;  // [8][32][33]; reused as the [4][32][33] transposition tile of Phase B
   __shared__ bool is_last;
   if (nq > 1) {
-    float* dgs = smem;               // [H][36]  dG_next of this quarter, transposed (j, b)
-    float* red = smem + H * 36;      // [8][32][33]
-    for (int idx = tid; idx < 32 * H; idx += 256) {
-      const int b = idx / H, j = idx % H;
-      float v = 0.f;
-      if (b0 + b < q.B) v = q.dG[((static_cast<long long>(b0 + b) * L + tn) * 2 + dir) * 4 * H + jq * H + j];
-      dgs[j * 36 + b] = v;
+    const float* src = q.dGT + ((s - 1) & 1) * gt_sz + ((static_cast<long long>(dir) * q.BC + bc) * 4 * H + jq * H) * 32;
+    for (int idx = tid; idx < H * 8; idx += 256) cp_async16(dgs + idx * 4, src + idx * 4);
+    const float* W = q.w_hh[dir] + static_cast<long long>(jq) * H * H + ug * 32;
+    for (int idx = tid; idx < H * 8; idx += 256) {
+      const int j = idx >> 3, c = idx & 7;
+      cp_async16(wsm + j * 32 + c * 4, W + static_cast<long long>(j) * H + c * 4);
     }
+    cp_async_wait_all();
     __syncthreads();
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     const int jw = H / 8;  // rows per warp
-    const float* W = q.w_hh[dir] + (static_cast<long long>(jq) * H + w * jw) * H + ug * 32 + lane;
 #pragma unroll 2
-    for (int j = 0; j < jw; ++j) {
-      const float wv = __ldg(W + static_cast<long long>(j) * H);
-      const float4* d4 = reinterpret_cast<const float4*>(dgs + (w * jw + j) * 36);
+    for (int j = w * jw; j < (w + 1) * jw; ++j) {
+      const float wv = wsm[j * 32 + lane];
+      const float4* d4 = reinterpret_cast<const float4*>(dgs + j * 32);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 d = d4[i];
@@ -345,33 +424,44 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(QeDev q, int s, int 
   for (int idx = tid; idx < 1024; idx += 256) {
     const int bl = idx >> 5, u = idx & 31;
     const int b = b0 + bl, unit = ug * 32 + u;
-    if (b >= q.B) continue;
-    float dhrec = 0.f;
-    if (nq > 1) {
-#pragma unroll
-      for (int qq = 0; qq < BWD_JQ; ++qq) dhrec += __ldcg(part + qq * 1024 + idx);
-    }
-    const long long r = static_cast<long long>(b) * L + t;
-    const bool live = t < q.lengths[b];
     float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, carry = 0.f;
-    if (live) {
-      const float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
-      const float gi = G[0], gf = G[H], gg = G[2 * H], go = G[3 * H];
-      const float c = q.Cst[(r * 2 + dir) * H + unit];
-      const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
-      const float dh = q.dH[r * 2 * H + dir * H + unit] + dhrec;
-      const float tc = tanhf(c);
-      float dc = dh * go * (1.f - tc * tc);
-      if (s > 0) dc += q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit];
-      d_i = dc * gg * gi * (1.f - gi);
-      d_f = dc * cp * gf * (1.f - gf);
-      d_g = dc * gi * (1.f - gg * gg);
-      d_o = dh * tc * go * (1.f - go);
-      carry = dc * gf;
+    if (b < q.B) {
+      float dhrec = 0.f;
+      if (nq > 1) {
+#pragma unroll
+        for (int qq = 0; qq < BWD_JQ; ++qq) dhrec += __ldcg(part + qq * 1024 + idx);
+      }
+      const long long r = static_cast<long long>(b) * L + t;
+      if (t < q.lengths[b]) {
+        const float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+        const float gi = G[0], gf = G[H], gg = G[2 * H], go = G[3 * H];
+        const float c = q.Cst[(r * 2 + dir) * H + unit];
+        const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+        const float dh = q.dH[r * 2 * H + dir * H + unit] + dhrec;
+        const float tc = tanhf(c);
+        float dc = dh * go * (1.f - tc * tc);
+        if (s > 0) dc += q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit];
+        d_i = dc * gg * gi * (1.f - gi);
+        d_f = dc * cp * gf * (1.f - gf);
+        d_g = dc * gi * (1.f - gg * gg);
+        d_o = dh * tc * go * (1.f - go);
+        carry = dc * gf;
+      }
+      float* dG = q.dG + ((r * 2 + dir) * 4) * H + unit;
+      dG[0] = d_i; dG[H] = d_f; dG[2 * H] = d_g; dG[3 * H] = d_o;
+      q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit] = carry;
     }
-    float* dG = q.dG + ((r * 2 + dir) * 4) * H + unit;
-    dG[0] = d_i; dG[H] = d_f; dG[2 * H] = d_g; dG[3 * H] = d_o;
-    q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit] = carry;
+    red[(0 * 32 + u) * 33 + bl] = d_i;
+    red[(1 * 32 + u) * 33 + bl] = d_f;
+    red[(2 * 32 + u) * 33 + bl] = d_g;
+    red[(3 * 32 + u) * 33 + bl] = d_o;
+  }
+  __syncthreads();
+  float* dgt = q.dGT + (s & 1) * gt_sz + (static_cast<long long>(dir) * q.BC + bc) * 4 * H * 32;
+  for (int idx = tid; idx < 4096; idx += 256) {  // (gate, unit) rows x 32 samples, coalesced over samples
+    const int row = idx >> 5, bl = idx & 31;
+    const int g = row >> 5, u = row & 31;
+    dgt[(static_cast<long long>(g) * H + ug * 32 + u) * 32 + bl] = red[row * 33 + bl];
   }
   if (tid == 0 && nq > 1) q.cnt[slot] = 0u;
 }
@@ -448,59 +538,79 @@ __global__ void __launch_bounds__(256) qe_attn_fwd_kernel(QeDev q, const float* 
   }
 }
 
-// grid (B): writes dH[b] (all L rows), dc3[t][b], accumulates d cmd_inter2logits
-__global__ void __launch_bounds__(256) qe_attn_bwd_kernel(QeDev q, const float* __restrict__ wa, const float* dcmd0,
-                                                          const float* dcmd1, const float* dcmd2, float* __restrict__ g_wa,
-                                                          float* __restrict__ g_ba) {
-  __shared__ float da[QE_MAX_L], dr[QE_MAX_L], al[QE_MAX_L];
-  __shared__ float sdot_s;
+// Backward of the attention, two launches.  (1) grid (B, 3): softmax backward scalars dr[t][b][j] = alpha_j (dalpha_j - sum_i
+// alpha_i dalpha_i), dalpha_j = dcmd . H[b,j]; zero at masked positions (alpha = 0).
+__global__ void __launch_bounds__(256) qe_attn_bwd_scalars_kernel(QeDev q, const float* dcmd0, const float* dcmd1,
+                                                                  const float* dcmd2, float* __restrict__ g_ba) {
+  __shared__ float da[QE_MAX_L];
   const int D = 2 * q.H, L = q.L;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x, t = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const float* Hb = q.Hout + static_cast<long long>(b) * L * D;
-  float* dHb = q.dH + static_cast<long long>(b) * L * D;
-  float dba = 0.f;
-  for (int t = 0; t < 3; ++t) {
-    const float* dcmd = (t == 0 ? dcmd0 : (t == 1 ? dcmd1 : dcmd2)) + static_cast<long long>(b) * D;
-    const float* c = q.c3 + (static_cast<long long>(t) * q.B + b) * D;
-    const float* alpha = q.alpha + (static_cast<long long>(t) * q.B + b) * L;
-    for (int j = w; j < L; j += 8) {
-      float sdot = 0.f;
-      for (int d = lane; d < D; d += 32) sdot = fmaf(dcmd[d], Hb[static_cast<long long>(j) * D + d], sdot);
-      sdot = warp_sum(sdot);
-      if (lane == 0) {
-        da[j] = sdot;
-        al[j] = alpha[j];
-      }
-    }
-    __syncthreads();
-    if (w == 0) {
-      float sdot = 0.f;
-      for (int j = lane; j < L; j += 32) sdot = fmaf(al[j], da[j], sdot);
-      sdot = warp_sum(sdot);
-      if (lane == 0) sdot_s = sdot;
-    }
-    __syncthreads();
-    if (tid < L) dr[tid] = al[tid] * (da[tid] - sdot_s);  // softmax backward; 0 at masked positions (alpha = 0)
-    __syncthreads();
-    if (tid == 0)
-      for (int j = 0; j < L; ++j) dba += dr[j];
-    for (int d = tid; d < D; d += 256) {
-      const float wad = wa[d], cd = c[d], dcd = dcmd[d];
-      float hsum = 0.f;
-      for (int j = 0; j < L; ++j) {
-        const float hv = Hb[static_cast<long long>(j) * D + d];
-        hsum = fmaf(dr[j], hv, hsum);
-        const float g = al[j] * dcd + dr[j] * wad * cd;
-        if (t == 0) dHb[static_cast<long long>(j) * D + d] = g;
-        else dHb[static_cast<long long>(j) * D + d] += g;
-      }
-      q.dc3[(static_cast<long long>(t) * q.B + b) * D + d] = wad * hsum;
-      if (g_wa) atomicAdd(g_wa + d, cd * hsum);
-    }
-    __syncthreads();
+  const float* dcmd = (t == 0 ? dcmd0 : (t == 1 ? dcmd1 : dcmd2)) + static_cast<long long>(b) * D;
+  const float* alpha = q.alpha + (static_cast<long long>(t) * q.B + b) * L;
+  for (int j = w; j < L; j += 8) {
+    float sdot = 0.f;
+    for (int d = lane; d < D; d += 32) sdot = fmaf(dcmd[d], Hb[static_cast<long long>(j) * D + d], sdot);
+    sdot = warp_sum(sdot);
+    if (lane == 0) da[j] = sdot;
   }
-  if (tid == 0 && g_ba) atomicAdd(g_ba, dba);
+  __syncthreads();
+  if (w == 0) {
+    float sdot = 0.f;
+    for (int j = lane; j < L; j += 32) sdot = fmaf(alpha[j], da[j], sdot);
+    sdot = warp_sum(sdot);
+    float dba = 0.f;
+    for (int j = lane; j < L; j += 32) {
+      const float dr = alpha[j] * (da[j] - sdot);
+      q.dr[(static_cast<long long>(t) * q.B + b) * L + j] = dr;
+      dba += dr;
+    }
+    dba = warp_sum(dba);
+    if (lane == 0 && g_ba) atomicAdd(g_ba, dba);
+  }
+}
+// (2) grid (B, 2H/256), one thread per channel d: dH[b,j,d] = sum_t alpha_tj dcmd_t[d] + dr_tj wa[d] c_t[d];
+// dc_t[b,d] = wa[d] sum_j dr_tj H[b,j,d]; d cmd_inter2logits.weight[d] += sum_t c_t[d] sum_j dr_tj H[b,j,d].
+__global__ void __launch_bounds__(256) qe_attn_bwd_apply_kernel(QeDev q, const float* __restrict__ wa, const float* dcmd0,
+                                                                const float* dcmd1, const float* dcmd2,
+                                                                float* __restrict__ g_wa) {
+  __shared__ float al[3][QE_MAX_L], dr[3][QE_MAX_L];
+  const int D = 2 * q.H, L = q.L;
+  const int b = blockIdx.x, d = blockIdx.y * 256 + threadIdx.x;
+  for (int i = threadIdx.x; i < 3 * L; i += 256) {
+    const int t = i / L, j = i % L;
+    al[t][j] = q.alpha[(static_cast<long long>(t) * q.B + b) * L + j];
+    dr[t][j] = q.dr[(static_cast<long long>(t) * q.B + b) * L + j];
+  }
+  __syncthreads();
+  if (d >= D) return;
+  const float wad = wa[d];
+  float cd[3], dcd[3], hsum[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    cd[t] = q.c3[(static_cast<long long>(t) * q.B + b) * D + d];
+    dcd[t] = (t == 0 ? dcmd0 : (t == 1 ? dcmd1 : dcmd2))[static_cast<long long>(b) * D + d];
+  }
+  const float* Hb = q.Hout + static_cast<long long>(b) * L * D + d;
+  float* dHb = q.dH + static_cast<long long>(b) * L * D + d;
+  for (int j = 0; j < L; ++j) {
+    const float hv = Hb[static_cast<long long>(j) * D];
+    float g = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+      hsum[t] = fmaf(dr[t][j], hv, hsum[t]);
+      g += al[t][j] * dcd[t] + dr[t][j] * wad * cd[t];
+    }
+    dHb[static_cast<long long>(j) * D] = g;
+  }
+  float gw = 0.f;
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    q.dc3[(static_cast<long long>(t) * q.B + b) * D + d] = wad * hsum[t];
+    gw = fmaf(cd[t], hsum[t], gw);
+  }
+  if (g_wa) atomicAdd(g_wa + d, gw);
 }
 
 __global__ void colsum_rows_kernel(const float* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out) {
@@ -547,10 +657,14 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
   float* part = take(2 * BC * (H / 32) * BWD_JQ * 1024);
   float* dE = take(R * E);
   float* cnt = take(2 * BC * (H / 32));
+  float* HT = take(2 * 2 * BC * H * 32);
+  float* dGT = take(2 * 2 * BC * 4 * H * 32);
+  float* dr = take(3 * B * L);
   if (q) {
     q->Ebuf = Ebuf; q->xg = xg; q->G = G; q->Cst = Cst; q->Hout = Hout; q->Hprev = Hprev; q->v = v;
     q->hid = hid; q->c3 = c3; q->alpha = alpha; q->dH = dH; q->dc3 = dc3; q->dhid = dhid; q->dhid_pre = dhid_pre; q->dv = dv;
     q->dG = dG; q->dcarry = dcarry; q->part = part; q->dE = dE; q->cnt = reinterpret_cast<unsigned*>(cnt);
+    q->HT = HT; q->dGT = dGT; q->dr = dr;
   }
   return off;
 }
@@ -612,12 +726,14 @@ extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
   for (int dir = 0; dir < 2; ++dir)  // xg = E W_ih^T + b_ih + b_hh, all time steps at once
     TRY(sgemm(st, q.Ebuf, E, 1, a->w_ih[dir], 1, E, q.xg + dir * 4 * H, 8 * H, R, 4 * H, E, a->b_ih[dir], a->b_hh[dir], 0, 0,
               false));  // forward: no split-K atomics, run-to-run reproducible
-  const size_t smem_f = (32 * H + H * 33) * sizeof(float);
+  const size_t smem_f = (32 * H + H * 32) * sizeof(float);
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_step_kernel), smem_f, "lstm_fwd_step"));
   for (int s = 0; s < L; ++s) {
     lstm_fwd_step_kernel<<<dim3(H / 8, 2, q.BC), 256, smem_f, st>>>(q, s);
     TRY(check_launch("lstm_fwd_step"));
   }
+  qe_hprev_kernel<<<148, 256, 0, st>>>(q);
+  TRY(check_launch("qe_hprev"));
   qe_vgather_kernel<<<B, 256, 0, st>>>(q);
   TRY(check_launch("qe_vgather"));
   TRY(linear_small(st, q.v, 4 * H, a->w1, 4 * H, a->b1, q.hid, H, B, H, 4 * H, 1));
@@ -633,8 +749,10 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
   cudaStream_t st = ST(stream);
   const int B = q.B, L = q.L, H = q.H, E = q.E, R = B * L, D = 2 * H;
   if (!a->dcmd[0] || !a->dcmd[1] || !a->dcmd[2]) return fail(DRN_EINVAL, "drn_qe_backward: dcmd missing");
-  qe_attn_bwd_kernel<<<B, 256, 0, st>>>(q, a->wa, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_wa, a->g_ba);
-  TRY(check_launch("qe_attn_bwd"));
+  qe_attn_bwd_scalars_kernel<<<dim3(B, 3), 256, 0, st>>>(q, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_ba);
+  TRY(check_launch("qe_attn_bwd_scalars"));
+  qe_attn_bwd_apply_kernel<<<dim3(B, ceil_div(D, 256)), 256, 0, st>>>(q, a->wa, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_wa);
+  TRY(check_launch("qe_attn_bwd_apply"));
   for (int t = 0; t < 3; ++t) {
     const float* dc = q.dc3 + static_cast<long long>(t) * B * D;
     TRY(sgemm(st, dc, D, 1, a->w2[t], H, 1, q.dhid, H, B, H, D, nullptr, nullptr, 0, t > 0));
@@ -648,7 +766,7 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
   if (a->g_b1) TRY(colsum(st, q.dhid_pre, B, H, H, a->g_b1));
   qe_vscatter_kernel<<<B, 256, 0, st>>>(q);
   TRY(check_launch("qe_vscatter"));
-  const size_t smem_b = (H * 36 + 8 * 32 * 33) * sizeof(float);
+  const size_t smem_b = (2 * H * 32 + 8 * 32 * 33) * sizeof(float);
   TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_step_kernel), smem_b, "lstm_bwd_step"));
   for (int s = 0; s < L; ++s) {
     const int nq = s == 0 ? 1 : BWD_JQ;
