@@ -57,6 +57,24 @@ __global__ void __launch_bounds__(EW_THREADS) split_planes_kernel(const float* _
   }
 }
 
+// ---- query gate on fp32 rows (model/backbone.py:28-30, level 0): dst planes[b,t,col0+c] = q[b,c] * x[b,t,c] ---------------
+__global__ void __launch_bounds__(EW_THREADS) gate_planes_kernel(const float* __restrict__ x, const float* __restrict__ q, int T,
+                                                                 int C8, long long total, __nv_bfloat16* __restrict__ dst,
+                                                                 long long dst_ld, int dst_col0, long long plane_stride) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / C8;
+    const int c = static_cast<int>(i % C8) * 8;
+    const long long b = r / T;
+    float v[8], g[8];
+    load8(x + r * (C8 * 8LL) + c, v);
+    load8(q + b * (C8 * 8LL) + c, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= g[j];
+    store8_planes(dst + r * dst_ld + dst_col0 + c, plane_stride, v);
+  }
+}
+
 // ---- conv / linear weights [O][C][k] fp32 -> tap-major planes [k][Ototal][C]; one launch packs a whole table ------------
 constexpr int PACK_MAX_ITEMS = 24;
 struct PackItem {
@@ -484,6 +502,16 @@ extern "C" int drn_split_planes(const float* src, int64_t rows, int C, int64_t s
   split_planes_kernel<<<ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream)>>>(src, rows, C / 8, src_ld, static_cast<__nv_bfloat16*>(dst),
                                                                               dst_ld, dst_col0, dst_plane_stride);
   return check_launch("split_planes");
+}
+
+extern "C" int drn_gate_planes(const float* x, const float* q, int B, int T, int C, void* dst, int64_t dst_ld, int dst_col0,
+                               int64_t dst_plane_stride, void* stream) {
+  if (C % 8 || dst_ld % 8 || dst_col0 % 8 || dst_plane_stride % 8) return fail(DRN_EINVAL, "drn_gate_planes: alignment (C=%d)", C);
+  const long long total = static_cast<long long>(B) * T * (C / 8);
+  if (total <= 0) return 0;
+  gate_planes_kernel<<<ew_grid(total), EW_THREADS, 0, ST(stream)>>>(x, q, T, C / 8, total, static_cast<__nv_bfloat16*>(dst), dst_ld,
+                                                                    dst_col0, dst_plane_stride);
+  return check_launch("gate_planes");
 }
 
 static int fill_table(PackTable* t, int n, const drn_pack_item_t* items) {

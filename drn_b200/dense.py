@@ -7,6 +7,7 @@ moved by a kernel of the C-ABI library (include/drn_b200.h).  Layouts are channe
 split-BF16 planes (drn_b200/planes.py).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -57,6 +58,10 @@ class DensePath:
         assert T % 4 == 0, "T must be a multiple of 4 (two stride-2 levels)"
         self.cfg, self.B, self.T, self.dev = cfg, B, T, device
         self.L, self.qe_H, self.qe_E = L, qe_hidden, qe_embed
+        # independent branches of the schedule (weight gradients next to the data-gradient chain, the query encoder next
+        # to prop_fc) are enqueued on a second stream; inside a CUDA-graph capture this becomes a forked graph branch
+        self.overlap = os.environ.get("DRN_NO_OVERLAP", "0") != "1"
+        self.side = torch.cuda.Stream(device=device)
         D = cfg[cfg["feature_type"]]["feature_dim"]
         c1, F = cfg["first_output_dim"], cfg["fpn_feature_dim"]
         self.D, self.C0, self.c = D, D + 256, (c1, 2 * c1, 4 * c1)
@@ -290,18 +295,27 @@ class DensePath:
         h = "fcos.head."
         self.launches = self.launches_stage
         self.pack_weights(p)
+        # prop_fc (main_model.py:59) does not depend on the query: it runs on the side stream beside the query encoder, a
+        # latency-bound chain of small kernels that would otherwise leave the GPU mostly idle for ~0.4 ms
+        if self.overlap:
+            self._fork()
+        with torch.cuda.stream(self.side if self.overlap else torch.cuda.current_stream()):
+            self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
+                       out=self.Pre)
         # query encoder -> three command vectors (model/main_model.py:47, language_module.py:38-62)
         self._chk(lib.drn_qe_forward(C.byref(self._qe_desc(p)), _st()), "qe_forward")
-        self.launches += 9 + self.L  # launches enqueued inside drn_qe_forward
+        self.launches += 10 + self.L  # launches enqueued inside drn_qe_forward
         # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50): exact fp32 on CUDA cores (M = B rows only)
         K = self.cmd_dim
         for i in range(3):
             n = self.qdim[i]
             self._chk(lib.drn_linear_fwd(_vp(self.cmd[i]), C.c_int64(K), _vp(p["qInput%d.weight" % i]), C.c_int64(K),
                                          _vp(p["qInput%d.bias" % i]), _vp(self.q[i]), C.c_int64(n), B, n, K, 0, _st()), "gate")
-        # prop_fc with the level-0 gate fused in the epilogue -> X0[:, :, :D] (main_model.py:59, backbone.py:28-30)
-        self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
-                   out2=self.Pre, rowscale=self.q[0], outp=self.X0)
+        if self.overlap:
+            self._join()
+        # level-0 gate q0 * prop_fc(f) -> X0[:, :, :D] (backbone.py:28-30; the cat with the position channels is the layout)
+        self._chk(lib.drn_gate_planes(_vp(self.Pre), _vp(self.q[0]), B, T, self.D, _vp(self.X0.data), C.c_int64(self.C0), 0,
+                                      C.c_int64(self.X0.plane_stride), _st()), "gate_planes")
         # backbone (backbone.py:27-34)
         src = self.X0
         for i in range(3):
@@ -363,8 +377,29 @@ class DensePath:
         self._chk(lib.drn_bn_bwd_apply(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), _vp(blk.bcoef),
                                        _vp(blk.dy.data), C.c_int64(blk.dy.plane_stride), _st()), "bn_bwd_apply")
 
+    def _fork(self):
+        """Side stream waits for everything enqueued so far on the current stream."""
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side.wait_event(ev)
+
+    def _join(self):
+        """Current stream waits for everything enqueued so far on the side stream."""
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        torch.cuda.current_stream().wait_event(ev)
+
     def _wgrad(self, blk, x_pl, out, accumulate=False):
-        """out: [k][cout][cin] fp32 (workspace, or the gradient itself when k == 1)."""
+        """out: [k][cout][cin] fp32 (workspace, or the gradient itself when k == 1).  Nothing on the data-gradient chain
+        depends on a weight gradient, so it runs on the side stream (joined before the gradients are unpacked)."""
+        if self.overlap:
+            self._fork()
+            with torch.cuda.stream(self.side):
+                self._wgrad_launch(blk, x_pl, out, accumulate)
+        else:
+            self._wgrad_launch(blk, x_pl, out, accumulate)
+
+    def _wgrad_launch(self, blk, x_pl, out, accumulate):
         taps = K1 if blk.k == 1 else (K3 if blk.stride == 1 else K3S2)
         tiles = -(-blk.cout // 256) * -(-blk.cin // 256) * blk.k   # 256 x 256 tiles of the CTA-pair kernel
         kblocks = max(1, blk.rows // 64)
@@ -457,9 +492,13 @@ class DensePath:
         self._chk(lib.drn_pos_bwd(_vp(self.dX0), C.c_int64(self.C0), self.D, _vp(self.pos_in), C.c_int64(B * self.T), 256,
                                   _vp(grads["position_transform.weight"]), _vp(grads["position_transform.bias"]), _st()),
                   "pos_bwd")
-        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D] (the largest contraction of the backward pass)
-        self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
-                   out_ld=self.D, out_tap_stride=0)
+        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D] (the largest contraction of the backward pass); the gates and the
+        # query-encoder backward (a latency-bound chain of small kernels) run beside it
+        if self.overlap:
+            self._fork()
+        with torch.cuda.stream(self.side if self.overlap else torch.cuda.current_stream()):
+            self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
+                       out_ld=self.D, out_tap_stride=0)
         # gates: dW = dq^T cmd, db = colsum(dq), dcmd = dq W
         K = self.cmd_dim
         for i in range(3):
@@ -471,6 +510,8 @@ class DensePath:
         # query encoder backward (BPTT), gradients accumulated into the zeroed buffers
         self._chk(lib.drn_qe_backward(C.byref(self._qe_desc(p, grads)), _st()), "qe_backward")
         self.launches += 30 + self.L
+        if self.overlap:
+            self._join()
         # tap-major workspaces -> parameter layout [O][C][k], one launch
         items = []
         for i in range(3):

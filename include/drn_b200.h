@@ -112,6 +112,9 @@ int drn_gemm(const drn_gemm_t* g, void* stream);
  * Used for the C3D clip features (input of prop_fc, model/main_model.py:59) and small host-side vectors. */
 int drn_split_planes(const float* src, int64_t rows, int C, int64_t src_ld, void* dst, int64_t dst_ld, int dst_col0,
                      int64_t dst_plane_stride, void* stream);
+/* Level-0 query gate (model/backbone.py:28-30) on the fp32 prop_fc output x [B][T][C]: planes[b,t,dst_col0+c] = q[b][c] * x[b,t,c]. */
+int drn_gate_planes(const float* x, const float* q, int B, int T, int C, void* dst, int64_t dst_ld, int dst_col0,
+                    int64_t dst_plane_stride, void* stream);
 /* Table-driven weight packing, ONE launch for all layers.  Item: nn.Conv1d / nn.Linear weight `src` [O][C][k] fp32 ->
  * planes [k][Ototal][C] at row offset o0 (tap-major operand of drn_gemm).  drn_unpack_conv_wgrads goes the other way for
  * weight gradients: workspace `src` [k][Ototal][C] fp32 -> parameter gradient `grad` [O][C][k]. */
