@@ -83,6 +83,8 @@ struct PackItem {
   float* grad;  // unpack only
   int O, C, k, Ototal, o0;
   long long plane_stride;
+  int nslices;              // unpack only: partial sums to add up (K-splits x pyramid levels)
+  long long slice_stride;
 };
 struct PackTable {
   int n;
@@ -116,14 +118,21 @@ __global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const Pack
   }
 }
 
-// ---- weight-gradient workspaces [k][Ototal][C] -> parameter gradients [O][C][k] ---------------------------------------
+// ---- weight-gradient workspaces [slice][k][Ototal][C] -> parameter gradients [O][C][k], summing the slices ------------------
+// (the K-splits of drn_gemm WGRAD and the three pyramid levels of a shared head conv store their partial sums side by side:
+// deterministic, no atomics, no zero-fill).  Reads are coalesced over C; gridDim.y = table item.
 __global__ void __launch_bounds__(EW_THREADS) unpack_conv_wgrad_kernel(const PackTable tab) {
   const PackItem& e = tab.it[blockIdx.y];
   const long long total = static_cast<long long>(e.O) * e.C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int o = static_cast<int>(i / e.C), c = static_cast<int>(i % e.C);
-    for (int r = 0; r < e.k; ++r) e.grad[i * e.k + r] = e.w[(static_cast<long long>(r) * e.Ototal + e.o0 + o) * e.C + c];
+    for (int r = 0; r < e.k; ++r) {
+      const float* src = e.w + (static_cast<long long>(r) * e.Ototal + e.o0 + o) * e.C + c;
+      float acc = 0.f;
+      for (int sl = 0; sl < e.nslices; ++sl) acc += src[sl * e.slice_stride];
+      e.grad[i * e.k + r] = acc;
+    }
   }
 }
 
@@ -520,7 +529,8 @@ static int fill_table(PackTable* t, int n, const drn_pack_item_t* items) {
   for (int i = 0; i < n; ++i) {
     if (items[i].C % 8) return fail(DRN_EINVAL, "pack table: C %% 8 (item %d, C=%d)", i, items[i].C);
     t->it[i] = PackItem{items[i].src, static_cast<__nv_bfloat16*>(items[i].planes), items[i].grad, items[i].O, items[i].C,
-                        items[i].k, items[i].Ototal, items[i].o0, items[i].plane_stride};
+                        items[i].k, items[i].Ototal, items[i].o0, items[i].plane_stride,
+                        items[i].nslices < 1 ? 1 : items[i].nslices, items[i].slice_stride};
   }
   return 0;
 }
@@ -537,7 +547,7 @@ extern "C" int drn_unpack_conv_wgrads(int n, const drn_pack_item_t* items, void*
   PackTable t;
   int rc = fill_table(&t, n, items);
   if (rc) return rc;
-  unpack_conv_wgrad_kernel<<<dim3(74, n), EW_THREADS, 0, ST(stream)>>>(t);
+  unpack_conv_wgrad_kernel<<<dim3(148 * 2, n), EW_THREADS, 0, ST(stream)>>>(t);
   return check_launch("unpack_conv_wgrads");
 }
 

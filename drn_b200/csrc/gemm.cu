@@ -354,16 +354,28 @@ static int launch_tc(const GemmKParams& kp, const CUtensorMap& ma, const CUtenso
   return check_launch("gemm_tc_kernel");
 }
 
-int launch_pair(const GemmKParams& kp, const CUtensorMap& ma, const CUtensorMap& mb, int num_tiles, int n_tiles, int m_tiles,
-                int sm_count, cudaStream_t st);  // gemm2.cu
+int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaStream_t st);  // gemm2.cu
 
-}  // namespace drn
+static int sm_count_cached() {
+  static int sm_count = 0;
+  if (!sm_count) {
+    sm_count = drn_sm_count();
+    if (sm_count <= 0) sm_count = 148;
+  }
+  return sm_count;
+}
 
-using namespace drn;
+struct Prepared {
+  GemmKParams kp;
+  bool wgrad;
+  int m_sub;                                 // 128-row sub-tiles (ROWS) / 128-channel sub-tiles (WGRAD)
+  int pair_n_tiles, pair_m_tiles, pair_tiles;  // 256 x 256 tiling of the CTA-pair kernel
+  int cost;                                  // k-iterations per pair tile (load-balance key)
+};
 
-extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
+// Validate a descriptor and derive the kernel-side parameters (no tensor maps yet).
+static int prepare(const drn_gemm_t* g, Prepared* out) {
   if (!g) return fail(DRN_EINVAL, "drn_gemm: null descriptor");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool wgrad = g->form == DRN_GEMM_WGRAD;
   if (g->form != DRN_GEMM_ROWS && !wgrad) return fail(DRN_EINVAL, "drn_gemm: unknown form %d", g->form);
   if (g->nprod != 1 && g->nprod != 3 && g->nprod != 4) return fail(DRN_EINVAL, "drn_gemm: nprod must be 1, 3 or 4");
@@ -388,6 +400,7 @@ extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
   kp.split_k = g->split_k < 1 ? 1 : g->split_k;
   kp.out = g->out; kp.out_ld = g->out_ld; kp.out_col0 = g->out_col0; kp.out_mode = g->out_mode;
   kp.out_tap_stride = g->out_tap_stride;
+  kp.out_split_stride = g->out_split_stride;
   kp.out_T = g->out_T; kp.out_t_mul = g->out_t_mul; kp.out_t_add = g->out_t_add;
   kp.bias = g->bias; kp.rowscale = g->rowscale; kp.rowscale_ld = g->rowscale_ld;
   kp.out2 = g->out2; kp.out2_ld = g->out2_ld;
@@ -396,26 +409,28 @@ extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
   kp.a = PlanesView{static_cast<const __nv_bfloat16*>(g->a.ptr), g->a.plane_stride, g->a.B, g->a.T, g->a.P, g->a.C};
   kp.b = PlanesView{static_cast<const __nv_bfloat16*>(g->b.ptr), g->b.plane_stride, g->b.B, g->b.T, g->b.P, g->b.C};
   kp.dbg_lbo = g->dbg_lbo; kp.dbg_sbo = g->dbg_sbo; kp.dbg_kadv = g->dbg_kadv;
-  if (kp.split_k > 1 && kp.out_mode != DRN_OUT_ATOMIC) return fail(DRN_EINVAL, "drn_gemm: split_k needs atomic output");
+  if (!wgrad && kp.split_k > 1) return fail(DRN_EINVAL, "drn_gemm: split_k is a WGRAD option");
+  if (kp.split_k > 1 && kp.out_split_stride == 0 && kp.out_mode != DRN_OUT_ATOMIC)
+    return fail(DRN_EINVAL, "drn_gemm: split_k needs an atomic output or out_split_stride");
   if (kp.split_k > 1 && (kp.out2 || kp.outp || kp.bias || kp.rowscale))
-    return fail(DRN_EINVAL, "drn_gemm: split_k supports only the plain atomic output");
+    return fail(DRN_EINVAL, "drn_gemm: split_k supports only the plain output");
 
-  bool vec = true;
-  if (kp.out) vec = vec && (reinterpret_cast<uintptr_t>(kp.out) % 16 == 0) && (kp.out_ld % 4 == 0) && (kp.out_col0 % 4 == 0) &&
-                    (kp.out_tap_stride % 4 == 0);
-  if (kp.out2) vec = vec && (reinterpret_cast<uintptr_t>(kp.out2) % 16 == 0) && (kp.out2_ld % 4 == 0);
-  if (kp.outp) vec = vec && (reinterpret_cast<uintptr_t>(kp.outp) % 16 == 0) && (kp.outp_ld % 8 == 0) && (kp.outp_col0 % 8 == 0) &&
-                     (kp.outp_plane_stride % 8 == 0);
-  kp.vec_ok = vec ? 1 : 0;
-
-  if (g->engine == 1) {
-    const int Mtot = wgrad ? g->M : g->B * g->T;
-    dim3 grid(ceil_div(Mtot, 64), ceil_div(g->N, 64), wgrad ? g->ntaps : 1);
-    gemm_simt_kernel<<<grid, 256, 0, st>>>(kp);
-    return check_launch("gemm_simt_kernel");
+  bool vec = true, vec8 = true;
+  auto al = [](const void* p, uintptr_t a) { return reinterpret_cast<uintptr_t>(p) % a == 0; };
+  if (kp.out) {
+    vec = vec && al(kp.out, 16) && (kp.out_ld % 4 == 0) && (kp.out_col0 % 4 == 0) && (kp.out_tap_stride % 4 == 0) &&
+          (kp.out_split_stride % 4 == 0);
+    vec8 = vec8 && al(kp.out, 32) && (kp.out_ld % 8 == 0) && (kp.out_col0 % 8 == 0) && (kp.out_tap_stride % 8 == 0) &&
+           (kp.out_split_stride % 8 == 0);
   }
+  if (kp.out2) {
+    vec = vec && al(kp.out2, 16) && (kp.out2_ld % 4 == 0);
+    vec8 = vec8 && al(kp.out2, 32) && (kp.out2_ld % 8 == 0);
+  }
+  if (kp.outp) vec = vec && al(kp.outp, 16) && (kp.outp_ld % 8 == 0) && (kp.outp_col0 % 8 == 0) && (kp.outp_plane_stride % 8 == 0);
+  kp.vec_ok = vec ? 1 : 0;
+  kp.vec8_ok = (vec && vec8) ? 1 : 0;
 
-  // ---- engine selection: 0 = auto, 2 = persistent CTA-pair kernel (gemm2.cu), 3 = one-tile-per-CTA kernel -------------
   if (!wgrad) {
     if (g->T >= 128) { kp.Rm = 128; kp.Bbm = 1; }
     else { kp.Rm = pow2_ceil(g->T); kp.Bbm = 128 / kp.Rm; }
@@ -425,39 +440,101 @@ extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
     else { kp.Rk = pow2_ceil(g->T); kp.Bbk = 64 / kp.Rk; }
     kp.kblocks_per_sample = ceil_div(g->T, kp.Rk);
     kp.num_kblocks = (kp.Bbk == 1) ? g->B * kp.kblocks_per_sample : ceil_div(g->B, kp.Bbk);
-    if (kp.split_k > kp.num_kblocks) kp.split_k = kp.num_kblocks;
+    if (kp.split_k > kp.num_kblocks) {
+      if (kp.out_split_stride != 0) return fail(DRN_EINVAL, "drn_gemm: split_k %d exceeds the %d K-blocks (slices would stay unwritten)", kp.split_k, kp.num_kblocks);
+      kp.split_k = kp.num_kblocks;
+    }
   }
-  const int m_sub = wgrad ? ceil_div(g->M, BLOCK_M) : ((kp.Bbm == 1) ? g->B * kp.tiles_per_sample : ceil_div(g->B, kp.Bbm));
-  const int pair_n_tiles = ceil_div(g->N, 256);
-  const int pair_m_tiles = ceil_div(m_sub, 2);
-  const int pair_tiles = pair_m_tiles * pair_n_tiles * (wgrad ? g->ntaps * kp.split_k : 1);
-  static int sm_count = 0;
-  if (!sm_count) {
-    sm_count = drn_sm_count();
-    if (sm_count <= 0) sm_count = 148;
+  out->kp = kp;
+  out->wgrad = wgrad;
+  out->m_sub = wgrad ? ceil_div(g->M, BLOCK_M) : ((kp.Bbm == 1) ? g->B * kp.tiles_per_sample : ceil_div(g->B, kp.Bbm));
+  out->pair_n_tiles = ceil_div(g->N, 256);
+  out->pair_m_tiles = ceil_div(out->m_sub, 2);
+  out->pair_tiles = out->pair_m_tiles * out->pair_n_tiles * (wgrad ? g->ntaps * kp.split_k : 1);
+  out->cost = wgrad ? ceil_div(kp.num_kblocks, kp.split_k) : g->ntaps * (g->K / BLOCK_K);
+  return 0;
+}
+
+static int pair_maps(const drn_gemm_t* g, const Prepared& pr, CUtensorMap* ma, CUtensorMap* mb) {
+  int rc;
+  if (!pr.wgrad) {
+    if ((rc = make_map(ma, g->a, pr.kp.Rm, pr.kp.Bbm)) != 0) return rc;
+    return make_map(mb, g->b, g->b_mn ? 64 : 128, 1);
   }
-  bool use_pair = (g->engine == 2) || (g->engine == 0 && pair_tiles >= sm_count / 4);
+  if ((rc = make_map(ma, g->a, pr.kp.Rk, pr.kp.Bbk)) != 0) return rc;
+  return make_map(mb, g->b, pr.kp.Rk, pr.kp.Bbk);
+}
+
+}  // namespace drn
+
+using namespace drn;
+
+// One launch for up to GROUP_MAX independent problems (persistent CTA-pair kernel).  Tiles are ordered by decreasing
+// k-iterations per tile so the static round-robin over the 74 SM pairs ends with the cheapest tiles.
+extern "C" int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream) {
+  if (n < 1 || n > GROUP_MAX) return fail(DRN_EINVAL, "drn_gemm_group: 1..%d problems (got %d)", GROUP_MAX, n);
+  if (!descs) return fail(DRN_EINVAL, "drn_gemm_group: null descriptors");
+  Prepared pr[GROUP_MAX];
+  int order[GROUP_MAX];
+  int rc;
+  for (int i = 0; i < n; ++i) {
+    if (descs[i].engine == 1 || descs[i].engine == 3) return fail(DRN_EINVAL, "drn_gemm_group: problems run on the CTA-pair engine only");
+    if ((rc = prepare(&descs[i], &pr[i])) != 0) return rc;
+    order[i] = i;
+  }
+  for (int i = 1; i < n; ++i)  // insertion sort, descending cost, stable
+    for (int j = i; j > 0 && pr[order[j]].cost > pr[order[j - 1]].cost; --j) {
+      const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+    }
+  static thread_local GroupParams gp;
+  static thread_local GroupMaps gm;
+  gp.nprob = n;
+  gp.tile_start[0] = 0;
+  for (int k = 0; k < n; ++k) {
+    const int i = order[k];
+    gp.p[k] = pr[i].kp;
+    gp.n_tiles[k] = pr[i].pair_n_tiles;
+    gp.m_tiles[k] = pr[i].pair_m_tiles;
+    gp.tile_start[k + 1] = gp.tile_start[k] + pr[i].pair_tiles;
+    if ((rc = pair_maps(&descs[i], pr[i], &gm.a[k], &gm.b[k])) != 0) return rc;
+  }
+  for (int k = n; k < GROUP_MAX; ++k) gp.tile_start[k + 1] = gp.tile_start[n];
+  return launch_group(gp, gm, sm_count_cached(), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
+  Prepared pr;
+  int rc = prepare(g, &pr);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GemmKParams& kp = pr.kp;
+  const bool wgrad = pr.wgrad;
+
+  if (g->engine == 1) {
+    if (kp.out_split_stride != 0 && kp.split_k > 1) return fail(DRN_EINVAL, "drn_gemm: the checker engine has no K-split");
+    const int Mtot = wgrad ? g->M : g->B * g->T;
+    dim3 grid(ceil_div(Mtot, 64), ceil_div(g->N, 64), wgrad ? g->ntaps : 1);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(kp);
+    return check_launch("gemm_simt_kernel");
+  }
+
+  // ---- engine selection: 0 = auto, 2 = persistent CTA-pair kernel (gemm2.cu), 3 = one-tile-per-CTA kernel -------------
+  const int sm_count = sm_count_cached();
+  bool use_pair = (g->engine == 2) || (g->engine == 0 && pr.pair_tiles >= sm_count / 4);
   if (g->engine == 3) use_pair = false;
   if (g->dbg_lbo || g->dbg_sbo || g->dbg_kadv) use_pair = false;
+  if (use_pair) return drn_gemm_group(1, g, stream);
+  if (kp.out_split_stride != 0 && kp.split_k > 1) return drn_gemm_group(1, g, stream);  // slices exist only in the pair kernel
 
+  // one tile per CTA: 128 x 256 tiles unless that leaves most SMs idle, then 128 x 128
+  int block_n = (g->N > 128) ? 256 : 128;
+  if (block_n == 256 && pr.m_sub * ceil_div(g->N, 256) * (wgrad ? g->ntaps * kp.split_k : 1) < (sm_count * 2) / 3) block_n = 128;
   CUtensorMap ma, mb;
-  int rc;
-  if (use_pair) {
-    if (!wgrad) {
-      if ((rc = make_map(&ma, g->a, kp.Rm, kp.Bbm)) != 0) return rc;
-      if ((rc = make_map(&mb, g->b, g->b_mn ? 64 : 128, 1)) != 0) return rc;
-    } else {
-      if ((rc = make_map(&ma, g->a, kp.Rk, kp.Bbk)) != 0) return rc;
-      if ((rc = make_map(&mb, g->b, kp.Rk, kp.Bbk)) != 0) return rc;
-    }
-    return launch_pair(kp, ma, mb, pair_tiles, pair_n_tiles, pair_m_tiles, sm_count, st);
-  }
-  const int block_n = (g->N > 128) ? 256 : 128;
   dim3 grid;
   if (!wgrad) {
     if ((rc = make_map(&ma, g->a, kp.Rm, kp.Bbm)) != 0) return rc;
     if ((rc = make_map(&mb, g->b, g->b_mn ? 64 : block_n, 1)) != 0) return rc;
-    grid = dim3(m_sub, ceil_div(g->N, block_n), 1);
+    grid = dim3(pr.m_sub, ceil_div(g->N, block_n), 1);
   } else {
     if ((rc = make_map(&ma, g->a, kp.Rk, kp.Bbk)) != 0) return rc;
     if ((rc = make_map(&mb, g->b, kp.Rk, kp.Bbk)) != 0) return rc;

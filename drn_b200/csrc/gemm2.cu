@@ -1,13 +1,16 @@
-// drn_gemm, engine 0 for large problems: PERSISTENT kernel on CTA PAIRS (tcgen05 cta_group::2).
+// drn_gemm / drn_gemm_group, engine 0 for large problems: PERSISTENT kernel on CTA PAIRS (tcgen05 cta_group::2) that walks the
+// 256 x 256 output tiles of up to GROUP_MAX independent problems in ONE launch.
 //
-//   * one cluster of 2 CTAs per SM pair (74 pairs on a B200) walks 256 x 256 output tiles; each CTA stages its own 128 rows
-//     of A and its own 128 columns of B (hi and lo planes) by TMA, the leader CTA's single MMA thread issues
-//     256 x 256 x 16 UMMAs that read both CTAs' shared memory, so every staged byte feeds twice the math of the 1-CTA kernel
-//     (64 KB per 1536 tensor cycles and CTA instead of 96 KB) -- this is what lifts the smem-capacity/latency bound that kept
-//     the one-tile-per-CTA kernel (gemm.cu) at ~40 % tensor-pipe utilisation;
-//   * 3-stage TMA->MMA pipeline that runs across tile boundaries;
+//   * one cluster of 2 CTAs per SM pair (74 pairs on a B200); each CTA stages its own 128 rows of A and its own 128
+//     columns of B (hi and lo planes) by TMA, the leader CTA's single MMA thread issues 256 x 256 x 16 UMMAs that read both
+//     CTAs' shared memory, so every staged byte feeds twice the math of the 1-CTA kernel (gemm.cu);
+//   * 3-stage TMA->MMA pipeline that runs across tile AND problem boundaries;
 //   * the fp32 accumulator is double-buffered in TMEM (2 x 256 columns), so the epilogue of tile i (TMEM -> registers ->
-//     global, bias / gate / split-plane outputs) overlaps the MMAs of tile i+1.
+//     global) overlaps the MMAs of tile i+1;
+//   * grouping: the DRN path is dominated by ~40 small contractions per step (FPN / head convs of three pyramid levels,
+//     their data- and weight-gradients).  Launched one by one each pays pipeline fill/drain and leaves most of a wave
+//     idle (5-27 % tensor-pipe utilisation measured); as one tile list they fill the waves and share one fill/drain.
+//     ROWS (conv forward / dgrad) and WGRAD problems mix freely in a group.
 // Operand forms, tensor maps and epilogue semantics are those of gemm.cu (include/drn_b200.h).
 #include <cuda.h>
 
@@ -23,19 +26,29 @@ constexpr int P2_THREADS = 192;
 constexpr int P2_TILE = 256;
 
 struct PairTile {
+  int prob;       // problem of the group
   int b0, t0;     // ROWS: first (sample, time slot) of this CTA's 128 rows
   int m0;         // WGRAD: first A channel (= output row) of this CTA
   int nb;         // first column of B staged by this CTA
   int n0;         // first output column of the pair's tile
   int tap;        // WGRAD: tap handled by this tile
+  int split;      // WGRAD: K-split index
   int it_begin, nk;
 };
 
-__device__ __forceinline__ PairTile decode_tile(const GemmKParams& p, int tile, int rank, int n_tiles, int m_tiles) {
+__device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile, int rank) {
   PairTile t{};
+  int pr = 0;
+#pragma unroll
+  for (int i = 1; i < GROUP_MAX; ++i)
+    if (i < gp.nprob && tile >= gp.tile_start[i]) pr = i;
+  t.prob = pr;
+  const GemmKParams& p = gp.p[pr];
+  const int local = tile - gp.tile_start[pr];
+  const int n_tiles = gp.n_tiles[pr], m_tiles = gp.m_tiles[pr];
   const bool wgrad = (p.form == DRN_GEMM_WGRAD);
-  const int nt = tile % n_tiles;
-  int rest = tile / n_tiles;
+  const int nt = local % n_tiles;
+  int rest = local / n_tiles;
   t.n0 = nt * P2_TILE;
   t.nb = t.n0 + rank * 128;
   if (!wgrad) {
@@ -54,16 +67,15 @@ __device__ __forceinline__ PairTile decode_tile(const GemmKParams& p, int tile, 
     const int z = rest / m_tiles;
     t.m0 = mt * P2_TILE + rank * 128;
     t.tap = z / p.split_k;
-    const int split = z % p.split_k;
-    t.it_begin = static_cast<int>(static_cast<long long>(p.num_kblocks) * split / p.split_k);
-    t.nk = static_cast<int>(static_cast<long long>(p.num_kblocks) * (split + 1) / p.split_k) - t.it_begin;
+    t.split = z % p.split_k;
+    t.it_begin = static_cast<int>(static_cast<long long>(p.num_kblocks) * t.split / p.split_k);
+    t.nk = static_cast<int>(static_cast<long long>(p.num_kblocks) * (t.split + 1) / p.split_k) - t.it_begin;
   }
   return t;
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
-gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tma_a,
-                 const __grid_constant__ CUtensorMap tma_b, int num_tiles, int n_tiles, int m_tiles) {
+gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ GroupMaps gm, int num_tiles) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[P2_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[P2_STAGES];
@@ -76,17 +88,14 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = (rank == 0);
-  const bool wgrad = (p.form == DRN_GEMM_WGRAD);
-  const bool a_mn = wgrad;
-  const bool b_mn = wgrad || (p.b_mn != 0);
-  const int nplanes = (p.nprod == 1) ? 1 : 2;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int kpt = wgrad ? 1 : p.K / BLOCK_K;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
+    for (int i = 0; i < gp.nprob; ++i) {
+      tma_prefetch_desc(&gm.a[i]);
+      tma_prefetch_desc(&gm.b[i]);
+    }
     for (int s = 0; s < P2_STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -109,10 +118,17 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer (one thread per CTA; completion is signalled on the LEADER's full barrier) =====
     if (lane == 0) {
-      const uint32_t tx = 2u * nplanes * 2u * P2_HALF;  // both CTAs' bytes land on the leader's barrier
-      int g = 0;                                        // global k-iteration counter (pipeline runs across tiles)
+      int g = 0;  // global k-iteration counter (pipeline runs across tiles and problems)
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const PairTile t = decode_tile(p, tile, rank, n_tiles, m_tiles);
+        const PairTile t = decode_tile(gp, tile, rank);
+        const GemmKParams& p = gp.p[t.prob];
+        const CUtensorMap* tma_a = &gm.a[t.prob];
+        const CUtensorMap* tma_b = &gm.b[t.prob];
+        const bool wgrad = (p.form == DRN_GEMM_WGRAD);
+        const bool b_mn = wgrad || (p.b_mn != 0);
+        const int nplanes = (p.nprod == 1) ? 1 : 2;
+        const int kpt = wgrad ? 1 : p.K / BLOCK_K;
+        const uint32_t tx = 2u * nplanes * 2u * P2_HALF;  // both CTAs' bytes land on the leader's barrier
         for (int i = 0; i < t.nk; ++i, ++g) {
           const int s = g % P2_STAGES;
           const uint32_t ph = (g / P2_STAGES) & 1;
@@ -125,14 +141,14 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
           if (!wgrad) {
             const int tap = it / kpt, kb = it % kpt;
             for (int pl = 0; pl < nplanes; ++pl) {
-              tma_load_5d_pair(sa + pl * P2_HALF, &tma_a, fb, p.a_c0 + kb * BLOCK_K, p.tap_par[tap], t.t0 + p.tap_shift[tap],
+              tma_load_5d_pair(sa + pl * P2_HALF, tma_a, fb, p.a_c0 + kb * BLOCK_K, p.tap_par[tap], t.t0 + p.tap_shift[tap],
                                t.b0, pl);
               if (!b_mn) {
-                tma_load_5d_pair(sb + pl * P2_HALF, &tma_b, fb, p.b_c0 + kb * BLOCK_K, 0, t.nb, p.tap_w[tap], pl);
+                tma_load_5d_pair(sb + pl * P2_HALF, tma_b, fb, p.b_c0 + kb * BLOCK_K, 0, t.nb, p.tap_w[tap], pl);
               } else {
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
-                  tma_load_5d_pair(sb + pl * P2_HALF + j * 8192, &tma_b, fb, p.b_c0 + t.nb + j * 64, 0, kb * BLOCK_K,
+                  tma_load_5d_pair(sb + pl * P2_HALF + j * 8192, tma_b, fb, p.b_c0 + t.nb + j * 64, 0, kb * BLOCK_K,
                                    p.tap_w[tap], pl);
               }
             }
@@ -148,8 +164,8 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
             for (int pl = 0; pl < nplanes; ++pl) {
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
-                tma_load_5d_pair(sa + pl * P2_HALF + j * 8192, &tma_a, fb, p.a_c0 + t.m0 + j * 64, 0, tk, bk, pl);
-                tma_load_5d_pair(sb + pl * P2_HALF + j * 8192, &tma_b, fb, p.b_c0 + t.nb + j * 64, p.tap_par[t.tap],
+                tma_load_5d_pair(sa + pl * P2_HALF + j * 8192, tma_a, fb, p.a_c0 + t.m0 + j * 64, 0, tk, bk, pl);
+                tma_load_5d_pair(sb + pl * P2_HALF + j * 8192, tma_b, fb, p.b_c0 + t.nb + j * 64, p.tap_par[t.tap],
                                  tk + p.tap_shift[t.tap], bk, pl);
               }
             }
@@ -165,13 +181,18 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA =====
     if (leader && lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(P2_TILE, P2_TILE, a_mn, b_mn);
-      const uint32_t a_lbo = a_mn ? 8192u : 0u, a_kadv = a_mn ? 2048u : 32u;
-      const uint32_t b_lbo = b_mn ? 8192u : 0u, b_kadv = b_mn ? 2048u : 32u;
       int g = 0, lt = 0;  // lt counts the tiles that actually use an accumulator stage
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const PairTile t = decode_tile(p, tile, rank, n_tiles, m_tiles);
+        const PairTile t = decode_tile(gp, tile, rank);
         if (t.nk <= 0) continue;
+        const GemmKParams& p = gp.p[t.prob];
+        const bool wgrad = (p.form == DRN_GEMM_WGRAD);
+        const bool a_mn = wgrad;
+        const bool b_mn = wgrad || (p.b_mn != 0);
+        const uint32_t idesc = umma_idesc_bf16(P2_TILE, P2_TILE, a_mn, b_mn);
+        const uint32_t a_lbo = a_mn ? 8192u : 0u, a_kadv = a_mn ? 2048u : 32u;
+        const uint32_t b_lbo = b_mn ? 8192u : 0u, b_kadv = b_mn ? 2048u : 32u;
+        const int nprod = p.nprod;
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
         ++lt;
@@ -186,7 +207,7 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = smem_base + s * P2_STAGE;
           const uint32_t sb = sa + 2 * P2_HALF;
-          for (int prod = 0; prod < p.nprod; ++prod) {
+          for (int prod = 0; prod < nprod; ++prod) {
             const uint32_t pa = (prod >> 1) & 1, pb = prod & 1;  // (hi,hi) (hi,lo) (lo,hi) (lo,lo)
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
@@ -208,8 +229,10 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
     const int row = q * 32 + lane;
     int lt = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const PairTile t = decode_tile(p, tile, rank, n_tiles, m_tiles);
+      const PairTile t = decode_tile(gp, tile, rank);
       if (t.nk <= 0) continue;
+      const GemmKParams& p = gp.p[t.prob];
+      const bool wgrad = (p.form == DRN_GEMM_WGRAD);
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       ++lt;
@@ -227,7 +250,7 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
       } else {
         valid = (t.m0 + row) < p.M;
         orow = t.m0 + row;
-        if (out_base) out_base += p.tap_w[t.tap] * p.out_tap_stride;
+        if (out_base) out_base += p.tap_w[t.tap] * p.out_tap_stride + t.split * p.out_split_stride;
       }
       const uint32_t taddr = tmem_base + as * P2_TILE + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
@@ -248,18 +271,18 @@ gemm_pair_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ 
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
-int launch_pair(const GemmKParams& kp, const CUtensorMap& ma, const CUtensorMap& mb, int num_tiles, int n_tiles, int m_tiles,
-                int sm_count, cudaStream_t st) {
+int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(gemm_pair): %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  const int num_tiles = gp.tile_start[gp.nprob];
   int clusters = sm_count / 2;
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
-  gemm_pair_kernel<<<2 * clusters, P2_THREADS, P2_SMEM, st>>>(kp, ma, mb, num_tiles, n_tiles, m_tiles);
+  gemm_pair_kernel<<<2 * clusters, P2_THREADS, P2_SMEM, st>>>(gp, gm, num_tiles);
   return check_launch("gemm_pair_kernel");
 }
 

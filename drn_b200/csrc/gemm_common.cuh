@@ -26,6 +26,7 @@ struct GemmKParams {
   long long out_ld;
   int out_col0, out_mode;
   long long out_tap_stride;
+  long long out_split_stride;  // WGRAD: != 0 -> K-split s stores its partial sum at out + s*out_split_stride (no atomics)
   int out_T, out_t_mul, out_t_add;
   const float* bias;
   const float* rowscale;
@@ -36,9 +37,23 @@ struct GemmKParams {
   long long outp_ld;
   int outp_col0;
   long long outp_plane_stride;
-  int vec_ok;
+  int vec_ok;   // 16-byte vector accesses are aligned
+  int vec8_ok;  // 32-byte (full-sector) stores are aligned
   PlanesView a, b;
   int dbg_lbo, dbg_sbo, dbg_kadv;
+};
+
+// A group of independent problems walked by ONE persistent launch of the CTA-pair kernel (gemm2.cu)
+constexpr int GROUP_MAX = 6;
+struct GroupParams {
+  int nprob;
+  int tile_start[GROUP_MAX + 1];  // prefix sums of the per-problem 256 x 256 tile counts
+  int n_tiles[GROUP_MAX], m_tiles[GROUP_MAX];
+  GemmKParams p[GROUP_MAX];
+};
+struct GroupMaps {
+  CUtensorMap a[GROUP_MAX];
+  CUtensorMap b[GROUP_MAX];
 };
 
 constexpr int BLOCK_M = 128;
@@ -53,6 +68,14 @@ struct TileCfg {
   static constexpr int STAGES = (BLOCK_N >= 256) ? 2 : 3;
   static constexpr uint32_t SMEM = STAGES * STAGE + 1024;
 };
+
+// 32-byte store: one full L2 sector per thread, so a row-per-thread epilogue never leaves half-written sectors behind
+// (16-byte stores made L2 fetch the other half from DRAM: 2x the output size in extra reads, ncu r01 v4).
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue for one 32-column chunk held in registers (one row per thread).
@@ -70,7 +93,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, b
   }
   if (p.out2) {
     float* o2 = p.out2 + orow * p.out2_ld + ncol0;
-    if (full && p.vec_ok) {
+    if (full && p.vec8_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) st_global_v8(o2 + j, v + j);
+    } else if (full && p.vec_ok) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o2 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
@@ -91,6 +117,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, b
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < cnt) atomicAdd(o + j, v[j]);
+    } else if (full && p.vec8_ok) {
+      if (p.out_mode == DRN_OUT_ADD) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          const float4 t0 = *reinterpret_cast<const float4*>(o + j), t1 = *reinterpret_cast<const float4*>(o + j + 4);
+          float w[8] = {t0.x + v[j],     t0.y + v[j + 1], t0.z + v[j + 2], t0.w + v[j + 3],
+                        t1.x + v[j + 4], t1.y + v[j + 5], t1.z + v[j + 6], t1.w + v[j + 7]};
+          st_global_v8(o + j, w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) st_global_v8(o + j, v + j);
+      }
     } else if (full && p.vec_ok) {
       if (p.out_mode == DRN_OUT_ADD) {
 #pragma unroll

@@ -143,17 +143,23 @@ class DensePath:
             self.wp["inner%d" % i] = Planes.empty(1, F, self.c[i], dev)
             self.wp["layer%d" % i] = Planes.empty(3, F, F, dev)
         self.tower_bias = e(2 * F)
-        ws_shapes = {"conv0": (3, c1, self.C0), "conv1": (3, 2 * c1, c1), "conv2": (3, 4 * c1, 2 * c1),
-                     "towers": (3, 2 * F, F), "iouc": (3, F // 2, F)}
+        # weight-gradient workspaces: [slices][k][cout][cin] fp32 partial sums (K-splits x pyramid levels), summed and
+        # re-laid out to the parameter layout [cout][cin][k] by ONE drn_unpack_conv_wgrads launch at the end of the backward
+        self.ws, self.ws_split = {}, {}
+
+        def ws_alloc(name, blks):
+            blk0 = blks[0]
+            splits = [self._wgrad_split(blk) for blk in blks]
+            self.ws_split[name] = splits
+            self.ws[name] = e(sum(splits), blk0.k, blk0.cout, blk0.cin)
+
         for i in range(3):
-            ws_shapes["layer%d" % i] = (3, F, F)
-        tot = sum(a * b * c for a, b, c in ws_shapes.values())
-        self.ws_flat = z(tot)
-        self.ws, o = {}, 0
-        for k, s in ws_shapes.items():
-            m = s[0] * s[1] * s[2]
-            self.ws[k] = self.ws_flat[o:o + m].view(*s)
-            o += m
+            ws_alloc("conv%d" % i, [self.conv[i]])
+            ws_alloc("inner%d" % i, [self.inner[i]])
+            ws_alloc("layer%d" % i, [self.layer[i]])
+        ws_alloc("towers", self.tower)
+        ws_alloc("mix", self.mix)
+        ws_alloc("iouc", self.iouc)
         self.iou_branch_on = not cfg["is_first_stage"]
         self.gamma = float(cfg["fcos_loss_gamma"][0] if isinstance(cfg["fcos_loss_gamma"], (list, tuple)) else cfg["fcos_loss_gamma"])
         self.alpha = float(cfg["fcos_loss_alpha"][0] if isinstance(cfg["fcos_loss_alpha"], (list, tuple)) else cfg["fcos_loss_alpha"])
@@ -202,17 +208,20 @@ class DensePath:
                                           C.c_int64(dst.C), dst_col0, C.c_int64(dst.plane_stride), _st()), "split_planes")
 
     @staticmethod
-    def _pack_item(w, dst, o0=0, grad=None, ws=None):
-        """weight w [O][C][k] <-> tap-major planes `dst` (pack) or fp32 workspace `ws` -> `grad` (unpack)."""
-        t = grad if grad is not None else w
-        O, Cn = t.shape[0], t.shape[1]
-        k = t.shape[2] if t.dim() == 3 else 1
+    def _pack_item(w, dst, o0=0):
+        """weight w [O][C][k] fp32 -> tap-major planes `dst` [k][Ototal][C] at row offset o0."""
         it = L.PackItem()
-        if grad is None:
-            it.src, it.planes, it.Ototal, it.plane_stride = w.data_ptr(), dst.data.data_ptr(), dst.T, dst.plane_stride
-        else:
-            it.src, it.grad, it.Ototal = ws.data_ptr(), grad.data_ptr(), ws.shape[1]
-        it.O, it.C, it.k, it.o0 = O, Cn, k, o0
+        it.src, it.planes, it.Ototal, it.plane_stride = w.data_ptr(), dst.data.data_ptr(), dst.T, dst.plane_stride
+        it.O, it.C, it.k, it.o0 = w.shape[0], w.shape[1], (w.shape[2] if w.dim() == 3 else 1), o0
+        return it
+
+    def _unpack_item(self, grad, name, o0=0):
+        """workspace `name` [slices][k][Ototal][C] fp32 -> gradient [O][C][k] = sum of the slices (rows o0 .. o0+O)."""
+        ws = self.ws[name]
+        it = L.PackItem()
+        it.src, it.grad, it.Ototal = ws.data_ptr(), grad.data_ptr(), ws.shape[2]
+        it.O, it.C, it.k, it.o0 = grad.shape[0], grad.shape[1], (grad.shape[2] if grad.dim() == 3 else 1), o0
+        it.nslices, it.slice_stride = ws.shape[0], ws.stride(0)
         return it
 
     def pack_weights(self, p):
@@ -259,11 +268,16 @@ class DensePath:
             _vp(out_qa.data) if out_qa is not None else None, C.c_int64(out_qa.plane_stride if out_qa is not None else 0),
             _st()), "bn_relu_apply")
 
-    def _conv(self, blk, a_pl, w_pl, bias=None):
+    def _conv_desc(self, blk, a_pl, w_pl, bias=None, engine=None):
         par = blk.stride
         taps = K1 if blk.k == 1 else (K3 if blk.stride == 1 else K3S2)
-        self._gemm(L.GEMM_ROWS, a_pl.desc(par), w_pl.desc(), self.B, blk.t_out, blk.cout, K=blk.cin, taps=taps,
-                   out=blk.y, bias=bias)
+        return ops.desc(L.GEMM_ROWS, a_pl.desc(par), w_pl.desc(), self.B, blk.t_out, blk.cout, K=blk.cin, taps=taps,
+                        out=blk.y, bias=bias, engine=engine)
+
+    def _conv(self, blk, a_pl, w_pl, bias=None):
+        self.launches += 1
+        g = self._conv_desc(blk, a_pl, w_pl, bias)
+        L.check(_lib().drn_gemm(C.byref(g), _st()), "drn_gemm")
 
     # ---------------------------------------------------------------------------------------------------------------
     # forward
@@ -327,27 +341,35 @@ class DensePath:
                 src = self.QC[i]
             else:
                 self._apply(blk, self.Cact[i])
-        # FPN top-down (FPN.py:54-69); BN update order inner3, layer3, inner2, layer2, inner1, layer1
+        # FPN top-down (FPN.py:54-69).  The three lateral 1x1 convs are independent -> one grouped launch; their applies run
+        # top-down (the upsample-add needs the level above); then the three 3-tap output convs, again one launch.  Every FPN
+        # block owns its BatchNorm module, so the order of the running-statistics updates is immaterial here.
+        self._group([self._conv_desc(self.inner[i], self.Cact[i], self.wp["inner%d" % i], engine=2) for i in range(3)])
         for i in (2, 1, 0):
-            self._conv(self.inner[i], self.Cact[i], self.wp["inner%d" % i])
             self._bn_fwd(self.inner[i], p, training)
             self._apply(self.inner[i], self.I[i], up=self.I[i + 1] if i < 2 else None)
-            self._conv(self.layer[i], self.I[i], self.wp["layer%d" % i])
+        self._group([self._conv_desc(self.layer[i], self.I[i], self.wp["layer%d" % i], engine=2) for i in range(3)])
+        for i in range(3):
             self._bn_fwd(self.layer[i], p, training)
             self._apply(self.layer[i], self.Pf[i])
-        # head (fcos.py:93-102), levels ascending, BN order cls_tower, bbox_tower, mix_fc, iou_scores
+        # head (fcos.py:93-102): shared weights, per-level batch statistics.  Each shared conv runs its three levels in ONE
+        # grouped launch; the BatchNorm statistics kernels follow in level order, which keeps the order of the three
+        # running-statistics updates of every shared module (levels ascending) exactly as in the reference.
+        self._group([self._conv_desc(self.tower[l], self.Pf[l], self.wp["towers"], bias=self.tower_bias, engine=2) for l in range(3)])
+        for l in range(3):
+            self._bn_fwd(self.tower[l], p, training)
+            self._apply(self.tower[l], self.TW[l])
+        self._group([self._conv_desc(self.mix[l], self.TW[l], self.wp["mix"], bias=p[h + "mix_fc.0.bias"], engine=2) for l in range(3)])
+        for l in range(3):
+            self._bn_fwd(self.mix[l], p, training)
+            self._apply(self.mix[l], self.MX[l])
+        self._group([self._conv_desc(self.iouc[l], self.MX[l], self.wp["iouc"], bias=p[h + "iou_scores.0.bias"], engine=2) for l in range(3)])
+        for l in range(3):
+            self._bn_fwd(self.iouc[l], p, training)
+            self._apply(self.iouc[l], self.HI[l])
         for l in range(3):
             Tl = self.Tl[l]
             o = self.lvl_off[l]
-            self._conv(self.tower[l], self.Pf[l], self.wp["towers"], bias=self.tower_bias)
-            self._bn_fwd(self.tower[l], p, training)
-            self._apply(self.tower[l], self.TW[l])
-            self._conv(self.mix[l], self.TW[l], self.wp["mix"], bias=p[h + "mix_fc.0.bias"])
-            self._bn_fwd(self.mix[l], p, training)
-            self._apply(self.mix[l], self.MX[l])
-            self._conv(self.iouc[l], self.MX[l], self.wp["iouc"], bias=p[h + "iou_scores.0.bias"])
-            self._bn_fwd(self.iouc[l], p, training)
-            self._apply(self.iouc[l], self.HI[l])
             tw, hi = self.TW[l], self.HI[l]
             self._chk(lib.drn_skinny_conv_fwd(_vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, self.F, B, Tl, 1, 3,
                                               _vp(p[h + "cls_logits.weight"]), _vp(p[h + "cls_logits.bias"]),
@@ -389,37 +411,33 @@ class DensePath:
         ev.record(self.side)
         torch.cuda.current_stream().wait_event(ev)
 
-    def _wgrad(self, blk, x_pl, out, accumulate=False):
-        """out: [k][cout][cin] fp32 (workspace, or the gradient itself when k == 1).  Nothing on the data-gradient chain
-        depends on a weight gradient, so it runs on the side stream (joined before the gradients are unpacked)."""
-        if self.overlap:
-            self._fork()
-            with torch.cuda.stream(self.side):
-                self._wgrad_launch(blk, x_pl, out, accumulate)
-        else:
-            self._wgrad_launch(blk, x_pl, out, accumulate)
+    def _group(self, descs):
+        """Independent contractions -> one launch of the persistent CTA-pair kernel per <= 6 problems."""
+        self.launches += ops.gemm_group(descs)
 
-    def _wgrad_launch(self, blk, x_pl, out, accumulate):
+    @staticmethod
+    def _wgrad_split(blk):
+        """K-splits of a weight gradient: ~2048 contraction rows (32 K-blocks) per 256 x 256 tile, so the tiles of the three
+        pyramid levels (8192 / 4096 / 2048 rows at B=32, T=256) cost the same and fill the 74 SM pairs evenly."""
+        return max(1, min(8, blk.rows // 2048))
+
+    def _wgrad_desc(self, blk, x_pl, name, idx=0):
+        """Weight gradient of `blk` into its slices of the workspace `name` (idx = pyramid level for shared head convs)."""
+        ws, splits = self.ws[name], self.ws_split[name]
         taps = K1 if blk.k == 1 else (K3 if blk.stride == 1 else K3S2)
-        tiles = -(-blk.cout // 256) * -(-blk.cin // 256) * blk.k   # 256 x 256 tiles of the CTA-pair kernel
-        kblocks = max(1, blk.rows // 64)
-        split = 1
-        if tiles < SM_COUNT // 2:
-            split = max(1, min(kblocks // 4, SM_COUNT // tiles, 16))
-        mode = L.OUT_ATOMIC if (split > 1 or accumulate) else L.OUT_STORE
-        self._gemm(L.GEMM_WGRAD, blk.dy.desc(), x_pl.desc(blk.stride), self.B, blk.t_out, blk.cin, M=blk.cout, taps=taps,
-                   out=out, out_ld=blk.cin, out_tap_stride=blk.cout * blk.cin, out_mode=mode, split_k=split)
+        s0 = sum(splits[:idx])
+        return ops.desc(L.GEMM_WGRAD, blk.dy.desc(), x_pl.desc(blk.stride), self.B, blk.t_out, blk.cin, M=blk.cout, taps=taps,
+                        out=ws[s0], out_ld=blk.cin, out_tap_stride=blk.cout * blk.cin, out_split_stride=ws.stride(0),
+                        split_k=splits[idx], engine=2)
 
-    def _dgrad(self, blk, w_pl, out, mode=L.OUT_STORE, rowscale=None, out2=None):
+    def _dgrad_descs(self, blk, w_pl, out, mode=L.OUT_STORE, rowscale=None, out2=None):
         if blk.stride == 1:
             taps = K1 if blk.k == 1 else K3_DGRAD
-            self._gemm(L.GEMM_ROWS, blk.dy.desc(), w_pl.desc(), self.B, blk.t_out, blk.cin, K=blk.cout, taps=taps, b_mn=1,
-                       out=out, out_mode=mode, rowscale=rowscale, out2=out2)
-        else:
-            for par in (0, 1):
-                self._gemm(L.GEMM_ROWS, blk.dy.desc(), w_pl.desc(), self.B, blk.t_out, blk.cin, K=blk.cout, taps=S2_DGRAD[par],
-                           b_mn=1, out=out, out_mode=mode, rowscale=rowscale, out2=out2, out_T=blk.t_in, out_t_mul=2,
-                           out_t_add=par)
+            return [ops.desc(L.GEMM_ROWS, blk.dy.desc(), w_pl.desc(), self.B, blk.t_out, blk.cin, K=blk.cout, taps=taps, b_mn=1,
+                             out=out, out_mode=mode, rowscale=rowscale, out2=out2, engine=2)]
+        return [ops.desc(L.GEMM_ROWS, blk.dy.desc(), w_pl.desc(), self.B, blk.t_out, blk.cin, K=blk.cout, taps=S2_DGRAD[par],
+                         b_mn=1, out=out, out_mode=mode, rowscale=rowscale, out2=out2, out_T=blk.t_in, out_t_mul=2,
+                         out_t_add=par, engine=2) for par in (0, 1)]
 
     def backward(self, p, grads, upstream):
         """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
@@ -429,7 +447,6 @@ class DensePath:
         F = self.F
         self.launches = 0
         iou_on = self.iou_branch_on and (h + "mix_fc.0.weight") in grads
-        self.ws_flat.zero_()
         self.pgrad.zero_()
         for t in self.dq:
             t.zero_()
@@ -437,55 +454,62 @@ class DensePath:
                                         _vp(self.scales), _vp(self.gt), C.c_float(self.gamma), C.c_float(self.alpha),
                                         1 if self.iou_branch_on else 0, _vp(self.acc), _vp(upstream), _vp(self.dcls),
                                         _vp(self.dbox), _vp(self.diou), _vp(self.pgrad), _st()), "fcos_loss_bwd")
-        for l in range(3):
-            Tl, o = self.Tl[l], self.lvl_off[l]
-            tw, hi = self.TW[l], self.HI[l]
-            if iou_on:
+        # Every layer's data- and weight-gradients (and, for the shared head / FPN convs, all three pyramid levels) depend only
+        # on the BatchNorm backward before them: they go out as ONE grouped launch per layer.
+        lv = range(3)
+        if iou_on:
+            for l in lv:
+                hi, o = self.HI[l], self.lvl_off[l]
                 self._chk(lib.drn_skinny_conv_bwd(_vp(self.diou[o:]), _vp(hi.data), C.c_int64(hi.plane_stride), hi.C, 0, F // 2,
-                                                  B, Tl, 1, 1, _vp(p[h + "iou_scores.3.weight"]), _vp(self.dHI[l]), F // 2, 0,
+                                                  B, self.Tl[l], 1, 1, _vp(p[h + "iou_scores.3.weight"]), _vp(self.dHI[l]), F // 2, 0,
                                                   _vp(grads[h + "iou_scores.3.weight"]), _st()), "iou3_bwd")
                 self._bn_bwd(self.iouc[l], self.dHI[l], p, grads)
-                self._wgrad(self.iouc[l], self.MX[l], self.ws["iouc"], accumulate=True)
-                self._dgrad(self.iouc[l], self.wp["iouc"], self.dMX[l])
+            self._group([self._wgrad_desc(self.iouc[l], self.MX[l], "iouc", l) for l in lv] +
+                        [d for l in lv for d in self._dgrad_descs(self.iouc[l], self.wp["iouc"], self.dMX[l])])
+            for l in lv:
                 self._bn_bwd(self.mix[l], self.dMX[l], p, grads)
-                self._wgrad(self.mix[l], tw, grads[h + "mix_fc.0.weight"], accumulate=True)
+        for l in lv:
+            Tl, o, tw = self.Tl[l], self.lvl_off[l], self.TW[l]
             self._chk(lib.drn_skinny_conv_bwd(_vp(self.dcls[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, F, B, Tl, 1, 3,
                                               _vp(p[h + "cls_logits.weight"]), _vp(self.dTW[l]), 2 * F, 0,
                                               _vp(grads[h + "cls_logits.weight"]), _st()), "cls_logits_bwd")
             self._chk(lib.drn_skinny_conv_bwd(_vp(self.dbox[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, F, F, B, Tl, 2, 3,
                                               _vp(p[h + "bbox_pred.weight"]), _vp(self.dTW[l]), 2 * F, 0,
                                               _vp(grads[h + "bbox_pred.weight"]), _st()), "bbox_pred_bwd")
-            if iou_on:
-                self._dgrad(self.mix[l], self.wp["mix"], self.dTW[l], mode=L.OUT_ADD)
+        if iou_on:  # mix_fc: weight gradients + data gradients added onto the tower gradient (fcos.py:101 cat)
+            self._group([self._wgrad_desc(self.mix[l], self.TW[l], "mix", l) for l in lv] +
+                        [d for l in lv for d in self._dgrad_descs(self.mix[l], self.wp["mix"], self.dTW[l], mode=L.OUT_ADD)])
+        for l in lv:
             self._bn_bwd(self.tower[l], self.dTW[l], p, grads)
-            self._wgrad(self.tower[l], self.Pf[l], self.ws["towers"], accumulate=True)
-            self._dgrad(self.tower[l], self.wp["towers"], self.dPf[l])
-        # FPN
-        for i in range(3):
+        self._group([self._wgrad_desc(self.tower[l], self.Pf[l], "towers", l) for l in lv] +
+                    [d for l in lv for d in self._dgrad_descs(self.tower[l], self.wp["towers"], self.dPf[l])])
+        # FPN output convs
+        for i in lv:
             self._bn_bwd(self.layer[i], self.dPf[i], p, grads)
-            self._wgrad(self.layer[i], self.I[i], self.ws["layer%d" % i])
-            self._dgrad(self.layer[i], self.wp["layer%d" % i], self.dI[i])
-            if i > 0:
-                self._chk(lib.drn_pair_sum_add(_vp(self.dI[i]), _vp(self.dI[i - 1]), C.c_int64(B * self.Tl[i]), F, _st()),
-                          "pair_sum_add")
-        for i in range(3):
+        self._group([self._wgrad_desc(self.layer[i], self.I[i], "layer%d" % i) for i in lv] +
+                    [d for i in lv for d in self._dgrad_descs(self.layer[i], self.wp["layer%d" % i], self.dI[i])])
+        for i in (1, 2):  # backward of the top-down upsample-add chain (FPN.py:63-68)
+            self._chk(lib.drn_pair_sum_add(_vp(self.dI[i]), _vp(self.dI[i - 1]), C.c_int64(B * self.Tl[i]), F, _st()),
+                      "pair_sum_add")
+        # FPN lateral convs
+        for i in lv:
             self._bn_bwd(self.inner[i], self.dI[i], p, grads)
-            self._wgrad(self.inner[i], self.Cact[i], grads["fpn.fpn_inner%d.0.weight" % (i + 1)].view(1, F, self.c[i]))
-            self._dgrad(self.inner[i], self.wp["inner%d" % i], self.dC[i])
+        self._group([self._wgrad_desc(self.inner[i], self.Cact[i], "inner%d" % i) for i in lv] +
+                    [d for i in lv for d in self._dgrad_descs(self.inner[i], self.wp["inner%d" % i], self.dC[i])])
         # backbone
         for i in (2, 1):
             blk = self.conv[i]
             self._bn_bwd(blk, self.dC[i], p, grads)
-            self._wgrad(blk, self.QC[i - 1], self.ws["conv%d" % i])
-            self._dgrad(blk, self.wp["conv%d" % i], self.dC[i - 1], mode=L.OUT_ADD, rowscale=self.q[i], out2=self.dQC[i - 1])
+            self._group([self._wgrad_desc(blk, self.QC[i - 1], "conv%d" % i)] +
+                        self._dgrad_descs(blk, self.wp["conv%d" % i], self.dC[i - 1], mode=L.OUT_ADD, rowscale=self.q[i],
+                                          out2=self.dQC[i - 1]))
             a = self.Cact[i - 1]
             self._chk(lib.drn_gate_reduce(_vp(self.dQC[i - 1]), C.c_int64(a.C), _vp(a.data), C.c_int64(a.C),
                                           C.c_int64(a.plane_stride), 1, B, self.Tl[i - 1], a.C, _vp(self.dq[i]), None, None,
                                           C.c_int64(0), None, _st()), "gate_reduce")
         blk = self.conv[0]
         self._bn_bwd(blk, self.dC[0], p, grads)
-        self._wgrad(blk, self.X0, self.ws["conv0"])
-        self._dgrad(blk, self.wp["conv0"], self.dX0)
+        self._group([self._wgrad_desc(blk, self.X0, "conv0")] + self._dgrad_descs(blk, self.wp["conv0"], self.dX0))
         self._chk(lib.drn_gate_reduce(_vp(self.dX0), C.c_int64(self.C0), _vp(self.Pre), C.c_int64(self.D), C.c_int64(0), 0, B,
                                       self.T, self.D, _vp(self.dq[0]), _vp(self.q[0]), _vp(self.dP_pl.data),
                                       C.c_int64(self.dP_pl.plane_stride), _vp(grads["prop_fc.bias"]), _st()), "gate0_bwd")
@@ -512,15 +536,17 @@ class DensePath:
         self.launches += 30 + self.L
         if self.overlap:
             self._join()
-        # tap-major workspaces -> parameter layout [O][C][k], one launch
+        # partial sums (K-splits x levels) in tap-major workspaces -> parameter layout [O][C][k], one launch
         items = []
         for i in range(3):
-            items.append(self._pack_item(None, None, 0, grads["backbone_net.forward_conv%d.0.weight" % i], self.ws["conv%d" % i]))
-            items.append(self._pack_item(None, None, 0, grads["fpn.fpn_layer%d.0.weight" % (i + 1)], self.ws["layer%d" % i]))
-        items.append(self._pack_item(None, None, 0, grads[h + "cls_tower.0.weight"], self.ws["towers"]))
-        items.append(self._pack_item(None, None, F, grads[h + "bbox_tower.0.weight"], self.ws["towers"]))
+            items.append(self._unpack_item(grads["backbone_net.forward_conv%d.0.weight" % i], "conv%d" % i))
+            items.append(self._unpack_item(grads["fpn.fpn_inner%d.0.weight" % (i + 1)], "inner%d" % i))
+            items.append(self._unpack_item(grads["fpn.fpn_layer%d.0.weight" % (i + 1)], "layer%d" % i))
+        items.append(self._unpack_item(grads[h + "cls_tower.0.weight"], "towers", 0))
+        items.append(self._unpack_item(grads[h + "bbox_tower.0.weight"], "towers", F))
         if iou_on:
-            items.append(self._pack_item(None, None, 0, grads[h + "iou_scores.0.weight"], self.ws["iouc"]))
+            items.append(self._unpack_item(grads[h + "mix_fc.0.weight"], "mix"))
+            items.append(self._unpack_item(grads[h + "iou_scores.0.weight"], "iouc"))
         arr = (L.PackItem * len(items))(*items)
         self._chk(lib.drn_unpack_conv_wgrads(len(items), arr, _st()), "unpack_conv_wgrads")
         # scalar parameter gradients gathered by the loss kernel

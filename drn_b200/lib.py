@@ -29,7 +29,7 @@ class GemmDesc(C.Structure):
         ("a_c0", C.c_int32), ("b_c0", C.c_int32),
         ("nprod", C.c_int32), ("split_k", C.c_int32),
         ("out", C.c_void_p), ("out_ld", C.c_int64), ("out_col0", C.c_int32), ("out_mode", C.c_int32),
-        ("out_tap_stride", C.c_int64),
+        ("out_tap_stride", C.c_int64), ("out_split_stride", C.c_int64),
         ("out_T", C.c_int32), ("out_t_mul", C.c_int32), ("out_t_add", C.c_int32),
         ("bias", C.c_void_p),
         ("rowscale", C.c_void_p), ("rowscale_ld", C.c_int32),
@@ -49,7 +49,7 @@ class BnPart(C.Structure):
 class PackItem(C.Structure):
     _fields_ = [("src", C.c_void_p), ("planes", C.c_void_p), ("grad", C.c_void_p),
                 ("O", C.c_int32), ("C", C.c_int32), ("k", C.c_int32), ("Ototal", C.c_int32), ("o0", C.c_int32),
-                ("plane_stride", C.c_int64)]
+                ("plane_stride", C.c_int64), ("nslices", C.c_int32), ("slice_stride", C.c_int64)]
 
 
 class Qe(C.Structure):

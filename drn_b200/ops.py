@@ -15,10 +15,10 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def gemm(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=0, nprod=None, split_k=1,
-         out=None, out_ld=None, out_col0=0, out_mode=L.OUT_STORE, out_tap_stride=0, out_T=None, out_t_mul=1,
+def desc(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=0, nprod=None, split_k=1,
+         out=None, out_ld=None, out_col0=0, out_mode=L.OUT_STORE, out_tap_stride=0, out_split_stride=0, out_T=None, out_t_mul=1,
          out_t_add=0, bias=None, rowscale=None, out2=None, outp=None, outp_col0=0, engine=None, dbg=(0, 0, 0)):
-    """a, b: L.Planes descriptors.  taps: sequence of (shift, parity, weight_tap).  See include/drn_b200.h."""
+    """Fill a drn_gemm_t.  a, b: L.Planes descriptors.  taps: sequence of (shift, parity, weight_tap).  See include/drn_b200.h."""
     g = L.GemmDesc()
     g.form, g.b_mn = form, b_mn
     g.a, g.b = a, b
@@ -32,7 +32,7 @@ def gemm(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=
     if out is not None:
         g.out = out.data_ptr()
         g.out_ld = out_ld if out_ld is not None else out.shape[-1]
-    g.out_col0, g.out_mode, g.out_tap_stride = out_col0, out_mode, out_tap_stride
+    g.out_col0, g.out_mode, g.out_tap_stride, g.out_split_stride = out_col0, out_mode, out_tap_stride, out_split_stride
     g.out_T = T if out_T is None else out_T
     g.out_t_mul, g.out_t_add = out_t_mul, out_t_add
     if bias is not None:
@@ -50,4 +50,24 @@ def gemm(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=
         g.outp_plane_stride = outp.plane_stride
     g.engine = ENGINE if engine is None else engine
     g.dbg_lbo, g.dbg_sbo, g.dbg_kadv = dbg
+    return g
+
+
+def gemm(*a, **k):
+    """One contraction, one launch (engine chosen by the library)."""
+    g = desc(*a, **k)
     L.check(L.load().drn_gemm(C.byref(g), L.stream_ptr()), "drn_gemm")
+
+
+GROUP_MAX = 6
+
+
+def gemm_group(descs):
+    """Independent contractions in ONE launch of the persistent CTA-pair kernel (drn_gemm_group).  Returns the launch count."""
+    n = 0
+    for i in range(0, len(descs), GROUP_MAX):
+        chunk = descs[i:i + GROUP_MAX]
+        arr = (L.GemmDesc * len(chunk))(*chunk)
+        L.check(L.load().drn_gemm_group(len(chunk), arr, L.stream_ptr()), "drn_gemm_group")
+        n += 1
+    return n

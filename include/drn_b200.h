@@ -92,6 +92,8 @@ typedef struct {
   /* epilogue */
   float* out; int64_t out_ld; int32_t out_col0; int32_t out_mode;
   int64_t out_tap_stride; /* WGRAD: tap i is written at out + tap_w[i]*out_tap_stride */
+  int64_t out_split_stride; /* WGRAD, split_k > 1: != 0 -> K-split s STORES its partial sum at out + s*out_split_stride
+                               (deterministic, no atomics, no zero-fill; the caller sums the slices, see drn_unpack_conv_wgrads) */
   int32_t out_T, out_t_mul, out_t_add;
   const float* bias;
   const float* rowscale; int32_t rowscale_ld;
@@ -103,6 +105,10 @@ typedef struct {
 } drn_gemm_t;
 
 int drn_gemm(const drn_gemm_t* g, void* stream);
+/* ONE launch of the persistent CTA-pair kernel over the 256 x 256 tiles of n <= 6 independent problems (any mix of forms):
+ * the three pyramid levels of a shared head / FPN conv, or the data- and weight-gradients of one layer.  Small problems
+ * launched one by one leave most of the 148 SMs idle and each pay pipeline fill and drain. */
+int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound kernels (drn_b200/csrc/elementwise.cu).  "planes" arguments are the hi plane pointer of a
@@ -117,13 +123,16 @@ int drn_gate_planes(const float* x, const float* q, int B, int T, int C, void* d
                     int64_t dst_plane_stride, void* stream);
 /* Table-driven weight packing, ONE launch for all layers.  Item: nn.Conv1d / nn.Linear weight `src` [O][C][k] fp32 ->
  * planes [k][Ototal][C] at row offset o0 (tap-major operand of drn_gemm).  drn_unpack_conv_wgrads goes the other way for
- * weight gradients: workspace `src` [k][Ototal][C] fp32 -> parameter gradient `grad` [O][C][k]. */
+ * weight gradients: workspace `src` [nslices][k][Ototal][C] fp32 (partial sums of the K-splits / pyramid levels, see
+ * drn_gemm_t.out_split_stride) -> parameter gradient `grad` [O][C][k] = sum over the slices. */
 typedef struct {
   const float* src;
   void* planes;   /* pack: destination hi plane */
   float* grad;    /* unpack: destination */
   int32_t O, C, k, Ototal, o0;
   int64_t plane_stride;
+  int32_t nslices;      /* unpack: `src` holds nslices partial sums [k][Ototal][C], slice_stride elements apart, to be added */
+  int64_t slice_stride;
 } drn_pack_item_t;
 int drn_pack_conv_weights(int n, const drn_pack_item_t* items, void* stream);
 int drn_unpack_conv_wgrads(int n, const drn_pack_item_t* items, void* stream);

@@ -158,3 +158,59 @@ def test_epilogue_options(engine):
     ref0 = ref_rows(a, w, ((0, 0, 0),), 1, B, T, N, Cin, 0)
     assert (out[:, 1::2].double() - ref0).abs().max().item() / s < 2e-5
     assert out[:, 0::2].abs().max().item() == 0
+
+
+def test_group_mixed_forms_and_split_slices():
+    """drn_gemm_group: three ROWS problems of different sizes (the pyramid levels of a shared conv), a stride-2 data gradient
+    pair and a weight gradient whose K-splits store their partial sums in slices (no atomics), all in ONE launch."""
+    descs, checks, keep = [], [], []  # descriptors hold raw pointers: keep every operand alive until the launch
+    w = Planes.from_float(_rand(3, 512, 256, seed=11, scale=(3 * 256) ** -0.5))
+    for i, T in enumerate((256, 128, 64)):
+        a = Planes.from_float(_rand(4, T, 256, seed=20 + i))
+        keep.append(a)
+        out = torch.full((4, T, 512), float("nan"), device=DEV)
+        descs.append(ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), 4, T, 512, K=256, taps=K3, out=out, engine=2))
+        checks.append((out, ref_rows(a, w, K3, 1, 4, T, 512, 256, 0)))
+    # weight gradient with 3 K-splits -> 3 slices, summed by the caller
+    B, T, Co, Ci = 6, 128, 256, 320
+    dy, x = Planes.from_float(_rand(B, T, Co, seed=31)), Planes.from_float(_rand(B, T, Ci, seed=32))
+    ws = torch.full((3, 3, Co, Ci), float("nan"), device=DEV)
+    descs.append(ops.desc(L.GEMM_WGRAD, dy.desc(), x.desc(), B, T, Ci, M=Co, taps=K3, out=ws[0], out_ld=Ci,
+                          out_tap_stride=Co * Ci, out_split_stride=ws.stride(0), split_k=3, engine=2))
+    DY, X = dy.to_float().double(), x.to_float().double()
+    ref_w = torch.zeros(3, Co, Ci, dtype=torch.float64, device=DEV)
+    for (sh, par, wt) in K3:
+        src = torch.zeros(B, T, Ci, dtype=torch.float64, device=DEV)
+        lo, hi = max(0, -sh), min(T, T - sh)
+        src[:, lo:hi] = X[:, lo + sh:hi + sh]
+        ref_w[wt] = torch.einsum("bto,btc->oc", DY, src)
+    assert ops.gemm_group(descs) == 1
+    torch.cuda.synchronize()
+    for out, ref in checks:
+        assert (out.double() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+    assert not torch.isnan(ws).any()
+    assert (ws.double().sum(0) - ref_w).abs().max().item() / ref_w.abs().max().item() < 2e-5
+    # deterministic: a second launch reproduces every slice bit for bit
+    ws2 = ws.clone()
+    ops.gemm_group(descs)
+    torch.cuda.synchronize()
+    assert torch.equal(ws, ws2)
+
+
+def test_group_rejects_bad_arguments():
+    a = Planes.from_float(_rand(2, 128, 128, seed=1))
+    w = Planes.from_float(_rand(1, 128, 128, seed=2))
+    out = torch.zeros(2, 128, 128, device=DEV)
+    d = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), 2, 128, 128, K=128, out=out, engine=2)
+    arr = (L.GemmDesc * 7)(*([d] * 7))
+    assert L.load().drn_gemm_group(7, arr, L.stream_ptr()) == -1
+    d1 = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), 2, 128, 128, K=128, out=out, engine=1)
+    arr = (L.GemmDesc * 1)(d1)
+    assert L.load().drn_gemm_group(1, arr, L.stream_ptr()) == -1
+    # more K-splits than K-blocks would leave slices unwritten
+    dy, x = Planes.from_float(_rand(1, 64, 128, seed=3)), Planes.from_float(_rand(1, 64, 128, seed=4))
+    ws = torch.zeros(4, 1, 128, 128, device=DEV)
+    d2 = ops.desc(L.GEMM_WGRAD, dy.desc(), x.desc(), 1, 64, 128, M=128, out=ws[0], out_ld=128, out_tap_stride=128 * 128,
+                  out_split_stride=ws.stride(0), split_k=4, engine=2)
+    arr = (L.GemmDesc * 1)(d2)
+    assert L.load().drn_gemm_group(1, arr, L.stream_ptr()) == -1
