@@ -106,9 +106,9 @@ def time_dominant_kernel(path, p, reps=10):
     from drn_b200 import ops
     D = path.D
 
-    def launch():
+    def launch():  # exactly the call DensePath.forward_core makes for prop_fc (model/main_model.py:59)
         ops.gemm(L.GEMM_ROWS, path.f_pl.desc(), path.wp["prop_fc"].desc(), path.B, path.T, D, K=D, bias=p["prop_fc.bias"],
-                 out2=path.Pre, rowscale=path.q[0], outp=path.X0)
+                 out=path.Pre)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     tot = 0.0
     for i in range(reps + 2):
@@ -234,6 +234,10 @@ def run_ours(args):
     pk, pk_src = peaks()
     k_ms, k_flops = time_dominant_kernel(path, core._tensor_dict())
     achieved = k_flops / (k_ms * 1e-3) / 1e12
+    traffic = None  # DRAM bytes of one prop_fc forward launch from the committed `ncu --set full` capture (profiles/)
+    tp = os.path.join(REPO, "profiles", "r01_prop_fc_fwd_traffic.json")
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     value = world * B_PER_GPU / (ms * 1e-3)
     line = {
         "metric": "video-query pairs/sec (fwd+bwd) at T=256 C3D-4096", "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -246,11 +250,15 @@ def run_ours(args):
         "e2e": {"value": world * B_PER_GPU / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<256> (prop_fc forward, M=8192 N=K=4096)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_pair_kernel (prop_fc forward, M=8192 N=K=4096: 27 % of the step's FLOPs; "
+                     "the same kernel runs every contraction of the path)",
                      "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],
-                     "traffic": None, "peak_source": pk_src + " burst cuBLAS bf16",
-                     "note": "algorithmic fp32 FLOPs; the kernel issues 3 BF16 MMAs per product, so issued-MMA rate = 3x achieved",
-                     "ms_per_launch": k_ms},
+                     "traffic": traffic, "peak_source": pk_src + " burst cuBLAS bf16 (kernel timed alone, L2 flushed between launches)",
+                     "note": "achieved = ALGORITHMIC fp32 FLOPs (2*M*N*K) / launch time; parity mode issues 3 BF16 MMAs per "
+                             "product (hi*hi + hi*lo + lo*hi), so the issued-MMA rate is 3x achieved and frac_issued = 3x frac",
+                     "frac_issued": 3.0 * achieved / pk["bf16_tflops"], "ms_per_launch": k_ms,
+                     "step_algorithmic_tflops_per_gpu": value / world * FLOP_PER_PAIR / 1e12,
+                     "step_frac_of_sustained_peak_issued": 3.0 * value / world * FLOP_PER_PAIR / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"])},
     }
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on the host cores
     if world == 1 and not args.no_cpu_baseline:

@@ -13,6 +13,7 @@
 //     ROWS (conv forward / dgrad) and WGRAD problems mix freely in a group.
 // Operand forms, tensor maps and epilogue semantics are those of gemm.cu (include/drn_b200.h).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "gemm_common.cuh"
 
@@ -280,6 +281,12 @@ int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaS
   }
   const int num_tiles = gp.tile_start[gp.nprob];
   int clusters = sm_count / 2;
+  static int cap = -1;  // DRN_PAIR_CLUSTERS: leave SM pairs free for kernels of other streams (tuning / probing knob)
+  if (cap < 0) {
+    const char* e = getenv("DRN_PAIR_CLUSTERS");
+    cap = e ? atoi(e) : 0;
+  }
+  if (cap > 0 && clusters > cap) clusters = cap;
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
   gemm_pair_kernel<<<2 * clusters, P2_THREADS, P2_SMEM, st>>>(gp, gm, num_tiles);

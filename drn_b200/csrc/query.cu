@@ -129,6 +129,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
   }
 }
 
+// The query-encoder kernels are meant to run BESIDE the persistent tcgen05 GEMM (which configures every SM for the maximum
+// shared-memory carve-out); a kernel preferring a different L1/shared split cannot become co-resident on such an SM.
+template <typename F>
+static void prefer_max_smem(F* fn) {
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 // accumulate = 0: C is overwritten; 1: C += (C must hold valid data, e.g. a zeroed gradient buffer)
 static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
                  float* C, long long ldc, int M, int N, int K, const float* bias, const float* bias2, int relu, int accumulate,
@@ -148,6 +155,12 @@ static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, 
   if (splits > 1 && !accumulate) {
     cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, N * sizeof(float), M, st);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_sgemm memset: %s", cudaGetErrorString(e));
+  }
+  static bool carve = false;
+  if (!carve) {
+    prefer_max_smem(sgemm_kernel<32>);
+    prefer_max_smem(sgemm_kernel<64>);
+    carve = true;
   }
   dim3 grid(ceil_div(M, bm), ceil_div(N, 64), splits);
   if (bm == 32) sgemm_kernel<32><<<grid, 256, 0, st>>>(p);
