@@ -185,6 +185,35 @@ struct BnParts {  // the fused cls|bbox tower output carries two BatchNorm modul
   float* dbeta[BN_MAX_PARTS];
 };
 
+// One BatchNorm application (a conv block on one pyramid level).  Up to BN_MAX_JOBS independent applications -- the three
+// levels of a shared head / FPN block -- are served by ONE launch (blockIdx.z / blockIdx.y = job).
+constexpr int BN_MAX_JOBS = 3;
+struct BnJob {
+  const float* y;
+  const float* da;
+  long long rows;
+  int B, T, C;
+  float* coef;
+  double* sums;
+  unsigned* counter;
+  float* bcoef;
+  BnParts parts;
+  const __nv_bfloat16* up;
+  long long up_ps;
+  const float* gate;
+  __nv_bfloat16* out_a;
+  long long a_ps;
+  __nv_bfloat16* out_qa;
+  long long qa_ps;
+  __nv_bfloat16* dy;
+  long long dy_ps;
+};
+struct BnJobs {
+  int n;
+  BnJob j[BN_MAX_JOBS];
+};
+
+// coef rows: 0 scale, 1 shift, 2 batch mean, 3 invstd, 4 unbiased batch variance (what the running average absorbs)
 __device__ __forceinline__ void bn_coef_from_stats(double mean, double var, float gamma, float beta, float eps, int c, int C,
                                                    float* coef) {
   const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -196,15 +225,23 @@ __device__ __forceinline__ void bn_coef_from_stats(double mean, double var, floa
 }
 
 template <int MODE>  // 0: sum y, sum y^2 ; 1: BN backward sums (sum g, sum g*xhat) with g = relu-masked da
-__global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict__ y, const float* __restrict__ da,
-                                                        long long rows, int C, float* __restrict__ coef,
-                                                        double* __restrict__ sums, unsigned* __restrict__ counter,
-                                                        BnParts parts, float momentum, float eps, float* __restrict__ bcoef) {
+__global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float momentum, float eps, int update_running) {
   __shared__ float red[2][8][128];
   __shared__ bool is_last;
+  const BnJob& J = jobs.j[blockIdx.z];
+  const float* __restrict__ y = J.y;
+  const float* __restrict__ da = J.da;
+  const long long rows = J.rows;
+  const int C = J.C;
+  float* __restrict__ coef = J.coef;
+  double* __restrict__ sums = J.sums;
+  unsigned* __restrict__ counter = J.counter;
+  float* __restrict__ bcoef = J.bcoef;
+  const BnParts& parts = J.parts;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 128 + tx * 4;
   const long long r0 = static_cast<long long>(blockIdx.y) * STAT_ROWS;
+  if (blockIdx.x * 128 >= C || r0 >= rows) return;  // block outside this job's extent (grid is sized for the largest job)
   float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
   if (c < C) {
     float sc[4], sh[4], mu[4], is[4];
@@ -258,7 +295,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
   __threadfence();
   __syncthreads();
   if (t == 0) {
-    const unsigned total = gridDim.x * gridDim.y;
+    const unsigned total = static_cast<unsigned>((C + 127) / 128) * static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS);
     is_last = (atomicAdd(counter, 1u) == total - 1);
   }
   __syncthreads();
@@ -276,25 +313,52 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const float* __restrict_
         double var = a1 / n - mean * mean;
         if (var < 0) var = 0;
         const double unbiased = (rows > 1) ? var * n / (n - 1.0) : var;
-        parts.running_mean[p][i] = (1.f - momentum) * parts.running_mean[p][i] + momentum * static_cast<float>(mean);
-        parts.running_var[p][i] = (1.f - momentum) * parts.running_var[p][i] + momentum * static_cast<float>(unbiased);
+        if (update_running) {
+          parts.running_mean[p][i] = (1.f - momentum) * parts.running_mean[p][i] + momentum * static_cast<float>(mean);
+          parts.running_var[p][i] = (1.f - momentum) * parts.running_var[p][i] + momentum * static_cast<float>(unbiased);
+        }
+        coef[4 * C + cc] = static_cast<float>(unbiased);
         bn_coef_from_stats(mean, var, parts.gamma[p][i], parts.beta[p][i], eps, cc, C, coef);
       } else {
         bcoef[cc] = static_cast<float>(a0 / n);
         bcoef[C + cc] = static_cast<float>(a1 / n);
-        if (parts.dgamma[p]) {
-          parts.dbeta[p][i] += static_cast<float>(a0);
-          parts.dgamma[p][i] += static_cast<float>(a1);
+        if (parts.dgamma[p]) {  // atomics: the levels of a shared head block finalise concurrently in one launch
+          atomicAdd(parts.dbeta[p] + i, static_cast<float>(a0));
+          atomicAdd(parts.dgamma[p] + i, static_cast<float>(a1));
         }
       }
     }
-    if (MODE == 0 && t == 0 && parts.nbt[p]) parts.nbt[p][0] += 1;
+    if (MODE == 0 && update_running && t == 0 && parts.nbt[p]) parts.nbt[p][0] += 1;
   }
   if (t == 0) *counter = 0u;
 }
 
+// ---- ordered running-statistics update of jobs that SHARE BatchNorm modules (the head applied to three pyramid levels,
+// model/fcos.py:93-102): running <- (1-m) running + m stat, job after job, exactly the order of the reference's level loop.
+__global__ void bn_running_update_kernel(const BnJobs jobs, float momentum) {
+  const int p = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jobs.j[0].parts.n[p]; i += gridDim.x * blockDim.x) {
+    for (int k = 0; k < jobs.n; ++k) {
+      const BnJob& J = jobs.j[k];
+      if (p >= J.parts.nparts) continue;
+      const int cc = J.parts.c0[p] + i;
+      float* rm = J.parts.running_mean[p] + i;
+      float* rv = J.parts.running_var[p] + i;
+      *rm = (1.f - momentum) * *rm + momentum * J.coef[2 * J.C + cc];
+      *rv = (1.f - momentum) * *rv + momentum * J.coef[4 * J.C + cc];
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int k = 0; k < jobs.n; ++k)
+      if (p < jobs.j[k].parts.nparts && jobs.j[k].parts.nbt[p]) jobs.j[k].parts.nbt[p][0] += 1;
+}
+
 // ---- eval-mode BN: coefficients from the running statistics ----------------------------------------------------------------
-__global__ void bn_eval_coef_kernel(int C, BnParts parts, float eps, float* __restrict__ coef) {
+__global__ void bn_eval_coef_kernel(const BnJobs jobs, float eps) {
+  const BnJob& J = jobs.j[blockIdx.y];
+  const int C = J.C;
+  const BnParts& parts = J.parts;
+  float* __restrict__ coef = J.coef;
   for (int p = 0; p < parts.nparts; ++p)
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < parts.n[p]; i += gridDim.x * blockDim.x)
       bn_coef_from_stats(parts.running_mean[p][i], parts.running_var[p][i], parts.gamma[p][i], parts.beta[p][i], eps,
@@ -302,12 +366,18 @@ __global__ void bn_eval_coef_kernel(int C, BnParts parts, float eps, float* __re
 }
 
 // ---- BN apply + ReLU (+ nearest x2 upsample add, + query gate) -> planes ---------------------------------------------
-__global__ void __launch_bounds__(EW_THREADS) bn_relu_apply_kernel(const float* __restrict__ y, int B, int T, int C,
-                                                                   const float* __restrict__ coef,
-                                                                   const __nv_bfloat16* __restrict__ up, long long up_ps,
-                                                                   const float* __restrict__ gate,
-                                                                   __nv_bfloat16* __restrict__ out_a, long long a_ps,
-                                                                   __nv_bfloat16* __restrict__ out_qa, long long qa_ps) {
+__global__ void __launch_bounds__(EW_THREADS) bn_relu_apply_kernel(const BnJobs jobs) {
+  const BnJob& J = jobs.j[blockIdx.y];
+  const float* __restrict__ y = J.y;
+  const int B = J.B, T = J.T, C = J.C;
+  const float* __restrict__ coef = J.coef;
+  const __nv_bfloat16* __restrict__ up = J.up;
+  const long long up_ps = J.up_ps;
+  const float* __restrict__ gate = J.gate;
+  __nv_bfloat16* __restrict__ out_a = J.out_a;
+  const long long a_ps = J.a_ps;
+  __nv_bfloat16* __restrict__ out_qa = J.out_qa;
+  const long long qa_ps = J.qa_ps;
   const int C8 = C >> 3;
   const long long total = static_cast<long long>(B) * T * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -339,10 +409,16 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_apply_kernel(const float* 
 }
 
 // ---- BN backward apply: dy = scale * (g - mean(g) - xhat * mean(g*xhat)) -> planes ------------------------------------
-__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ da, const float* __restrict__ y,
-                                                                  long long rows, int C, const float* __restrict__ coef,
-                                                                  const float* __restrict__ bcoef,
-                                                                  __nv_bfloat16* __restrict__ dy, long long dy_ps) {
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnJobs jobs) {
+  const BnJob& J = jobs.j[blockIdx.y];
+  const float* __restrict__ da = J.da;
+  const float* __restrict__ y = J.y;
+  const long long rows = J.rows;
+  const int C = J.C;
+  const float* __restrict__ coef = J.coef;
+  const float* __restrict__ bcoef = J.bcoef;
+  __nv_bfloat16* __restrict__ dy = J.dy;
+  const long long dy_ps = J.dy_ps;
   const int C8 = C >> 3;
   const long long total = rows * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -575,50 +651,146 @@ static int fill_parts(BnParts* bp, int nparts, const drn_bn_part_t* parts) {
   return 0;
 }
 
-extern "C" int drn_bn_stats(const float* y, int64_t rows, int C, int nparts, const drn_bn_part_t* parts, float momentum, float eps,
-                            int training, float* coef, double* sums, unsigned* counter, void* stream) {
-  if (C % 4) return fail(DRN_EINVAL, "drn_bn_stats: C %% 4");
-  BnParts bp;
-  int rc = fill_parts(&bp, nparts, parts);
+static int fill_jobs(BnJobs* t, int n, const drn_bn_job_t* jobs, const char* who) {
+  if (n < 1 || n > BN_MAX_JOBS) return fail(DRN_EINVAL, "%s: 1..%d jobs (got %d)", who, BN_MAX_JOBS, n);
+  t->n = n;
+  for (int i = 0; i < n; ++i) {
+    const drn_bn_job_t& s = jobs[i];
+    BnJob& d = t->j[i];
+    if (s.C % 8 || s.B < 1 || s.T < 1) return fail(DRN_EINVAL, "%s: job %d needs C %% 8 == 0 and B, T >= 1 (C=%d)", who, i, s.C);
+    d.y = s.y; d.da = s.da;
+    d.rows = static_cast<long long>(s.B) * s.T;
+    d.B = s.B; d.T = s.T; d.C = s.C;
+    d.coef = s.coef; d.sums = s.sums; d.counter = s.counter; d.bcoef = s.bcoef;
+    int rc = fill_parts(&d.parts, s.nparts, s.parts);
+    if (rc) return rc;
+    d.up = static_cast<const __nv_bfloat16*>(s.up); d.up_ps = s.up_plane_stride;
+    d.gate = s.gate;
+    d.out_a = static_cast<__nv_bfloat16*>(s.out_a); d.a_ps = s.a_plane_stride;
+    d.out_qa = static_cast<__nv_bfloat16*>(s.out_qa); d.qa_ps = s.qa_plane_stride;
+    d.dy = static_cast<__nv_bfloat16*>(s.dy); d.dy_ps = s.dy_plane_stride;
+  }
+  return 0;
+}
+
+static void stats_grid(const BnJobs& t, dim3* grid) {
+  int cmax = 0;
+  long long rmax = 0;
+  for (int i = 0; i < t.n; ++i) {
+    cmax = t.j[i].C > cmax ? t.j[i].C : cmax;
+    rmax = t.j[i].rows > rmax ? t.j[i].rows : rmax;
+  }
+  *grid = dim3(ceil_div(cmax, 128), static_cast<unsigned>((rmax + STAT_ROWS - 1) / STAT_ROWS), t.n);
+}
+static int ew_grid_jobs(const BnJobs& t) {
+  long long m = 0;
+  for (int i = 0; i < t.n; ++i) {
+    const long long tot = t.j[i].rows * (t.j[i].C / 8);
+    m = tot > m ? tot : m;
+  }
+  return ew_grid(m);
+}
+
+extern "C" int drn_bn_stats_multi(int n, const drn_bn_job_t* jobs, float momentum, float eps, int training, void* stream) {
+  BnJobs t{};
+  int rc = fill_jobs(&t, n, jobs, "drn_bn_stats_multi");
   if (rc) return rc;
   if (!training) {
-    bn_eval_coef_kernel<<<ceil_div(C, 256), 256, 0, ST(stream)>>>(C, bp, eps, coef);
+    int cmax = 0;
+    for (int i = 0; i < n; ++i) cmax = t.j[i].C > cmax ? t.j[i].C : cmax;
+    bn_eval_coef_kernel<<<dim3(ceil_div(cmax, 256), n), 256, 0, ST(stream)>>>(t, eps);
     return check_launch("bn_eval_coef");
   }
-  dim3 grid(ceil_div(C, 128), static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS));
-  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, nullptr, rows, C, coef, sums, counter, bp, momentum, eps, nullptr);
+  dim3 grid;
+  stats_grid(t, &grid);
+  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, momentum, eps, training == 1 ? 1 : 0);
   return check_launch("bn_stats");
 }
 
-extern "C" int drn_bn_relu_apply(const float* y, int B, int T, int C, const float* coef, const void* up, int64_t up_plane_stride,
-                                 const float* gate, void* out_a, int64_t a_plane_stride, void* out_qa, int64_t qa_plane_stride,
-                                 void* stream) {
-  if (C % 8) return fail(DRN_EINVAL, "drn_bn_relu_apply: C %% 8");
-  if (up && (T % 2)) return fail(DRN_EINVAL, "drn_bn_relu_apply: upsample-add needs even T");
-  if (out_qa && !gate) return fail(DRN_EINVAL, "drn_bn_relu_apply: gated output without gate");
-  bn_relu_apply_kernel<<<ew_grid(static_cast<long long>(B) * T * (C / 8)), EW_THREADS, 0, ST(stream)>>>(
-      y, B, T, C, coef, static_cast<const __nv_bfloat16*>(up), up_plane_stride, gate, static_cast<__nv_bfloat16*>(out_a),
-      a_plane_stride, static_cast<__nv_bfloat16*>(out_qa), qa_plane_stride);
+extern "C" int drn_bn_running_update(int n, const drn_bn_job_t* jobs, float momentum, void* stream) {
+  BnJobs t{};
+  int rc = fill_jobs(&t, n, jobs, "drn_bn_running_update");
+  if (rc) return rc;
+  for (int i = 1; i < n; ++i)
+    if (t.j[i].parts.nparts != t.j[0].parts.nparts) return fail(DRN_EINVAL, "drn_bn_running_update: jobs must share their BatchNorm modules");
+  int nmax = 0;
+  for (int p = 0; p < t.j[0].parts.nparts; ++p) nmax = t.j[0].parts.n[p] > nmax ? t.j[0].parts.n[p] : nmax;
+  bn_running_update_kernel<<<dim3(ceil_div(nmax, 256), t.j[0].parts.nparts), 256, 0, ST(stream)>>>(t, momentum);
+  return check_launch("bn_running_update");
+}
+
+extern "C" int drn_bn_relu_apply_multi(int n, const drn_bn_job_t* jobs, void* stream) {
+  BnJobs t{};
+  int rc = fill_jobs(&t, n, jobs, "drn_bn_relu_apply_multi");
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    if (t.j[i].up && (t.j[i].T % 2)) return fail(DRN_EINVAL, "drn_bn_relu_apply: upsample-add needs even T");
+    if (t.j[i].out_qa && !t.j[i].gate) return fail(DRN_EINVAL, "drn_bn_relu_apply: gated output without gate");
+  }
+  bn_relu_apply_kernel<<<dim3(ew_grid_jobs(t), n), EW_THREADS, 0, ST(stream)>>>(t);
   return check_launch("bn_relu_apply");
 }
 
-extern "C" int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, float* coef, int nparts,
-                                 const drn_bn_part_t* parts, double* sums, unsigned* counter, float* bcoef, void* stream) {
-  if (C % 4) return fail(DRN_EINVAL, "drn_bn_bwd_reduce: C %% 4");
-  BnParts bp;
-  int rc = fill_parts(&bp, nparts, parts);
+extern "C" int drn_bn_bwd_reduce_multi(int n, const drn_bn_job_t* jobs, void* stream) {
+  BnJobs t{};
+  int rc = fill_jobs(&t, n, jobs, "drn_bn_bwd_reduce_multi");
   if (rc) return rc;
-  dim3 grid(ceil_div(C, 128), static_cast<unsigned>((rows + STAT_ROWS - 1) / STAT_ROWS));
-  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(y, da, rows, C, coef, sums, counter, bp, 0.f, 0.f, bcoef);
+  dim3 grid;
+  stats_grid(t, &grid);
+  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, 0.f, 0.f, 0);
   return check_launch("bn_bwd_reduce");
 }
 
+extern "C" int drn_bn_bwd_apply_multi(int n, const drn_bn_job_t* jobs, void* stream) {
+  BnJobs t{};
+  int rc = fill_jobs(&t, n, jobs, "drn_bn_bwd_apply_multi");
+  if (rc) return rc;
+  bn_bwd_apply_kernel<<<dim3(ew_grid_jobs(t), n), EW_THREADS, 0, ST(stream)>>>(t);
+  return check_launch("bn_bwd_apply");
+}
+
+// single-application forms
+static drn_bn_job_t one_job(const float* y, int64_t rows, int B, int T, int C, int nparts, const drn_bn_part_t* parts) {
+  drn_bn_job_t j{};
+  j.y = y;
+  j.B = B > 0 ? B : 1;
+  j.T = B > 0 ? T : static_cast<int>(rows);
+  j.C = C;
+  j.nparts = nparts;
+  for (int i = 0; i < nparts && i < 2; ++i) j.parts[i] = parts[i];
+  return j;
+}
+extern "C" int drn_bn_stats(const float* y, int64_t rows, int C, int nparts, const drn_bn_part_t* parts, float momentum, float eps,
+                            int training, float* coef, double* sums, unsigned* counter, void* stream) {
+  if (nparts < 1 || nparts > 2) return fail(DRN_EINVAL, "drn_bn_stats: 1..2 parts");
+  drn_bn_job_t j = one_job(y, rows, 0, 0, C, nparts, parts);
+  j.coef = coef; j.sums = sums; j.counter = counter;
+  return drn_bn_stats_multi(1, &j, momentum, eps, training, stream);
+}
+extern "C" int drn_bn_relu_apply(const float* y, int B, int T, int C, const float* coef, const void* up, int64_t up_plane_stride,
+                                 const float* gate, void* out_a, int64_t a_plane_stride, void* out_qa, int64_t qa_plane_stride,
+                                 void* stream) {
+  static const drn_bn_part_t none{};
+  drn_bn_job_t j = one_job(y, 0, B, T, C, 1, &none);
+  j.coef = const_cast<float*>(coef);
+  j.up = up; j.up_plane_stride = up_plane_stride; j.gate = gate;
+  j.out_a = out_a; j.a_plane_stride = a_plane_stride; j.out_qa = out_qa; j.qa_plane_stride = qa_plane_stride;
+  return drn_bn_relu_apply_multi(1, &j, stream);
+}
+extern "C" int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, float* coef, int nparts,
+                                 const drn_bn_part_t* parts, double* sums, unsigned* counter, float* bcoef, void* stream) {
+  if (nparts < 1 || nparts > 2) return fail(DRN_EINVAL, "drn_bn_bwd_reduce: 1..2 parts");
+  drn_bn_job_t j = one_job(y, rows, 0, 0, C, nparts, parts);
+  j.da = da; j.coef = coef; j.sums = sums; j.counter = counter; j.bcoef = bcoef;
+  return drn_bn_bwd_reduce_multi(1, &j, stream);
+}
 extern "C" int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const float* bcoef,
                                 void* dy, int64_t dy_plane_stride, void* stream) {
-  if (C % 8) return fail(DRN_EINVAL, "drn_bn_bwd_apply: C %% 8");
-  bn_bwd_apply_kernel<<<ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream)>>>(da, y, rows, C, coef, bcoef,
-                                                                              static_cast<__nv_bfloat16*>(dy), dy_plane_stride);
-  return check_launch("bn_bwd_apply");
+  static const drn_bn_part_t none{};
+  drn_bn_job_t j = one_job(y, rows, 0, 0, C, 1, &none);
+  j.da = da; j.coef = const_cast<float*>(coef); j.bcoef = const_cast<float*>(bcoef);
+  j.dy = dy; j.dy_plane_stride = dy_plane_stride;
+  return drn_bn_bwd_apply_multi(1, &j, stream);
 }
 
 extern "C" int drn_pair_sum_add(float* dst, const float* src, int64_t rows_half, int C, void* stream) {

@@ -83,35 +83,48 @@ __global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict
       }
   const long long rows = static_cast<long long>(B) * T;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
-  for (int i = 0; i < rows_per_block; ++i) {
-    const long long row = r0 + i;
-    if (row >= rows) break;
-    const int t = static_cast<int>(row % T);
-    const __nv_bfloat16* xp = x + row * x_ld + c0 + c;
-    const uint32_t xh = *reinterpret_cast<const uint32_t*>(xp), xl = *reinterpret_cast<const uint32_t*>(xp + x_ps);
-    const float xv[2] = {__uint_as_float(xh << 16) + __uint_as_float(xl << 16),
-                         __uint_as_float(xh & 0xffff0000u) + __uint_as_float(xl & 0xffff0000u)};
-    float g[2] = {0.f, 0.f};
+  constexpr int U = 4;  // rows in flight per thread: the activation loads of U rows are issued before any of them is used
+  for (int i0 = 0; i0 < rows_per_block; i0 += U) {
+    uint32_t xh[U], xl[U];
 #pragma unroll
-    for (int r = 0; r < K; ++r) {
-      const int td = t + PAD - r;
-      if (td < 0 || td >= T) continue;
-#pragma unroll
-      for (int o = 0; o < NOUT; ++o) {
-        const float e = __ldg(d + (row + PAD - r) * NOUT + o);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          g[h] = fmaf(e, w[h][o][r], g[h]);
-          gw[h][o][r] = fmaf(e, xv[h], gw[h][o][r]);
-        }
+    for (int u = 0; u < U; ++u) {
+      const long long row = r0 + i0 + u;
+      xh[u] = xl[u] = 0u;
+      if (i0 + u < rows_per_block && row < rows) {
+        const __nv_bfloat16* xp = x + row * x_ld + c0 + c;
+        xh[u] = *reinterpret_cast<const uint32_t*>(xp);
+        xl[u] = *reinterpret_cast<const uint32_t*>(xp + x_ps);
       }
     }
-    float2* dp = reinterpret_cast<float2*>(dx + row * dx_ld + c0 + c);
-    if (dx_accumulate) {
-      const float2 old = *dp;
-      *dp = make_float2(old.x + g[0], old.y + g[1]);
-    } else {
-      *dp = make_float2(g[0], g[1]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long row = r0 + i0 + u;
+      if (i0 + u >= rows_per_block || row >= rows) break;
+      const int t = static_cast<int>(row % T);
+      const float xv[2] = {__uint_as_float(xh[u] << 16) + __uint_as_float(xl[u] << 16),
+                           __uint_as_float(xh[u] & 0xffff0000u) + __uint_as_float(xl[u] & 0xffff0000u)};
+      float g[2] = {0.f, 0.f};
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+        const int td = t + PAD - r;
+        if (td < 0 || td >= T) continue;
+#pragma unroll
+        for (int o = 0; o < NOUT; ++o) {
+          const float e = __ldg(d + (row + PAD - r) * NOUT + o);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            g[h] = fmaf(e, w[h][o][r], g[h]);
+            gw[h][o][r] = fmaf(e, xv[h], gw[h][o][r]);
+          }
+        }
+      }
+      float2* dp = reinterpret_cast<float2*>(dx + row * dx_ld + c0 + c);
+      if (dx_accumulate) {
+        const float2 old = *dp;
+        *dp = make_float2(old.x + g[0], old.y + g[1]);
+      } else {
+        *dp = make_float2(g[0], g[1]);
+      }
     }
   }
   if (dW) {
@@ -361,8 +374,10 @@ extern "C" int drn_skinny_conv_bwd(const float* d, const void* x, int64_t x_plan
                                    int nout, int k, const float* W, float* dx, int dx_ld, int dx_accumulate, float* dW,
                                    void* stream) {
   if (Cw % 2 || c0 % 2 || dx_ld % 2 || x_ld % 2) return fail(DRN_EINVAL, "drn_skinny_conv_bwd: alignment");
-  const int rpb = 16;
-  dim3 grid(ceil_div(Cw, 512), static_cast<unsigned>((static_cast<long long>(B) * T + rpb - 1) / rpb));
+  const long long rows_total = static_cast<long long>(B) * T;
+  int rpb = 16;  // ~2 waves of CTAs: fewer, longer CTAs cut the dW atomics (one set per CTA) without starving the SMs
+  while (rpb < 64 && rows_total / rpb > 2 * 148) rpb *= 2;
+  dim3 grid(ceil_div(Cw, 512), static_cast<unsigned>((rows_total + rpb - 1) / rpb));
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
   if (nout == 1 && k == 3) skinny_bwd_kernel<1, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
   else if (nout == 2 && k == 3) skinny_bwd_kernel<2, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);

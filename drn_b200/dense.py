@@ -44,7 +44,7 @@ class ConvBN:
         self.t_in, self.t_out = t_in, t_in // stride
         self.rows = B * self.t_out
         self.y = torch.empty(B, self.t_out, cout, device=dev)
-        self.coef = torch.empty(4, cout, device=dev)
+        self.coef = torch.empty(5, cout, device=dev)
         self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)   # kept zero between uses by the kernels
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bcoef = torch.empty(2, cout, device=dev)
@@ -240,33 +240,58 @@ class DensePath:
         self._chk(_lib().drn_pack_conv_weights(len(items), arr, _st()), "pack_conv_weights")
         torch.cat([p[h + "cls_tower.0.bias"], p[h + "bbox_tower.0.bias"]], out=self.tower_bias)
 
-    @staticmethod
-    def _bn_parts(blk, p, grads=None):
-        arr = (L.BnPart * len(blk.bn_parts))()
+    def _bn_job(self, blk, p, grads=None, da=None, out_a=None, up=None, gate=None, out_qa=None):
+        """drn_bn_job_t of one conv block (model/basic_blocks.py:22-30): statistics / apply / backward operands."""
+        j = L.BnJob()
+        j.y, j.B, j.T, j.C = blk.y.data_ptr(), self.B, blk.t_out, blk.cout
+        j.nparts = len(blk.bn_parts)
         for i, (pre, c0, n) in enumerate(blk.bn_parts):
-            a = arr[i]
+            a = j.parts[i]
             a.c0, a.n = c0, n
             a.gamma, a.beta = p[pre + ".weight"].data_ptr(), p[pre + ".bias"].data_ptr()
             a.running_mean, a.running_var = p[pre + ".running_mean"].data_ptr(), p[pre + ".running_var"].data_ptr()
             a.num_batches_tracked = p[pre + ".num_batches_tracked"].data_ptr()
             if grads is not None and (pre + ".weight") in grads:
                 a.dgamma, a.dbeta = grads[pre + ".weight"].data_ptr(), grads[pre + ".bias"].data_ptr()
-        return arr
+        j.coef, j.sums, j.counter, j.bcoef = blk.coef.data_ptr(), blk.sums.data_ptr(), blk.counter.data_ptr(), blk.bcoef.data_ptr()
+        if up is not None:
+            j.up, j.up_plane_stride = up.data.data_ptr(), up.plane_stride
+        if gate is not None:
+            j.gate = gate.data_ptr()
+        if out_a is not None:
+            j.out_a, j.a_plane_stride = out_a.data.data_ptr(), out_a.plane_stride
+        if out_qa is not None:
+            j.out_qa, j.qa_plane_stride = out_qa.data.data_ptr(), out_qa.plane_stride
+        if da is not None:
+            j.da = da.data_ptr()
+        j.dy, j.dy_plane_stride = blk.dy.data.data_ptr(), blk.dy.plane_stride
+        return j
 
-    def _bn_fwd(self, blk, p, training):
-        parts = self._bn_parts(blk, p)
-        self._chk(_lib().drn_bn_stats(_vp(blk.y), C.c_int64(blk.rows), blk.cout, len(blk.bn_parts), parts,
-                                      C.c_float(BN_MOMENTUM), C.c_float(BN_EPS), 1 if training else 0, _vp(blk.coef),
-                                      _vp(blk.sums), _vp(blk.counter), _st()), "bn_stats")
+    def _bn_fwd(self, jobs, training, shared=False):
+        """Train-mode BatchNorm + ReLU of up to 3 independent conv blocks: ONE statistics launch + ONE apply launch.
+        shared=True: the jobs are the pyramid levels of ONE head block (same BatchNorm modules); their running statistics are
+        then updated by a separate ordered kernel, level after level as in the reference (fcos.py:93-102)."""
+        arr = (L.BnJob * len(jobs))(*jobs)
+        mode = 0 if not training else (2 if shared else 1)
+        self._chk(_lib().drn_bn_stats_multi(len(jobs), arr, C.c_float(BN_MOMENTUM), C.c_float(BN_EPS), mode, _st()), "bn_stats")
+        if mode == 2:
+            self._chk(_lib().drn_bn_running_update(len(jobs), arr, C.c_float(BN_MOMENTUM), _st()), "bn_running_update")
+        self._chk(_lib().drn_bn_relu_apply_multi(len(jobs), arr, _st()), "bn_relu_apply")
 
-    def _apply(self, blk, out_a, up=None, gate=None, out_qa=None):
-        self._chk(_lib().drn_bn_relu_apply(
-            _vp(blk.y), self.B, blk.t_out, blk.cout, _vp(blk.coef),
-            _vp(up.data) if up is not None else None, C.c_int64(up.plane_stride if up is not None else 0),
-            _vp(gate), _vp(out_a.data) if out_a is not None else None,
-            C.c_int64(out_a.plane_stride if out_a is not None else 0),
-            _vp(out_qa.data) if out_qa is not None else None, C.c_int64(out_qa.plane_stride if out_qa is not None else 0),
-            _st()), "bn_relu_apply")
+    def _bn_stats(self, jobs, training):
+        arr = (L.BnJob * len(jobs))(*jobs)
+        self._chk(_lib().drn_bn_stats_multi(len(jobs), arr, C.c_float(BN_MOMENTUM), C.c_float(BN_EPS), 1 if training else 0, _st()),
+                  "bn_stats")
+
+    def _bn_apply(self, jobs):
+        arr = (L.BnJob * len(jobs))(*jobs)
+        self._chk(_lib().drn_bn_relu_apply_multi(len(jobs), arr, _st()), "bn_relu_apply")
+
+    def _bn_bwd(self, jobs):
+        """BatchNorm + ReLU backward of up to 3 conv blocks: sums of g and g*xhat (+ dgamma / dbeta), then dy planes."""
+        arr = (L.BnJob * len(jobs))(*jobs)
+        self._chk(_lib().drn_bn_bwd_reduce_multi(len(jobs), arr, _st()), "bn_bwd_reduce")
+        self._chk(_lib().drn_bn_bwd_apply_multi(len(jobs), arr, _st()), "bn_bwd_apply")
 
     def _conv_desc(self, blk, a_pl, w_pl, bias=None, engine=None):
         par = blk.stride
@@ -335,38 +360,30 @@ class DensePath:
         for i in range(3):
             blk = self.conv[i]
             self._conv(blk, src, self.wp["conv%d" % i])
-            self._bn_fwd(blk, p, training)
             if i < 2:
-                self._apply(blk, self.Cact[i], gate=self.q[i + 1], out_qa=self.QC[i])
+                self._bn_fwd([self._bn_job(blk, p, out_a=self.Cact[i], gate=self.q[i + 1], out_qa=self.QC[i])], training)
                 src = self.QC[i]
             else:
-                self._apply(blk, self.Cact[i])
+                self._bn_fwd([self._bn_job(blk, p, out_a=self.Cact[i])], training)
         # FPN top-down (FPN.py:54-69).  The three lateral 1x1 convs are independent -> one grouped launch; their applies run
         # top-down (the upsample-add needs the level above); then the three 3-tap output convs, again one launch.  Every FPN
         # block owns its BatchNorm module, so the order of the running-statistics updates is immaterial here.
         self._group([self._conv_desc(self.inner[i], self.Cact[i], self.wp["inner%d" % i], engine=2) for i in range(3)])
-        for i in (2, 1, 0):
-            self._bn_fwd(self.inner[i], p, training)
-            self._apply(self.inner[i], self.I[i], up=self.I[i + 1] if i < 2 else None)
+        jobs = [self._bn_job(self.inner[i], p, out_a=self.I[i], up=self.I[i + 1] if i < 2 else None) for i in range(3)]
+        self._bn_stats(jobs, training)
+        for i in (2, 1, 0):  # the upsample-add reads the level above: applies run top-down
+            self._bn_apply([jobs[i]])
         self._group([self._conv_desc(self.layer[i], self.I[i], self.wp["layer%d" % i], engine=2) for i in range(3)])
-        for i in range(3):
-            self._bn_fwd(self.layer[i], p, training)
-            self._apply(self.layer[i], self.Pf[i])
+        self._bn_fwd([self._bn_job(self.layer[i], p, out_a=self.Pf[i]) for i in range(3)], training)
         # head (fcos.py:93-102): shared weights, per-level batch statistics.  Each shared conv runs its three levels in ONE
         # grouped launch; the BatchNorm statistics kernels follow in level order, which keeps the order of the three
         # running-statistics updates of every shared module (levels ascending) exactly as in the reference.
         self._group([self._conv_desc(self.tower[l], self.Pf[l], self.wp["towers"], bias=self.tower_bias, engine=2) for l in range(3)])
-        for l in range(3):
-            self._bn_fwd(self.tower[l], p, training)
-            self._apply(self.tower[l], self.TW[l])
+        self._bn_fwd([self._bn_job(self.tower[l], p, out_a=self.TW[l]) for l in range(3)], training, shared=True)
         self._group([self._conv_desc(self.mix[l], self.TW[l], self.wp["mix"], bias=p[h + "mix_fc.0.bias"], engine=2) for l in range(3)])
-        for l in range(3):
-            self._bn_fwd(self.mix[l], p, training)
-            self._apply(self.mix[l], self.MX[l])
+        self._bn_fwd([self._bn_job(self.mix[l], p, out_a=self.MX[l]) for l in range(3)], training, shared=True)
         self._group([self._conv_desc(self.iouc[l], self.MX[l], self.wp["iouc"], bias=p[h + "iou_scores.0.bias"], engine=2) for l in range(3)])
-        for l in range(3):
-            self._bn_fwd(self.iouc[l], p, training)
-            self._apply(self.iouc[l], self.HI[l])
+        self._bn_fwd([self._bn_job(self.iouc[l], p, out_a=self.HI[l]) for l in range(3)], training, shared=True)
         for l in range(3):
             Tl = self.Tl[l]
             o = self.lvl_off[l]
@@ -391,14 +408,6 @@ class DensePath:
     # ---------------------------------------------------------------------------------------------------------------
     # backward
     # ---------------------------------------------------------------------------------------------------------------
-    def _bn_bwd(self, blk, da, p, grads):
-        lib = _lib()
-        parts = self._bn_parts(blk, p, grads)
-        self._chk(lib.drn_bn_bwd_reduce(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), len(blk.bn_parts),
-                                        parts, _vp(blk.sums), _vp(blk.counter), _vp(blk.bcoef), _st()), "bn_bwd_reduce")
-        self._chk(lib.drn_bn_bwd_apply(_vp(da), _vp(blk.y), C.c_int64(blk.rows), blk.cout, _vp(blk.coef), _vp(blk.bcoef),
-                                       _vp(blk.dy.data), C.c_int64(blk.dy.plane_stride), _st()), "bn_bwd_apply")
-
     def _fork(self):
         """Side stream waits for everything enqueued so far on the current stream."""
         ev = torch.cuda.Event()
@@ -463,11 +472,10 @@ class DensePath:
                 self._chk(lib.drn_skinny_conv_bwd(_vp(self.diou[o:]), _vp(hi.data), C.c_int64(hi.plane_stride), hi.C, 0, F // 2,
                                                   B, self.Tl[l], 1, 1, _vp(p[h + "iou_scores.3.weight"]), _vp(self.dHI[l]), F // 2, 0,
                                                   _vp(grads[h + "iou_scores.3.weight"]), _st()), "iou3_bwd")
-                self._bn_bwd(self.iouc[l], self.dHI[l], p, grads)
+            self._bn_bwd([self._bn_job(self.iouc[l], p, grads, da=self.dHI[l]) for l in lv])
             self._group([self._wgrad_desc(self.iouc[l], self.MX[l], "iouc", l) for l in lv] +
                         [d for l in lv for d in self._dgrad_descs(self.iouc[l], self.wp["iouc"], self.dMX[l])])
-            for l in lv:
-                self._bn_bwd(self.mix[l], self.dMX[l], p, grads)
+            self._bn_bwd([self._bn_job(self.mix[l], p, grads, da=self.dMX[l]) for l in lv])
         for l in lv:
             Tl, o, tw = self.Tl[l], self.lvl_off[l], self.TW[l]
             self._chk(lib.drn_skinny_conv_bwd(_vp(self.dcls[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, F, B, Tl, 1, 3,
@@ -479,27 +487,24 @@ class DensePath:
         if iou_on:  # mix_fc: weight gradients + data gradients added onto the tower gradient (fcos.py:101 cat)
             self._group([self._wgrad_desc(self.mix[l], self.TW[l], "mix", l) for l in lv] +
                         [d for l in lv for d in self._dgrad_descs(self.mix[l], self.wp["mix"], self.dTW[l], mode=L.OUT_ADD)])
-        for l in lv:
-            self._bn_bwd(self.tower[l], self.dTW[l], p, grads)
+        self._bn_bwd([self._bn_job(self.tower[l], p, grads, da=self.dTW[l]) for l in lv])
         self._group([self._wgrad_desc(self.tower[l], self.Pf[l], "towers", l) for l in lv] +
                     [d for l in lv for d in self._dgrad_descs(self.tower[l], self.wp["towers"], self.dPf[l])])
         # FPN output convs
-        for i in lv:
-            self._bn_bwd(self.layer[i], self.dPf[i], p, grads)
+        self._bn_bwd([self._bn_job(self.layer[i], p, grads, da=self.dPf[i]) for i in lv])
         self._group([self._wgrad_desc(self.layer[i], self.I[i], "layer%d" % i) for i in lv] +
                     [d for i in lv for d in self._dgrad_descs(self.layer[i], self.wp["layer%d" % i], self.dI[i])])
         for i in (1, 2):  # backward of the top-down upsample-add chain (FPN.py:63-68)
             self._chk(lib.drn_pair_sum_add(_vp(self.dI[i]), _vp(self.dI[i - 1]), C.c_int64(B * self.Tl[i]), F, _st()),
                       "pair_sum_add")
         # FPN lateral convs
-        for i in lv:
-            self._bn_bwd(self.inner[i], self.dI[i], p, grads)
+        self._bn_bwd([self._bn_job(self.inner[i], p, grads, da=self.dI[i]) for i in lv])
         self._group([self._wgrad_desc(self.inner[i], self.Cact[i], "inner%d" % i) for i in lv] +
                     [d for i in lv for d in self._dgrad_descs(self.inner[i], self.wp["inner%d" % i], self.dC[i])])
         # backbone
         for i in (2, 1):
             blk = self.conv[i]
-            self._bn_bwd(blk, self.dC[i], p, grads)
+            self._bn_bwd([self._bn_job(blk, p, grads, da=self.dC[i])])
             self._group([self._wgrad_desc(blk, self.QC[i - 1], "conv%d" % i)] +
                         self._dgrad_descs(blk, self.wp["conv%d" % i], self.dC[i - 1], mode=L.OUT_ADD, rowscale=self.q[i],
                                           out2=self.dQC[i - 1]))
@@ -508,7 +513,7 @@ class DensePath:
                                           C.c_int64(a.plane_stride), 1, B, self.Tl[i - 1], a.C, _vp(self.dq[i]), None, None,
                                           C.c_int64(0), None, _st()), "gate_reduce")
         blk = self.conv[0]
-        self._bn_bwd(blk, self.dC[0], p, grads)
+        self._bn_bwd([self._bn_job(blk, p, grads, da=self.dC[0])])
         self._group([self._wgrad_desc(blk, self.X0, "conv0")] + self._dgrad_descs(blk, self.wp["conv0"], self.dX0))
         self._chk(lib.drn_gate_reduce(_vp(self.dX0), C.c_int64(self.C0), _vp(self.Pre), C.c_int64(self.D), C.c_int64(0), 0, B,
                                       self.T, self.D, _vp(self.dq[0]), _vp(self.q[0]), _vp(self.dP_pl.data),

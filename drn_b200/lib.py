@@ -46,6 +46,16 @@ class BnPart(C.Structure):
                 ("dgamma", C.c_void_p), ("dbeta", C.c_void_p)]
 
 
+class BnJob(C.Structure):
+    """drn_bn_job_t: one BatchNorm application (conv block x pyramid level) of a multi-job launch."""
+    _fields_ = [("y", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("nparts", C.c_int32),
+                ("parts", BnPart * 2),
+                ("coef", C.c_void_p), ("sums", C.c_void_p), ("counter", C.c_void_p), ("bcoef", C.c_void_p),
+                ("up", C.c_void_p), ("up_plane_stride", C.c_int64), ("gate", C.c_void_p),
+                ("out_a", C.c_void_p), ("a_plane_stride", C.c_int64), ("out_qa", C.c_void_p), ("qa_plane_stride", C.c_int64),
+                ("da", C.c_void_p), ("dy", C.c_void_p), ("dy_plane_stride", C.c_int64)]
+
+
 class PackItem(C.Structure):
     _fields_ = [("src", C.c_void_p), ("planes", C.c_void_p), ("grad", C.c_void_p),
                 ("O", C.c_int32), ("C", C.c_int32), ("k", C.c_int32), ("Ototal", C.c_int32), ("o0", C.c_int32),

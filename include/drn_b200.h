@@ -145,7 +145,7 @@ int drn_pos_bwd(const float* dx, int64_t dx_ld, int col0, const float* pos_in, i
  * A BatchNorm "part" names the parameters of one nn.BatchNorm1d covering channels [c0, c0+n) of y (the fused cls|bbox tower
  * output carries two modules side by side).
  *   drn_bn_stats      training: per-channel sum / sum of squares (fp64 atomics); the last CTA to finish writes
- *                     coef[0..3][c] = scale, shift, mean, invstd, updates running_mean/var (momentum, unbiased variance) and
+ *                     coef[0..4][c] = scale, shift, mean, invstd, unbiased variance, updates running_mean/var (momentum, unbiased variance) and
  *                     num_batches_tracked, and re-zeroes `sums` and `counter` (both must be zero before the first use).
  *                     eval (training = 0): coef from the running statistics.
  *   drn_bn_relu_apply a = relu(y*scale+shift) [+ nearest-x2 upsample of `up` (FPN top-down add, model/FPN.py:63-68)]
@@ -167,6 +167,26 @@ int drn_bn_bwd_reduce(const float* da, const float* y, int64_t rows, int C, floa
                       double* sums, unsigned* counter, float* bcoef, void* stream);
 int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const float* coef, const float* bcoef, void* dy,
                      int64_t dy_plane_stride, void* stream);
+/* The same four kernels over up to 3 independent BatchNorm applications per launch (the three pyramid levels of a shared head
+ * or FPN block): fewer launches and full SM occupancy for the small levels.  Fields as in the single forms above. */
+typedef struct {
+  const float* y;            /* conv output [B*T][C] fp32 */
+  int32_t B, T, C;
+  int32_t nparts; drn_bn_part_t parts[2];
+  float* coef; double* sums; unsigned* counter; float* bcoef;
+  const void* up; int64_t up_plane_stride; const float* gate;                  /* apply: FPN upsample-add source, query gate */
+  void* out_a; int64_t a_plane_stride; void* out_qa; int64_t qa_plane_stride;  /* apply outputs (planes) */
+  const float* da; void* dy; int64_t dy_plane_stride;                          /* backward */
+} drn_bn_job_t;
+/* training: 0 = eval (coef from the running statistics); 1 = batch statistics, each job's finaliser also updates its running
+ * statistics (jobs must own DISTINCT modules); 2 = batch statistics only -- the caller follows with drn_bn_running_update,
+ * which absorbs the jobs' statistics into the (shared) running buffers job after job, the order of the reference's level loop
+ * (model/fcos.py:93-102).  coef is [5][C]: scale, shift, mean, invstd, unbiased variance. */
+int drn_bn_stats_multi(int n, const drn_bn_job_t* jobs, float momentum, float eps, int training, void* stream);
+int drn_bn_running_update(int n, const drn_bn_job_t* jobs, float momentum, void* stream);
+int drn_bn_relu_apply_multi(int n, const drn_bn_job_t* jobs, void* stream);
+int drn_bn_bwd_reduce_multi(int n, const drn_bn_job_t* jobs, void* stream);
+int drn_bn_bwd_apply_multi(int n, const drn_bn_job_t* jobs, void* stream);
 /* backward of the FPN nearest-x2 upsample: dst[b][j] += src[b][2j] + src[b][2j+1]. */
 int drn_pair_sum_add(float* dst, const float* src, int64_t rows_half, int C, void* stream);
 /* backward of the query gate x = q[b][c] * a[b][t][c]: dq[b][c] += sum_t g*a; optionally dp planes = q*g and dbias[c] += sum q*g
