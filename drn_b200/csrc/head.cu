@@ -334,6 +334,59 @@ __global__ void __launch_bounds__(256) fcos_loss_bwd_kernel(LevelGeom g, const f
   }
 }
 
+// ---- eval-mode post-processing (model/inference.py:49-136 per level, 167-215 concatenation): one CTA per (level, sample) ----
+// sigmoid -> threshold on the CLASS score (before the IoU product, inference.py:71) -> keep the top_n by score ->
+// decode (loc -/+ reg)/32, clamp to [0,1] -> sqrt score.  Fixed-shape outputs [B][nlevels][top_n], kept candidates in
+// location order, so the host needs ONE small device->host copy and no per-image synchronisation.
+constexpr int POST_MAX_T = 2048;
+__global__ void __launch_bounds__(256) postprocess_kernel(LevelGeom g, const float* __restrict__ cls_raw,
+                                                          const float* __restrict__ bbox, const float* __restrict__ iou_raw,
+                                                          float thr, int top_n, int use_iou, float* __restrict__ out_det,
+                                                          float* __restrict__ out_score, float* __restrict__ out_loc,
+                                                          int* __restrict__ out_count) {
+  __shared__ float sc[POST_MAX_T];
+  __shared__ unsigned char keep[POST_MAX_T];
+  __shared__ int ncand_s;
+  const int lvl = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int T = g.T[lvl];
+  const long long base = static_cast<long long>(g.B) * g.off[lvl] + static_cast<long long>(b) * T;
+  if (tid == 0) ncand_s = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int t = tid; t < T; t += 256) {
+    const float c = 1.f / (1.f + expf(-cls_raw[base + t]));
+    const bool cand = c > thr;
+    float s = c;
+    if (use_iou) s = c * (1.f / (1.f + expf(-iou_raw[base + t])));
+    sc[t] = cand ? s : -1.f;
+    mine += cand ? 1 : 0;
+  }
+  if (mine) atomicAdd(&ncand_s, mine);
+  __syncthreads();
+  const int k = min(ncand_s, top_n);
+  for (int t = tid; t < T; t += 256) {
+    const float s = sc[t];
+    int rank = 0;
+    if (s >= 0.f)
+      for (int u = 0; u < T; ++u) rank += (sc[u] > s || (sc[u] == s && u < t)) ? 1 : 0;
+    keep[t] = (s >= 0.f && rank < k) ? 1 : 0;
+  }
+  __syncthreads();
+  const long long o = (static_cast<long long>(b) * g.nlevels + lvl) * top_n;
+  for (int t = tid; t < T; t += 256) {
+    if (!keep[t]) continue;
+    int pos = 0;
+    for (int u = 0; u < t; ++u) pos += keep[u];
+    const float loc = g.stride[lvl] * t + g.stride[lvl] * 0.5f;
+    const float l = bbox[2 * (base + t)], r = bbox[2 * (base + t) + 1];
+    out_det[2 * (o + pos)] = fminf(fmaxf((loc - l) / 32.f, 0.f), 1.f);
+    out_det[2 * (o + pos) + 1] = fminf(fmaxf((loc + r) / 32.f, 0.f), 1.f);
+    out_score[o + pos] = sqrtf(sc[t]);
+    out_loc[o + pos] = loc / 32.f;
+  }
+  if (tid == 0) out_count[b * g.nlevels + lvl] = k;
+}
+
 }  // namespace drn
 
 using namespace drn;
@@ -412,4 +465,18 @@ extern "C" int drn_fcos_loss_bwd(int nlevels, int B, const int* T, const float* 
   fcos_loss_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ST(stream)>>>(
       g, cls_raw, box_raw, iou_raw, scales, gt, gamma, alpha, iou_branch_on, acc, upstream, dcls, dbox, diou, pgrad);
   return check_launch("fcos_loss_bwd");
+}
+
+extern "C" int drn_postprocess(int nlevels, int B, const int* T, const float* strides, const float* cls_raw, const float* bbox,
+                               const float* iou_raw, float thr, int top_n, int use_iou, float* out_det, float* out_score,
+                               float* out_loc, int* out_count, void* stream) {
+  LevelGeom g;
+  int rc = make_geom(&g, nlevels, B, T, strides);
+  if (rc) return rc;
+  if (top_n < 1) return fail(DRN_EINVAL, "drn_postprocess: top_n must be positive");
+  for (int l = 0; l < nlevels; ++l)
+    if (T[l] > POST_MAX_T) return fail(DRN_EINVAL, "drn_postprocess: at most %d locations per level (got %d)", POST_MAX_T, T[l]);
+  postprocess_kernel<<<dim3(nlevels, B), 256, 0, ST(stream)>>>(g, cls_raw, bbox, iou_raw, thr, top_n, use_iou, out_det, out_score,
+                                                             out_loc, out_count);
+  return check_launch("postprocess");
 }

@@ -126,6 +126,11 @@ class DensePath:
         self.upstream = z(3)
         self.gt = e(B, 2)
         self.scales = e(3)
+        # eval-mode candidates (drn_postprocess): [B][3][top_n] detections / scores / locations + counts
+        self.top_n = int(cfg["fcos_pre_nms_top_n"])
+        self.post_det, self.post_score = z(B, 3, self.top_n, 2), z(B, 3, self.top_n)
+        self.post_loc = z(B, 3, self.top_n)
+        self.post_count = torch.zeros(B, 3, dtype=torch.int32, device=dev)
         self.graphs = {}
         self.launches_stage = 0
         self.Tl_c = (C.c_int * 3)(*self.Tl)
@@ -404,6 +409,16 @@ class DensePath:
                   "fcos_loss_fwd")
         self.launches += 1  # finalize kernel inside drn_fcos_loss_fwd
         self.launches_fwd = self.launches
+
+    def postprocess(self):
+        """Eval only (fcos.py:172-191 -> inference.py:49-136): candidate selection for every (sample, level) in one launch.
+        Returns CPU tensors (det, score, loc, count) after a single device->host copy each."""
+        cfg = self.cfg
+        self._chk(_lib().drn_postprocess(3, self.B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.bbox), _vp(self.iou_raw),
+                                         C.c_float(float(cfg["fcos_inference_thr"])), self.top_n,
+                                         0 if cfg["is_first_stage"] else 1, _vp(self.post_det), _vp(self.post_score),
+                                         _vp(self.post_loc), _vp(self.post_count), _st()), "postprocess")
+        return self.post_det.cpu(), self.post_score.cpu(), self.post_loc.cpu(), self.post_count.cpu()
 
     # ---------------------------------------------------------------------------------------------------------------
     # backward

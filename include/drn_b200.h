@@ -212,6 +212,16 @@ int drn_fcos_loss_bwd(int nlevels, int B, const int* T, const float* strides, co
                       const float* iou_raw, const float* scales, const float* gt, float gamma, float alpha, int iou_branch_on,
                       const double* acc, const float* upstream, float* dcls, float* dbox, float* diou, float* pgrad, void* stream);
 
+/* Eval-mode candidate selection, FCOSPostProcessor.forward_for_single_feature_map (model/inference.py:49-136) for every
+ * (sample, level) in one launch: sigmoid, threshold `thr` on the class score, top_n by score (class score, or class x
+ * sigmoid(IoU score) when use_iou), decode (loc -/+ reg)/32 clamped to [0,1], sqrt score.  bbox = exp'd regression
+ * [B*P][2] (drn_fcos_loss_fwd's bbox_out).  Outputs [B][nlevels][top_n] (x2 for out_det), out_count [B][nlevels]; slots
+ * beyond the count are untouched.  The concatenation over levels and the empty-result fallback (inference.py:167-215) are
+ * host-side list assembly on these arrays. */
+int drn_postprocess(int nlevels, int B, const int* T, const float* strides, const float* cls_raw, const float* bbox,
+                    const float* iou_raw, float thr, int top_n, int use_iou, float* out_det, float* out_score, float* out_loc,
+                    int* out_count, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Query encoder (drn_b200/csrc/query.cu): model/language_module.py:27-62 (QueryEncoder.forward +
  * extract_textual_command) with model/ops.py:16-25,74-85, forward and backward, exact fp32 FMA arithmetic.

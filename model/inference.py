@@ -1,42 +1,27 @@
-"""Eval-mode post-processing (reference model/inference.py:49-215): per level sigmoid -> threshold -> top-k -> decode ->
-clamp, levels concatenated, fallback detection when nothing passes.  Operates on the small raw head outputs
-([B, 1.75*T] values) after they are read back; the dense work happened in the kernels."""
+"""Eval-mode post-processing (reference model/inference.py:49-215).
+
+The arithmetic -- per level sigmoid -> threshold -> top-k -> decode -> clamp -> sqrt score -- runs in ONE fixed-shape kernel
+for all (sample, level) pairs (drn_postprocess, drn_b200/csrc/head.cu).  What is left here is the reference's list assembly
+on the [B, 3, top_n] result: concatenate the levels of every sample (inference.py:167-215) and substitute the fallback
+detection when nothing passed the threshold (inference.py:192-197)."""
 import torch
 
-DOWNSAMPLE = 32.0  # hard-coded in the reference (inference.py:45)
 
-
-def postprocess(cls_raw, bbox, iou_raw, Tl, strides, cfg, B):
-    """cls_raw [B*P], bbox [B*P,2], iou_raw [B*P] in level-major / sample / t order (CPU tensors)."""
-    thr, top_n = cfg["fcos_inference_thr"], cfg["fcos_pre_nms_top_n"]
-    first = cfg["is_first_stage"]
+def assemble(det, score, loc, count):
+    """det [B,L,K,2], score [B,L,K], loc [B,L,K], count [B,L] (CPU tensors from ONE device->host copy) -> the reference's
+    per-sample dicts {detections [n,2], labels [], scores [n], level list[list[int]], locations [n]}."""
+    B, nl = count.shape
+    counts = count.tolist()
     results = []
-    offs = [B * sum(Tl[:i]) for i in range(len(Tl))]
     for b in range(B):
-        dets, scores, levels, locs = [], [], [], []
-        for lvl, T in enumerate(Tl):
-            s = float(strides[lvl])
-            loc = torch.arange(0, T * s, step=s, dtype=torch.float32) + s / 2
-            sl = slice(offs[lvl] + b * T, offs[lvl] + (b + 1) * T)
-            c = torch.sigmoid(cls_raw[sl])
-            cand = c > thr
-            score = c if first else c * torch.sigmoid(iou_raw[sl])  # threshold applies to cls BEFORE the product
-            idx = cand.nonzero().squeeze(1)
-            sc = score[idx]
-            k = min(int(cand.sum()), top_n)
-            if idx.numel() > k:
-                sc, top = sc.topk(k, sorted=False)
-                idx = idx[top]
-            reg = bbox[sl][idx]
-            d = torch.stack([loc[idx] - reg[:, 0], loc[idx] + reg[:, 1]], dim=1) / DOWNSAMPLE
-            d = d.clamp(min=0, max=1)
-            d = d[(d[:, 1] - d[:, 0]) >= 0]
-            if d.shape[0]:
-                dets.append(d)
-            if sc.numel():
-                scores.append(torch.sqrt(sc))
-                locs.append(loc[idx] / 32)
-            levels.append([lvl] * d.shape[0])
+        dets, scores, locs, levels = [], [], [], []
+        for lvl in range(nl):
+            n = counts[b][lvl]
+            if n:
+                dets.append(det[b, lvl, :n])
+                scores.append(score[b, lvl, :n])
+                locs.append(loc[b, lvl, :n])
+            levels.append([lvl] * n)
         if not dets:  # inference.py:192-197
             results.append({"detections": torch.tensor([[0.0, 1.0]]), "labels": [], "scores": torch.tensor([1.0]),
                             "level": [[-1]], "locations": torch.tensor([0.5])})

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from drn_b200.dense import DensePath
-from model.inference import postprocess
+from model.inference import assemble
 from model.language_module import QueryEncoder
 from model.modules import FPN, Backbone, FCOSModule
 
@@ -177,7 +177,7 @@ class mainModel(nn.Module):
             loss_dict["loss_iou"] = losses[2]
         if training:
             return None, loss_dict
-        boxes = postprocess(path.cls_raw.cpu(), path.bbox.cpu(), path.iou_raw.cpu(), path.Tl, path.strides, self.cfg, B)
+        boxes = assemble(*path.postprocess())
         for d in boxes:
             for k in ("detections", "scores", "locations"):
                 d[k] = d[k].to(dev)

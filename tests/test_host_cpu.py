@@ -120,33 +120,19 @@ def test_tap_tables_are_the_reference_convolutions():
     assert torch.allclose(got, xx.grad, atol=1e-5)
 
 
-def test_postprocess_matches_oracle():
-    from model.inference import postprocess
-    from oracle import drn_oracle as O
-    torch.manual_seed(1)
-    for first in (True, False):
-        cfg = S.default_config(stage=1 if first else 3)
-        B, T = 3, 64
-        Tl = (T, T // 2, T // 4)
-        logits = [torch.randn(B, 1, t) * 2 - 1 for t in Tl]
-        bbox = [torch.rand(B, 2, t) * 8 for t in Tl]
-        iou = [torch.randn(B, 1, t) for t in Tl]
-        logits[0][2] = -20.0  # sample 2: nothing passes on level 0
-        locs = O.compute_locations(T, cfg["fpn_stride"])
-        ref = O.postprocess(locs, logits, bbox, iou, cfg)
-        cls_raw = torch.cat([x.permute(0, 2, 1).reshape(-1) for x in logits])
-        box = torch.cat([x.permute(0, 2, 1).reshape(-1, 2) for x in bbox])
-        iou_raw = torch.cat([x.permute(0, 2, 1).reshape(-1) for x in iou])
-        got = postprocess(cls_raw, box, iou_raw, Tl, cfg["fpn_stride"], cfg, B)
-        for g, r in zip(got, ref):
-            assert g["detections"].shape == r["detections"].shape
-            og = torch.argsort(g["scores"] + g["detections"][:, 0] * 1e-3)
-            orf = torch.argsort(r["scores"] + r["detections"][:, 0] * 1e-3)
-            assert torch.allclose(g["detections"][og], r["detections"][orf], atol=1e-6)
-            assert torch.allclose(g["scores"][og], r["scores"][orf], atol=1e-6)
-            assert g["level"] == r["level"]
-    # nothing anywhere -> the reference's fallback detection (inference.py:192-197)
-    cfg = S.default_config(stage=1)
-    n = 1 * (64 + 32 + 16)
-    got = postprocess(torch.full((n,), -20.0), torch.ones(n, 2), torch.zeros(n), (64, 32, 16), cfg["fpn_stride"], cfg, 1)
-    assert got[0]["detections"].tolist() == [[0.0, 1.0]] and got[0]["level"] == [[-1]]
+def test_postprocess_list_assembly():
+    """Host half of the eval post-processing (reference inference.py:167-215) on the fixed-shape arrays drn_postprocess writes:
+    level concatenation in order, per-level `level` lists, and the fallback detection when nothing passed."""
+    from model.inference import assemble
+    B, nl, K = 3, 3, 4
+    det = torch.arange(B * nl * K * 2, dtype=torch.float32).view(B, nl, K, 2) / 100
+    score = torch.arange(B * nl * K, dtype=torch.float32).view(B, nl, K) / 50
+    loc = score + 0.25
+    count = torch.tensor([[2, 0, 1], [0, 0, 0], [4, 4, 4]], dtype=torch.int32)
+    out = assemble(det, score, loc, count)
+    assert out[0]["detections"].tolist() == torch.cat([det[0, 0, :2], det[0, 2, :1]]).tolist()
+    assert out[0]["scores"].tolist() == torch.cat([score[0, 0, :2], score[0, 2, :1]]).tolist()
+    assert out[0]["level"] == [[0, 0], [], [2]] and out[0]["labels"] == []
+    assert out[1]["detections"].tolist() == [[0.0, 1.0]] and out[1]["level"] == [[-1]]
+    assert out[1]["scores"].tolist() == [1.0] and out[1]["locations"].tolist() == [0.5]
+    assert out[2]["detections"].shape == (12, 2) and out[2]["locations"].tolist() == loc[2].reshape(-1).tolist()
