@@ -204,6 +204,7 @@ def run_ours(args):
 
     # ---- end to end: pinned host inputs, double-buffered H2D on a copy stream, loss read back every step -------------
     copy_stream = torch.cuda.Stream()
+    copy_stream2 = torch.cuda.Stream()  # the 134 MB feature tensor is split over two copy engines (43 -> 55 GB/s measured)
     keys = ("query_tokens", "props_features", "props_start_end", "gt_start_end")
     bufs = [{k: torch.empty_like(dev_batch[k]) for k in keys} for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -212,13 +213,27 @@ def run_ours(args):
 
     def upload(i):
         s = i % 2
+        half = pinned["props_features"].shape[0] // 2
+        with torch.cuda.stream(copy_stream2):
+            copy_stream2.wait_event(consumed[s])
+            bufs[s]["props_features"][half:].copy_(pinned["props_features"][half:], non_blocking=True)
+            half_done = torch.cuda.Event()
+            half_done.record(copy_stream2)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[s])
             for k in keys:
-                bufs[s][k].copy_(pinned[k], non_blocking=True)
+                if k == "props_features":
+                    bufs[s][k][:half].copy_(pinned[k][:half], non_blocking=True)
+                else:
+                    bufs[s][k].copy_(pinned[k], non_blocking=True)
+            copy_stream.wait_event(half_done)
             ready[s].record(copy_stream)
 
-    host_loss = torch.empty(1, pin_memory=True)
+    # the step's result (loss) is read back EVERY step: a non-blocking D2H into pinned memory right behind the step, consumed
+    # by the host one step later (so the host can enqueue step i+1 while step i runs, as an asynchronous training loop does)
+    host_loss = [torch.empty(1, pin_memory=True) for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    loss_log = []
     for s in range(2):
         consumed[s].record()
     barrier()
@@ -234,9 +249,16 @@ def run_ours(args):
         b["query_length"] = pinned["query_length"]
         loss = step(b)
         consumed[s].record()
-        host_loss.copy_(loss.detach().reshape(1), non_blocking=False)  # D2H read of the step's result
+        host_loss[s].copy_(loss.detach().reshape(1), non_blocking=True)  # D2H read of the step's result
+        loss_ready[s].record()
+        if i > 0:
+            loss_ready[1 - s].synchronize()
+            loss_log.append(float(host_loss[1 - s]))
+    loss_ready[(args.steps - 1) % 2].synchronize()
+    loss_log.append(float(host_loss[(args.steps - 1) % 2]))
     e3.record()
     barrier()
+    assert len(loss_log) == args.steps and all(x == x for x in loss_log)
     ms_e2e = e2.elapsed_time(e3) / args.steps
     sampler.stop_flag = True
     sampler.join(timeout=2)

@@ -7,8 +7,13 @@
 //   ("packed") BiLSTM, one launch per step for both directions -> q_vector gather -> qInput / qInput0..2 -> attention
 //   over the words (mask -1e30, softmax) -> the three command vectors; backward = the same chain reversed (BPTT).
 // Layouts: R = B*L rows (b-major); xg / G / dG [R][2 dirs][4 gates i,f,g,o][H]; Hout [R][2H]; Cst [R][2][H].
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace drn {
 
@@ -251,7 +256,9 @@ struct QeDev {
   const long long* tokens;
   const long long* lengths;
   const float* w_hh[2];
-  float *Ebuf, *xg, *G, *Cst, *Hout, *Hprev, *v, *hid, *c3, *alpha;
+  int EP;  // embedding width rounded up to the 64-element K-block of the tensor-core contraction (zero padded)
+  float *xg, *G, *Cst, *Hout, *v, *hid, *c3, *alpha, *bias_sum;
+  __nv_bfloat16 *E_pl, *Wih_pl, *dG_pl, *Hprev_pl;  // split-BF16 planes (hi, lo) of the operands of the big projections
   float *dH, *dc3, *dhid, *dhid_pre, *dv, *dG, *dcarry, *part, *dE, *HT, *dGT, *dr;
   unsigned* cnt;
 };
@@ -263,7 +270,31 @@ __global__ void __launch_bounds__(256) qe_embed_kernel(QeDev q, const float* __r
   const int r = blockIdx.x;
   const int b = r / q.L, t = r % q.L;
   const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
-  for (int e = threadIdx.x; e < q.E; e += blockDim.x) q.Ebuf[static_cast<long long>(r) * q.E + e] = emb[tok * q.E + e];
+  const long long ps = static_cast<long long>(q.B) * q.L * q.EP;
+  for (int e = threadIdx.x; e < q.EP; e += blockDim.x) {
+    __nv_bfloat16 h, l;
+    split_bf16(e < q.E ? emb[tok * q.E + e] : 0.f, h, l);
+    q.E_pl[static_cast<long long>(r) * q.EP + e] = h;
+    q.E_pl[ps + static_cast<long long>(r) * q.EP + e] = l;
+  }
+}
+// W_ih of both directions -> one [8H][EP] planes operand (rows = dir, gate, unit; zero-padded columns), bias_sum = b_ih + b_hh
+__global__ void __launch_bounds__(256) qe_pack_wih_kernel(QeDev q, const float* __restrict__ w0, const float* __restrict__ w1,
+                                                          const float* __restrict__ bi0, const float* __restrict__ bh0,
+                                                          const float* __restrict__ bi1, const float* __restrict__ bh1) {
+  const int H4 = 4 * q.H;
+  const long long total = 2LL * H4 * q.EP, ps = total;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
+    const int e = static_cast<int>(i % q.EP);
+    const long long row = i / q.EP;
+    const float* w = row < H4 ? w0 : w1;
+    const long long rr = row < H4 ? row : row - H4;
+    __nv_bfloat16 h, l;
+    split_bf16(e < q.E ? w[rr * q.E + e] : 0.f, h, l);
+    q.Wih_pl[i] = h;
+    q.Wih_pl[ps + i] = l;
+    if (e == 0) q.bias_sum[row] = row < H4 ? bi0[rr] + bh0[rr] : bi1[rr] + bh1[rr];
+  }
 }
 __global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __restrict__ g_emb) {
   const int r = blockIdx.x;
@@ -280,107 +311,126 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// ---- one recurrent step, both directions (language_module.py:42-46; torch.nn.LSTM gate order i,f,g,o) -----------------
+// ---- the recurrence, both directions (language_module.py:42-46; torch.nn.LSTM gate order i,f,g,o) ---------------------
 // grid (H/8, 2, BC); warp = one hidden unit (its 4 gate rows of W_hh), lane = sample.  Packed-sequence semantics: a sample
 // is live at time t iff t < length; the reverse direction starts at t = length-1 from the zero state, which falls out of
 // the state being zero at every non-live position.  The hidden state is also kept TRANSPOSED ([unit][32 samples],
-// double-buffered over steps) so that the next step stages it, like its 64 KB slice of W_hh, with straight 16-byte
-// cp.async copies -- no per-element transposition, all loads in flight at once.
-__global__ void __launch_bounds__(256) lstm_fwd_step_kernel(QeDev q, int s) {
+// double-buffered over steps) so that a step stages it, like its 64 KB slice of W_hh, with straight 16-byte cp.async
+// copies.  PERSIST: ONE cooperative launch walks all L steps with the W_hh slice resident in shared memory and a grid
+// barrier between steps (used when the grid fits the GPU: B <= 32); otherwise one launch per step.
+template <bool PERSIST>
+__global__ void __launch_bounds__(256) lstm_fwd_kernel(QeDev q, int s0, int s1) {
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
   float* ws = smem;                 // [32][H]   rows (unit w, gate g) -> w*4+g
   float* hs = smem + 32 * H;        // [H][32]   previous hidden state of this sample chunk, unit-major
   const int ug = blockIdx.x, dir = blockIdx.y, bc = blockIdx.z, b0 = bc * 32;
-  const int t = dir == 0 ? s : L - 1 - s;
-  const int tp = dir == 0 ? t - 1 : t + 1;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const long long ht_sz = 2LL * q.BC * H * 32;
-  if (s > 0) {
-    const float* W = q.w_hh[dir];
-    const float* hprev = q.HT + ((s - 1) & 1) * ht_sz + (static_cast<long long>(dir) * q.BC + bc) * H * 32;
-    const int c4 = H / 4;  // 16-byte chunks per W row
-    for (int idx = tid; idx < 32 * c4; idx += 256) {
-      const int row = idx / c4, k4 = idx % c4;
-      const int unit = ug * 8 + (row >> 2), g = row & 3;
-      cp_async16(ws + row * H + k4 * 4, W + (static_cast<long long>(g) * H + unit) * H + k4 * 4);
-    }
-    for (int idx = tid; idx < H * 8; idx += 256) cp_async16(hs + idx * 4, hprev + idx * 4);
-    cp_async_wait_all();
-    __syncthreads();
-  }
   const int b = b0 + lane;
   const int unit = ug * 8 + w;
   const bool inb = b < q.B;
-  const long long r = static_cast<long long>(inb ? b : 0) * L + t;
-  float acc[4];
+  const int len = inb ? static_cast<int>(q.lengths[b]) : 0;
+  bool w_loaded = false;
+  for (int s = s0; s < s1; ++s) {
+    const int t = dir == 0 ? s : L - 1 - s;
+    const int tp = dir == 0 ? t - 1 : t + 1;
+    if (s > 0) {
+      if (!w_loaded) {
+        const float* W = q.w_hh[dir];
+        const int c4 = H / 4;  // 16-byte chunks per W row
+        for (int idx = tid; idx < 32 * c4; idx += 256) {
+          const int row = idx / c4, k4 = idx % c4;
+          const int u = ug * 8 + (row >> 2), g = row & 3;
+          cp_async16(ws + row * H + k4 * 4, W + (static_cast<long long>(g) * H + u) * H + k4 * 4);
+        }
+        w_loaded = true;
+      }
+      const float* hprev = q.HT + ((s - 1) & 1) * ht_sz + (static_cast<long long>(dir) * q.BC + bc) * H * 32;
+      for (int idx = tid; idx < H * 8; idx += 256) cp_async16(hs + idx * 4, hprev + idx * 4);
+      cp_async_wait_all();
+      __syncthreads();
+    }
+    const long long r = static_cast<long long>(inb ? b : 0) * L + t;
+    float acc[4];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) acc[g] = inb ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
-  if (s > 0) {
-    const float* wr = ws + (w * 4) * H;
+    for (int g = 0; g < 4; ++g) acc[g] = inb ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
+    if (s > 0) {
+      const float* wr = ws + (w * 4) * H;
 #pragma unroll 2
-    for (int k = 0; k < H; k += 4) {
-      const float h0 = hs[(k + 0) * 32 + lane], h1 = hs[(k + 1) * 32 + lane], h2 = hs[(k + 2) * 32 + lane],
-                  h3 = hs[(k + 3) * 32 + lane];
+      for (int k = 0; k < H; k += 4) {
+        const float h0 = hs[(k + 0) * 32 + lane], h1 = hs[(k + 1) * 32 + lane], h2 = hs[(k + 2) * 32 + lane],
+                    h3 = hs[(k + 3) * 32 + lane];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float4 wv = *reinterpret_cast<const float4*>(wr + g * H + k);
-        acc[g] = fmaf(h0, wv.x, acc[g]);
-        acc[g] = fmaf(h1, wv.y, acc[g]);
-        acc[g] = fmaf(h2, wv.z, acc[g]);
-        acc[g] = fmaf(h3, wv.w, acc[g]);
+        for (int g = 0; g < 4; ++g) {
+          const float4 wv = *reinterpret_cast<const float4*>(wr + g * H + k);
+          acc[g] = fmaf(h0, wv.x, acc[g]);
+          acc[g] = fmaf(h1, wv.y, acc[g]);
+          acc[g] = fmaf(h2, wv.z, acc[g]);
+          acc[g] = fmaf(h3, wv.w, acc[g]);
+        }
       }
     }
+    const bool live = inb && t < len;
+    float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
+    if (live) {
+      gi = sigmoidf_(acc[0]);
+      gf = sigmoidf_(acc[1]);
+      gg = tanhf(acc[2]);
+      go = sigmoidf_(acc[3]);
+      const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+      c = gf * cp + gi * gg;
+      h = go * tanhf(c);
+    }
+    q.HT[(s & 1) * ht_sz + ((static_cast<long long>(dir) * q.BC + bc) * H + unit) * 32 + lane] = h;
+    if (inb) {
+      float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+      G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
+      q.Cst[(r * 2 + dir) * H + unit] = c;
+      q.Hout[r * 2 * H + dir * H + unit] = h;
+    }
+    if (PERSIST && s + 1 < s1) {
+      __threadfence();
+      cg::this_grid().sync();
+    }
   }
-  const bool live = inb && t < q.lengths[b];
-  float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
-  if (live) {
-    gi = sigmoidf_(acc[0]);
-    gf = sigmoidf_(acc[1]);
-    gg = tanhf(acc[2]);
-    go = sigmoidf_(acc[3]);
-    const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
-    c = gf * cp + gi * gg;
-    h = go * tanhf(c);
-  }
-  q.HT[(s & 1) * ht_sz + ((static_cast<long long>(dir) * q.BC + bc) * H + unit) * 32 + lane] = h;
-  if (!inb) return;
-  float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
-  G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
-  q.Cst[(r * 2 + dir) * H + unit] = c;
-  q.Hout[r * 2 * H + dir * H + unit] = h;
 }
 
-// Hprev[dir][b][t] = hidden state the recurrence consumed at step t (operand of the W_hh weight gradient)
+// Hprev planes [dir][b][t] = hidden state the recurrence consumed at step t (operand of the W_hh weight gradient)
 __global__ void __launch_bounds__(256) qe_hprev_kernel(QeDev q) {
   const int H = q.H, L = q.L;
-  const long long total = 2LL * q.B * L * (H / 4);
+  const long long total = 2LL * q.B * L * H, ps = total;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
-    const int k4 = static_cast<int>(i % (H / 4));
-    const long long rr = i / (H / 4);
+    const int k = static_cast<int>(i % H);
+    const long long rr = i / H;
     const int t = static_cast<int>(rr % L);
     const long long db = rr / L;
     const int b = static_cast<int>(db % q.B), dir = static_cast<int>(db / q.B);
     const int tp = dir == 0 ? t - 1 : t + 1;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tp >= 0 && tp < L) v = *reinterpret_cast<const float4*>(q.Hout + (static_cast<long long>(b) * L + tp) * 2 * H + dir * H + k4 * 4);
-    *reinterpret_cast<float4*>(q.Hprev + ((static_cast<long long>(dir) * q.B + b) * L + t) * H + k4 * 4) = v;
+    float v = 0.f;
+    if (tp >= 0 && tp < L) v = q.Hout[(static_cast<long long>(b) * L + tp) * 2 * H + dir * H + k];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    q.Hprev_pl[i] = h;
+    q.Hprev_pl[ps + i] = l;
   }
 }
 
-// ---- one BPTT step, both directions -------------------------------------------------------------------------------------
+// ---- BPTT, both directions ------------------------------------------------------------------------------------------------
 // grid (H/32, nq, 2*BC).  Phase A: the CTA (unit group ug, quarter jq of the 4H gate rows) forms its part of
-//   dh_rec[b][u] = sum_j dG_next[b][j] * W_hh[j][u]   (lane = unit u, 32 accumulators = samples), writes it to `part`;
-// the LAST of the nq CTAs of a unit group (device counter, no spinning) sums the parts and does the cell backward
-// (Phase B), producing dG at this time step and the carried dc.  nq = 1 on the first step (no recurrent gradient yet).
+//   dh_rec[b][u] = sum_j dG_next[b][j] * W_hh[j][u]   (lane = unit u, 32 accumulators = samples) and writes it to `part`.
+// Phase B: the parts are summed and the cell backward produces dG of this time step and the carried dc.
+//   per-step launches: Phase B runs in the LAST of the nq CTAs of a unit group (device counter, no spinning); nq = 1 on the
+//     first step (no recurrent gradient yet);
+//   PERSIST: one cooperative launch, W_hh tile resident, grid barriers between Phase A, Phase B and the next step; the
+//     jq = 0 CTA of each unit group runs Phase B.
 // dG is also kept transposed ([gate row][32 samples], double-buffered) so Phase A stages both operands with cp.async.
 constexpr int BWD_JQ = 4;
-__global__ void __launch_bounds__(256) lstm_bwd_step_kernel(QeDev q, int s, int nq) {
+template <bool PERSIST>
+__global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, int nq_launch) {
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
   const int ug = blockIdx.x, jq = blockIdx.y, dir = blockIdx.z / q.BC, bc = blockIdx.z % q.BC, b0 = bc * 32;
-  const int t = dir == 0 ? L - 1 - s : s;
-  const int tp = dir == 0 ? t - 1 : t + 1;  // recurrence predecessor (source of c_prev)
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int UG = H / 32;
   const long long slot = (static_cast<long long>(dir) * q.BC + bc) * UG + ug;
@@ -390,93 +440,123 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(QeDev q, int s, int 
   float* wsm = smem + H * 32;      // [H][32]  W_hh[jq*H + j][ug*32 + u]
   float* red = smem + 2 * H * 32;  // [8][32][33]; reused as the [4][32][33] transposition tile of Phase B
   __shared__ bool is_last;
-  if (nq > 1) {
-    const float* src = q.dGT + ((s - 1) & 1) * gt_sz + ((static_cast<long long>(dir) * q.BC + bc) * 4 * H + jq * H) * 32;
-    for (int idx = tid; idx < H * 8; idx += 256) cp_async16(dgs + idx * 4, src + idx * 4);
-    const float* W = q.w_hh[dir] + static_cast<long long>(jq) * H * H + ug * 32;
-    for (int idx = tid; idx < H * 8; idx += 256) {
-      const int j = idx >> 3, c = idx & 7;
-      cp_async16(wsm + j * 32 + c * 4, W + static_cast<long long>(j) * H + c * 4);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    float acc[32];
+  bool w_loaded = false;
+  for (int s = s0; s < s1; ++s) {
+    const int t = dir == 0 ? L - 1 - s : s;
+    const int tp = dir == 0 ? t - 1 : t + 1;  // recurrence predecessor (source of c_prev)
+    const int nq = PERSIST ? (s == 0 ? 1 : BWD_JQ) : nq_launch;
+    bool do_b = PERSIST ? (jq == 0) : true;
+    if (nq > 1) {
+      const float* src = q.dGT + ((s - 1) & 1) * gt_sz + ((static_cast<long long>(dir) * q.BC + bc) * 4 * H + jq * H) * 32;
+      for (int idx = tid; idx < H * 8; idx += 256) cp_async16(dgs + idx * 4, src + idx * 4);
+      if (!w_loaded) {
+        const float* W = q.w_hh[dir] + static_cast<long long>(jq) * H * H + ug * 32;
+        for (int idx = tid; idx < H * 8; idx += 256) {
+          const int j = idx >> 3, c = idx & 7;
+          cp_async16(wsm + j * 32 + c * 4, W + static_cast<long long>(j) * H + c * 4);
+        }
+        w_loaded = PERSIST;
+      }
+      cp_async_wait_all();
+      __syncthreads();
+      float acc[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    const int jw = H / 8;  // rows per warp
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      const int jw = H / 8;  // rows per warp
 #pragma unroll 2
-    for (int j = w * jw; j < (w + 1) * jw; ++j) {
-      const float wv = wsm[j * 32 + lane];
-      const float4* d4 = reinterpret_cast<const float4*>(dgs + j * 32);
+      for (int j = w * jw; j < (w + 1) * jw; ++j) {
+        const float wv = wsm[j * 32 + lane];
+        const float4* d4 = reinterpret_cast<const float4*>(dgs + j * 32);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 d = d4[i];
-        acc[4 * i + 0] = fmaf(d.x, wv, acc[4 * i + 0]);
-        acc[4 * i + 1] = fmaf(d.y, wv, acc[4 * i + 1]);
-        acc[4 * i + 2] = fmaf(d.z, wv, acc[4 * i + 2]);
-        acc[4 * i + 3] = fmaf(d.w, wv, acc[4 * i + 3]);
+        for (int i = 0; i < 8; ++i) {
+          const float4 d = d4[i];
+          acc[4 * i + 0] = fmaf(d.x, wv, acc[4 * i + 0]);
+          acc[4 * i + 1] = fmaf(d.y, wv, acc[4 * i + 1]);
+          acc[4 * i + 2] = fmaf(d.z, wv, acc[4 * i + 2]);
+          acc[4 * i + 3] = fmaf(d.w, wv, acc[4 * i + 3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) red[(w * 32 + i) * 33 + lane] = acc[i];
+      __syncthreads();
+      for (int idx = tid; idx < 1024; idx += 256) {
+        const int bb = idx >> 5, u = idx & 31;
+        float sum = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) sum += red[(ww * 32 + bb) * 33 + u];
+        part[jq * 1024 + idx] = sum;
+      }
+      __threadfence();
+      if (PERSIST) {
+        cg::this_grid().sync();
+      } else {
+        __syncthreads();
+        if (tid == 0) is_last = (atomicAdd(q.cnt + slot, 1u) == static_cast<unsigned>(nq - 1));
+        __syncthreads();
+        do_b = is_last;
+        __threadfence();
       }
     }
+    if (do_b) {
+      for (int idx = tid; idx < 1024; idx += 256) {
+        const int bl = idx >> 5, u = idx & 31;
+        const int b = b0 + bl, unit = ug * 32 + u;
+        float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, carry = 0.f;
+        if (b < q.B) {
+          float dhrec = 0.f;
+          if (nq > 1) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) red[(w * 32 + i) * 33 + lane] = acc[i];
-    __syncthreads();
-    for (int idx = tid; idx < 1024; idx += 256) {
-      const int b = idx >> 5, u = idx & 31;
-      float sum = 0.f;
+            for (int qq = 0; qq < BWD_JQ; ++qq) dhrec += __ldcg(part + qq * 1024 + idx);
+          }
+          const long long r = static_cast<long long>(b) * L + t;
+          if (t < q.lengths[b]) {
+            const float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+            const float gi = G[0], gf = G[H], gg = G[2 * H], go = G[3 * H];
+            const float c = q.Cst[(r * 2 + dir) * H + unit];
+            const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+            const float dh = q.dH[r * 2 * H + dir * H + unit] + dhrec;
+            const float tc = tanhf(c);
+            float dc = dh * go * (1.f - tc * tc);
+            if (s > 0) dc += q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit];
+            d_i = dc * gg * gi * (1.f - gi);
+            d_f = dc * cp * gf * (1.f - gf);
+            d_g = dc * gi * (1.f - gg * gg);
+            d_o = dh * tc * go * (1.f - go);
+            carry = dc * gf;
+          }
+          const long long go_ = ((r * 2 + dir) * 4) * H + unit;
+          float* dG = q.dG + go_;
+          dG[0] = d_i; dG[H] = d_f; dG[2 * H] = d_g; dG[3 * H] = d_o;
+          const long long gps = static_cast<long long>(q.B) * L * 8 * H;
+          const float dv4[4] = {d_i, d_f, d_g, d_o};
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) sum += red[(ww * 32 + b) * 33 + u];
-      part[jq * 1024 + idx] = sum;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) is_last = (atomicAdd(q.cnt + slot, 1u) == static_cast<unsigned>(nq - 1));
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-  }
-  for (int idx = tid; idx < 1024; idx += 256) {
-    const int bl = idx >> 5, u = idx & 31;
-    const int b = b0 + bl, unit = ug * 32 + u;
-    float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, carry = 0.f;
-    if (b < q.B) {
-      float dhrec = 0.f;
-      if (nq > 1) {
-#pragma unroll
-        for (int qq = 0; qq < BWD_JQ; ++qq) dhrec += __ldcg(part + qq * 1024 + idx);
+          for (int g4 = 0; g4 < 4; ++g4) {
+            __nv_bfloat16 hh, ll;
+            split_bf16(dv4[g4], hh, ll);
+            q.dG_pl[go_ + g4 * H] = hh;
+            q.dG_pl[gps + go_ + g4 * H] = ll;
+          }
+          q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit] = carry;
+        }
+        red[(0 * 32 + u) * 33 + bl] = d_i;
+        red[(1 * 32 + u) * 33 + bl] = d_f;
+        red[(2 * 32 + u) * 33 + bl] = d_g;
+        red[(3 * 32 + u) * 33 + bl] = d_o;
       }
-      const long long r = static_cast<long long>(b) * L + t;
-      if (t < q.lengths[b]) {
-        const float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
-        const float gi = G[0], gf = G[H], gg = G[2 * H], go = G[3 * H];
-        const float c = q.Cst[(r * 2 + dir) * H + unit];
-        const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
-        const float dh = q.dH[r * 2 * H + dir * H + unit] + dhrec;
-        const float tc = tanhf(c);
-        float dc = dh * go * (1.f - tc * tc);
-        if (s > 0) dc += q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit];
-        d_i = dc * gg * gi * (1.f - gi);
-        d_f = dc * cp * gf * (1.f - gf);
-        d_g = dc * gi * (1.f - gg * gg);
-        d_o = dh * tc * go * (1.f - go);
-        carry = dc * gf;
+      __syncthreads();
+      float* dgt = q.dGT + (s & 1) * gt_sz + (static_cast<long long>(dir) * q.BC + bc) * 4 * H * 32;
+      for (int idx = tid; idx < 4096; idx += 256) {  // (gate, unit) rows x 32 samples, coalesced over samples
+        const int row = idx >> 5, bl = idx & 31;
+        const int g = row >> 5, u = row & 31;
+        dgt[(static_cast<long long>(g) * H + ug * 32 + u) * 32 + bl] = red[row * 33 + bl];
       }
-      float* dG = q.dG + ((r * 2 + dir) * 4) * H + unit;
-      dG[0] = d_i; dG[H] = d_f; dG[2 * H] = d_g; dG[3 * H] = d_o;
-      q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit] = carry;
+      if (!PERSIST && tid == 0 && nq > 1) q.cnt[slot] = 0u;
     }
-    red[(0 * 32 + u) * 33 + bl] = d_i;
-    red[(1 * 32 + u) * 33 + bl] = d_f;
-    red[(2 * 32 + u) * 33 + bl] = d_g;
-    red[(3 * 32 + u) * 33 + bl] = d_o;
+    if (PERSIST && s + 1 < s1) {
+      __threadfence();
+      cg::this_grid().sync();
+    }
   }
-  __syncthreads();
-  float* dgt = q.dGT + (s & 1) * gt_sz + (static_cast<long long>(dir) * q.BC + bc) * 4 * H * 32;
-  for (int idx = tid; idx < 4096; idx += 256) {  // (gate, unit) rows x 32 samples, coalesced over samples
-    const int row = idx >> 5, bl = idx & 31;
-    const int g = row >> 5, u = row & 31;
-    dgt[(static_cast<long long>(g) * H + ug * 32 + u) * 32 + bl] = red[row * 33 + bl];
-  }
-  if (tid == 0 && nq > 1) q.cnt[slot] = 0u;
 }
 
 // ---- q_vector = [H[b,0] | H[b,len-1]] (language_module.py:50-55) and the scatter of its gradient ------------------------
@@ -650,12 +730,16 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
     off += ((nfloat * sizeof(float) + 255) / 256) * 256;
     return p;
   };
-  float* Ebuf = take(R * E);
+  const size_t EP = (E + 63) / 64 * 64;
+  float* E_pl = take(R * EP);          // 2 planes of bf16 = R*EP floats
+  float* Wih_pl = take(8 * H * EP);    // [8H][EP] x 2 planes of bf16
+  float* bias_sum = take(8 * H);
+  float* dG_pl = take(R * 8 * H);
+  float* Hprev_pl = take(2 * R * H);
   float* xg = take(R * 8 * H);
   float* G = take(R * 8 * H);
   float* Cst = take(R * 2 * H);
   float* Hout = take(R * 2 * H);
-  float* Hprev = take(2 * R * H);
   float* v = take(B * 4 * H);
   float* hid = take(B * H);
   float* c3 = take(3 * B * 2 * H);
@@ -674,7 +758,11 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
   float* dGT = take(2 * 2 * BC * 4 * H * 32);
   float* dr = take(3 * B * L);
   if (q) {
-    q->Ebuf = Ebuf; q->xg = xg; q->G = G; q->Cst = Cst; q->Hout = Hout; q->Hprev = Hprev; q->v = v;
+    q->EP = static_cast<int>(EP);
+    q->E_pl = reinterpret_cast<__nv_bfloat16*>(E_pl); q->Wih_pl = reinterpret_cast<__nv_bfloat16*>(Wih_pl);
+    q->dG_pl = reinterpret_cast<__nv_bfloat16*>(dG_pl); q->Hprev_pl = reinterpret_cast<__nv_bfloat16*>(Hprev_pl);
+    q->bias_sum = bias_sum;
+    q->xg = xg; q->G = G; q->Cst = Cst; q->Hout = Hout; q->v = v;
     q->hid = hid; q->c3 = c3; q->alpha = alpha; q->dH = dH; q->dc3 = dc3; q->dhid = dhid; q->dhid_pre = dhid_pre; q->dv = dv;
     q->dG = dG; q->dcarry = dcarry; q->part = part; q->dE = dE; q->cnt = reinterpret_cast<unsigned*>(cnt);
     q->HT = HT; q->dGT = dGT; q->dr = dr;
@@ -697,6 +785,43 @@ static int make_dev(const drn_qe_t* a, QeDev* q, const char* who) {
   q->w_hh[1] = a->w_hh[1];
   carve(a, q);
   return 0;
+}
+
+// A cooperative (grid-barrier) launch needs every CTA resident at once.  DRN_QE_PERSIST=0 forces the per-step launches.
+static bool fits_cooperative(const void* fn, dim3 grid, size_t smem) {
+  static int allow = -1;
+  if (allow < 0) {
+    const char* e = getenv("DRN_QE_PERSIST");
+    allow = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!allow) return false;
+  int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem) != cudaSuccess) return false;
+  return static_cast<long long>(grid.x) * grid.y * grid.z <= static_cast<long long>(sms) * per_sm;
+}
+
+// drn_gemm_t helpers: a [rows][C] planes matrix as the (c, parity, t, b, plane) view of the tensor-core contraction
+static drn_planes_t planes_view(const __nv_bfloat16* p, long long plane_stride, int rows, int C) {
+  drn_planes_t v;
+  v.ptr = const_cast<__nv_bfloat16*>(p);
+  v.plane_stride = plane_stride;
+  v.B = 1; v.T = rows; v.P = 1; v.C = C;
+  return v;
+}
+static drn_gemm_t qe_gemm_base(int form, int rows) {
+  drn_gemm_t g{};
+  g.form = form;
+  g.B = 1; g.T = rows;
+  g.ntaps = 1;
+  g.nprod = 3;
+  g.split_k = 1;
+  g.out_mode = DRN_OUT_STORE;
+  g.out_T = rows; g.out_t_mul = 1;
+  g.engine = 2;
+  return g;
 }
 
 static int set_smem(const void* fn, size_t bytes, const char* what) {
@@ -736,14 +861,32 @@ extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
   if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_qe_forward memset: %s", cudaGetErrorString(e));
   qe_embed_kernel<<<R, 256, 0, st>>>(q, a->emb);
   TRY(check_launch("qe_embed"));
-  for (int dir = 0; dir < 2; ++dir)  // xg = E W_ih^T + b_ih + b_hh, all time steps at once
-    TRY(sgemm(st, q.Ebuf, E, 1, a->w_ih[dir], 1, E, q.xg + dir * 4 * H, 8 * H, R, 4 * H, E, a->b_ih[dir], a->b_hh[dir], 0, 0,
-              false));  // forward: no split-K atomics, run-to-run reproducible
+  // xg = E [W_ih ; W_ih_reverse]^T + b_ih + b_hh for all time steps and both directions: ONE tensor-core contraction
+  // (split-BF16, deterministic) on the persistent CTA-pair kernel
+  qe_pack_wih_kernel<<<148, 256, 0, st>>>(q, a->w_ih[0], a->w_ih[1], a->b_ih[0], a->b_hh[0], a->b_ih[1], a->b_hh[1]);
+  TRY(check_launch("qe_pack_wih"));
+  {
+    drn_gemm_t g = qe_gemm_base(DRN_GEMM_ROWS, R);
+    g.a = planes_view(q.E_pl, static_cast<long long>(R) * q.EP, R, q.EP);
+    g.b = planes_view(q.Wih_pl, 8LL * H * q.EP, 8 * H, q.EP);
+    g.N = 8 * H; g.K = q.EP;
+    g.out = q.xg; g.out_ld = 8 * H; g.bias = q.bias_sum;
+    TRY(drn_gemm_group(1, &g, stream));
+  }
   const size_t smem_f = (32 * H + H * 32) * sizeof(float);
-  TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_step_kernel), smem_f, "lstm_fwd_step"));
-  for (int s = 0; s < L; ++s) {
-    lstm_fwd_step_kernel<<<dim3(H / 8, 2, q.BC), 256, smem_f, st>>>(q, s);
-    TRY(check_launch("lstm_fwd_step"));
+  TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), smem_f, "lstm_fwd"));
+  TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<false>), smem_f, "lstm_fwd"));
+  const dim3 grid_f(H / 8, 2, q.BC);
+  if (fits_cooperative(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, smem_f)) {
+    int s0 = 0, s1 = L;
+    void* args[] = {&q, &s0, &s1};
+    cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, dim3(256), args, smem_f, st);
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "lstm_fwd (cooperative): %s", cudaGetErrorString(ce));
+  } else {
+    for (int s = 0; s < L; ++s) {
+      lstm_fwd_kernel<false><<<grid_f, 256, smem_f, st>>>(q, s, s + 1);
+      TRY(check_launch("lstm_fwd_step"));
+    }
   }
   qe_hprev_kernel<<<148, 256, 0, st>>>(q);
   TRY(check_launch("qe_hprev"));
@@ -780,24 +923,58 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
   qe_vscatter_kernel<<<B, 256, 0, st>>>(q);
   TRY(check_launch("qe_vscatter"));
   const size_t smem_b = (2 * H * 32 + 8 * 32 * 33) * sizeof(float);
-  TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_step_kernel), smem_b, "lstm_bwd_step"));
-  for (int s = 0; s < L; ++s) {
-    const int nq = s == 0 ? 1 : BWD_JQ;
-    lstm_bwd_step_kernel<<<dim3(H / 32, nq, 2 * q.BC), 256, smem_b, st>>>(q, s, nq);
-    TRY(check_launch("lstm_bwd_step"));
+  TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), smem_b, "lstm_bwd"));
+  TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<false>), smem_b, "lstm_bwd"));
+  const dim3 grid_b(H / 32, BWD_JQ, 2 * q.BC);
+  if (fits_cooperative(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), grid_b, smem_b)) {
+    int s0 = 0, s1 = L, nq = BWD_JQ;
+    void* args[] = {&q, &s0, &s1, &nq};
+    cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), grid_b, dim3(256), args, smem_b, st);
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "lstm_bwd (cooperative): %s", cudaGetErrorString(ce));
+  } else {
+    for (int s = 0; s < L; ++s) {
+      const int nq = s == 0 ? 1 : BWD_JQ;
+      lstm_bwd_kernel<false><<<dim3(H / 32, nq, 2 * q.BC), 256, smem_b, st>>>(q, s, s + 1, nq);
+      TRY(check_launch("lstm_bwd_step"));
+    }
+  }
+  // The five big projections of the LSTM backward in ONE grouped tensor-core launch (split-BF16 planes written by the
+  // kernels above): dW_ih, dW_hh of both directions (weight-gradient form over the R = B*L rows) and dE = dG [W_ih ; W_ih_r].
+  {
+    drn_gemm_t g[5];
+    int n = 0;
+    const drn_planes_t dGp = planes_view(q.dG_pl, static_cast<long long>(R) * 8 * H, R, 8 * H);
+    for (int dir = 0; dir < 2; ++dir) {
+      if (a->g_w_ih[dir]) {
+        drn_gemm_t& w = g[n++] = qe_gemm_base(DRN_GEMM_WGRAD, R);
+        w.a = dGp; w.a_c0 = dir * 4 * H; w.M = 4 * H;
+        w.b = planes_view(q.E_pl, static_cast<long long>(R) * q.EP, R, q.EP);
+        w.N = E;
+        w.out = a->g_w_ih[dir]; w.out_ld = E; w.out_mode = DRN_OUT_ADD;
+      }
+      if (a->g_w_hh[dir]) {
+        drn_gemm_t& w = g[n++] = qe_gemm_base(DRN_GEMM_WGRAD, R);
+        w.a = dGp; w.a_c0 = dir * 4 * H; w.M = 4 * H;
+        w.b = planes_view(q.Hprev_pl + static_cast<long long>(dir) * R * H, 2LL * R * H, R, H);
+        w.N = H;
+        w.out = a->g_w_hh[dir]; w.out_ld = H; w.out_mode = DRN_OUT_ADD;
+      }
+    }
+    if (a->g_emb) {
+      drn_gemm_t& d = g[n++] = qe_gemm_base(DRN_GEMM_ROWS, R);
+      d.a = dGp;
+      d.b = planes_view(q.Wih_pl, 8LL * H * q.EP, 8 * H, q.EP);
+      d.b_mn = 1; d.N = E; d.K = 8 * H;
+      d.out = q.dE; d.out_ld = E;
+    }
+    if (n) TRY(drn_gemm_group(n, g, stream));
   }
   for (int dir = 0; dir < 2; ++dir) {
     const float* dG = q.dG + dir * 4 * H;  // [R] rows of stride 8H
-    if (a->g_w_ih[dir]) TRY(sgemm(st, dG, 1, 8 * H, q.Ebuf, E, 1, a->g_w_ih[dir], E, 4 * H, E, R, nullptr, nullptr, 0, 1));
-    if (a->g_w_hh[dir])
-      TRY(sgemm(st, dG, 1, 8 * H, q.Hprev + static_cast<long long>(dir) * R * H, H, 1, a->g_w_hh[dir], H, 4 * H, H, R, nullptr,
-                nullptr, 0, 1));
     if (a->g_b_ih[dir]) TRY(colsum(st, dG, R, 4 * H, 8 * H, a->g_b_ih[dir]));
     if (a->g_b_hh[dir]) TRY(colsum(st, dG, R, 4 * H, 8 * H, a->g_b_hh[dir]));
   }
   if (a->g_emb) {
-    for (int dir = 0; dir < 2; ++dir)
-      TRY(sgemm(st, q.dG + dir * 4 * H, 8 * H, 1, a->w_ih[dir], E, 1, q.dE, E, R, E, 4 * H, nullptr, nullptr, 0, dir > 0));
     qe_embed_bwd_kernel<<<R, 256, 0, st>>>(q, a->g_emb);
     TRY(check_launch("qe_embed_bwd"));
   }

@@ -55,7 +55,14 @@ def test_query_encoder_forward_backward(sd, name, B, Lc, lengths):
     cfg = S.default_config(stage=1)
     tok, lens = _tokens(B, Lc, lengths), torch.tensor(lengths, dtype=torch.int64)
     leaf = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items() if k.startswith("query_encoder.")}
-    cmds, _ = O.query_encoder(leaf, tok, lens)
+    cmds, Hs = O.query_encoder(leaf, tok, lens)
+    # hidden units of relu(qInput(q_vector)) that sit within 1e-4 of the ReLU kink for some sample: a 1e-6 rounding
+    # difference flips their mask, so their rows of d qInput.{weight,bias} are excluded from the comparison
+    with torch.no_grad():
+        vq = torch.cat([Hs[:, 0], Hs[torch.arange(B), lens - 1]], dim=-1)
+        pre = torch.nn.functional.linear(vq, leaf["query_encoder.qInput.weight"], leaf["query_encoder.qInput.bias"])
+        safe_units = ~(pre.abs() < 1e-4).any(dim=0)
+    assert int(safe_units.sum()) > 400
     g = torch.Generator().manual_seed(1)
     dcmd = [torch.randn(B, 1024, generator=g) for _ in range(3)]
     sum((c * d).sum() for c, d in zip(cmds, dcmd)).backward()
@@ -78,6 +85,8 @@ def test_query_encoder_forward_backward(sd, name, B, Lc, lengths):
         if float(ref.norm()) < 1e-5:  # softmax is shift invariant: d cmd_inter2logits.bias == 0
             assert float(gk.norm()) < 1e-4, k
             continue
+        if k in ("query_encoder.qInput.weight", "query_encoder.qInput.bias"):
+            gk, ref = gk.cpu()[safe_units], ref[safe_units]
         assert _rel_l2(gk, ref) <= 1e-3, (name, k, _rel_l2(gk, ref))
     assert float(grads["query_encoder.embedding.weight"][0].abs().max()) == 0.0  # padding_idx row
     # second call on the same workspace gives identical results (self-resetting counters / carried state)
