@@ -318,17 +318,20 @@ __device__ __forceinline__ void cp_async_wait_all() {
 // double-buffered over steps) so that a step stages it, like its 64 KB slice of W_hh, with straight 16-byte cp.async
 // copies.  PERSIST: ONE cooperative launch walks all L steps with the W_hh slice resident in shared memory and a grid
 // barrier between steps (used when the grid fits the GPU: B <= 32); otherwise one launch per step.
+constexpr int LSTM_THREADS = 512;  // 16 warps: two per hidden unit (each takes half of the contraction), 8 units per CTA
 template <bool PERSIST>
-__global__ void __launch_bounds__(256) lstm_fwd_kernel(QeDev q, int s0, int s1) {
+__global__ void __launch_bounds__(LSTM_THREADS) lstm_fwd_kernel(QeDev q, int s0, int s1) {
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
-  float* ws = smem;                 // [32][H]   rows (unit w, gate g) -> w*4+g
+  float* ws = smem;                 // [32][H]   rows (unit, gate) -> unit*4+g
   float* hs = smem + 32 * H;        // [H][32]   previous hidden state of this sample chunk, unit-major
+  float* comb = smem + 64 * H;      // [8][4][32] partial gate sums of the upper K half
   const int ug = blockIdx.x, dir = blockIdx.y, bc = blockIdx.z, b0 = bc * 32;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ul = w >> 1, kh = w & 1;  // local unit, K half
   const long long ht_sz = 2LL * q.BC * H * 32;
   const int b = b0 + lane;
-  const int unit = ug * 8 + w;
+  const int unit = ug * 8 + ul;
   const bool inb = b < q.B;
   const int len = inb ? static_cast<int>(q.lengths[b]) : 0;
   bool w_loaded = false;
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(QeDev q, int s0, int s1) 
       if (!w_loaded) {
         const float* W = q.w_hh[dir];
         const int c4 = H / 4;  // 16-byte chunks per W row
-        for (int idx = tid; idx < 32 * c4; idx += 256) {
+        for (int idx = tid; idx < 32 * c4; idx += LSTM_THREADS) {
           const int row = idx / c4, k4 = idx % c4;
           const int u = ug * 8 + (row >> 2), g = row & 3;
           cp_async16(ws + row * H + k4 * 4, W + (static_cast<long long>(g) * H + u) * H + k4 * 4);
@@ -347,18 +350,19 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(QeDev q, int s0, int s1) 
         w_loaded = true;
       }
       const float* hprev = q.HT + ((s - 1) & 1) * ht_sz + (static_cast<long long>(dir) * q.BC + bc) * H * 32;
-      for (int idx = tid; idx < H * 8; idx += 256) cp_async16(hs + idx * 4, hprev + idx * 4);
+      for (int idx = tid; idx < H * 8; idx += LSTM_THREADS) cp_async16(hs + idx * 4, hprev + idx * 4);
       cp_async_wait_all();
       __syncthreads();
     }
     const long long r = static_cast<long long>(inb ? b : 0) * L + t;
     float acc[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) acc[g] = inb ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
+    for (int g = 0; g < 4; ++g) acc[g] = (inb && kh == 0) ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
     if (s > 0) {
-      const float* wr = ws + (w * 4) * H;
+      const float* wr = ws + (ul * 4) * H;
+      const int kbeg = kh * (H / 2), kend = kbeg + H / 2;
 #pragma unroll 2
-      for (int k = 0; k < H; k += 4) {
+      for (int k = kbeg; k < kend; k += 4) {
         const float h0 = hs[(k + 0) * 32 + lane], h1 = hs[(k + 1) * 32 + lane], h2 = hs[(k + 2) * 32 + lane],
                     h3 = hs[(k + 3) * 32 + lane];
 #pragma unroll
@@ -370,28 +374,41 @@ __global__ void __launch_bounds__(256) lstm_fwd_kernel(QeDev q, int s0, int s1) 
           acc[g] = fmaf(h3, wv.w, acc[g]);
         }
       }
+      if (kh == 1) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) comb[(ul * 4 + g) * 32 + lane] = acc[g];
+      }
+      __syncthreads();
+      if (kh == 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) acc[g] += comb[(ul * 4 + g) * 32 + lane];
+      }
     }
-    const bool live = inb && t < len;
-    float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
-    if (live) {
-      gi = sigmoidf_(acc[0]);
-      gf = sigmoidf_(acc[1]);
-      gg = tanhf(acc[2]);
-      go = sigmoidf_(acc[3]);
-      const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
-      c = gf * cp + gi * gg;
-      h = go * tanhf(c);
-    }
-    q.HT[(s & 1) * ht_sz + ((static_cast<long long>(dir) * q.BC + bc) * H + unit) * 32 + lane] = h;
-    if (inb) {
-      float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
-      G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
-      q.Cst[(r * 2 + dir) * H + unit] = c;
-      q.Hout[r * 2 * H + dir * H + unit] = h;
+    if (kh == 0) {
+      const bool live = inb && t < len;
+      float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
+      if (live) {
+        gi = sigmoidf_(acc[0]);
+        gf = sigmoidf_(acc[1]);
+        gg = tanhf(acc[2]);
+        go = sigmoidf_(acc[3]);
+        const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+        c = gf * cp + gi * gg;
+        h = go * tanhf(c);
+      }
+      q.HT[(s & 1) * ht_sz + ((static_cast<long long>(dir) * q.BC + bc) * H + unit) * 32 + lane] = h;
+      if (inb) {
+        float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+        G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
+        q.Cst[(r * 2 + dir) * H + unit] = c;
+        q.Hout[r * 2 * H + dir * H + unit] = h;
+      }
     }
     if (PERSIST && s + 1 < s1) {
       __threadfence();
       cg::this_grid().sync();
+    } else if (!PERSIST) {
+      __syncthreads();
     }
   }
 }
@@ -427,7 +444,7 @@ __global__ void __launch_bounds__(256) qe_hprev_kernel(QeDev q) {
 // dG is also kept transposed ([gate row][32 samples], double-buffered) so Phase A stages both operands with cp.async.
 constexpr int BWD_JQ = 4;
 template <bool PERSIST>
-__global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, int nq_launch) {
+__global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0, int s1, int nq_launch) {
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
   const int ug = blockIdx.x, jq = blockIdx.y, dir = blockIdx.z / q.BC, bc = blockIdx.z % q.BC, b0 = bc * 32;
@@ -438,7 +455,8 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, 
   float* part = q.part + slot * BWD_JQ * 1024;
   float* dgs = smem;               // [H][32]  dG_next rows of this quarter, (gate row j, sample b)
   float* wsm = smem + H * 32;      // [H][32]  W_hh[jq*H + j][ug*32 + u]
-  float* red = smem + 2 * H * 32;  // [8][32][33]; reused as the [4][32][33] transposition tile of Phase B
+  float* red = smem + 2 * H * 32;  // [16][32][33]; reused as the [4][32][33] transposition tile of Phase B
+  constexpr int NW = LSTM_THREADS / 32;
   __shared__ bool is_last;
   bool w_loaded = false;
   for (int s = s0; s < s1; ++s) {
@@ -448,10 +466,10 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, 
     bool do_b = PERSIST ? (jq == 0) : true;
     if (nq > 1) {
       const float* src = q.dGT + ((s - 1) & 1) * gt_sz + ((static_cast<long long>(dir) * q.BC + bc) * 4 * H + jq * H) * 32;
-      for (int idx = tid; idx < H * 8; idx += 256) cp_async16(dgs + idx * 4, src + idx * 4);
+      for (int idx = tid; idx < H * 8; idx += LSTM_THREADS) cp_async16(dgs + idx * 4, src + idx * 4);
       if (!w_loaded) {
         const float* W = q.w_hh[dir] + static_cast<long long>(jq) * H * H + ug * 32;
-        for (int idx = tid; idx < H * 8; idx += 256) {
+        for (int idx = tid; idx < H * 8; idx += LSTM_THREADS) {
           const int j = idx >> 3, c = idx & 7;
           cp_async16(wsm + j * 32 + c * 4, W + static_cast<long long>(j) * H + c * 4);
         }
@@ -462,7 +480,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, 
       float acc[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-      const int jw = H / 8;  // rows per warp
+      const int jw = H / NW;  // rows per warp
 #pragma unroll 2
       for (int j = w * jw; j < (w + 1) * jw; ++j) {
         const float wv = wsm[j * 32 + lane];
@@ -479,11 +497,11 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, 
 #pragma unroll
       for (int i = 0; i < 32; ++i) red[(w * 32 + i) * 33 + lane] = acc[i];
       __syncthreads();
-      for (int idx = tid; idx < 1024; idx += 256) {
+      for (int idx = tid; idx < 1024; idx += LSTM_THREADS) {
         const int bb = idx >> 5, u = idx & 31;
         float sum = 0.f;
 #pragma unroll
-        for (int ww = 0; ww < 8; ++ww) sum += red[(ww * 32 + bb) * 33 + u];
+        for (int ww = 0; ww < NW; ++ww) sum += red[(ww * 32 + bb) * 33 + u];
         part[jq * 1024 + idx] = sum;
       }
       __threadfence();
@@ -498,7 +516,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, 
       }
     }
     if (do_b) {
-      for (int idx = tid; idx < 1024; idx += 256) {
+      for (int idx = tid; idx < 1024; idx += LSTM_THREADS) {
         const int bl = idx >> 5, u = idx & 31;
         const int b = b0 + bl, unit = ug * 32 + u;
         float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, carry = 0.f;
@@ -545,7 +563,7 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(QeDev q, int s0, int s1, 
       }
       __syncthreads();
       float* dgt = q.dGT + (s & 1) * gt_sz + (static_cast<long long>(dir) * q.BC + bc) * 4 * H * 32;
-      for (int idx = tid; idx < 4096; idx += 256) {  // (gate, unit) rows x 32 samples, coalesced over samples
+      for (int idx = tid; idx < 4096; idx += LSTM_THREADS) {  // (gate, unit) rows x 32 samples, coalesced over samples
         const int row = idx >> 5, bl = idx & 31;
         const int g = row >> 5, u = row & 31;
         dgt[(static_cast<long long>(g) * H + ug * 32 + u) * 32 + bl] = red[row * 33 + bl];
@@ -799,7 +817,7 @@ static bool fits_cooperative(const void* fn, dim3 grid, size_t smem) {
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem) != cudaSuccess) return false;
+  if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, LSTM_THREADS, smem) != cudaSuccess) return false;
   return static_cast<long long>(grid.x) * grid.y * grid.z <= static_cast<long long>(sms) * per_sm;
 }
 
@@ -856,7 +874,7 @@ extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
   QeDev q;
   TRY(make_dev(a, &q, "drn_qe_forward"));
   cudaStream_t st = ST(stream);
-  const int B = q.B, L = q.L, H = q.H, E = q.E, R = B * L, D = 2 * H;
+  const int B = q.B, L = q.L, H = q.H, R = B * L, D = 2 * H;
   cudaError_t e = cudaMemsetAsync(q.cnt, 0, sizeof(unsigned) * 2 * q.BC * (H / 32), st);
   if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_qe_forward memset: %s", cudaGetErrorString(e));
   qe_embed_kernel<<<R, 256, 0, st>>>(q, a->emb);
@@ -873,18 +891,18 @@ extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
     g.out = q.xg; g.out_ld = 8 * H; g.bias = q.bias_sum;
     TRY(drn_gemm_group(1, &g, stream));
   }
-  const size_t smem_f = (32 * H + H * 32) * sizeof(float);
+  const size_t smem_f = (32 * H + H * 32 + 8 * 4 * 32) * sizeof(float);
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), smem_f, "lstm_fwd"));
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<false>), smem_f, "lstm_fwd"));
   const dim3 grid_f(H / 8, 2, q.BC);
   if (fits_cooperative(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, smem_f)) {
     int s0 = 0, s1 = L;
     void* args[] = {&q, &s0, &s1};
-    cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, dim3(256), args, smem_f, st);
+    cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, dim3(LSTM_THREADS), args, smem_f, st);
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "lstm_fwd (cooperative): %s", cudaGetErrorString(ce));
   } else {
     for (int s = 0; s < L; ++s) {
-      lstm_fwd_kernel<false><<<grid_f, 256, smem_f, st>>>(q, s, s + 1);
+      lstm_fwd_kernel<false><<<grid_f, LSTM_THREADS, smem_f, st>>>(q, s, s + 1);
       TRY(check_launch("lstm_fwd_step"));
     }
   }
@@ -922,19 +940,19 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
   if (a->g_b1) TRY(colsum(st, q.dhid_pre, B, H, H, a->g_b1));
   qe_vscatter_kernel<<<B, 256, 0, st>>>(q);
   TRY(check_launch("qe_vscatter"));
-  const size_t smem_b = (2 * H * 32 + 8 * 32 * 33) * sizeof(float);
+  const size_t smem_b = (2 * H * 32 + (LSTM_THREADS / 32) * 32 * 33) * sizeof(float);
   TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), smem_b, "lstm_bwd"));
   TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<false>), smem_b, "lstm_bwd"));
   const dim3 grid_b(H / 32, BWD_JQ, 2 * q.BC);
   if (fits_cooperative(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), grid_b, smem_b)) {
     int s0 = 0, s1 = L, nq = BWD_JQ;
     void* args[] = {&q, &s0, &s1, &nq};
-    cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), grid_b, dim3(256), args, smem_b, st);
+    cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), grid_b, dim3(LSTM_THREADS), args, smem_b, st);
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "lstm_bwd (cooperative): %s", cudaGetErrorString(ce));
   } else {
     for (int s = 0; s < L; ++s) {
       const int nq = s == 0 ? 1 : BWD_JQ;
-      lstm_bwd_kernel<false><<<dim3(H / 32, nq, 2 * q.BC), 256, smem_b, st>>>(q, s, s + 1, nq);
+      lstm_bwd_kernel<false><<<dim3(H / 32, nq, 2 * q.BC), LSTM_THREADS, smem_b, st>>>(q, s, s + 1, nq);
       TRY(check_launch("lstm_bwd_step"));
     }
   }
