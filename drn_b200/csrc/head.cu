@@ -63,12 +63,11 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const __nv_bfloat16* __
 // ---- skinny conv backward: dX[b,t,c0+c] = sum_o sum_r d[b,t+pad-r,o] W[o][c][r];  dW[o][c][r] += sum X[b,t,c] d[b,t+pad-r,o]
 // one thread per channel PAIR (4-byte plane loads, 8-byte stores), a block walks a chunk of rows.
 template <int NOUT, int K>
-__global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict__ d, const __nv_bfloat16* __restrict__ x,
-                                                         long long x_ps, int x_ld, int c0, int Cw, int B, int T,
-                                                         const float* __restrict__ W, int rows_per_block,
-                                                         float* __restrict__ dx, int dx_ld, int dx_accumulate,
-                                                         float* __restrict__ dW) {
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+__device__ __forceinline__ void skinny_bwd_body(const float* __restrict__ d, const __nv_bfloat16* __restrict__ x, long long x_ps,
+                                                int x_ld, int c0, int Cw, int B, int T, const float* __restrict__ W,
+                                                int rows_per_block, float* __restrict__ dx, int dx_ld, int dx_accumulate,
+                                                float* __restrict__ dW, int cblock, int rblock) {
+  const int c = (cblock * blockDim.x + threadIdx.x) * 2;
   if (c >= Cw) return;
   constexpr int PAD = (K - 1) / 2;
   float w[2][NOUT][K], gw[2][NOUT][K];
@@ -82,7 +81,8 @@ __global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict
         gw[h][o][r] = 0.f;
       }
   const long long rows = static_cast<long long>(B) * T;
-  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r0 = static_cast<long long>(rblock) * rows_per_block;
+  if (r0 >= rows) return;
   constexpr int U = 4;  // rows in flight per thread: the activation loads of U rows are issued before any of them is used
   for (int i0 = 0; i0 < rows_per_block; i0 += U) {
     uint32_t xh[U], xl[U];
@@ -135,6 +135,125 @@ __global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict
 #pragma unroll
         for (int r = 0; r < K; ++r) atomicAdd(dW + (static_cast<long long>(o) * Cw + c + h) * K + r, gw[h][o][r]);
   }
+}
+
+template <int NOUT, int K>
+__global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict__ d, const __nv_bfloat16* __restrict__ x,
+                                                         long long x_ps, int x_ld, int c0, int Cw, int B, int T,
+                                                         const float* __restrict__ W, int rows_per_block,
+                                                         float* __restrict__ dx, int dx_ld, int dx_accumulate,
+                                                         float* __restrict__ dW) {
+  skinny_bwd_body<NOUT, K>(d, x, x_ps, x_ld, c0, Cw, B, T, W, rows_per_block, dx, dx_ld, dx_accumulate, dW, blockIdx.x, blockIdx.y);
+}
+
+// ---- all pyramid levels, cls_logits + bbox_pred (+ iou_scores.3) in ONE launch -----------------------------------------------
+struct HeadLevels {
+  int nlevels, B, F;              // F = tower channels per branch (512); the tower tensor carries [cls | bbox] = 2F channels
+  int T[MAX_LEVELS], off[MAX_LEVELS];
+  const __nv_bfloat16* tw[MAX_LEVELS];
+  long long tw_ps[MAX_LEVELS];
+  const __nv_bfloat16* hi[MAX_LEVELS];  // iou_scores hidden activations (F/2 channels); null = skip the IoU projection
+  long long hi_ps[MAX_LEVELS];
+  float* dtw[MAX_LEVELS];         // backward: gradient w.r.t. the tower tensor, fp32 [B*T][2F]
+};
+
+// forward: one warp per location; weights staged tap-major in shared memory once per CTA
+__global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const float* __restrict__ Wc, const float* __restrict__ bc,
+                                                            const float* __restrict__ Wb, const float* __restrict__ bb,
+                                                            const float* __restrict__ Wi, const float* __restrict__ bi,
+                                                            float* __restrict__ cls_raw, float* __restrict__ box_raw,
+                                                            float* __restrict__ iou_raw, long long total) {
+  extern __shared__ __align__(16) float hsm[];
+  const int F = g.F;
+  float* wc = hsm;              // [3][F]
+  float* wb = hsm + 3 * F;      // [2][3][F]
+  float* wi = hsm + 9 * F;      // [F/2]
+  for (int i = threadIdx.x; i < 3 * F; i += 256) {
+    const int r = i / F, c = i % F;
+    wc[i] = Wc[c * 3 + r];
+    wb[i] = Wb[c * 3 + r];
+    wb[3 * F + i] = Wb[(F + c) * 3 + r];
+  }
+  for (int i = threadIdx.x; i < F / 2; i += 256) wi[i] = Wi[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long nwarp = static_cast<long long>(gridDim.x) * 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5); i < total; i += nwarp) {
+    int lvl = 0;
+#pragma unroll
+    for (int l = 1; l < MAX_LEVELS; ++l)
+      if (l < g.nlevels && i >= static_cast<long long>(g.B) * g.off[l]) lvl = l;
+    const long long j = i - static_cast<long long>(g.B) * g.off[lvl];
+    const int T = g.T[lvl];
+    const int t = static_cast<int>(j % T);
+    float a_cls = 0.f, a_b0 = 0.f, a_b1 = 0.f, a_iou = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ts = t + r - 1;
+      if (ts < 0 || ts >= T) continue;
+      const __nv_bfloat16* row = g.tw[lvl] + (j + r - 1) * (2 * F);
+      for (int c = lane * 8; c < 2 * F; c += 256) {
+        const uint4 h = *reinterpret_cast<const uint4*>(row + c);
+        const uint4 l = *reinterpret_cast<const uint4*>(row + c + g.tw_ps[lvl]);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[2 * k] = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+          v[2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+        }
+        if (c < F) {
+          const float4 w0 = *reinterpret_cast<const float4*>(wc + r * F + c), w1 = *reinterpret_cast<const float4*>(wc + r * F + c + 4);
+          a_cls += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+        } else {
+          const int cc = c - F;
+          const float4 p0 = *reinterpret_cast<const float4*>(wb + r * F + cc), p1 = *reinterpret_cast<const float4*>(wb + r * F + cc + 4);
+          const float4 q0 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + cc), q1 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + cc + 4);
+          a_b0 += v[0] * p0.x + v[1] * p0.y + v[2] * p0.z + v[3] * p0.w + v[4] * p1.x + v[5] * p1.y + v[6] * p1.z + v[7] * p1.w;
+          a_b1 += v[0] * q0.x + v[1] * q0.y + v[2] * q0.z + v[3] * q0.w + v[4] * q1.x + v[5] * q1.y + v[6] * q1.z + v[7] * q1.w;
+        }
+      }
+    }
+    if (g.hi[lvl]) {
+      const __nv_bfloat16* row = g.hi[lvl] + j * (F / 2);
+      for (int c = lane * 8; c < F / 2; c += 256) {
+        const uint4 h = *reinterpret_cast<const uint4*>(row + c);
+        const uint4 l = *reinterpret_cast<const uint4*>(row + c + g.hi_ps[lvl]);
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          a_iou += (__uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16)) * wi[c + 2 * k];
+          a_iou += (__uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u)) * wi[c + 2 * k + 1];
+        }
+      }
+    }
+    a_cls = warp_sum(a_cls);
+    a_b0 = warp_sum(a_b0);
+    a_b1 = warp_sum(a_b1);
+    a_iou = warp_sum(a_iou);
+    if (lane == 0) {
+      cls_raw[i] = a_cls + bc[0];
+      box_raw[2 * i] = a_b0 + bb[0];
+      box_raw[2 * i + 1] = a_b1 + bb[1];
+      if (g.hi[lvl]) iou_raw[i] = a_iou + bi[0];
+    }
+  }
+}
+
+// backward of cls_logits (blockIdx.x = 0: channels [0,F)) and bbox_pred (blockIdx.x = 1: channels [F,2F)) on every level
+// (blockIdx.z); blockIdx.y = chunk of rows
+__global__ void __launch_bounds__(256) head_proj_bwd_kernel(HeadLevels g, const float* __restrict__ dcls,
+                                                            const float* __restrict__ dbox, const float* __restrict__ Wc,
+                                                            const float* __restrict__ Wb, int rows_per_block,
+                                                            float* __restrict__ dWc, float* __restrict__ dWb) {
+  const int lvl = blockIdx.z, F = g.F;
+  const long long o = static_cast<long long>(g.B) * g.off[lvl];
+  if (blockIdx.x == 0)
+    skinny_bwd_body<1, 3>(dcls + o, g.tw[lvl], g.tw_ps[lvl], 2 * F, 0, F, g.B, g.T[lvl], Wc, rows_per_block, g.dtw[lvl], 2 * F, 0, dWc,
+                          0, blockIdx.y);
+  else
+    skinny_bwd_body<2, 3>(dbox + 2 * o, g.tw[lvl], g.tw_ps[lvl], 2 * F, F, F, g.B, g.T[lvl], Wb, rows_per_block, g.dtw[lvl], 2 * F, 0,
+                          dWb, 0, blockIdx.y);
 }
 
 // ---- loss ---------------------------------------------------------------------------------------------------------------
@@ -479,4 +598,58 @@ extern "C" int drn_postprocess(int nlevels, int B, const int* T, const float* st
   postprocess_kernel<<<dim3(nlevels, B), 256, 0, ST(stream)>>>(g, cls_raw, bbox, iou_raw, thr, top_n, use_iou, out_det, out_score,
                                                              out_loc, out_count);
   return check_launch("postprocess");
+}
+
+static int make_head_levels(HeadLevels* g, const drn_head_levels_t* h, const char* who) {
+  if (!h || h->nlevels < 1 || h->nlevels > 3) return fail(DRN_EINVAL, "%s: 1..3 levels", who);
+  if (h->F < 16 || h->F % 16 || h->B < 1) return fail(DRN_EINVAL, "%s: tower channels must be a multiple of 16 (F=%d)", who, h->F);
+  g->nlevels = h->nlevels;
+  g->B = h->B;
+  g->F = h->F;
+  int off = 0;
+  for (int l = 0; l < h->nlevels; ++l) {
+    g->T[l] = h->T[l];
+    g->off[l] = off;
+    off += h->T[l];
+    g->tw[l] = static_cast<const __nv_bfloat16*>(h->tower[l]);
+    g->tw_ps[l] = h->tower_plane_stride[l];
+    g->hi[l] = static_cast<const __nv_bfloat16*>(h->iou_hidden[l]);
+    g->hi_ps[l] = h->iou_hidden_plane_stride[l];
+    g->dtw[l] = h->d_tower[l];
+    if (!g->tw[l] || g->tw_ps[l] % 8) return fail(DRN_EINVAL, "%s: level %d tower planes missing / misaligned", who, l);
+  }
+  return off;
+}
+
+extern "C" int drn_head_proj_fwd(const drn_head_levels_t* h, const float* Wc, const float* bc, const float* Wb, const float* bb,
+                                 const float* Wi, const float* bi, float* cls_raw, float* box_raw, float* iou_raw, void* stream) {
+  HeadLevels g{};
+  const int P = make_head_levels(&g, h, "drn_head_proj_fwd");
+  if (P < 0) return P;
+  const long long total = static_cast<long long>(g.B) * P;
+  const size_t smem = (9 * g.F + g.F / 2) * sizeof(float);
+  if (smem > 48 * 1024) return fail(DRN_EINVAL, "drn_head_proj_fwd: F=%d too large for the weight stage", g.F);
+  long long ctas = (total + 7) / 8;
+  if (ctas > 148 * 4) ctas = 148 * 4;
+  head_proj_fwd_kernel<<<static_cast<unsigned>(ctas), 256, smem, ST(stream)>>>(g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
+  return check_launch("head_proj_fwd");
+}
+
+extern "C" int drn_head_proj_bwd(const drn_head_levels_t* h, const float* dcls, const float* dbox, const float* Wc, const float* Wb,
+                                 float* dWc, float* dWb, void* stream) {
+  HeadLevels g{};
+  const int P = make_head_levels(&g, h, "drn_head_proj_bwd");
+  if (P < 0) return P;
+  if (g.F > 512) return fail(DRN_EINVAL, "drn_head_proj_bwd: at most 512 tower channels per branch (F=%d)", g.F);
+  long long rows_max = 0;
+  for (int l = 0; l < g.nlevels; ++l) {
+    if (!g.dtw[l]) return fail(DRN_EINVAL, "drn_head_proj_bwd: d_tower[%d] missing", l);
+    const long long r = static_cast<long long>(g.B) * g.T[l];
+    rows_max = r > rows_max ? r : rows_max;
+  }
+  int rpb = 16;
+  while (rpb < 64 && static_cast<long long>(g.B) * P / rpb > 148) rpb *= 2;  // ~2 waves over (2 halves x levels x row chunks)
+  dim3 grid(2, static_cast<unsigned>((rows_max + rpb - 1) / rpb), g.nlevels);
+  head_proj_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(g, dcls, dbox, Wc, Wb, rpb, dWc, dWb);
+  return check_launch("head_proj_bwd");
 }

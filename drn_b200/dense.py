@@ -389,19 +389,11 @@ class DensePath:
         self._bn_fwd([self._bn_job(self.mix[l], p, out_a=self.MX[l]) for l in range(3)], training, shared=True)
         self._group([self._conv_desc(self.iouc[l], self.MX[l], self.wp["iouc"], bias=p[h + "iou_scores.0.bias"], engine=2) for l in range(3)])
         self._bn_fwd([self._bn_job(self.iouc[l], p, out_a=self.HI[l]) for l in range(3)], training, shared=True)
-        for l in range(3):
-            Tl = self.Tl[l]
-            o = self.lvl_off[l]
-            tw, hi = self.TW[l], self.HI[l]
-            self._chk(lib.drn_skinny_conv_fwd(_vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, self.F, B, Tl, 1, 3,
-                                              _vp(p[h + "cls_logits.weight"]), _vp(p[h + "cls_logits.bias"]),
-                                              _vp(self.cls_raw[o:]), _st()), "cls_logits")
-            self._chk(lib.drn_skinny_conv_fwd(_vp(tw.data), C.c_int64(tw.plane_stride), tw.C, self.F, self.F, B, Tl, 2, 3,
-                                              _vp(p[h + "bbox_pred.weight"]), _vp(p[h + "bbox_pred.bias"]),
-                                              _vp(self.box_raw[o:]), _st()), "bbox_pred")
-            self._chk(lib.drn_skinny_conv_fwd(_vp(hi.data), C.c_int64(hi.plane_stride), hi.C, 0, self.F // 2, B, Tl, 1, 1,
-                                              _vp(p[h + "iou_scores.3.weight"]), _vp(p[h + "iou_scores.3.bias"]),
-                                              _vp(self.iou_raw[o:]), _st()), "iou_scores.3")
+        # cls_logits / bbox_pred / iou_scores.3 on every level: one launch (fcos.py:95-102)
+        self._chk(lib.drn_head_proj_fwd(C.byref(self._head_levels()), _vp(p[h + "cls_logits.weight"]), _vp(p[h + "cls_logits.bias"]),
+                                        _vp(p[h + "bbox_pred.weight"]), _vp(p[h + "bbox_pred.bias"]),
+                                        _vp(p[h + "iou_scores.3.weight"]), _vp(p[h + "iou_scores.3.bias"]), _vp(self.cls_raw),
+                                        _vp(self.box_raw), _vp(self.iou_raw), _st()), "head_proj_fwd")
         torch.cat([p[h + "scales.%d.scale" % l] for l in range(3)], out=self.scales)
         self._chk(lib.drn_fcos_loss_fwd(3, B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.box_raw), _vp(self.iou_raw),
                                         _vp(self.scales), _vp(self.gt), C.c_float(self.gamma), C.c_float(self.alpha),
@@ -409,6 +401,16 @@ class DensePath:
                   "fcos_loss_fwd")
         self.launches += 1  # finalize kernel inside drn_fcos_loss_fwd
         self.launches_fwd = self.launches
+
+    def _head_levels(self):
+        hl = L.HeadLevels()
+        hl.nlevels, hl.B, hl.F = 3, self.B, self.F
+        for l in range(3):
+            hl.T[l] = self.Tl[l]
+            hl.tower[l], hl.tower_plane_stride[l] = self.TW[l].data.data_ptr(), self.TW[l].plane_stride
+            hl.iou_hidden[l], hl.iou_hidden_plane_stride[l] = self.HI[l].data.data_ptr(), self.HI[l].plane_stride
+            hl.d_tower[l] = self.dTW[l].data_ptr()
+        return hl
 
     def postprocess(self):
         """Eval only (fcos.py:172-191 -> inference.py:49-136): candidate selection for every (sample, level) in one launch.
@@ -491,14 +493,9 @@ class DensePath:
             self._group([self._wgrad_desc(self.iouc[l], self.MX[l], "iouc", l) for l in lv] +
                         [d for l in lv for d in self._dgrad_descs(self.iouc[l], self.wp["iouc"], self.dMX[l])])
             self._bn_bwd([self._bn_job(self.mix[l], p, grads, da=self.dMX[l]) for l in lv])
-        for l in lv:
-            Tl, o, tw = self.Tl[l], self.lvl_off[l], self.TW[l]
-            self._chk(lib.drn_skinny_conv_bwd(_vp(self.dcls[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, 0, F, B, Tl, 1, 3,
-                                              _vp(p[h + "cls_logits.weight"]), _vp(self.dTW[l]), 2 * F, 0,
-                                              _vp(grads[h + "cls_logits.weight"]), _st()), "cls_logits_bwd")
-            self._chk(lib.drn_skinny_conv_bwd(_vp(self.dbox[o:]), _vp(tw.data), C.c_int64(tw.plane_stride), tw.C, F, F, B, Tl, 2, 3,
-                                              _vp(p[h + "bbox_pred.weight"]), _vp(self.dTW[l]), 2 * F, 0,
-                                              _vp(grads[h + "bbox_pred.weight"]), _st()), "bbox_pred_bwd")
+        self._chk(lib.drn_head_proj_bwd(C.byref(self._head_levels()), _vp(self.dcls), _vp(self.dbox), _vp(p[h + "cls_logits.weight"]),
+                                        _vp(p[h + "bbox_pred.weight"]), _vp(grads[h + "cls_logits.weight"]),
+                                        _vp(grads[h + "bbox_pred.weight"]), _st()), "head_proj_bwd")
         if iou_on:  # mix_fc: weight gradients + data gradients added onto the tower gradient (fcos.py:101 cat)
             self._group([self._wgrad_desc(self.mix[l], self.TW[l], "mix", l) for l in lv] +
                         [d for l in lv for d in self._dgrad_descs(self.mix[l], self.wp["mix"], self.dTW[l], mode=L.OUT_ADD)])

@@ -56,6 +56,14 @@ class BnJob(C.Structure):
                 ("da", C.c_void_p), ("dy", C.c_void_p), ("dy_plane_stride", C.c_int64)]
 
 
+class HeadLevels(C.Structure):
+    """drn_head_levels_t: per-level operands of the fused head projections."""
+    _fields_ = [("nlevels", C.c_int32), ("B", C.c_int32), ("F", C.c_int32), ("T", C.c_int32 * 3),
+                ("tower", C.c_void_p * 3), ("tower_plane_stride", C.c_int64 * 3),
+                ("iou_hidden", C.c_void_p * 3), ("iou_hidden_plane_stride", C.c_int64 * 3),
+                ("d_tower", C.c_void_p * 3)]
+
+
 class PackItem(C.Structure):
     _fields_ = [("src", C.c_void_p), ("planes", C.c_void_p), ("grad", C.c_void_p),
                 ("O", C.c_int32), ("C", C.c_int32), ("k", C.c_int32), ("Ototal", C.c_int32), ("o0", C.c_int32),

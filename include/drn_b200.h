@@ -203,6 +203,22 @@ int drn_skinny_conv_fwd(const void* x, int64_t x_plane_stride, int x_ld, int c0,
                         const float* W, const float* bias, float* out, void* stream);
 int drn_skinny_conv_bwd(const float* d, const void* x, int64_t x_plane_stride, int x_ld, int c0, int Cw, int B, int T, int nout,
                         int k, const float* W, float* dx, int dx_ld, int dx_accumulate, float* dW, void* stream);
+/* The three skinny projections of the shared head on ALL pyramid levels in one launch (model/fcos.py:93-102):
+ * cls_logits (k3, F -> 1) on tower channels [0,F), bbox_pred (k3, F -> 2) on tower channels [F,2F) -- the tower tensor is the
+ * fused [cls_tower | bbox_tower] output -- and iou_scores.3 (k1, F/2 -> 1) on the iou_scores hidden activations (skipped where
+ * iou_hidden[l] is null).  Outputs in the reference's flatten order (level, sample, t).  Backward: gradient w.r.t. the tower
+ * tensor (fp32 [B*T_l][2F], stored) and weight gradients (accumulated); bias gradients come from drn_fcos_loss_bwd's pgrad. */
+typedef struct {
+  int32_t nlevels, B, F;
+  int32_t T[3];
+  const void* tower[3]; int64_t tower_plane_stride[3];            /* planes [B][T_l][2F] */
+  const void* iou_hidden[3]; int64_t iou_hidden_plane_stride[3];  /* planes [B][T_l][F/2] */
+  float* d_tower[3];                                              /* backward only */
+} drn_head_levels_t;
+int drn_head_proj_fwd(const drn_head_levels_t* h, const float* Wc, const float* bc, const float* Wb, const float* bb, const float* Wi,
+                      const float* bi, float* cls_raw, float* box_raw, float* iou_raw, void* stream);
+int drn_head_proj_bwd(const drn_head_levels_t* h, const float* dcls, const float* dbox, const float* Wc, const float* Wb, float* dWc,
+                      float* dWb, void* stream);
 /* FCOSLossComputation.__call__ (model/loss.py:134-239) on raw head outputs in the reference's flatten order
  * (level-major, then sample, then t).  losses = {loss_cls, loss_reg, loss_iou, n_pos, n_iou}; acc = 8 doubles of scratch kept for backward. */
 int drn_fcos_loss_fwd(int nlevels, int B, const int* T, const float* strides, const float* cls_raw, const float* box_raw,

@@ -41,6 +41,7 @@ def test_ctypes_structs_match_c_layout():
 #include <stddef.h>
 #include "drn_b200.h"
 int main(void) {
+  printf("%zu %zu %zu ", sizeof(drn_head_levels_t), offsetof(drn_head_levels_t, tower), offsetof(drn_head_levels_t, d_tower));
   printf("%zu %zu %zu %zu ", sizeof(drn_bn_job_t), offsetof(drn_bn_job_t, coef), offsetof(drn_bn_job_t, out_qa), offsetof(drn_bn_job_t, dy_plane_stride));
   printf("%zu %zu %zu %zu ", sizeof(drn_qe_t), offsetof(drn_qe_t, tokens), offsetof(drn_qe_t, g_w2), offsetof(drn_qe_t, workspace_bytes));
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(drn_planes_t), sizeof(drn_gemm_t), offsetof(drn_gemm_t, b), offsetof(drn_gemm_t, tap_w),
@@ -56,7 +57,8 @@ int main(void) {
         out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     G = L.GemmDesc
     J = L.BnJob
-    mine = [ctypes.sizeof(J), J.coef.offset, J.out_qa.offset, J.dy_plane_stride.offset, ctypes.sizeof(L.Qe), L.Qe.tokens.offset, L.Qe.g_w2.offset, L.Qe.workspace_bytes.offset, ctypes.sizeof(L.Planes), ctypes.sizeof(G), G.b.offset, G.tap_w.offset, G.out_split_stride.offset,
+    HL = L.HeadLevels
+    mine = [ctypes.sizeof(HL), HL.tower.offset, HL.d_tower.offset, ctypes.sizeof(J), J.coef.offset, J.out_qa.offset, J.dy_plane_stride.offset, ctypes.sizeof(L.Qe), L.Qe.tokens.offset, L.Qe.g_w2.offset, L.Qe.workspace_bytes.offset, ctypes.sizeof(L.Planes), ctypes.sizeof(G), G.b.offset, G.tap_w.offset, G.out_split_stride.offset,
             G.outp_plane_stride.offset, G.dbg_kadv.offset, ctypes.sizeof(L.BnPart), L.BnPart.dbeta.offset,
             ctypes.sizeof(L.PackItem), L.PackItem.slice_stride.offset]
     assert [int(x) for x in out] == mine
