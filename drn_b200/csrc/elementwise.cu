@@ -189,7 +189,8 @@ struct BnParts {  // the fused cls|bbox tower output carries two BatchNorm modul
 // levels of a shared head / FPN block -- are served by ONE launch (blockIdx.z / blockIdx.y = job).
 constexpr int BN_MAX_JOBS = 3;
 struct BnJob {
-  const float* y;
+  float* y;
+  const float* y2;  // optional second K-split slice of the conv output: the statistics pass folds it into y
   const float* da;
   long long rows;
   int B, T, C;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
   __shared__ float red[2][8][128];
   __shared__ bool is_last;
   const BnJob& J = jobs.j[blockIdx.z];
-  const float* __restrict__ y = J.y;
+  float* __restrict__ y = J.y;
   const float* __restrict__ da = J.da;
   const long long rows = J.rows;
   const int C = J.C;
@@ -257,7 +258,12 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
     for (int i = ty; i < STAT_ROWS; i += 8) {
       const long long r = r0 + i;
       if (r >= rows) break;
-      const float4 v4 = *reinterpret_cast<const float4*>(y + r * C + c);
+      float4 v4 = *reinterpret_cast<const float4*>(y + r * C + c);
+      if (MODE == 0 && J.y2) {  // y <- y + y2 (K-split slices of the contraction), summed once, here
+        const float4 w4 = *reinterpret_cast<const float4*>(J.y2 + r * C + c);
+        v4.x += w4.x; v4.y += w4.y; v4.z += w4.z; v4.w += w4.w;
+        *reinterpret_cast<float4*>(y + r * C + c) = v4;
+      }
       const float v[4] = {v4.x, v4.y, v4.z, v4.w};
       if (MODE == 0) {
 #pragma unroll
@@ -543,14 +549,23 @@ __global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ 
   if (c >= Cp) return;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   float a0 = 0, a1 = 0, a2 = 0, ab = 0;
-  for (int i = 0; i < rows_per_block; ++i) {
-    const long long r = r0 + i;
-    if (r >= rows) break;
-    const float g = dx[r * dx_ld + col0 + c];
-    a0 = fmaf(g, pos_in[3 * r], a0);
-    a1 = fmaf(g, pos_in[3 * r + 1], a1);
-    a2 = fmaf(g, pos_in[3 * r + 2], a2);
-    ab += g;
+  constexpr int U = 8;  // rows in flight per thread
+  for (int i0 = 0; i0 < rows_per_block; i0 += U) {
+    float g[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + i0 + u;
+      g[u] = (i0 + u < rows_per_block && r < rows) ? dx[r * dx_ld + col0 + c] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + i0 + u;
+      if (i0 + u >= rows_per_block || r >= rows) break;
+      a0 = fmaf(g[u], pos_in[3 * r], a0);
+      a1 = fmaf(g[u], pos_in[3 * r + 1], a1);
+      a2 = fmaf(g[u], pos_in[3 * r + 2], a2);
+      ab += g[u];
+    }
   }
   atomicAdd(dWp + 3 * c, a0);
   atomicAdd(dWp + 3 * c + 1, a1);
@@ -658,7 +673,7 @@ static int fill_jobs(BnJobs* t, int n, const drn_bn_job_t* jobs, const char* who
     const drn_bn_job_t& s = jobs[i];
     BnJob& d = t->j[i];
     if (s.C % 8 || s.B < 1 || s.T < 1) return fail(DRN_EINVAL, "%s: job %d needs C %% 8 == 0 and B, T >= 1 (C=%d)", who, i, s.C);
-    d.y = s.y; d.da = s.da;
+    d.y = const_cast<float*>(s.y); d.y2 = s.y2; d.da = s.da;
     d.rows = static_cast<long long>(s.B) * s.T;
     d.B = s.B; d.T = s.T; d.C = s.C;
     d.coef = s.coef; d.sums = s.sums; d.counter = s.counter; d.bcoef = s.bcoef;
@@ -817,7 +832,7 @@ extern "C" int drn_gate_reduce(const float* g, int64_t g_ld, const void* a, int6
 extern "C" int drn_pos_bwd(const float* dx, int64_t dx_ld, int col0, const float* pos_in, int64_t rows, int Cp, float* dWp,
                            float* dbp, void* stream) {
   if (Cp > 256) return fail(DRN_EINVAL, "drn_pos_bwd: Cp > 256");
-  const int rpb = 64;
+  const int rpb = 32;
   pos_bwd_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, 0, ST(stream)>>>(dx, dx_ld, col0, pos_in, rows, Cp, rpb, dWp,
                                                                                        dbp);
   return check_launch("pos_bwd");

@@ -409,7 +409,8 @@ static int prepare(const drn_gemm_t* g, Prepared* out) {
   kp.a = PlanesView{static_cast<const __nv_bfloat16*>(g->a.ptr), g->a.plane_stride, g->a.B, g->a.T, g->a.P, g->a.C};
   kp.b = PlanesView{static_cast<const __nv_bfloat16*>(g->b.ptr), g->b.plane_stride, g->b.B, g->b.T, g->b.P, g->b.C};
   kp.dbg_lbo = g->dbg_lbo; kp.dbg_sbo = g->dbg_sbo; kp.dbg_kadv = g->dbg_kadv;
-  if (!wgrad && kp.split_k > 1) return fail(DRN_EINVAL, "drn_gemm: split_k is a WGRAD option");
+  if (!wgrad && kp.split_k > 1 && kp.out_split_stride == 0)
+    return fail(DRN_EINVAL, "drn_gemm: a ROWS problem splits K only into slices (out_split_stride)");
   if (kp.split_k > 1 && kp.out_split_stride == 0 && kp.out_mode != DRN_OUT_ATOMIC)
     return fail(DRN_EINVAL, "drn_gemm: split_k needs an atomic output or out_split_stride");
   if (kp.split_k > 1 && (kp.out2 || kp.outp || kp.bias || kp.rowscale))
@@ -435,6 +436,7 @@ static int prepare(const drn_gemm_t* g, Prepared* out) {
     if (g->T >= 128) { kp.Rm = 128; kp.Bbm = 1; }
     else { kp.Rm = pow2_ceil(g->T); kp.Bbm = 128 / kp.Rm; }
     kp.tiles_per_sample = ceil_div(g->T, kp.Rm);
+    if (kp.split_k > g->ntaps * (g->K / BLOCK_K)) return fail(DRN_EINVAL, "drn_gemm: split_k %d exceeds the K-blocks", kp.split_k);
   } else {
     if (g->T >= 64) { kp.Rk = 64; kp.Bbk = 1; }
     else { kp.Rk = pow2_ceil(g->T); kp.Bbk = 64 / kp.Rk; }
@@ -450,8 +452,8 @@ static int prepare(const drn_gemm_t* g, Prepared* out) {
   out->m_sub = wgrad ? ceil_div(g->M, BLOCK_M) : ((kp.Bbm == 1) ? g->B * kp.tiles_per_sample : ceil_div(g->B, kp.Bbm));
   out->pair_n_tiles = ceil_div(g->N, 256);
   out->pair_m_tiles = ceil_div(out->m_sub, 2);
-  out->pair_tiles = out->pair_m_tiles * out->pair_n_tiles * (wgrad ? g->ntaps * kp.split_k : 1);
-  out->cost = wgrad ? ceil_div(kp.num_kblocks, kp.split_k) : g->ntaps * (g->K / BLOCK_K);
+  out->pair_tiles = out->pair_m_tiles * out->pair_n_tiles * (wgrad ? g->ntaps * kp.split_k : kp.split_k);
+  out->cost = wgrad ? ceil_div(kp.num_kblocks, kp.split_k) : ceil_div(g->ntaps * (g->K / BLOCK_K), kp.split_k);
   return 0;
 }
 
@@ -524,7 +526,7 @@ extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
   if (g->engine == 3) use_pair = false;
   if (g->dbg_lbo || g->dbg_sbo || g->dbg_kadv) use_pair = false;
   if (use_pair) return drn_gemm_group(1, g, stream);
-  if (kp.out_split_stride != 0 && kp.split_k > 1) return drn_gemm_group(1, g, stream);  // slices exist only in the pair kernel
+  if (kp.split_k > 1 && (kp.out_split_stride != 0 || !wgrad)) return drn_gemm_group(1, g, stream);  // slices: pair kernel only
 
   // one tile per CTA: 128 x 256 tiles unless that leaves most SMs idle, then 128 x 128
   int block_n = (g->N > 128) ? 256 : 128;

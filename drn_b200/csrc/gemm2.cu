@@ -53,7 +53,9 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
   t.n0 = nt * P2_TILE;
   t.nb = t.n0 + rank * 128;
   if (!wgrad) {
-    const int ms = 2 * rest + rank;  // 128-row sub-tile of this CTA
+    const int mt = rest % m_tiles;
+    t.split = rest / m_tiles;        // K-split of a ROWS problem (conv0 forward: few tiles, very long K)
+    const int ms = 2 * mt + rank;    // 128-row sub-tile of this CTA
     if (p.Bbm == 1) {
       t.b0 = ms / p.tiles_per_sample;
       t.t0 = (ms % p.tiles_per_sample) * p.Rm;
@@ -61,8 +63,9 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
       t.b0 = ms * p.Bbm;
       t.t0 = 0;
     }
-    t.it_begin = 0;
-    t.nk = p.ntaps * (p.K / BLOCK_K);
+    const int its = p.ntaps * (p.K / BLOCK_K);
+    t.it_begin = static_cast<int>(static_cast<long long>(its) * t.split / p.split_k);
+    t.nk = static_cast<int>(static_cast<long long>(its) * (t.split + 1) / p.split_k) - t.it_begin;
   } else {
     const int mt = rest % m_tiles;
     const int z = rest / m_tiles;
@@ -248,6 +251,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         const int tt = t.t0 + row % p.Rm;
         valid = (bb < p.B) && (tt < p.T);
         orow = static_cast<long long>(bb) * p.out_T + static_cast<long long>(tt) * p.out_t_mul + p.out_t_add;
+        if (out_base) out_base += t.split * p.out_split_stride;
       } else {
         valid = (t.m0 + row) < p.M;
         orow = t.m0 + row;

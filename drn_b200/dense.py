@@ -44,6 +44,7 @@ class ConvBN:
         self.t_in, self.t_out = t_in, t_in // stride
         self.rows = B * self.t_out
         self.y = torch.empty(B, self.t_out, cout, device=dev)
+        self.y2 = None  # second K-split slice of the forward contraction (conv0 only)
         self.coef = torch.empty(5, cout, device=dev)
         self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)   # kept zero between uses by the kernels
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -83,7 +84,13 @@ class DensePath:
         self.qe_ws = torch.zeros(int(_lib().drn_qe_workspace_bytes(B, L, qe_hidden, qe_embed)), dtype=torch.uint8, device=dev)
         self.qdim = (D, c1, 2 * c1)
         self.q = [e(B, n) for n in self.qdim]
-        self.dq = [z(B, n) for n in self.qdim]
+        # accumulators the backward re-zeroes with ONE fill: gate gradients dq_i [B, n_i] and the 8 scalar gradients of the loss
+        self.bwd_zero = z(B * sum(self.qdim) + 8)
+        self.dq, o = [], 0
+        for n in self.qdim:
+            self.dq.append(self.bwd_zero[o:o + B * n].view(B, n))
+            o += B * n
+        self.pgrad = self.bwd_zero[o:o + 8]
         self.pos_in = e(B * T, 3)
         self.Pre = e(B, T, D)                       # prop_fc output before gating
         self.X0 = Planes.empty(B, T, self.C0, dev)  # [q0 * prop_fc(f) | position feature]
@@ -93,6 +100,9 @@ class DensePath:
         self.conv = [ConvBN("backbone_net.forward_conv0", self.C0, c1, 3, 1, B, T, dev),
                      ConvBN("backbone_net.forward_conv1", c1, 2 * c1, 3, 2, B, T, dev),
                      ConvBN("backbone_net.forward_conv2", 2 * c1, 4 * c1, 3, 2, B, T // 2, dev)]
+        if B * T >= 4096:  # enough rows for the K-split of conv0 to pay (see forward_core)
+            ys = torch.empty(2, B, T, c1, device=dev)
+            self.conv[0].y, self.conv[0].y2 = ys[0], ys[1]
         self.Cact = [Planes.empty(B, self.Tl[i], self.c[i], dev) for i in range(3)]
         self.QC = [Planes.empty(B, self.Tl[i], self.c[i], dev) for i in range(2)]
         self.dC = [e(B, self.Tl[i], self.c[i]) for i in range(3)]
@@ -122,7 +132,6 @@ class DensePath:
         self.dcls, self.dbox, self.diou = e(n), e(n, 2), e(n)
         self.acc = torch.zeros(8, dtype=torch.float64, device=dev)
         self.losses = z(8)
-        self.pgrad = z(8)
         self.upstream = z(3)
         self.gt = e(B, 2)
         self.scales = e(3)
@@ -245,10 +254,12 @@ class DensePath:
         self._chk(_lib().drn_pack_conv_weights(len(items), arr, _st()), "pack_conv_weights")
         torch.cat([p[h + "cls_tower.0.bias"], p[h + "bbox_tower.0.bias"]], out=self.tower_bias)
 
-    def _bn_job(self, blk, p, grads=None, da=None, out_a=None, up=None, gate=None, out_qa=None):
+    def _bn_job(self, blk, p, grads=None, da=None, out_a=None, up=None, gate=None, out_qa=None, y2=None):
         """drn_bn_job_t of one conv block (model/basic_blocks.py:22-30): statistics / apply / backward operands."""
         j = L.BnJob()
         j.y, j.B, j.T, j.C = blk.y.data_ptr(), self.B, blk.t_out, blk.cout
+        if y2 is not None:
+            j.y2 = y2.data_ptr()
         j.nparts = len(blk.bn_parts)
         for i, (pre, c0, n) in enumerate(blk.bn_parts):
             a = j.parts[i]
@@ -364,9 +375,18 @@ class DensePath:
         src = self.X0
         for i in range(3):
             blk = self.conv[i]
-            self._conv(blk, src, self.wp["conv%d" % i])
+            y2 = None
+            if i == 0 and training and blk.y2 is not None:
+                # conv0: one 256-wide N tile and K = 3 x 4352: only 32 pair tiles -> split K in two slices (64 of the 74 SM
+                # pairs busy); the BatchNorm statistics pass folds the second slice into y
+                g = self._conv_desc(blk, src, self.wp["conv0"], engine=2)
+                g.split_k, g.out_split_stride = 2, blk.y2.data_ptr() - blk.y.data_ptr() >> 2
+                self._group([g])
+                y2 = blk.y2
+            else:
+                self._conv(blk, src, self.wp["conv%d" % i])
             if i < 2:
-                self._bn_fwd([self._bn_job(blk, p, out_a=self.Cact[i], gate=self.q[i + 1], out_qa=self.QC[i])], training)
+                self._bn_fwd([self._bn_job(blk, p, out_a=self.Cact[i], gate=self.q[i + 1], out_qa=self.QC[i], y2=y2)], training)
                 src = self.QC[i]
             else:
                 self._bn_fwd([self._bn_job(blk, p, out_a=self.Cact[i])], training)
@@ -473,9 +493,7 @@ class DensePath:
         F = self.F
         self.launches = 0
         iou_on = self.iou_branch_on and (h + "mix_fc.0.weight") in grads
-        self.pgrad.zero_()
-        for t in self.dq:
-            t.zero_()
+        self.bwd_zero.zero_()
         self._chk(lib.drn_fcos_loss_bwd(3, B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.box_raw), _vp(self.iou_raw),
                                         _vp(self.scales), _vp(self.gt), C.c_float(self.gamma), C.c_float(self.alpha),
                                         1 if self.iou_branch_on else 0, _vp(self.acc), _vp(upstream), _vp(self.dcls),

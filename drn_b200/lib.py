@@ -48,7 +48,7 @@ class BnPart(C.Structure):
 
 class BnJob(C.Structure):
     """drn_bn_job_t: one BatchNorm application (conv block x pyramid level) of a multi-job launch."""
-    _fields_ = [("y", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("nparts", C.c_int32),
+    _fields_ = [("y", C.c_void_p), ("y2", C.c_void_p), ("B", C.c_int32), ("T", C.c_int32), ("C", C.c_int32), ("nparts", C.c_int32),
                 ("parts", BnPart * 2),
                 ("coef", C.c_void_p), ("sums", C.c_void_p), ("counter", C.c_void_p), ("bcoef", C.c_void_p),
                 ("up", C.c_void_p), ("up_plane_stride", C.c_int64), ("gate", C.c_void_p),

@@ -171,6 +171,7 @@ int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, int C, const
  * or FPN block): fewer launches and full SM occupancy for the small levels.  Fields as in the single forms above. */
 typedef struct {
   const float* y;            /* conv output [B*T][C] fp32 */
+  const float* y2;           /* optional: second K-split slice of the contraction; drn_bn_stats_multi (training) folds it into y */
   int32_t B, T, C;
   int32_t nparts; drn_bn_part_t parts[2];
   float* coef; double* sums; unsigned* counter; float* bcoef;

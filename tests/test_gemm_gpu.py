@@ -214,3 +214,20 @@ def test_group_rejects_bad_arguments():
                   out_split_stride=ws.stride(0), split_k=4, engine=2)
     arr = (L.GemmDesc * 1)(d2)
     assert L.load().drn_gemm_group(1, arr, L.stream_ptr()) == -1
+
+
+def test_rows_k_split_slices():
+    """conv0-forward shape class: one N tile, long K (3 taps x 1024): the K-split of a ROWS problem stores two slices whose sum is
+    the convolution."""
+    B, T, Cin, N = 8, 128, 1024, 256
+    a = Planes.from_float(_rand(B, T, Cin, seed=41))
+    w = Planes.from_float(_rand(3, N, Cin, seed=42, scale=(3 * Cin) ** -0.5))
+    ys = torch.full((2, B, T, N), float("nan"), device=DEV)
+    d = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=ys[0], out_split_stride=ys.stride(0), split_k=2,
+                 engine=2)
+    assert ops.gemm_group([d]) == 1
+    torch.cuda.synchronize()
+    ref = ref_rows(a, w, K3, 1, B, T, N, Cin, 0)
+    assert not torch.isnan(ys).any()
+    assert float(ys[1].abs().max()) > 0
+    assert (ys.double().sum(0) - ref).abs().max().item() / ref.abs().max().item() < 2e-5
