@@ -35,31 +35,60 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks / clock-event (throttle) reasons while the timed region runs: NVML in-process every 5 ms (the timed
+    region of a default run is < 0.5 s, too short for repeated `nvidia-smi` invocations), `nvidia-smi` if NVML is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:  # noqa: BLE001
+            self.nvml = None
 
     def run(self):
+        if self.nvml is not None:
+            n = self.nvml
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    try:
+                        mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:  # noqa: BLE001
+                        mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    self.rows.append((sm, mx, [name for bit, name in self.REASONS.items() if mask & bit]))
+                except Exception:  # noqa: BLE001
+                    pass
+                time.sleep(0.005)
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                r = [x.strip() for x in out.split(",")]
+                if len(r) >= 6 and r[0].isdigit():
+                    self.rows.append((int(r[0]), int(r[1]), [n for n, v in zip(names, r[2:6]) if v.lower().startswith("active")]))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        mx = max([int(r[1]) for r in self.rows if r[1].isdigit()] or [0])
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({n for r in self.rows for n in r[2]})
+        mx = max([r[1] for r in self.rows] or [0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_inputs(world_rank):

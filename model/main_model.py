@@ -150,11 +150,13 @@ class mainModel(nn.Module):
         dev = self.prop_fc.weight.device
         if dev.type != "cuda":
             raise RuntimeError("mainModel runs on a B200 through libdrn_sm100.so only (no CPU / torch fallback): call .cuda()")
-        tokens = torch.as_tensor(query_tokens).to(dev, dtype=torch.int64).contiguous()
-        lengths = torch.as_tensor(query_length).to(dev, dtype=torch.int64).contiguous()
-        feats = props_features.to(dev, dtype=torch.float32).contiguous()
-        pse = props_start_end.to(dev, dtype=torch.float64).contiguous()
-        gt = gt_start_end.to(dev).float().contiguous()  # `.float()` as at main_model.py:74
+        # non_blocking: a synchronous host->device copy would drain the stream every step (the host could then never run ahead
+        # of the GPU); pageable sources are staged by the runtime, pinned ones are the caller's to keep unchanged until used
+        tokens = torch.as_tensor(query_tokens).to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+        lengths = torch.as_tensor(query_length).to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+        feats = props_features.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        pse = props_start_end.to(dev, dtype=torch.float64, non_blocking=True).contiguous()
+        gt = gt_start_end.to(dev, non_blocking=True).float().contiguous()  # `.float()` as at main_model.py:74
         B, T = feats.shape[0], feats.shape[1]
         path = self._path(B, T, tokens.shape[1], dev)
         names, tensors = self._dense_trainable()

@@ -97,3 +97,20 @@ def test_oracle_matches_reference_golden(name, golden_dir):
             _close(d["locations"].numpy()[o1], g["det/%d/locations" % b][o2], 2e-5, "locations")
             lv = np.array([x for l in d["level"] for x in l], dtype=np.int64)
             assert (np.sort(lv) == np.sort(g["det/%d/level" % b])).all()
+
+
+def test_metric_restatement_matches_reference_golden(golden_dir):
+    """oracle/metrics.py (temporal NMS + unclamped IoU of utils/evaluate_utils.py:192-236) against outputs of the reference's own
+    functions on seeded random segments (oracle/make_metric_goldens.py), and recall@k on a hand-checkable case."""
+    import json
+    from oracle import metrics as M
+    cases = json.load(open(os.path.join(golden_dir, "metric_nms.json")))
+    assert len(cases) == 100
+    for c in cases:
+        assert M.nms_temporal(c["x1"], c["x2"], c["s"], 0.45) == c["picks"]
+        for a, b, ref in zip(c["x1"], c["x2"], c["iou"]):
+            assert abs(M.calculate_iou(c["gt"], (a, b)) - ref) < 1e-12
+    res = [{"detections": torch.tensor([[0.0, 0.5], [0.5, 1.0], [0.0, 0.0]]), "scores": torch.tensor([0.9, 0.8, 0.99])},
+           {"detections": torch.tensor([[0.0, 1.0]]), "scores": torch.tensor([1.0])}]
+    r = M.recall_at(res, [(0.5, 1.0), (0.1, 0.2)])  # zero-duration detection dropped; 2nd pick hits query 0; query 1 misses
+    assert r[1] == 0.0 and r[5] == 0.5
