@@ -100,6 +100,27 @@ def main():
             if leaf is not None:
                 rb, _, _ = O.forward(leaf, cfg, b, training=False)
                 res_r += rb
+    # ---- same-checkpoint parity: each side's trained weights evaluated by the OTHER implementation ----
+    cross = {}
+    if leaf is not None:
+        ours_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+        res_x = []
+        with torch.no_grad():
+            for j in range(a.eval_batches):
+                b = S.synth_batch(B, T, max_len=10, embedding=emb, seed=S.SEED + 900000 + j)
+                rb, _, _ = O.forward(ours_sd, cfg, b, training=False)
+                res_x += rb
+        cross["cuda_trained_weights_on_oracle"] = M.recall_at(res_x, gts)
+        m2 = mainModel(1301, S.config_namespace(stage=1))
+        m2.load_state_dict({k: v.detach() for k, v in leaf.items()})
+        m2 = m2.cuda().eval()
+        res_y = []
+        with torch.no_grad():
+            for j in range(a.eval_batches):
+                b = S.synth_batch(B, T, max_len=10, embedding=emb, seed=S.SEED + 900000 + j)
+                boxes, _ = m2(b["query_tokens"], b["query_length"], b["props_features"], b["props_start_end"], b["gt_start_end"], None, None)
+                res_y += boxes
+        cross["oracle_trained_weights_on_cuda"] = M.recall_at(res_y, gts)
     ro = M.recall_at(res_o, gts)
     out = {"steps": a.steps, "B": B, "T": T, "eval_pairs": len(gts), "ours": {"R@1": ro[1], "R@5": ro[5], "final_loss": ours_loss[-1],
            "loss_first_last10": [sum(ours_loss[:10]) / 10, sum(ours_loss[-10:]) / 10], "train_s": round(t_ours, 2)}}
@@ -107,9 +128,17 @@ def main():
         rr = M.recall_at(res_r, gts)
         out["oracle_cpu"] = {"R@1": rr[1], "R@5": rr[5], "final_loss": ref_loss[-1],
                              "loss_first_last10": [sum(ref_loss[:10]) / 10, sum(ref_loss[-10:]) / 10], "train_s": round(t_ref, 2)}
-        out["R@1_diff_pp"] = 100 * (ro[1] - rr[1])
-        out["R@5_diff_pp"] = 100 * (ro[5] - rr[5])
-        out["max_rel_loss_gap_first20"] = max(abs(x - y) / max(abs(y), 1e-9) for x, y in zip(ours_loss[:20], ref_loss[:20]))
+        out["independent_training_R@1_diff_pp"] = 100 * (ro[1] - rr[1])
+        out["independent_training_R@5_diff_pp"] = 100 * (ro[5] - rr[5])
+        out["same_weights"] = {
+            "cuda_trained: R@1 cuda vs oracle": [ro[1], cross["cuda_trained_weights_on_oracle"][1]],
+            "cuda_trained: R@5 cuda vs oracle": [ro[5], cross["cuda_trained_weights_on_oracle"][5]],
+            "oracle_trained: R@1 cuda vs oracle": [cross["oracle_trained_weights_on_cuda"][1], rr[1]],
+            "oracle_trained: R@5 cuda vs oracle": [cross["oracle_trained_weights_on_cuda"][5], rr[5]],
+            "max_R@1_diff_pp": 100 * max(abs(ro[1] - cross["cuda_trained_weights_on_oracle"][1]),
+                                         abs(cross["oracle_trained_weights_on_cuda"][1] - rr[1]))}
+        out["loss_head"] = {"ours": [round(x, 5) for x in ours_loss[:8]], "oracle_cpu": [round(x, 5) for x in ref_loss[:8]]}
+        out["rel_loss_gap_step0"] = abs(ours_loss[0] - ref_loss[0]) / abs(ref_loss[0])
     print(json.dumps(out))
 
 
