@@ -1,6 +1,8 @@
 // HBM-bound kernels of the path: plane splitting / weight packing, train-mode BatchNorm (+ReLU, +FPN upsample-add,
 // +query gate) forward and backward, gate reductions.  All are coalesced 16-byte-vectorised streaming kernels; the
 // per-channel reductions use per-thread fp32 partials -> shared-memory tree -> one fp64 atomic per channel per CTA.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(EW_THREADS) pos_feature_kernel(const double* _
 // The LAST block to finish (device-wide counter) finalises: MODE 0 -> BatchNorm coefficients + running statistics,
 // MODE 1 -> mean(g), mean(g*xhat) + dgamma/dbeta accumulation.  It also re-zeroes the fp64 sums and the counter, so
 // no memset / finalize launches are needed between uses.
-constexpr int STAT_ROWS = 64;
+constexpr int STAT_ROWS_MAX = 256;
 constexpr int BN_MAX_PARTS = 2;
 
 struct BnParts {  // the fused cls|bbox tower output carries two BatchNorm modules side by side
@@ -226,7 +228,8 @@ __device__ __forceinline__ void bn_coef_from_stats(double mean, double var, floa
 }
 
 template <int MODE>  // 0: sum y, sum y^2 ; 1: BN backward sums (sum g, sum g*xhat) with g = relu-masked da
-__global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float momentum, float eps, int update_running) {
+__global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float momentum, float eps, int update_running,
+                                                        int STAT_ROWS) {
   __shared__ float red[2][8][128];
   __shared__ bool is_last;
   const BnJob& J = jobs.j[blockIdx.z];
@@ -255,30 +258,44 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
         is[j] = coef[3 * C + c + j];
       }
     }
-    for (int i = ty; i < STAT_ROWS; i += 8) {
-      const long long r = r0 + i;
-      if (r >= rows) break;
-      float4 v4 = *reinterpret_cast<const float4*>(y + r * C + c);
-      if (MODE == 0 && J.y2) {  // y <- y + y2 (K-split slices of the contraction), summed once, here
-        const float4 w4 = *reinterpret_cast<const float4*>(J.y2 + r * C + c);
-        v4.x += w4.x; v4.y += w4.y; v4.z += w4.z; v4.w += w4.w;
-        *reinterpret_cast<float4*>(y + r * C + c) = v4;
-      }
-      const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-      if (MODE == 0) {
+    constexpr int U = 4;  // rows in flight per thread
+    for (int i0 = ty; i0 < STAT_ROWS; i0 += 8 * U) {
+      float4 v4[U], g4[U];
+      bool ok[U];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          s0[j] += v[j];
-          s1[j] = fmaf(v[j], v[j], s1[j]);
+      for (int u = 0; u < U; ++u) {
+        const long long r = r0 + i0 + 8 * u;
+        ok[u] = (i0 + 8 * u < STAT_ROWS) && (r < rows);
+        v4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g4[u] = v4[u];
+        if (ok[u]) {
+          v4[u] = *reinterpret_cast<const float4*>(y + r * C + c);
+          if (MODE == 0 && J.y2) {  // y <- y + y2 (K-split slices of the contraction), summed once, here
+            const float4 w4 = *reinterpret_cast<const float4*>(J.y2 + r * C + c);
+            v4[u].x += w4.x; v4[u].y += w4.y; v4[u].z += w4.z; v4[u].w += w4.w;
+            *reinterpret_cast<float4*>(y + r * C + c) = v4[u];
+          }
+          if (MODE == 1) g4[u] = *reinterpret_cast<const float4*>(da + r * C + c);
         }
-      } else {
-        const float4 g4 = *reinterpret_cast<const float4*>(da + r * C + c);
-        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float gm = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
-          s0[j] += gm;
-          s1[j] = fmaf(gm, (v[j] - mu[j]) * is[j], s1[j]);
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s0[j] += v[j];
+            s1[j] = fmaf(v[j], v[j], s1[j]);
+          }
+        } else {
+          const float g[4] = {g4[u].x, g4[u].y, g4[u].z, g4[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float gm = (fmaf(v[j], sc[j], sh[j]) > 0.f) ? g[j] : 0.f;
+            s0[j] += gm;
+            s1[j] = fmaf(gm, (v[j] - mu[j]) * is[j], s1[j]);
+          }
         }
       }
     }
@@ -688,14 +705,26 @@ static int fill_jobs(BnJobs* t, int n, const drn_bn_job_t* jobs, const char* who
   return 0;
 }
 
-static void stats_grid(const BnJobs& t, dim3* grid) {
+// Rows per statistics block.  Measured on B200 (scripts/ab_bench.sh, r01): 64 rows (more, smaller blocks) beats 256 by ~1.5 % of the
+// step -- the fp64 atomics that end each block are not the bottleneck.  DRN_STAT_ROWS = 64 | 128 | 256 overrides (tuning).
+static int stats_grid(const BnJobs& t, dim3* grid) {
   int cmax = 0;
-  long long rmax = 0;
+  long long rmax = 0, elems = 0;
   for (int i = 0; i < t.n; ++i) {
     cmax = t.j[i].C > cmax ? t.j[i].C : cmax;
     rmax = t.j[i].rows > rmax ? t.j[i].rows : rmax;
+    elems += t.j[i].rows * t.j[i].C;
   }
-  *grid = dim3(ceil_div(cmax, 128), static_cast<unsigned>((rmax + STAT_ROWS - 1) / STAT_ROWS), t.n);
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("DRN_STAT_ROWS");
+    forced = e ? atoi(e) : 0;
+  }
+  int sr = 64;
+  (void)elems;
+  if (forced == 64 || forced == 128 || forced == 256) sr = forced;
+  *grid = dim3(ceil_div(cmax, 128), static_cast<unsigned>((rmax + sr - 1) / sr), t.n);
+  return sr;
 }
 static int ew_grid_jobs(const BnJobs& t) {
   long long m = 0;
@@ -717,8 +746,8 @@ extern "C" int drn_bn_stats_multi(int n, const drn_bn_job_t* jobs, float momentu
     return check_launch("bn_eval_coef");
   }
   dim3 grid;
-  stats_grid(t, &grid);
-  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, momentum, eps, training == 1 ? 1 : 0);
+  const int sr = stats_grid(t, &grid);
+  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, momentum, eps, training == 1 ? 1 : 0, sr);
   return check_launch("bn_stats");
 }
 
@@ -751,8 +780,8 @@ extern "C" int drn_bn_bwd_reduce_multi(int n, const drn_bn_job_t* jobs, void* st
   int rc = fill_jobs(&t, n, jobs, "drn_bn_bwd_reduce_multi");
   if (rc) return rc;
   dim3 grid;
-  stats_grid(t, &grid);
-  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, 0.f, 0.f, 0);
+  const int sr = stats_grid(t, &grid);
+  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, 0.f, 0.f, 0, sr);
   return check_launch("bn_bwd_reduce");
 }
 

@@ -251,6 +251,7 @@ static int linear_small(cudaStream_t st, const float* x, long long ldx, const fl
 // ------------------------------------------------------------------------------------------------------------------------
 // Query encoder device view
 // ------------------------------------------------------------------------------------------------------------------------
+constexpr int DE_SLICES = 8;  // dE = dG [W_ih ; W_ih_r] contracts over 8H = 4096 gate rows with only 4 output tiles: K-split slices
 struct QeDev {
   int B, L, H, E, tok_ld, BC;  // BC = ceil(B / 32) sample chunks
   const long long* tokens;
@@ -301,7 +302,13 @@ __global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __res
   const int b = r / q.L, t = r % q.L;
   const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
   if (tok == 0 || t >= q.lengths[b]) return;
-  for (int e = threadIdx.x; e < q.E; e += blockDim.x) atomicAdd(g_emb + tok * q.E + e, q.dE[static_cast<long long>(r) * q.E + e]);
+  const long long slice = static_cast<long long>(q.B) * q.L * q.E;
+  for (int e = threadIdx.x; e < q.E; e += blockDim.x) {
+    float v = 0.f;
+#pragma unroll
+    for (int sl = 0; sl < DE_SLICES; ++sl) v += q.dE[sl * slice + static_cast<long long>(r) * q.E + e];  // K-split slices of dE
+    atomicAdd(g_emb + tok * q.E + e, v);
+  }
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -770,7 +777,7 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
   float* dG = take(R * 8 * H);
   float* dcarry = take(2 * B * H);
   float* part = take(2 * BC * (H / 32) * BWD_JQ * 1024);
-  float* dE = take(R * E);
+  float* dE = take(DE_SLICES * R * E);
   float* cnt = take(2 * BC * (H / 32));
   float* HT = take(2 * 2 * BC * H * 32);
   float* dGT = take(2 * 2 * BC * 4 * H * 32);
@@ -984,6 +991,7 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
       d.b = planes_view(q.Wih_pl, 8LL * H * q.EP, 8 * H, q.EP);
       d.b_mn = 1; d.N = E; d.K = 8 * H;
       d.out = q.dE; d.out_ld = E;
+      d.split_k = DE_SLICES; d.out_split_stride = static_cast<long long>(R) * E;
     }
     if (n) TRY(drn_gemm_group(n, g, stream));
   }
