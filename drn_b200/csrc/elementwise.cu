@@ -172,7 +172,6 @@ __global__ void __launch_bounds__(EW_THREADS) pos_feature_kernel(const double* _
 // The LAST block to finish (device-wide counter) finalises: MODE 0 -> BatchNorm coefficients + running statistics,
 // MODE 1 -> mean(g), mean(g*xhat) + dgamma/dbeta accumulation.  It also re-zeroes the fp64 sums and the counter, so
 // no memset / finalize launches are needed between uses.
-constexpr int STAT_ROWS_MAX = 256;
 constexpr int BN_MAX_PARTS = 2;
 
 struct BnParts {  // the fused cls|bbox tower output carries two BatchNorm modules side by side

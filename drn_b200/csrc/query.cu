@@ -36,14 +36,14 @@ struct SgemmP {
 };
 
 template <int BM>
-__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
+__device__ __forceinline__ void sgemm_body(const SgemmP& p, int bx, int by, int bz) {
   constexpr int BN = 64, BK = 16, TM = BM / 16;
   __shared__ float As[BK][BM + 1];
   __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int kbeg = blockIdx.z * p.kchunk;
+  const int m0 = bx * BM, n0 = by * BN;
+  const int kbeg = bz * p.kchunk;
   const int kend = min(p.K, kbeg + p.kchunk);
   float acc[TM][4];
 #pragma unroll
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
       const int gn = n0 + tx * 4 + j;
       if (gn >= p.N) continue;
       float v = acc[i][j];
-      if (blockIdx.z == 0) {
+      if (bz == 0) {
         if (p.bias) v += __ldg(p.bias + gn);
         if (p.bias2) v += __ldg(p.bias2 + gn);
       }
@@ -140,6 +140,66 @@ template <typename F>
 static void prefer_max_smem(F* fn) {
   cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
+
+template <int BM>
+__global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
+  sgemm_body<BM>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Several small contractions in ONE launch (the query encoder / gate backward is a chain of ~20 of them, each far too small
+// to fill the GPU and each paying a launch): CTA -> job by prefix sums, then the single-problem body.
+constexpr int SG_MAX_JOBS = 12;
+struct SgemmJobs {
+  int n;
+  int cta_start[SG_MAX_JOBS + 1];
+  int gx[SG_MAX_JOBS], gy[SG_MAX_JOBS], bm[SG_MAX_JOBS];
+  SgemmP p[SG_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) sgemm_multi_kernel(const SgemmJobs jobs) {
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i < SG_MAX_JOBS; ++i)
+    if (i < jobs.n && static_cast<int>(blockIdx.x) >= jobs.cta_start[i]) j = i;
+  const int local = blockIdx.x - jobs.cta_start[j];
+  const int bx = local % jobs.gx[j];
+  const int by = (local / jobs.gx[j]) % jobs.gy[j];
+  const int bz = local / (jobs.gx[j] * jobs.gy[j]);
+  if (jobs.bm[j] == 32) sgemm_body<32>(jobs.p[j], bx, by, bz);
+  else sgemm_body<64>(jobs.p[j], bx, by, bz);
+}
+
+// Host-side batch: add() problems (all ACCUMULATING into their outputs, i.e. C must hold valid data -- the batch never
+// zero-fills), launch() once.
+struct SgemmBatch {
+  SgemmJobs jobs;
+  SgemmBatch() { jobs.n = 0; jobs.cta_start[0] = 0; }
+  int add(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C, long long ldc, int M,
+          int N, int K, const float* bias = nullptr) {
+    if (jobs.n >= SG_MAX_JOBS) return fail(DRN_EINVAL, "sgemm batch: more than %d problems", SG_MAX_JOBS);
+    if (M < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "sgemm batch: empty problem (%d,%d,%d)", M, N, K);
+    const int i = jobs.n++;
+    const int bm = (M <= 32) ? 32 : 64;
+    const int tiles = ceil_div(M, bm) * ceil_div(N, 64);
+    int splits = 1;
+    if (tiles < 74) splits = max(1, min(ceil_div(148, tiles), ceil_div(K, 64)));
+    const int kchunk = ceil_div(ceil_div(K, splits), 16) * 16;
+    splits = ceil_div(K, kchunk);
+    jobs.p[i] = SgemmP{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, nullptr, 0, 1, kchunk};
+    jobs.gx[i] = ceil_div(M, bm);
+    jobs.gy[i] = ceil_div(N, 64);
+    jobs.bm[i] = bm;
+    jobs.cta_start[i + 1] = jobs.cta_start[i] + jobs.gx[i] * jobs.gy[i] * splits;
+    return 0;
+  }
+  int launch(cudaStream_t st) {
+    if (jobs.n == 0) return 0;
+    for (int i = jobs.n; i < SG_MAX_JOBS; ++i) jobs.cta_start[i + 1] = jobs.cta_start[jobs.n];
+    sgemm_multi_kernel<<<jobs.cta_start[jobs.n], 256, 0, st>>>(jobs);
+    jobs.n = 0;
+    jobs.cta_start[0] = 0;
+    return check_launch("sgemm_multi");
+  }
+};
 
 // accumulate = 0: C is overwritten; 1: C += (C must hold valid data, e.g. a zeroed gradient buffer)
 static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn,
@@ -180,15 +240,41 @@ static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, 
 // lane = sample, W row segments live in registers and are broadcast with shuffles.
 // ------------------------------------------------------------------------------------------------------------------------
 constexpr int LIN_NT = 8, LIN_WARPS = 16;
-__global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const float* __restrict__ x, long long ldx,
-                                                                      const float* __restrict__ W, long long ldw,
-                                                                      const float* __restrict__ bias, float* __restrict__ out,
-                                                                      long long ldo, int Bn, int N, int K, int relu) {
+struct LinP {
+  const float* x; long long ldx;
+  const float* W; long long ldw;
+  const float* bias;
+  float* out; long long ldo;
+  int Bn, N, K, relu;
+};
+constexpr int LIN_MAX_JOBS = 4;
+struct LinJobs {
+  int n;
+  int cta_start[LIN_MAX_JOBS + 1];
+  int gx[LIN_MAX_JOBS];
+  LinP p[LIN_MAX_JOBS];
+};
+__global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const LinJobs jobs) {
+  int jb = 0;
+#pragma unroll
+  for (int i = 1; i < LIN_MAX_JOBS; ++i)
+    if (i < jobs.n && static_cast<int>(blockIdx.x) >= jobs.cta_start[i]) jb = i;
+  const LinP& P = jobs.p[jb];
+  const int local = blockIdx.x - jobs.cta_start[jb];
+  const int bxx = local % jobs.gx[jb], byy = local / jobs.gx[jb];
+  const float* __restrict__ x = P.x;
+  const long long ldx = P.ldx;
+  const float* __restrict__ W = P.W;
+  const long long ldw = P.ldw;
+  const float* __restrict__ bias = P.bias;
+  float* __restrict__ out = P.out;
+  const long long ldo = P.ldo;
+  const int Bn = P.Bn, N = P.N, K = P.K, relu = P.relu;
   extern __shared__ __align__(16) float lin_smem[];
   float (*xs)[32][33] = reinterpret_cast<float (*)[32][33]>(lin_smem);              // [LIN_WARPS][32][33]
   float (*red)[LIN_NT][32] = reinterpret_cast<float (*)[LIN_NT][32]>(lin_smem);     // reused after the main loop
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int n0 = blockIdx.x * LIN_NT, b0 = blockIdx.y * 32;
+  const int n0 = bxx * LIN_NT, b0 = byy * 32;
   const int kper = ((K + LIN_WARPS - 1) / LIN_WARPS + 31) / 32 * 32;  // K slice per warp, multiple of 32
   const int kbeg = w * kper, kend = min(K, kbeg + kper);
   float acc[LIN_NT];
@@ -233,9 +319,7 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const floa
     }
   }
 }
-static int linear_small(cudaStream_t st, const float* x, long long ldx, const float* W, long long ldw, const float* bias,
-                        float* out, long long ldo, int Bn, int N, int K, int relu) {
-  if (Bn < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "drn_linear_fwd: empty problem (%d,%d,%d)", Bn, N, K);
+static int linear_launch(cudaStream_t st, LinJobs& jobs) {
   constexpr size_t smem = LIN_WARPS * 32 * 33 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
@@ -243,9 +327,28 @@ static int linear_small(cudaStream_t st, const float* x, long long ldx, const fl
     if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(linear_small): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  linear_small_kernel<<<dim3(ceil_div(N, LIN_NT), ceil_div(Bn, 32)), LIN_WARPS * 32, smem, st>>>(x, ldx, W, ldw, bias, out, ldo, Bn, N,
-                                                                                               K, relu);
+  for (int i = jobs.n; i < LIN_MAX_JOBS; ++i) jobs.cta_start[i + 1] = jobs.cta_start[jobs.n];
+  linear_small_kernel<<<jobs.cta_start[jobs.n], LIN_WARPS * 32, smem, st>>>(jobs);
   return check_launch("linear_small");
+}
+static int linear_add(LinJobs& jobs, const float* x, long long ldx, const float* W, long long ldw, const float* bias, float* out,
+                      long long ldo, int Bn, int N, int K, int relu) {
+  if (jobs.n >= LIN_MAX_JOBS) return fail(DRN_EINVAL, "drn_linear_fwd: more than %d problems in a batch", LIN_MAX_JOBS);
+  if (Bn < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "drn_linear_fwd: empty problem (%d,%d,%d)", Bn, N, K);
+  const int i = jobs.n++;
+  if (i == 0) jobs.cta_start[0] = 0;
+  jobs.p[i] = LinP{x, ldx, W, ldw, bias, out, ldo, Bn, N, K, relu};
+  jobs.gx[i] = ceil_div(N, LIN_NT);
+  jobs.cta_start[i + 1] = jobs.cta_start[i] + jobs.gx[i] * ceil_div(Bn, 32);
+  return 0;
+}
+static int linear_small(cudaStream_t st, const float* x, long long ldx, const float* W, long long ldw, const float* bias,
+                        float* out, long long ldo, int Bn, int N, int K, int relu) {
+  LinJobs jobs;
+  jobs.n = 0;
+  int rc = linear_add(jobs, x, ldx, W, ldw, bias, out, ldo, Bn, N, K, relu);
+  if (rc) return rc;
+  return linear_launch(st, jobs);
 }
 
 // ------------------------------------------------------------------------------------------------------------------------
@@ -260,7 +363,7 @@ struct QeDev {
   int EP;  // embedding width rounded up to the 64-element K-block of the tensor-core contraction (zero padded)
   float *xg, *G, *Cst, *Hout, *v, *hid, *c3, *alpha, *bias_sum;
   __nv_bfloat16 *E_pl, *Wih_pl, *dG_pl, *Hprev_pl;  // split-BF16 planes (hi, lo) of the operands of the big projections
-  float *dH, *dc3, *dhid, *dhid_pre, *dv, *dG, *dcarry, *part, *dE, *HT, *dGT, *dr;
+  float *dH, *dc3, *dhid, *dhid_pre, *dv, *dG, *dcarry, *part, *dE, *HT, *dGT, *dr, *one;
   unsigned* cnt;
 };
 
@@ -272,6 +375,7 @@ __global__ void __launch_bounds__(256) qe_embed_kernel(QeDev q, const float* __r
   const int b = r / q.L, t = r % q.L;
   const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
   const long long ps = static_cast<long long>(q.B) * q.L * q.EP;
+  if (r == 0 && threadIdx.x == 0) q.one[0] = 1.f;  // the constant the column-sum contractions multiply by
   for (int e = threadIdx.x; e < q.EP; e += blockDim.x) {
     __nv_bfloat16 h, l;
     split_bf16(e < q.E ? emb[tok * q.E + e] : 0.f, h, l);
@@ -731,19 +835,6 @@ __global__ void __launch_bounds__(256) qe_attn_bwd_apply_kernel(QeDev q, const f
   if (g_wa) atomicAdd(g_wa + d, gw);
 }
 
-__global__ void colsum_rows_kernel(const float* __restrict__ x, long long rows, int C, long long ld, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float acc = 0.f;
-  for (long long r = blockIdx.y; r < rows; r += gridDim.y) acc += x[r * ld + c];
-  atomicAdd(out + c, acc);
-}
-static int colsum(cudaStream_t st, const float* x, long long rows, int C, long long ld, float* out) {
-  dim3 grid(ceil_div(C, 256), static_cast<unsigned>(rows < 32 ? rows : 32));
-  colsum_rows_kernel<<<grid, 256, 0, st>>>(x, rows, C, ld, out);
-  return check_launch("qe colsum");
-}
-
 // ---- workspace carving ------------------------------------------------------------------------------------------------
 static size_t carve(const drn_qe_t* a, QeDev* q) {
   const size_t B = a->B, L = a->L, H = a->H, E = a->E, R = B * L;
@@ -782,6 +873,7 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
   float* HT = take(2 * 2 * BC * H * 32);
   float* dGT = take(2 * 2 * BC * 4 * H * 32);
   float* dr = take(3 * B * L);
+  float* one = take(1);
   if (q) {
     q->EP = static_cast<int>(EP);
     q->E_pl = reinterpret_cast<__nv_bfloat16*>(E_pl); q->Wih_pl = reinterpret_cast<__nv_bfloat16*>(Wih_pl);
@@ -790,7 +882,7 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
     q->xg = xg; q->G = G; q->Cst = Cst; q->Hout = Hout; q->v = v;
     q->hid = hid; q->c3 = c3; q->alpha = alpha; q->dH = dH; q->dc3 = dc3; q->dhid = dhid; q->dhid_pre = dhid_pre; q->dv = dv;
     q->dG = dG; q->dcarry = dcarry; q->part = part; q->dE = dE; q->cnt = reinterpret_cast<unsigned*>(cnt);
-    q->HT = HT; q->dGT = dGT; q->dr = dr;
+    q->HT = HT; q->dGT = dGT; q->dr = dr; q->one = one;
   }
   return off;
 }
@@ -871,6 +963,27 @@ extern "C" int drn_linear_fwd(const float* x, int64_t ldx, const float* W, int64
   return linear_small(ST(stream), x, ldx, W, ldw, bias, out, ldo, B, N, K, relu);
 }
 
+extern "C" int drn_sgemm_batch(int n, const drn_sgemm_job_t* jobs, void* stream) {
+  if (n < 1 || n > SG_MAX_JOBS || !jobs) return fail(DRN_EINVAL, "drn_sgemm_batch: 1..%d jobs (got %d)", SG_MAX_JOBS, n);
+  SgemmBatch sb;
+  for (int i = 0; i < n; ++i) {
+    const drn_sgemm_job_t& j = jobs[i];
+    TRY(sb.add(j.A, j.sam, j.sak, j.B, j.sbk, j.sbn, j.C, j.ldc, j.M, j.N, j.K, j.bias));
+  }
+  return sb.launch(ST(stream));
+}
+
+extern "C" int drn_linear_fwd_batch(int n, const drn_linear_job_t* jobs, void* stream) {
+  if (n < 1 || n > LIN_MAX_JOBS || !jobs) return fail(DRN_EINVAL, "drn_linear_fwd_batch: 1..%d jobs (got %d)", LIN_MAX_JOBS, n);
+  LinJobs lj;
+  lj.n = 0;
+  for (int i = 0; i < n; ++i) {
+    const drn_linear_job_t& j = jobs[i];
+    TRY(linear_add(lj, j.x, j.ldx, j.W, j.ldw, j.bias, j.out, j.ldo, j.B, j.N, j.K, j.relu));
+  }
+  return linear_launch(ST(stream), lj);
+}
+
 extern "C" size_t drn_qe_workspace_bytes(int B, int L, int H, int E) {
   drn_qe_t a{};
   a.B = B; a.L = L; a.H = H; a.E = E;
@@ -918,8 +1031,13 @@ extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
   qe_vgather_kernel<<<B, 256, 0, st>>>(q);
   TRY(check_launch("qe_vgather"));
   TRY(linear_small(st, q.v, 4 * H, a->w1, 4 * H, a->b1, q.hid, H, B, H, 4 * H, 1));
-  for (int t = 0; t < 3; ++t)
-    TRY(linear_small(st, q.hid, H, a->w2[t], H, a->b2[t], q.c3 + static_cast<long long>(t) * B * D, D, B, D, H, 0));
+  {
+    LinJobs lj;
+    lj.n = 0;
+    for (int t = 0; t < 3; ++t)
+      TRY(linear_add(lj, q.hid, H, a->w2[t], H, a->b2[t], q.c3 + static_cast<long long>(t) * B * D, D, B, D, H, 0));
+    TRY(linear_launch(st, lj));
+  }
   qe_attn_fwd_kernel<<<dim3(B, 3), 256, (D + L) * sizeof(float), st>>>(q, a->wa, a->ba, a->cmd[0], a->cmd[1], a->cmd[2]);
   return check_launch("qe_attn_fwd");
 }
@@ -934,17 +1052,26 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
   TRY(check_launch("qe_attn_bwd_scalars"));
   qe_attn_bwd_apply_kernel<<<dim3(B, ceil_div(D, 256)), 256, 0, st>>>(q, a->wa, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_wa);
   TRY(check_launch("qe_attn_bwd_apply"));
-  for (int t = 0; t < 3; ++t) {
-    const float* dc = q.dc3 + static_cast<long long>(t) * B * D;
-    TRY(sgemm(st, dc, D, 1, a->w2[t], H, 1, q.dhid, H, B, H, D, nullptr, nullptr, 0, t > 0));
-    if (a->g_w2[t]) TRY(sgemm(st, dc, 1, D, q.hid, H, 1, a->g_w2[t], H, D, H, B, nullptr, nullptr, 0, 1));
-    if (a->g_b2[t]) TRY(colsum(st, dc, B, D, D, a->g_b2[t]));
+  // dhid / dv accumulate from several contractions: one zero-fill of the contiguous [dhid | dhid_pre | dv] scratch
+  {
+    const size_t bytes = reinterpret_cast<char*>(q.dv + static_cast<size_t>(B) * 4 * H) - reinterpret_cast<char*>(q.dhid);
+    cudaError_t e = cudaMemsetAsync(q.dhid, 0, bytes, st);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_qe_backward memset: %s", cudaGetErrorString(e));
   }
+  SgemmBatch sb;
+  for (int t = 0; t < 3; ++t) {  // qInput0..2: d hid, d weight, d bias -- nine small contractions, one launch
+    const float* dc = q.dc3 + static_cast<long long>(t) * B * D;
+    TRY(sb.add(dc, D, 1, a->w2[t], H, 1, q.dhid, H, B, H, D));
+    if (a->g_w2[t]) TRY(sb.add(dc, 1, D, q.hid, H, 1, a->g_w2[t], H, D, H, B));
+    if (a->g_b2[t]) TRY(sb.add(dc, 1, D, q.one, 0, 0, a->g_b2[t], 1, D, 1, B));
+  }
+  TRY(sb.launch(st));
   relu_mask_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(q.dhid, q.hid, q.dhid_pre, B * H);
   TRY(check_launch("qe relu_mask"));
-  TRY(sgemm(st, q.dhid_pre, H, 1, a->w1, 4 * H, 1, q.dv, 4 * H, B, 4 * H, H, nullptr, nullptr, 0, 0));
-  if (a->g_w1) TRY(sgemm(st, q.dhid_pre, 1, H, q.v, 4 * H, 1, a->g_w1, 4 * H, H, 4 * H, B, nullptr, nullptr, 0, 1));
-  if (a->g_b1) TRY(colsum(st, q.dhid_pre, B, H, H, a->g_b1));
+  TRY(sb.add(q.dhid_pre, H, 1, a->w1, 4 * H, 1, q.dv, 4 * H, B, 4 * H, H));
+  if (a->g_w1) TRY(sb.add(q.dhid_pre, 1, H, q.v, 4 * H, 1, a->g_w1, 4 * H, H, 4 * H, B));
+  if (a->g_b1) TRY(sb.add(q.dhid_pre, 1, H, q.one, 0, 0, a->g_b1, 1, H, 1, B));
+  TRY(sb.launch(st));
   qe_vscatter_kernel<<<B, 256, 0, st>>>(q);
   TRY(check_launch("qe_vscatter"));
   const size_t smem_b = (2 * H * 32 + (LSTM_THREADS / 32) * 32 * 33) * sizeof(float);
@@ -995,10 +1122,14 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
     }
     if (n) TRY(drn_gemm_group(n, g, stream));
   }
-  for (int dir = 0; dir < 2; ++dir) {
-    const float* dG = q.dG + dir * 4 * H;  // [R] rows of stride 8H
-    if (a->g_b_ih[dir]) TRY(colsum(st, dG, R, 4 * H, 8 * H, a->g_b_ih[dir]));
-    if (a->g_b_hh[dir]) TRY(colsum(st, dG, R, 4 * H, 8 * H, a->g_b_hh[dir]));
+  {
+    SgemmBatch cb;  // LSTM bias gradients = column sums of dG (both biases of a direction receive the same sum)
+    for (int dir = 0; dir < 2; ++dir) {
+      const float* dG = q.dG + dir * 4 * H;  // [R] rows of stride 8H
+      if (a->g_b_ih[dir]) TRY(cb.add(dG, 1, 8 * H, q.one, 0, 0, a->g_b_ih[dir], 1, 4 * H, 1, R));
+      if (a->g_b_hh[dir]) TRY(cb.add(dG, 1, 8 * H, q.one, 0, 0, a->g_b_hh[dir], 1, 4 * H, 1, R));
+    }
+    TRY(cb.launch(st));
   }
   if (a->g_emb) {
     qe_embed_bwd_kernel<<<R, 256, 0, st>>>(q, a->g_emb);

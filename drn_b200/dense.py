@@ -80,17 +80,19 @@ class DensePath:
         self.lengths = torch.ones(B, dtype=torch.int64, device=dev)
         self.cmd_dim = 2 * qe_hidden
         self.cmd = [e(B, self.cmd_dim) for _ in range(3)]
-        self.dcmd = [e(B, self.cmd_dim) for _ in range(3)]
         self.qe_ws = torch.zeros(int(_lib().drn_qe_workspace_bytes(B, L, qe_hidden, qe_embed)), dtype=torch.uint8, device=dev)
         self.qdim = (D, c1, 2 * c1)
         self.q = [e(B, n) for n in self.qdim]
         # accumulators the backward re-zeroes with ONE fill: gate gradients dq_i [B, n_i] and the 8 scalar gradients of the loss
-        self.bwd_zero = z(B * sum(self.qdim) + 8)
+        self.one = torch.ones(1, device=dev)
+        self.bwd_zero = z(B * sum(self.qdim) + 8 + 3 * B * self.cmd_dim)
         self.dq, o = [], 0
         for n in self.qdim:
             self.dq.append(self.bwd_zero[o:o + B * n].view(B, n))
             o += B * n
         self.pgrad = self.bwd_zero[o:o + 8]
+        o += 8
+        self.dcmd = [self.bwd_zero[o + i * B * self.cmd_dim:o + (i + 1) * B * self.cmd_dim].view(B, self.cmd_dim) for i in range(3)]
         self.pos_in = e(B * T, 3)
         self.Pre = e(B, T, D)                       # prop_fc output before gating
         self.X0 = Planes.empty(B, T, self.C0, dev)  # [q0 * prop_fc(f) | position feature]
@@ -362,10 +364,12 @@ class DensePath:
         self.launches += 10 + self.L  # launches enqueued inside drn_qe_forward
         # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50): exact fp32 on CUDA cores (M = B rows only)
         K = self.cmd_dim
+        jobs = (L.LinearJob * 3)()
         for i in range(3):
-            n = self.qdim[i]
-            self._chk(lib.drn_linear_fwd(_vp(self.cmd[i]), C.c_int64(K), _vp(p["qInput%d.weight" % i]), C.c_int64(K),
-                                         _vp(p["qInput%d.bias" % i]), _vp(self.q[i]), C.c_int64(n), B, n, K, 0, _st()), "gate")
+            j, n = jobs[i], self.qdim[i]
+            j.x, j.ldx, j.W, j.ldw = self.cmd[i].data_ptr(), K, p["qInput%d.weight" % i].data_ptr(), K
+            j.bias, j.out, j.ldo, j.B, j.N, j.K, j.relu = p["qInput%d.bias" % i].data_ptr(), self.q[i].data_ptr(), n, B, n, K, 0
+        self._chk(lib.drn_linear_fwd_batch(3, jobs, _st()), "gates")
         if self.overlap:
             self._join()
         # level-0 gate q0 * prop_fc(f) -> X0[:, :, :D] (backbone.py:28-30; the cat with the position channels is the layout)
@@ -558,14 +562,21 @@ class DensePath:
         with torch.cuda.stream(self.side if self.overlap else torch.cuda.current_stream()):
             self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
                        out_ld=self.D, out_tap_stride=0)
-        # gates: dW = dq^T cmd, db = colsum(dq), dcmd = dq W
+        # gates: dW += dq^T cmd, db += colsum(dq), dcmd = dq W  -- nine small contractions, one launch (dcmd is zero-filled
+        # together with dq / pgrad at the start of the backward)
         K = self.cmd_dim
+        jobs = (L.SgemmJob * 9)()
         for i in range(3):
             n = self.qdim[i]
-            self._sgemm(self.dq[i], 1, n, self.cmd[i], K, 1, grads["qInput%d.weight" % i], K, n, K, B, accumulate=1)
-            self._chk(lib.drn_colsum(_vp(self.dq[i]), C.c_int64(B), n, C.c_int64(n), _vp(grads["qInput%d.bias" % i]), _st()),
-                      "colsum")
-            self._sgemm(self.dq[i], n, 1, p["qInput%d.weight" % i], K, 1, self.dcmd[i], K, B, K, n)
+            dq, cmd, W = self.dq[i].data_ptr(), self.cmd[i].data_ptr(), p["qInput%d.weight" % i].data_ptr()
+            jw, jb, jc = jobs[3 * i], jobs[3 * i + 1], jobs[3 * i + 2]
+            jw.A, jw.sam, jw.sak, jw.B, jw.sbk, jw.sbn = dq, 1, n, cmd, K, 1
+            jw.C, jw.ldc, jw.M, jw.N, jw.K = grads["qInput%d.weight" % i].data_ptr(), K, n, K, B
+            jb.A, jb.sam, jb.sak, jb.B, jb.sbk, jb.sbn = dq, 1, n, self.one.data_ptr(), 0, 0
+            jb.C, jb.ldc, jb.M, jb.N, jb.K = grads["qInput%d.bias" % i].data_ptr(), 1, n, 1, B
+            jc.A, jc.sam, jc.sak, jc.B, jc.sbk, jc.sbn = dq, n, 1, W, K, 1
+            jc.C, jc.ldc, jc.M, jc.N, jc.K = self.dcmd[i].data_ptr(), K, B, K, n
+        self._chk(lib.drn_sgemm_batch(9, jobs, _st()), "gates_bwd")
         # query encoder backward (BPTT), gradients accumulated into the zeroed buffers
         self._chk(lib.drn_qe_backward(C.byref(self._qe_desc(p, grads)), _st()), "qe_backward")
         self.launches += 30 + self.L

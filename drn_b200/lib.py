@@ -70,6 +70,16 @@ class PackItem(C.Structure):
                 ("plane_stride", C.c_int64), ("nslices", C.c_int32), ("slice_stride", C.c_int64)]
 
 
+class SgemmJob(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("sam", C.c_int64), ("sak", C.c_int64), ("B", C.c_void_p), ("sbk", C.c_int64), ("sbn", C.c_int64),
+                ("C", C.c_void_p), ("ldc", C.c_int64), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("bias", C.c_void_p)]
+
+
+class LinearJob(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ldx", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p),
+                ("out", C.c_void_p), ("ldo", C.c_int64), ("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("relu", C.c_int32)]
+
+
 class Qe(C.Structure):
     """drn_qe_t (include/drn_b200.h): query encoder parameters, gradients, outputs and workspace."""
     _fields_ = [

@@ -254,6 +254,26 @@ int drn_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
 int drn_linear_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* out, int64_t ldo, int B,
                    int N, int K, int relu, void* stream);
 
+/* Up to 12 small contractions / 4 small Linear forwards in ONE launch (the gate and query-encoder backward is a chain of ~20 of
+ * them).  drn_sgemm_batch jobs always ACCUMULATE into C (which must hold valid data; a column sum is the job B = a constant 1 with
+ * strides 0); drn_linear_fwd_batch jobs are independent deterministic forwards. */
+typedef struct {
+  const float* A; int64_t sam, sak;
+  const float* B; int64_t sbk, sbn;
+  float* C; int64_t ldc;
+  int32_t M, N, K;
+  const float* bias;
+} drn_sgemm_job_t;
+int drn_sgemm_batch(int n, const drn_sgemm_job_t* jobs, void* stream);
+typedef struct {
+  const float* x; int64_t ldx;
+  const float* W; int64_t ldw;
+  const float* bias;
+  float* out; int64_t ldo;
+  int32_t B, N, K, relu;
+} drn_linear_job_t;
+int drn_linear_fwd_batch(int n, const drn_linear_job_t* jobs, void* stream);
+
 typedef struct {
   int32_t B, L;            /* batch, padded query length = number of token columns processed (<= 64) */
   int32_t H, E;            /* LSTM hidden size per direction (512), embedding width (300) */
