@@ -489,6 +489,17 @@ class DensePath:
                          b_mn=1, out=out, out_mode=mode, rowscale=rowscale, out2=out2, out_T=blk.t_in, out_t_mul=2,
                          out_t_add=par, engine=2) for par in (0, 1)]
 
+    def stored_grad_names(self, names):
+        """Gradients a kernel of `backward` fully OVERWRITES (never accumulates into): prop_fc.weight (its contraction stores)
+        and every conv weight that goes through the slice workspaces + drn_unpack_conv_wgrads."""
+        h = "fcos.head."
+        st = {"prop_fc.weight", h + "cls_tower.0.weight", h + "bbox_tower.0.weight"}
+        for i in range(3):
+            st |= {"backbone_net.forward_conv%d.0.weight" % i, "fpn.fpn_inner%d.0.weight" % (i + 1), "fpn.fpn_layer%d.0.weight" % (i + 1)}
+        if self.iou_branch_on:
+            st |= {h + "mix_fc.0.weight", h + "iou_scores.0.weight"}
+        return {n for n in names if n in st}
+
     def backward(self, p, grads, upstream):
         """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
         upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou)."""

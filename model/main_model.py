@@ -44,28 +44,36 @@ def _run_backward(path, p, names, upstream, use_graphs):
     key = ("bwd", _sig(p), tuple(names))
     ent = path.graphs.get(key)
     if ent is None:
-        sizes = [p[n].numel() for n in names]
-        flat = torch.zeros(sum(sizes), device=upstream.device, dtype=torch.float32)
+        # ONE flat gradient buffer.  Layout: first the gradients the kernels ACCUMULATE into (atomics / +=; zero-filled every
+        # backward), then the ones a kernel fully overwrites (the big conv / prop_fc weight gradients: no zero-fill needed).
+        # Every slot starts on a 32-byte boundary so the contraction epilogues can use full-sector vector stores.
+        stored = path.stored_grad_names(names)
+        order = [n for n in names if n not in stored] + [n for n in names if n in stored]
+        pad = lambda k: (k + 7) // 8 * 8  # noqa: E731
+        total = sum(pad(p[n].numel()) for n in order)
+        nzero = sum(pad(p[n].numel()) for n in order if n not in stored)
+        flat = torch.zeros(total, device=upstream.device, dtype=torch.float32)
         grads, o = {}, 0
-        for n, sz in zip(names, sizes):
-            grads[n] = flat[o:o + sz].view_as(p[n])
-            o += sz
+        for n in order:
+            grads[n] = flat[o:o + p[n].numel()].view_as(p[n])
+            o += pad(p[n].numel())
+        zero_part = flat[:nzero]
         path.upstream.copy_(upstream)
         path.backward(p, grads, path.upstream)
         g = None
         if use_graphs:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                flat.zero_()
+                zero_part.zero_()
                 path.backward(p, grads, path.upstream)
-        path.graphs[key] = (g, flat, grads)
+        path.graphs[key] = (g, flat, grads, zero_part)
     else:
-        g, flat, grads = ent
+        g, flat, grads, zero_part = ent
         path.upstream.copy_(upstream)
         if g is not None:
             g.replay()
         else:
-            flat.zero_()
+            zero_part.zero_()
             path.backward(p, grads, path.upstream)
     return flat, grads
 
