@@ -2,6 +2,8 @@
 // assignment (model/loss.py:90-127), sigmoid focal loss (model/layers/sigmoid_focal_loss.py:40-52, stable log-sigmoid),
 // IoU regression loss (model/layers/iou_loss.py:5-24), the stage-2/3 IoU-score branch (model/loss.py:168-198) and
 // all of their backward passes.  One thread per location; scalars are reduced block-wise and accumulated in fp64.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -648,7 +650,15 @@ extern "C" int drn_head_proj_bwd(const drn_head_levels_t* h, const float* dcls, 
     rows_max = r > rows_max ? r : rows_max;
   }
   int rpb = 16;
-  while (rpb < 64 && static_cast<long long>(g.B) * P / rpb > 148) rpb *= 2;  // ~2 waves over (2 halves x levels x row chunks)
+  while (rpb < 32 && static_cast<long long>(g.B) * P / rpb > 148) rpb *= 2;  // A/B-measured: 16..128 within noise, 32 marginally best
+  {
+    static int forced = -1;  // DRN_HEAD_RPB: tuning override
+    if (forced < 0) {
+      const char* e = getenv("DRN_HEAD_RPB");
+      forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) rpb = forced;
+  }
   dim3 grid(2, static_cast<unsigned>((rows_max + rpb - 1) / rpb), g.nlevels);
   head_proj_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(g, dcls, dbox, Wc, Wb, rpb, dWc, dWb);
   return check_launch("head_proj_bwd");

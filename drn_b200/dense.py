@@ -500,9 +500,13 @@ class DensePath:
             st |= {h + "mix_fc.0.weight", h + "iou_scores.0.weight"}
         return {n for n in names if n in st}
 
-    def backward(self, p, grads, upstream):
+    def part2_grad_names(self, names):
+        """Gradients produced by `backward_tail` (everything else is final when `backward(..., tail=False)` returns)."""
+        return {n for n in names if n == "prop_fc.weight" or n.startswith("qInput") or n.startswith("query_encoder.")}
+
+    def backward(self, p, grads, upstream, tail=True):
         """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
-        upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou)."""
+        upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou).  tail=False stops before `backward_tail`."""
         lib, B = _lib(), self.B
         h = "fcos.head."
         F = self.F
@@ -566,6 +570,34 @@ class DensePath:
         self._chk(lib.drn_pos_bwd(_vp(self.dX0), C.c_int64(self.C0), self.D, _vp(self.pos_in), C.c_int64(B * self.T), 256,
                                   _vp(grads["position_transform.weight"]), _vp(grads["position_transform.bias"]), _st()),
                   "pos_bwd")
+        # partial sums (K-splits x levels) in tap-major workspaces -> parameter layout [O][C][k], one launch
+        items = []
+        for i in range(3):
+            items.append(self._unpack_item(grads["backbone_net.forward_conv%d.0.weight" % i], "conv%d" % i))
+            items.append(self._unpack_item(grads["fpn.fpn_inner%d.0.weight" % (i + 1)], "inner%d" % i))
+            items.append(self._unpack_item(grads["fpn.fpn_layer%d.0.weight" % (i + 1)], "layer%d" % i))
+        items.append(self._unpack_item(grads[h + "cls_tower.0.weight"], "towers", 0))
+        items.append(self._unpack_item(grads[h + "bbox_tower.0.weight"], "towers", F))
+        if iou_on:
+            items.append(self._unpack_item(grads[h + "mix_fc.0.weight"], "mix"))
+            items.append(self._unpack_item(grads[h + "iou_scores.0.weight"], "iouc"))
+        arr = (L.PackItem * len(items))(*items)
+        self._chk(lib.drn_unpack_conv_wgrads(len(items), arr, _st()), "unpack_conv_wgrads")
+        # scalar parameter gradients gathered by the loss kernel
+        grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
+        grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])
+        if iou_on:
+            grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
+        for l in range(3):
+            grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
+        self.launches_bwd = self.launches
+        if tail:
+            self.backward_tail(p, grads)
+
+    def backward_tail(self, p, grads):
+        """Second part of the backward: the prop_fc weight gradient, the gates and the query encoder.  Nothing of the first
+        part depends on it, so a data-parallel run all-reduces the first part's gradients while this runs (model/main_model.py)."""
+        lib, B = _lib(), self.B
         # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D] (the largest contraction of the backward pass); the gates and the
         # query-encoder backward (a latency-bound chain of small kernels) run beside it
         if self.overlap:
@@ -593,24 +625,4 @@ class DensePath:
         self.launches += 30 + self.L
         if self.overlap:
             self._join()
-        # partial sums (K-splits x levels) in tap-major workspaces -> parameter layout [O][C][k], one launch
-        items = []
-        for i in range(3):
-            items.append(self._unpack_item(grads["backbone_net.forward_conv%d.0.weight" % i], "conv%d" % i))
-            items.append(self._unpack_item(grads["fpn.fpn_inner%d.0.weight" % (i + 1)], "inner%d" % i))
-            items.append(self._unpack_item(grads["fpn.fpn_layer%d.0.weight" % (i + 1)], "layer%d" % i))
-        items.append(self._unpack_item(grads[h + "cls_tower.0.weight"], "towers", 0))
-        items.append(self._unpack_item(grads[h + "bbox_tower.0.weight"], "towers", F))
-        if iou_on:
-            items.append(self._unpack_item(grads[h + "mix_fc.0.weight"], "mix"))
-            items.append(self._unpack_item(grads[h + "iou_scores.0.weight"], "iouc"))
-        arr = (L.PackItem * len(items))(*items)
-        self._chk(lib.drn_unpack_conv_wgrads(len(items), arr, _st()), "unpack_conv_wgrads")
-        # scalar parameter gradients gathered by the loss kernel
-        grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
-        grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])
-        if iou_on:
-            grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
-        for l in range(3):
-            grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
         self.launches_bwd = self.launches

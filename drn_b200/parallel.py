@@ -4,7 +4,9 @@ NVLink/NVSwitch.  BatchNorm statistics and the loss norma
 reference's own (nominal) multi-GPU mode, nn.DataParallel at main.py:99, computes.
 
 The path (query encoder included) produces all of its gradients in one flat buffer (model/main_model.py:
-_DenseFn.backward); that buffer is all-reduced in place as soon as the hand-written backward has filled it.  Gradients
+_run_backward).  The backward runs in two parts: when the first (head, FPN, backbone) ends, its gradients -- a contiguous
+region of the buffer -- are all-reduced on NCCL's stream WHILE the tail (prop_fc weight gradient, gates, query encoder: ~0.9 ms)
+runs; the tail's two regions follow.  Gradients
 that autograd produced outside that buffer (none for the reference model; kept for wrapped modules that add their own
 parameters) are all-reduced in `finish_gradient_sync()` after `loss.backward()`.
 """
@@ -23,12 +25,33 @@ class DataParallelDRN(nn.Module):
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t, 0, group=process_group)
-        module._dp_hook = self._reduce_dense
+        module._dp = self
 
-    def _reduce_dense(self, flat):
-        if self.world > 1:
-            dist.all_reduce(flat, group=self.group)
-            flat.mul_(1.0 / self.world)
+    def reduce_regions(self, regions, wait=True):
+        """Average the given slices of the flat gradient buffer over the ranks (NCCL all-reduce, op = AVG; gloo: SUM then
+        scale).  wait=False returns the pending work handles: the collective runs on the backend's stream, ordered after
+        what is already enqueued on the current stream, while the caller enqueues more work (the backward tail)."""
+        if self.world == 1:
+            return []
+        nccl = dist.get_backend(self.group) == "nccl"
+        work = []
+        for t in regions:
+            if t.numel() == 0:
+                continue
+            if nccl:
+                work.append((dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group, async_op=True), None))
+            else:
+                work.append((dist.all_reduce(t, group=self.group, async_op=True), t))
+        if wait:
+            self.wait(work)
+            return []
+        return work
+
+    def wait(self, work):
+        for w, t in work:
+            w.wait()
+            if t is not None:
+                t.mul_(1.0 / self.world)
 
     def forward(self, *a, **k):
         return self.module(*a, **k)
@@ -42,8 +65,7 @@ class DataParallelDRN(nn.Module):
         if not grads:
             return
         flat = torch.cat([g.reshape(-1) for g in grads])
-        dist.all_reduce(flat, group=self.group)
-        flat.mul_(1.0 / self.world)
+        self.reduce_regions([flat])
         o = 0
         for g in grads:
             g.copy_(flat[o:o + g.numel()].view_as(g))

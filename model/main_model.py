@@ -40,41 +40,62 @@ def _run_forward_core(path, p, training, use_graphs):
         g.replay()
 
 
-def _run_backward(path, p, names, upstream, use_graphs):
-    key = ("bwd", _sig(p), tuple(names))
+def _run_backward(path, p, names, upstream, use_graphs, dp=None):
+    """Backward of the path into ONE flat gradient buffer.  Layout:
+        [A: accumulated, produced by the tail][B: accumulated, first part][C: stored, first part][D: prop_fc.weight (tail, stored)]
+    A+B are zero-filled every backward (atomics / += land there); C and D are fully overwritten by their kernels.  Every slot
+    starts on a 32-byte boundary (full-sector vector stores in the contraction epilogues).
+    Data parallel (dp = drn_b200.parallel.DataParallelDRN): the backward runs as TWO graphs; the gradients of the first part
+    (B+C, final when it ends) are all-reduced on NCCL's stream WHILE the tail (prop_fc weight gradient, gates, query encoder)
+    runs; A and D follow."""
+    key = ("bwd", _sig(p), tuple(names), dp is not None)
     ent = path.graphs.get(key)
     if ent is None:
-        # ONE flat gradient buffer.  Layout: first the gradients the kernels ACCUMULATE into (atomics / +=; zero-filled every
-        # backward), then the ones a kernel fully overwrites (the big conv / prop_fc weight gradients: no zero-fill needed).
-        # Every slot starts on a 32-byte boundary so the contraction epilogues can use full-sector vector stores.
-        stored = path.stored_grad_names(names)
-        order = [n for n in names if n not in stored] + [n for n in names if n in stored]
+        stored, tailn = path.stored_grad_names(names), path.part2_grad_names(names)
+        groups = [[n for n in names if n in tailn and n not in stored], [n for n in names if n not in tailn and n not in stored],
+                  [n for n in names if n not in tailn and n in stored], [n for n in names if n in tailn and n in stored]]
         pad = lambda k: (k + 7) // 8 * 8  # noqa: E731
-        total = sum(pad(p[n].numel()) for n in order)
-        nzero = sum(pad(p[n].numel()) for n in order if n not in stored)
-        flat = torch.zeros(total, device=upstream.device, dtype=torch.float32)
+        bounds = [0]
+        for g_ in groups:
+            bounds.append(bounds[-1] + sum(pad(p[n].numel()) for n in g_))
+        flat = torch.zeros(bounds[-1], device=upstream.device, dtype=torch.float32)
         grads, o = {}, 0
-        for n in order:
-            grads[n] = flat[o:o + p[n].numel()].view_as(p[n])
-            o += pad(p[n].numel())
-        zero_part = flat[:nzero]
+        for g_ in groups:
+            for n in g_:
+                grads[n] = flat[o:o + p[n].numel()].view_as(p[n])
+                o += pad(p[n].numel())
+        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:bounds[3]], "tail_a": flat[:bounds[1]], "tail_d": flat[bounds[3]:]}
         path.upstream.copy_(upstream)
         path.backward(p, grads, path.upstream)
-        g = None
+        g1 = g2 = None
         if use_graphs:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                zero_part.zero_()
-                path.backward(p, grads, path.upstream)
-        path.graphs[key] = (g, flat, grads, zero_part)
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                regions["zero"].zero_()
+                path.backward(p, grads, path.upstream, tail=dp is None)
+            if dp is not None:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    path.backward_tail(p, grads)
+        if dp is not None:  # the eager run above produced a complete local gradient: reduce it in one go
+            dp.reduce_regions([flat])
+        path.graphs[key] = (g1, g2, flat, grads, regions)
+        return flat, grads
+    g1, g2, flat, grads, regions = ent
+    path.upstream.copy_(upstream)
+    if g1 is not None:
+        g1.replay()
     else:
-        g, flat, grads, zero_part = ent
-        path.upstream.copy_(upstream)
-        if g is not None:
-            g.replay()
+        regions["zero"].zero_()
+        path.backward(p, grads, path.upstream, tail=dp is None)
+    if dp is not None:
+        work = dp.reduce_regions([regions["first"]], wait=False)  # overlaps the tail below
+        if g2 is not None:
+            g2.replay()
         else:
-            zero_part.zero_()
-            path.backward(p, grads, path.upstream)
+            path.backward_tail(p, grads)
+        dp.reduce_regions([regions["tail_a"], regions["tail_d"]])
+        dp.wait(work)
     return flat, grads
 
 
@@ -96,9 +117,8 @@ class _DenseFn(torch.autograd.Function):
         p = model._tensor_dict()
         # gradients are produced in ONE flat static buffer (graph-replayable, and the unit of the data-parallel all-reduce);
         # autograd copies the returned views into param.grad, so the buffer can be reused by the next step.
-        flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs)
-        if model._dp_hook is not None:  # data parallel: all-reduce the flat gradient buffer (drn_b200/parallel.py)
-            model._dp_hook(flat)
+        # data parallel: model._dp (drn_b200/parallel.py) all-reduces the flat gradient buffer, overlapped with the tail
+        flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs, dp=model._dp)
         return (None,) * 8 + tuple(grads[n] for n in names)
 
 
@@ -126,7 +146,7 @@ class mainModel(nn.Module):
             setattr(self, "qInput%d" % t, nn.Linear(1024, channels_list[t - 1][1] if t > 0 else self.feature_dim))
         self._paths = {}
         self._trainable_names = []
-        self._dp_hook = None
+        self._dp = None  # set by drn_b200.parallel.DataParallelDRN
         # CUDA graphs over the dense path (static shapes, library-owned buffers); DRN_NO_GRAPHS=1 launches kernel by kernel
         self.use_graphs = os.environ.get("DRN_NO_GRAPHS", "0") != "1"
 

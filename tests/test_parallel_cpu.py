@@ -26,7 +26,7 @@ class _Toy(nn.Module):
         with torch.no_grad():
             for p in self.parameters():
                 p.fill_(float(rank) + 1.0)
-        self._dp_hook = None
+        self._dp = None
         self._trainable_names = ["prop_fc.weight", "prop_fc.bias"]  # produced in the flat buffer of the path
 
 
@@ -38,7 +38,10 @@ def _worker(rank, world, port, q):
     dp = DataParallelDRN(toy)
     ok = all(bool((p == 1.0).all()) for p in toy.parameters()) and bool((toy.running == 0.0).all())  # replica 0 wins
     flat = torch.arange(6, dtype=torch.float32) * (rank + 1)
-    toy._dp_hook(flat)  # what _DenseFn.backward calls on the dense gradient buffer
+    ok = ok and toy._dp is dp
+    work = dp.reduce_regions([flat[:4]], wait=False)  # what _run_backward does: first region async, tail regions, then wait
+    dp.reduce_regions([flat[4:], flat[:0]])
+    dp.wait(work)
     ok = ok and torch.allclose(flat, torch.arange(6, dtype=torch.float32) * 1.5)
     for p in toy.query_encoder.parameters():
         p.grad = torch.full_like(p, float(rank))
