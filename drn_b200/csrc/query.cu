@@ -984,6 +984,22 @@ extern "C" int drn_linear_fwd_batch(int n, const drn_linear_job_t* jobs, void* s
   return linear_launch(ST(stream), lj);
 }
 
+// Kernels one drn_qe_forward / drn_qe_backward call launches (gpu_launches accounting of bench.py): the recurrence is ONE
+// cooperative launch when its grid fits the GPU, else one launch per time step.
+extern "C" int drn_qe_launch_count(int B, int L, int H, int backward) {
+  const int BC = (B + 31) / 32;
+  if (!backward) {
+    const size_t smem_f = (32 * H + H * 32 + 8 * 4 * 32) * sizeof(float);
+    set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), smem_f, "lstm_fwd");
+    const bool coop = fits_cooperative(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), dim3(H / 8, 2, BC), smem_f);
+    return 8 + (coop ? 1 : L);  // embed, pack_wih, xg contraction, hprev, vgather, qInput, qInput0-2, attention + recurrence
+  }
+  const size_t smem_b = (2 * H * 32 + (LSTM_THREADS / 32) * 32 * 33) * sizeof(float);
+  set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), smem_b, "lstm_bwd");
+  const bool coop = fits_cooperative(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), dim3(H / 32, BWD_JQ, 2 * BC), smem_b);
+  return 9 + (coop ? 1 : L);  // 2 attention, 2 small-contraction batches, relu mask, vscatter, grouped contraction, bias sums, embedding + BPTT
+}
+
 extern "C" size_t drn_qe_workspace_bytes(int B, int L, int H, int E) {
   drn_qe_t a{};
   a.B = B; a.L = L; a.H = H; a.E = E;

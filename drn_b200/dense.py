@@ -361,7 +361,7 @@ class DensePath:
                        out=self.Pre)
         # query encoder -> three command vectors (model/main_model.py:47, language_module.py:38-62)
         self._chk(lib.drn_qe_forward(C.byref(self._qe_desc(p)), _st()), "qe_forward")
-        self.launches += 10 + self.L  # launches enqueued inside drn_qe_forward
+        self.launches += lib.drn_qe_launch_count(B, self.L, self.qe_H, 0) - 1  # kernels enqueued inside drn_qe_forward
         # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50): exact fp32 on CUDA cores (M = B rows only)
         K = self.cmd_dim
         jobs = (L.LinearJob * 3)()
@@ -622,7 +622,7 @@ class DensePath:
         self._chk(lib.drn_sgemm_batch(9, jobs, _st()), "gates_bwd")
         # query encoder backward (BPTT), gradients accumulated into the zeroed buffers
         self._chk(lib.drn_qe_backward(C.byref(self._qe_desc(p, grads)), _st()), "qe_backward")
-        self.launches += 30 + self.L
+        self.launches += lib.drn_qe_launch_count(B, self.L, self.qe_H, 1) - 1  # kernels enqueued inside drn_qe_backward
         if self.overlap:
             self._join()
         self.launches_bwd = self.launches

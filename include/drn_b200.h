@@ -298,6 +298,8 @@ typedef struct {
 } drn_qe_t;
 
 size_t drn_qe_workspace_bytes(int B, int L, int H, int E);
+/* number of kernels one drn_qe_forward (backward = 0) / drn_qe_backward (backward = 1) call launches for this shape */
+int drn_qe_launch_count(int B, int L, int H, int backward);
 int drn_qe_forward(const drn_qe_t* q, void* stream);
 int drn_qe_backward(const drn_qe_t* q, void* stream);
 
