@@ -9,6 +9,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> global, one accumulator row per thread).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cudaTypedefs.h>
 
 #include "gemm_common.cuh"
@@ -491,6 +492,14 @@ extern "C" int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream) {
   static thread_local GroupParams gp;
   static thread_local GroupMaps gm;
   gp.nprob = n;
+  {
+    static int gm = -1;  // DRN_RASTER_GM: tuning override
+    if (gm < 0) {
+      const char* e = getenv("DRN_RASTER_GM");
+      gm = e ? atoi(e) : 0;
+    }
+    gp.raster_gm = gm > 0 ? gm : 1;  // A/B-measured r01: 1 / 4 / 8 / 16 within noise (DRAM is at ~18 % while the tensor pipe is at ~90 %)
+  }
   gp.tile_start[0] = 0;
   for (int k = 0; k < n; ++k) {
     const int i = order[k];

@@ -48,13 +48,23 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
   const int local = tile - gp.tile_start[pr];
   const int n_tiles = gp.n_tiles[pr], m_tiles = gp.m_tiles[pr];
   const bool wgrad = (p.form == DRN_GEMM_WGRAD);
-  const int nt = local % n_tiles;
-  int rest = local / n_tiles;
+  // Optional rasterisation: tiles walked in groups of raster_gm tile-rows, n-major inside a group, so concurrently running
+  // clusters share a few A row-blocks.  Measured neutral on B200 (prop_fc forward: 627 -> 611 MB of DRAM reads for 201 MB of
+  // operands, no change in time: the kernel sits at ~90 % tensor pipe / ~18 % DRAM), so the default is 1 = row-major order.
+  const int per = m_tiles * n_tiles;
+  const int idx = local % per;
+  const int z = local / per;  // WGRAD: (tap, split); ROWS: split
+  const int RASTER_GM = gp.raster_gm;
+  const int grp = idx / (RASTER_GM * n_tiles);
+  const int first_m = grp * RASTER_GM;
+  const int gm = min(RASTER_GM, m_tiles - first_m);
+  const int within = idx - grp * RASTER_GM * n_tiles;
+  const int mt = first_m + within % gm;
+  const int nt = within / gm;
   t.n0 = nt * P2_TILE;
   t.nb = t.n0 + rank * 128;
   if (!wgrad) {
-    const int mt = rest % m_tiles;
-    t.split = rest / m_tiles;        // K-split of a ROWS problem (conv0 forward: few tiles, very long K)
+    t.split = z;                     // K-split of a ROWS problem (conv0 forward: few tiles, very long K)
     const int ms = 2 * mt + rank;    // 128-row sub-tile of this CTA
     if (p.Bbm == 1) {
       t.b0 = ms / p.tiles_per_sample;
@@ -67,8 +77,6 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
     t.it_begin = static_cast<int>(static_cast<long long>(its) * t.split / p.split_k);
     t.nk = static_cast<int>(static_cast<long long>(its) * (t.split + 1) / p.split_k) - t.it_begin;
   } else {
-    const int mt = rest % m_tiles;
-    const int z = rest / m_tiles;
     t.m0 = mt * P2_TILE + rank * 128;
     t.tap = z / p.split_k;
     t.split = z % p.split_k;

@@ -47,6 +47,7 @@ struct GemmKParams {
 constexpr int GROUP_MAX = 6;
 struct GroupParams {
   int nprob;
+  int raster_gm;                  // tile-rows per rasterisation group (1 = plain row-major tile order)
   int tile_start[GROUP_MAX + 1];  // prefix sums of the per-problem 256 x 256 tile counts
   int n_tiles[GROUP_MAX], m_tiles[GROUP_MAX];
   GemmKParams p[GROUP_MAX];

@@ -502,7 +502,7 @@ class DensePath:
 
     def part2_grad_names(self, names):
         """Gradients produced by `backward_tail` (everything else is final when `backward(..., tail=False)` returns)."""
-        return {n for n in names if n == "prop_fc.weight" or n.startswith("qInput") or n.startswith("query_encoder.")}
+        return {n for n in names if n.startswith("qInput") or n.startswith("query_encoder.")}
 
     def backward(self, p, grads, upstream, tail=True):
         """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
@@ -590,21 +590,18 @@ class DensePath:
             grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
         for l in range(3):
             grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
+        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D], the largest contraction of the backward pass
+        self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
+                   out_ld=self.D, out_tap_stride=0)
         self.launches_bwd = self.launches
         if tail:
             self.backward_tail(p, grads)
 
     def backward_tail(self, p, grads):
-        """Second part of the backward: the prop_fc weight gradient, the gates and the query encoder.  Nothing of the first
-        part depends on it, so a data-parallel run all-reduces the first part's gradients while this runs (model/main_model.py)."""
+        """Second part of the backward: the gates and the query encoder -- a latency-bound chain of small kernels (~0.4 ms) that
+        leaves most SMs idle, which is where a data-parallel run hides the all-reduce of everything the first part produced
+        (model/main_model.py:_run_backward)."""
         lib, B = _lib(), self.B
-        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D] (the largest contraction of the backward pass); the gates and the
-        # query-encoder backward (a latency-bound chain of small kernels) run beside it
-        if self.overlap:
-            self._fork()
-        with torch.cuda.stream(self.side if self.overlap else torch.cuda.current_stream()):
-            self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
-                       out_ld=self.D, out_tap_stride=0)
         # gates: dW += dq^T cmd, db += colsum(dq), dcmd = dq W  -- nine small contractions, one launch (dcmd is zero-filled
         # together with dq / pgrad at the start of the backward)
         K = self.cmd_dim
@@ -623,6 +620,4 @@ class DensePath:
         # query encoder backward (BPTT), gradients accumulated into the zeroed buffers
         self._chk(lib.drn_qe_backward(C.byref(self._qe_desc(p, grads)), _st()), "qe_backward")
         self.launches += lib.drn_qe_launch_count(B, self.L, self.qe_H, 1) - 1  # kernels enqueued inside drn_qe_backward
-        if self.overlap:
-            self._join()
         self.launches_bwd = self.launches

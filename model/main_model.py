@@ -42,18 +42,19 @@ def _run_forward_core(path, p, training, use_graphs):
 
 def _run_backward(path, p, names, upstream, use_graphs, dp=None):
     """Backward of the path into ONE flat gradient buffer.  Layout:
-        [A: accumulated, produced by the tail][B: accumulated, first part][C: stored, first part][D: prop_fc.weight (tail, stored)]
-    A+B are zero-filled every backward (atomics / += land there); C and D are fully overwritten by their kernels.  Every slot
-    starts on a 32-byte boundary (full-sector vector stores in the contraction epilogues).
-    Data parallel (dp = drn_b200.parallel.DataParallelDRN): the backward runs as TWO graphs; the gradients of the first part
-    (B+C, final when it ends) are all-reduced on NCCL's stream WHILE the tail (prop_fc weight gradient, gates, query encoder)
-    runs; A and D follow."""
+        [A: accumulated, produced by the tail (gates, query encoder)][B: accumulated, first part][C: stored, first part]
+    A+B are zero-filled every backward (atomics / += land there); C (conv weights, prop_fc.weight) is fully overwritten by its
+    kernels.  Every slot starts on a 32-byte boundary (full-sector vector stores in the contraction epilogues).
+    Data parallel (dp = drn_b200.parallel.DataParallelDRN): the backward runs as TWO graphs.  When the first (head, FPN,
+    backbone, prop_fc) ends, its gradients B+C -- 77 % of the bytes, one contiguous region -- are all-reduced on NCCL's stream
+    WHILE the tail runs: a ~0.4 ms latency-bound chain of small kernels that leaves most SMs free for the collective.  The
+    tail's region A follows."""
     key = ("bwd", _sig(p), tuple(names), dp is not None)
     ent = path.graphs.get(key)
     if ent is None:
         stored, tailn = path.stored_grad_names(names), path.part2_grad_names(names)
-        groups = [[n for n in names if n in tailn and n not in stored], [n for n in names if n not in tailn and n not in stored],
-                  [n for n in names if n not in tailn and n in stored], [n for n in names if n in tailn and n in stored]]
+        groups = [[n for n in names if n in tailn], [n for n in names if n not in tailn and n not in stored],
+                  [n for n in names if n not in tailn and n in stored]]
         pad = lambda k: (k + 7) // 8 * 8  # noqa: E731
         bounds = [0]
         for g_ in groups:
@@ -64,7 +65,7 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
             for n in g_:
                 grads[n] = flat[o:o + p[n].numel()].view_as(p[n])
                 o += pad(p[n].numel())
-        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:bounds[3]], "tail_a": flat[:bounds[1]], "tail_d": flat[bounds[3]:]}
+        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:], "tail": flat[:bounds[1]]}
         path.upstream.copy_(upstream)
         path.backward(p, grads, path.upstream)
         g1 = g2 = None
@@ -94,7 +95,7 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
             g2.replay()
         else:
             path.backward_tail(p, grads)
-        dp.reduce_regions([regions["tail_a"], regions["tail_d"]])
+        dp.reduce_regions([regions["tail"]])
         dp.wait(work)
     return flat, grads
 
