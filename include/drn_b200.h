@@ -239,6 +239,16 @@ int drn_postprocess(int nlevels, int B, const int* T, const float* strides, cons
                     const float* iou_raw, float thr, int top_n, int use_iou, float* out_det, float* out_score, float* out_loc,
                     int* out_count, void* stream);
 
+/* Proposal feature pooling + padding, the step right before the path (dataset.py:105-155 CharadesSTA.get_data, 180-206
+ * collate_data): feats = the batch's per-video window features concatenated [sum n_win][D] fp32, video b owning rows
+ * [win_off[b], win_off[b+1]); proposal (b, p) = (p_start float frame, p_end = min(int(end), num_frames)).  For p < nprops[b]:
+ * out_feats[b][p] = element-wise max over the feature windows the proposal covers (index arithmetic of dataset.py:126-145 with
+ * window = ft_window_size, interval = int(window * (1 - ft_overlap)), clamped to the last window present), out_pse[b][p] =
+ * (p_start, p_end) / num_frames[b] in float64; rows p >= nprops[b] are zero.  Bit-exact with the reference (integer + max). */
+int drn_pool_proposals(const float* feats, const int64_t* win_off, const double* p_start, const int32_t* p_end,
+                       const int32_t* nprops, const int32_t* num_frames, int B, int P, int D, int window, int interval,
+                       float* out_feats, double* out_pse, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Query encoder (drn_b200/csrc/query.cu): model/language_module.py:27-62 (QueryEncoder.forward +
  * extract_textual_command) with model/ops.py:16-25,74-85, forward and backward, exact fp32 FMA arithmetic.

@@ -114,3 +114,27 @@ def test_metric_restatement_matches_reference_golden(golden_dir):
            {"detections": torch.tensor([[0.0, 1.0]]), "scores": torch.tensor([1.0])}]
     r = M.recall_at(res, [(0.5, 1.0), (0.1, 0.2)])  # zero-duration detection dropped; 2nd pick hits query 0; query 1 misses
     assert r[1] == 0.0 and r[5] == 0.5
+
+
+def _pool_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pool_props.npz"))
+    B = len(g["props_num"])
+    feats = [g["feat_%d" % k] for k in range(B)]
+    ps = [g["p_start_%d" % k] for k in range(B)]
+    pe = [g["p_end_%d" % k] for k in range(B)]
+    return g, feats, ps, pe
+
+
+def test_pooling_oracle_matches_reference_golden(golden_dir):
+    """oracle/pooling.py (dataset.py:105-155,180-206) against the output of the reference's own CharadesSTA.get_data +
+    collate_data on synthetic feature files (oracle/make_pool_goldens.py): bit-exact (integer index arithmetic + max)."""
+    from oracle import pooling as P
+    g, feats, ps, pe = _pool_golden(golden_dir)
+    out, pse = P.pool_and_pad(feats, ps, pe, [int(x) for x in g["num_frames"]], window=16, interval=8)
+    assert out.shape == g["props_features"].shape and np.array_equal(out, g["props_features"])
+    assert np.array_equal(pse, g["props_s_e"])
+    # the fixtures exercise both branches (single window / range) and the clamp to the last available window
+    lo_hi = [P.window_range(float(s), int(e), feats[k].shape[0], 16, 8) for k in range(len(feats)) for s, e in zip(ps[k], pe[k])]
+    assert any(lo == hi for lo, hi in lo_hi) and any(hi > lo for lo, hi in lo_hi)
+    assert any(hi == feats[k].shape[0] - 1 for k in range(len(feats)) for (lo, hi) in
+               [P.window_range(float(ps[k][-1]), int(pe[k][-1]), feats[k].shape[0], 16, 8)])
