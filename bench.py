@@ -137,7 +137,7 @@ def time_dominant_kernel(path, p, reps=10):
 
     def launch():  # exactly the call DensePath.forward_core makes for prop_fc (model/main_model.py:59)
         ops.gemm(L.GEMM_ROWS, path.f_pl.desc(), path.wp["prop_fc"].desc(), path.B, path.T, D, K=D, bias=p["prop_fc.bias"],
-                 out=path.Pre)
+                 out2=path.Pre, rowscale=path.q[0], outp=path.X0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     tot = 0.0
     for i in range(reps + 2):

@@ -59,10 +59,6 @@ class DensePath:
         assert T % 4 == 0, "T must be a multiple of 4 (two stride-2 levels)"
         self.cfg, self.B, self.T, self.dev = cfg, B, T, device
         self.L, self.qe_H, self.qe_E = L, qe_hidden, qe_embed
-        # independent branches of the schedule (weight gradients next to the data-gradient chain, the query encoder next
-        # to prop_fc) are enqueued on a second stream; inside a CUDA-graph capture this becomes a forked graph branch
-        self.overlap = os.environ.get("DRN_NO_OVERLAP", "0") != "1"
-        self.side = torch.cuda.Stream(device=device)
         D = cfg[cfg["feature_type"]]["feature_dim"]
         c1, F = cfg["first_output_dim"], cfg["fpn_feature_dim"]
         self.D, self.C0, self.c = D, D + 256, (c1, 2 * c1, 4 * c1)
@@ -352,13 +348,6 @@ class DensePath:
         h = "fcos.head."
         self.launches = self.launches_stage
         self.pack_weights(p)
-        # prop_fc (main_model.py:59) does not depend on the query: it runs on the side stream beside the query encoder, a
-        # latency-bound chain of small kernels that would otherwise leave the GPU mostly idle for ~0.4 ms
-        if self.overlap:
-            self._fork()
-        with torch.cuda.stream(self.side if self.overlap else torch.cuda.current_stream()):
-            self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
-                       out=self.Pre)
         # query encoder -> three command vectors (model/main_model.py:47, language_module.py:38-62)
         self._chk(lib.drn_qe_forward(C.byref(self._qe_desc(p)), _st()), "qe_forward")
         self.launches += lib.drn_qe_launch_count(B, self.L, self.qe_H, 0) - 1  # kernels enqueued inside drn_qe_forward
@@ -370,11 +359,18 @@ class DensePath:
             j.x, j.ldx, j.W, j.ldw = self.cmd[i].data_ptr(), K, p["qInput%d.weight" % i].data_ptr(), K
             j.bias, j.out, j.ldo, j.B, j.N, j.K, j.relu = p["qInput%d.bias" % i].data_ptr(), self.q[i].data_ptr(), n, B, n, K, 0
         self._chk(lib.drn_linear_fwd_batch(3, jobs, _st()), "gates")
-        if self.overlap:
-            self._join()
-        # level-0 gate q0 * prop_fc(f) -> X0[:, :, :D] (backbone.py:28-30; the cat with the position channels is the layout)
-        self._chk(lib.drn_gate_planes(_vp(self.Pre), _vp(self.q[0]), B, T, self.D, _vp(self.X0.data), C.c_int64(self.C0), 0,
-                                      C.c_int64(self.X0.plane_stride), _st()), "gate_planes")
+        # prop_fc (main_model.py:59) with the level-0 gate fused in the epilogue: Pre = W f + b (kept for the gate gradient),
+        # X0[:, :, :D] = planes(q0 * Pre) (backbone.py:28-30; the cat with the position channels is the layout).  Running it
+        # beside the query encoder on a second stream was measured to buy nothing (no SM co-residency with the persistent
+        # kernel, scripts/overlap_probe.py), while the separate gating pass cost 39 us.
+        if os.environ.get("DRN_FUSE_GATE", "1") == "1":
+            self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
+                       out2=self.Pre, rowscale=self.q[0], outp=self.X0)
+        else:  # A/B: separate gating pass
+            self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
+                       out=self.Pre)
+            self._chk(lib.drn_gate_planes(_vp(self.Pre), _vp(self.q[0]), B, T, self.D, _vp(self.X0.data), C.c_int64(self.C0), 0,
+                                          C.c_int64(self.X0.plane_stride), _st()), "gate_planes")
         # backbone (backbone.py:27-34)
         src = self.X0
         for i in range(3):
@@ -449,18 +445,6 @@ class DensePath:
     # ---------------------------------------------------------------------------------------------------------------
     # backward
     # ---------------------------------------------------------------------------------------------------------------
-    def _fork(self):
-        """Side stream waits for everything enqueued so far on the current stream."""
-        ev = torch.cuda.Event()
-        ev.record()
-        self.side.wait_event(ev)
-
-    def _join(self):
-        """Current stream waits for everything enqueued so far on the side stream."""
-        ev = torch.cuda.Event()
-        ev.record(self.side)
-        torch.cuda.current_stream().wait_event(ev)
-
     def _group(self, descs):
         """Independent contractions -> one launch of the persistent CTA-pair kernel per <= 6 problems."""
         self.launches += ops.gemm_group(descs)
