@@ -17,6 +17,13 @@ namespace cg = cooperative_groups;
 
 namespace drn {
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // Small fp32 contraction: C[m][n] (=|+=) sum_k A(m,k) * B(k,n) (+ bias[n] + bias2[n]) with arbitrary element strides, so the
 // same kernel serves x W^T (Linear forward), dy W (data gradient) and dy^T x (weight gradient).  64(32) x 64 x 16 tiles,
@@ -168,23 +175,23 @@ __global__ void __launch_bounds__(256) sgemm_multi_kernel(const SgemmJobs jobs) 
   else sgemm_body<64>(jobs.p[j], bx, by, bz);
 }
 
-// Host-side batch: add() problems (all ACCUMULATING into their outputs, i.e. C must hold valid data -- the batch never
-// zero-fills), launch() once.
+// Host-side batch: add() problems, launch() once.  A problem ACCUMULATES into its output with atomics (C must hold valid data;
+// small problems are K-split to fill the GPU) unless store = true: then it overwrites C with plain stores, unsplit.
 struct SgemmBatch {
   SgemmJobs jobs;
   SgemmBatch() { jobs.n = 0; jobs.cta_start[0] = 0; }
   int add(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C, long long ldc, int M,
-          int N, int K, const float* bias = nullptr) {
+          int N, int K, const float* bias = nullptr, bool store = false) {
     if (jobs.n >= SG_MAX_JOBS) return fail(DRN_EINVAL, "sgemm batch: more than %d problems", SG_MAX_JOBS);
     if (M < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "sgemm batch: empty problem (%d,%d,%d)", M, N, K);
     const int i = jobs.n++;
     const int bm = (M <= 32) ? 32 : 64;
     const int tiles = ceil_div(M, bm) * ceil_div(N, 64);
     int splits = 1;
-    if (tiles < 74) splits = max(1, min(ceil_div(148, tiles), ceil_div(K, 64)));
+    if (!store && tiles < 74) splits = max(1, min(ceil_div(148, tiles), ceil_div(K, 64)));
     const int kchunk = ceil_div(ceil_div(K, splits), 16) * 16;
     splits = ceil_div(K, kchunk);
-    jobs.p[i] = SgemmP{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, nullptr, 0, 1, kchunk};
+    jobs.p[i] = SgemmP{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, nullptr, 0, store ? 0 : 1, kchunk};
     jobs.gx[i] = ceil_div(M, bm);
     jobs.gy[i] = ceil_div(N, 64);
     jobs.bm[i] = bm;
@@ -235,11 +242,13 @@ static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, 
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Deterministic small-batch nn.Linear forward: out[b][n] = act(bias[n] + sum_k x[b][k] W[n][k]).  The forward of the path must
-// be run-to-run reproducible (train-mode BatchNorm amplifies 1e-7 input noise ~100x into the early-layer gradients), so the
-// contraction is split over the 8 warps of a CTA and reduced in a fixed order -- no atomics.  CTA = 32 samples x 8 outputs;
-// lane = sample, W row segments live in registers and are broadcast with shuffles.
+// be run-to-run reproducible (train-mode BatchNorm amplifies 1e-7 input noise ~100x into the early-layer gradients): every
+// output is ONE thread's sequential sum over k -- no atomics, no split.  This is a weight-streaming problem (B <= 32 rows of x
+// against N x K weights): a CTA stages a 32-sample chunk of x transposed in shared memory ([k][sample], K in chunks of 1024)
+// and each of its 16 warps owns LIN_NT output rows; lane = sample, the weights are read with 16-byte broadcast loads straight
+// from global memory (each weight is used exactly once per CTA, so staging it would buy nothing).
 // ------------------------------------------------------------------------------------------------------------------------
-constexpr int LIN_NT = 8, LIN_WARPS = 16;
+constexpr int LIN_NT = 4, LIN_WARPS = 8, LIN_KC = 256;  // 32 rows per 256-thread CTA, 66 KB of shared memory: 3 CTAs per SM
 struct LinP {
   const float* x; long long ldx;
   const float* W; long long ldw;
@@ -263,64 +272,92 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const LinJ
   const int local = blockIdx.x - jobs.cta_start[jb];
   const int bxx = local % jobs.gx[jb], byy = local / jobs.gx[jb];
   const float* __restrict__ x = P.x;
-  const long long ldx = P.ldx;
   const float* __restrict__ W = P.W;
-  const long long ldw = P.ldw;
-  const float* __restrict__ bias = P.bias;
-  float* __restrict__ out = P.out;
-  const long long ldo = P.ldo;
-  const int Bn = P.Bn, N = P.N, K = P.K, relu = P.relu;
-  extern __shared__ __align__(16) float lin_smem[];
-  float (*xs)[32][33] = reinterpret_cast<float (*)[32][33]>(lin_smem);              // [LIN_WARPS][32][33]
-  float (*red)[LIN_NT][32] = reinterpret_cast<float (*)[LIN_NT][32]>(lin_smem);     // reused after the main loop
+  const int Bn = P.Bn, N = P.N, K = P.K;
+  extern __shared__ __align__(16) float xs[];  // [LIN_KC + 4][33] staged samples, then [LIN_WARPS][LIN_NT][LIN_KC] weight strips
+  float* wbuf = xs + (LIN_KC + 4) * 33;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int n0 = bxx * LIN_NT, b0 = byy * 32;
-  const int kper = ((K + LIN_WARPS - 1) / LIN_WARPS + 31) / 32 * 32;  // K slice per warp, multiple of 32
-  const int kbeg = w * kper, kend = min(K, kbeg + kper);
+  const int b0 = byy * 32;
+  const int n0 = (bxx * LIN_WARPS + w) * LIN_NT;
   float acc[LIN_NT];
 #pragma unroll
   for (int j = 0; j < LIN_NT; ++j) acc[j] = 0.f;
-  float wr[LIN_NT], xr[32];
-  auto fetch = [&](int k0) {
-    const int k = k0 + lane;
+  const bool vec = (P.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  for (int kc = 0; kc < K; kc += LIN_KC) {
+    const int kn = min(LIN_KC, K - kc);
+    __syncthreads();
+    if (n0 < N) {  // request this warp's weight strip [LIN_NT][kn] (zero-filled up to a multiple of 4 columns)
+      float* wb = wbuf + w * (LIN_NT * LIN_KC);
 #pragma unroll
-    for (int j = 0; j < LIN_NT; ++j) wr[j] = (n0 + j < N && k < kend) ? __ldg(W + (n0 + j) * ldw + k) : 0.f;
+      for (int j = 0; j < LIN_NT; ++j) {
+        const float* wr = W + static_cast<long long>(min(n0 + j, N - 1)) * P.ldw + kc;
+        for (int k = lane * 4; k < kn; k += 128) {
+          if (vec && k + 4 <= kn) {
+            cp_async16(wb + j * LIN_KC + k, wr + k);
+          } else {
 #pragma unroll
-    for (int b = 0; b < 32; ++b) xr[b] = (b0 + b < Bn && k < kend) ? __ldg(x + (b0 + b) * ldx + k) : 0.f;
-  };
-  if (kbeg < kend) fetch(kbeg);
-  for (int k0 = kbeg; k0 < kend; k0 += 32) {
-    float wc[LIN_NT];
-#pragma unroll
-    for (int j = 0; j < LIN_NT; ++j) wc[j] = wr[j];
-#pragma unroll
-    for (int b = 0; b < 32; ++b) xs[w][lane][b] = xr[b];
-    __syncwarp();
-    if (k0 + 32 < kend) fetch(k0 + 32);
-#pragma unroll 8
-    for (int kk = 0; kk < 32; ++kk) {
-      const float xv = xs[w][kk][lane];
-#pragma unroll
-      for (int j = 0; j < LIN_NT; ++j) acc[j] = fmaf(xv, __shfl_sync(0xffffffffu, wc[j], kk), acc[j]);
+            for (int i = 0; i < 4; ++i) wb[j * LIN_KC + k + i] = (k + i < kn) ? __ldg(wr + k + i) : 0.f;
+          }
+        }
+      }
     }
-    __syncwarp();
+    {  // stage x[b0 .. b0+32)[kc .. kc+kn) transposed into [k][sample]: warp w owns 32 / LIN_WARPS samples, 16-byte loads along
+       // k (no index divisions: they were half of this kernel's instructions)
+      const bool xvec = (P.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (kn % 4 == 0);
+      constexpr int SPW = 32 / LIN_WARPS;
+#pragma unroll
+      for (int sb = 0; sb < SPW; ++sb) {
+        const int b = w * SPW + sb;
+        const bool live = b0 + b < Bn;
+        const float* xr = x + (b0 + b) * P.ldx + kc;
+        if (xvec) {
+#pragma unroll 2
+          for (int k4 = lane; k4 * 4 < kn; k4 += 32) {
+            const float4 v = live ? __ldg(reinterpret_cast<const float4*>(xr) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int k = k4 * 4;
+            xs[(k + 0) * 33 + b] = v.x;
+            xs[(k + 1) * 33 + b] = v.y;
+            xs[(k + 2) * 33 + b] = v.z;
+            xs[(k + 3) * 33 + b] = v.w;
+          }
+        } else {
+          for (int k = lane; k < kn; k += 32) xs[k * 33 + b] = live ? __ldg(xr + k) : 0.f;
+        }
+      }
+    }
+    if (tid < 4 * 32) xs[(kn + (tid >> 5)) * 33 + (tid & 31)] = 0.f;  // zero rows behind a ragged K tail
+    cp_async_wait_all();
+    __syncthreads();
+    // weights: every warp's LIN_NT x kn strip was requested with cp.async BEFORE the x staging above (all of a chunk's
+    // weight bytes are in flight at once: the kernel is a latency-bound weight stream otherwise); read back as broadcast float4s
+    if (n0 < N) {
+      const float* wb = wbuf + w * (LIN_NT * LIN_KC);
+#pragma unroll 4
+      for (int kk = 0; kk < kn; kk += 4) {  // columns beyond kn hold zero weights; xs rows kn..kn+3 are zero
+        const float x0 = xs[(kk + 0) * 33 + lane], x1 = xs[(kk + 1) * 33 + lane], x2 = xs[(kk + 2) * 33 + lane],
+                    x3 = xs[(kk + 3) * 33 + lane];
+#pragma unroll
+        for (int j = 0; j < LIN_NT; ++j) {
+          const float4 wv = *reinterpret_cast<const float4*>(wb + j * LIN_KC + kk);
+          acc[j] = fmaf(x0, wv.x, acc[j]);
+          acc[j] = fmaf(x1, wv.y, acc[j]);
+          acc[j] = fmaf(x2, wv.z, acc[j]);
+          acc[j] = fmaf(x3, wv.w, acc[j]);
+        }
+      }
+    }
   }
-  __syncthreads();
+  if (b0 + lane < Bn) {
 #pragma unroll
-  for (int j = 0; j < LIN_NT; ++j) red[w][j][lane] = acc[j];
-  __syncthreads();
-  if (tid < LIN_NT * 32) {
-    const int j = tid >> 5, b = tid & 31;
-    if (n0 + j < N && b0 + b < Bn) {
-      float v = bias ? __ldg(bias + n0 + j) : 0.f;
-#pragma unroll
-      for (int ww = 0; ww < LIN_WARPS; ++ww) v += red[ww][j][b];
-      out[(b0 + b) * ldo + n0 + j] = relu ? fmaxf(v, 0.f) : v;
+    for (int j = 0; j < LIN_NT; ++j) {
+      if (n0 + j >= N) continue;
+      float v = acc[j] + (P.bias ? __ldg(P.bias + n0 + j) : 0.f);
+      P.out[(b0 + lane) * P.ldo + n0 + j] = P.relu ? fmaxf(v, 0.f) : v;
     }
   }
 }
 static int linear_launch(cudaStream_t st, LinJobs& jobs) {
-  constexpr size_t smem = LIN_WARPS * 32 * 33 * sizeof(float);
+  constexpr size_t smem = ((LIN_KC + 4) * 33 + LIN_WARPS * LIN_NT * LIN_KC) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -338,7 +375,7 @@ static int linear_add(LinJobs& jobs, const float* x, long long ldx, const float*
   const int i = jobs.n++;
   if (i == 0) jobs.cta_start[0] = 0;
   jobs.p[i] = LinP{x, ldx, W, ldw, bias, out, ldo, Bn, N, K, relu};
-  jobs.gx[i] = ceil_div(N, LIN_NT);
+  jobs.gx[i] = ceil_div(N, LIN_NT * LIN_WARPS);
   jobs.cta_start[i + 1] = jobs.cta_start[i] + jobs.gx[i] * ceil_div(Bn, 32);
   return 0;
 }
@@ -415,12 +452,6 @@ __global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __res
   }
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 
 // ---- the recurrence, both directions (language_module.py:42-46; torch.nn.LSTM gate order i,f,g,o) ---------------------
 // grid (H/8, 2, BC); warp = one hidden unit (its 4 gate rows of W_hh), lane = sample.  Packed-sequence semantics: a sample
@@ -968,7 +999,7 @@ extern "C" int drn_sgemm_batch(int n, const drn_sgemm_job_t* jobs, void* stream)
   SgemmBatch sb;
   for (int i = 0; i < n; ++i) {
     const drn_sgemm_job_t& j = jobs[i];
-    TRY(sb.add(j.A, j.sam, j.sak, j.B, j.sbk, j.sbn, j.C, j.ldc, j.M, j.N, j.K, j.bias));
+    TRY(sb.add(j.A, j.sam, j.sak, j.B, j.sbk, j.sbn, j.C, j.ldc, j.M, j.N, j.K, j.bias, j.store != 0));
   }
   return sb.launch(ST(stream));
 }

@@ -477,7 +477,7 @@ class DensePath:
         """Gradients a kernel of `backward` fully OVERWRITES (never accumulates into): prop_fc.weight (its contraction stores)
         and every conv weight that goes through the slice workspaces + drn_unpack_conv_wgrads."""
         h = "fcos.head."
-        st = {"prop_fc.weight", h + "cls_tower.0.weight", h + "bbox_tower.0.weight"}
+        st = {"prop_fc.weight", h + "cls_tower.0.weight", h + "bbox_tower.0.weight", "qInput0.weight", "qInput1.weight", "qInput2.weight"}
         for i in range(3):
             st |= {"backbone_net.forward_conv%d.0.weight" % i, "fpn.fpn_inner%d.0.weight" % (i + 1), "fpn.fpn_layer%d.0.weight" % (i + 1)}
         if self.iou_branch_on:
@@ -596,6 +596,7 @@ class DensePath:
             jw, jb, jc = jobs[3 * i], jobs[3 * i + 1], jobs[3 * i + 2]
             jw.A, jw.sam, jw.sak, jw.B, jw.sbk, jw.sbn = dq, 1, n, cmd, K, 1
             jw.C, jw.ldc, jw.M, jw.N, jw.K = grads["qInput%d.weight" % i].data_ptr(), K, n, K, B
+            jw.store = 1  # the only contribution to this gradient: plain stores instead of 4 M atomics
             jb.A, jb.sam, jb.sak, jb.B, jb.sbk, jb.sbn = dq, 1, n, self.one.data_ptr(), 0, 0
             jb.C, jb.ldc, jb.M, jb.N, jb.K = grads["qInput%d.bias" % i].data_ptr(), 1, n, 1, B
             jc.A, jc.sam, jc.sak, jc.B, jc.sbk, jc.sbn = dq, n, 1, W, K, 1

@@ -72,7 +72,8 @@ class PackItem(C.Structure):
 
 class SgemmJob(C.Structure):
     _fields_ = [("A", C.c_void_p), ("sam", C.c_int64), ("sak", C.c_int64), ("B", C.c_void_p), ("sbk", C.c_int64), ("sbn", C.c_int64),
-                ("C", C.c_void_p), ("ldc", C.c_int64), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("bias", C.c_void_p)]
+                ("C", C.c_void_p), ("ldc", C.c_int64), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("bias", C.c_void_p),
+                ("store", C.c_int32)]
 
 
 class LinearJob(C.Structure):

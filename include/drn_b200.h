@@ -265,14 +265,15 @@ int drn_linear_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, con
                    int N, int K, int relu, void* stream);
 
 /* Up to 12 small contractions / 4 small Linear forwards in ONE launch (the gate and query-encoder backward is a chain of ~20 of
- * them).  drn_sgemm_batch jobs always ACCUMULATE into C (which must hold valid data; a column sum is the job B = a constant 1 with
- * strides 0); drn_linear_fwd_batch jobs are independent deterministic forwards. */
+ * them).  A drn_sgemm_batch job accumulates into C (which must then hold valid data) or overwrites it (`store`); a column sum is
+ * the job B = a constant 1 with strides 0.  drn_linear_fwd_batch jobs are independent deterministic forwards. */
 typedef struct {
   const float* A; int64_t sam, sak;
   const float* B; int64_t sbk, sbn;
   float* C; int64_t ldc;
   int32_t M, N, K;
   const float* bias;
+  int32_t store;   /* 0: C += (atomics, K-split when small); 1: C = (plain stores, no split) */
 } drn_sgemm_job_t;
 int drn_sgemm_batch(int n, const drn_sgemm_job_t* jobs, void* stream);
 typedef struct {
