@@ -249,6 +249,35 @@ int drn_pool_proposals(const float* feats, const int64_t* win_off, const double*
                        const int32_t* nprops, const int32_t* num_frames, int B, int P, int D, int window, int interval,
                        float* out_feats, double* out_pse, void* stream);
 
+/* Language-guided pooling, model/LGP.py:29-51 (dead code in the reference; standalone op `model/LGP.py` of this repo), reference
+ * layout: x [B][C][t] channels-first, t even.  Forward: z = query W^T (drn_linear_fwd) -> drn_lgp_bn: BatchNorm1d of the query
+ * tiled over t (statistics over the batch; running variance with n = B*t) -> qn, xhat [B][C], invstd [C] -> drn_lgp_pool_fwd:
+ * pair scores, softmax over each pair (att [B][t/2][2]), out [B][C][t/2].  Backward: drn_lgp_pool_bwd (dx, dqn) ->
+ * drn_lgp_bn_bwd (dz [B][C]; dgamma / dbeta accumulated) -> d query = dz W, dW += dz^T query (drn_sgemm_batch). */
+int drn_lgp_bn(const float* z, int B, int C, int t, const float* gamma, const float* beta, float* running_mean, float* running_var,
+               int64_t* num_batches_tracked, float momentum, float eps, int training, float* qn, float* xhat, float* invstd,
+               void* stream);
+int drn_lgp_pool_fwd(const float* x, const float* qn, int B, int C, int t, float* att, float* out, void* stream);
+int drn_lgp_pool_bwd(const float* x, const float* qn, const float* att, const float* dout, int B, int C, int t, float* dx, float* dqn,
+                     void* stream);
+int drn_lgp_bn_bwd(const float* dqn, const float* xhat, const float* invstd, const float* gamma, int B, int C, int training, float* dz,
+                   float* dgamma, float* dbeta, void* stream);
+
+/* Fused clip_grad_norm_ + Adam step, what main.py:239-244 does after every backward (opt-in: `drn_b200.optim.FusedClipAdam`).
+ * items: device array of drn_adam_item_t; (chunk_item[i], chunk_off[i]) = tensor and element offset of chunk i (chunks of
+ * drn_clip_adam_chunk() elements).  total_norm over every item with a gradient; clip_coef = min(1, max_norm / (norm + 1e-6));
+ * items with update = 1 take a torch.optim.Adam step (no amsgrad / weight decay) on the clipped gradient; steps[i] is the per-tensor
+ * step counter (device, zero before the first call; advanced only when the tensor has a gradient, as torch does).
+ * scratch: 3 doubles (sum of squares, total norm, clip coefficient) readable after the call.  No host synchronisation. */
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  int64_t numel;
+  int32_t update;
+} drn_adam_item_t;
+int drn_clip_adam(int nchunks, const void* items, const int32_t* chunk_item, const int64_t* chunk_off, double* scratch,
+                  int32_t* steps, float max_norm, float lr, float beta1, float beta2, float eps, void* stream);
+int drn_clip_adam_chunk(void);
+
 /* ------------------------------------------------------------------------------------------------
  * Query encoder (drn_b200/csrc/query.cu): model/language_module.py:27-62 (QueryEncoder.forward +
  * extract_textual_command) with model/ops.py:16-25,74-85, forward and backward, exact fp32 FMA arithmetic.

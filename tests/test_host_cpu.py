@@ -41,6 +41,7 @@ def test_ctypes_structs_match_c_layout():
 #include <stddef.h>
 #include "drn_b200.h"
 int main(void) {
+  printf("%zu %zu ", sizeof(drn_adam_item_t), offsetof(drn_adam_item_t, update));
   printf("%zu %zu %zu %zu ", sizeof(drn_sgemm_job_t), offsetof(drn_sgemm_job_t, bias), sizeof(drn_linear_job_t), offsetof(drn_linear_job_t, relu));
   printf("%zu %zu %zu ", sizeof(drn_head_levels_t), offsetof(drn_head_levels_t, tower), offsetof(drn_head_levels_t, d_tower));
   printf("%zu %zu %zu %zu ", sizeof(drn_bn_job_t), offsetof(drn_bn_job_t, coef), offsetof(drn_bn_job_t, out_qa), offsetof(drn_bn_job_t, dy_plane_stride));
@@ -59,7 +60,8 @@ int main(void) {
     G = L.GemmDesc
     J = L.BnJob
     HL = L.HeadLevels
-    mine = [ctypes.sizeof(L.SgemmJob), L.SgemmJob.bias.offset, ctypes.sizeof(L.LinearJob), L.LinearJob.relu.offset, ctypes.sizeof(HL), HL.tower.offset, HL.d_tower.offset, ctypes.sizeof(J), J.coef.offset, J.out_qa.offset, J.dy_plane_stride.offset, ctypes.sizeof(L.Qe), L.Qe.tokens.offset, L.Qe.g_w2.offset, L.Qe.workspace_bytes.offset, ctypes.sizeof(L.Planes), ctypes.sizeof(G), G.b.offset, G.tap_w.offset, G.out_split_stride.offset,
+    from drn_b200.optim import _Item
+    mine = [ctypes.sizeof(_Item), _Item.update.offset, ctypes.sizeof(L.SgemmJob), L.SgemmJob.bias.offset, ctypes.sizeof(L.LinearJob), L.LinearJob.relu.offset, ctypes.sizeof(HL), HL.tower.offset, HL.d_tower.offset, ctypes.sizeof(J), J.coef.offset, J.out_qa.offset, J.dy_plane_stride.offset, ctypes.sizeof(L.Qe), L.Qe.tokens.offset, L.Qe.g_w2.offset, L.Qe.workspace_bytes.offset, ctypes.sizeof(L.Planes), ctypes.sizeof(G), G.b.offset, G.tap_w.offset, G.out_split_stride.offset,
             G.outp_plane_stride.offset, G.dbg_kadv.offset, ctypes.sizeof(L.BnPart), L.BnPart.dbeta.offset,
             ctypes.sizeof(L.PackItem), L.PackItem.slice_stride.offset]
     assert [int(x) for x in out] == mine
