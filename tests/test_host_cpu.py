@@ -141,3 +141,24 @@ def test_postprocess_list_assembly():
     assert out[1]["detections"].tolist() == [[0.0, 1.0]] and out[1]["level"] == [[-1]]
     assert out[1]["scores"].tolist() == [1.0] and out[1]["locations"].tolist() == [0.5]
     assert out[2]["detections"].shape == (12, 2) and out[2]["locations"].tolist() == loc[2].reshape(-1).tolist()
+
+
+def test_reference_checkpoint_round_trip():
+    """main.py:104-111 / 369-373: `module.`-prefixed DataParallel state_dicts load into the bare model (partial, key-matched) and
+    checkpoints written for the reference carry the prefix and every reference key."""
+    from drn_b200.checkpoint import load_reference_checkpoint, reference_checkpoint
+    from model.main_model import mainModel
+    sp = spec_mod.state_dict_spec(S.default_config(stage=1))
+    src = S.synth_state_dict(sp)
+    ck = {"epoch": 3, "state_dict": {"module." + k: v for k, v in src.items()}, "loss": 0.1, "top1": 44.7, "top5": 87.9}
+    ck["state_dict"]["module.some_removed_layer.weight"] = torch.zeros(3)  # key-matched partial load skips unknown keys
+    m = mainModel(1301, S.config_namespace(stage=1))
+    loaded, skipped = load_reference_checkpoint(m, ck)
+    assert skipped == ["module.some_removed_layer.weight"] and len(loaded) == len(src)
+    got = m.state_dict()
+    assert all(torch.equal(got[k], v) for k, v in src.items())
+    out = reference_checkpoint(m, epoch=4)
+    assert sorted(out["state_dict"]) == sorted("module." + k for k in src) and out["epoch"] == 4
+    bad = {"state_dict": {"module.prop_fc.bias": torch.zeros(7)}}
+    with pytest.raises(RuntimeError, match="shape"):
+        load_reference_checkpoint(m, bad)
