@@ -85,7 +85,7 @@ __device__ __forceinline__ void skinny_bwd_body(const float* __restrict__ d, con
   const long long rows = static_cast<long long>(B) * T;
   const long long r0 = static_cast<long long>(rblock) * rows_per_block;
   if (r0 >= rows) return;
-  constexpr int U = 4;  // rows in flight per thread: the activation loads of U rows are issued before any of them is used
+  constexpr int U = 8;  // rows in flight per thread: the activation loads of U rows are issued before any of them is used
   for (int i0 = 0; i0 < rows_per_block; i0 += U) {
     uint32_t xh[U], xl[U];
 #pragma unroll
@@ -170,11 +170,15 @@ __global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const 
   float* wc = hsm;              // [3][F]
   float* wb = hsm + 3 * F;      // [2][3][F]
   float* wi = hsm + 9 * F;      // [F/2]
+  // weights tap-major and PERMUTED so that the warp's float4 reads below are lane-contiguous (conflict-free): channel
+  // c = chunk*256 + lane*8 + q*4 + e lives at ((chunk*2 + q)*32 + lane)*4 + e.  (The natural order cost 2.3 wavefronts per
+  // shared load and made this kernel shared-memory bound, ncu r01.)
   for (int i = threadIdx.x; i < 3 * F; i += 256) {
     const int r = i / F, c = i % F;
-    wc[i] = Wc[c * 3 + r];
-    wb[i] = Wb[c * 3 + r];
-    wb[3 * F + i] = Wb[(F + c) * 3 + r];
+    const int pidx = r * F + (((c >> 8) * 2 + ((c & 7) >> 2)) * 32 + ((c & 255) >> 3)) * 4 + (c & 3);
+    wc[pidx] = Wc[c * 3 + r];
+    wb[pidx] = Wb[c * 3 + r];
+    wb[3 * F + pidx] = Wb[(F + c) * 3 + r];
   }
   for (int i = threadIdx.x; i < F / 2; i += 256) wi[i] = Wi[i];
   __syncthreads();
@@ -204,14 +208,16 @@ __global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const 
           v[2 * k] = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
           v[2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
         }
+        const int cl = (c < F) ? c : c - F;               // channel inside its branch
+        const int p0 = ((cl >> 8) * 2) * 128 + lane * 4;  // permuted offsets of the lane's two float4s
+        const int p1 = p0 + 128;
         if (c < F) {
-          const float4 w0 = *reinterpret_cast<const float4*>(wc + r * F + c), w1 = *reinterpret_cast<const float4*>(wc + r * F + c + 4);
+          const float4 w0 = *reinterpret_cast<const float4*>(wc + r * F + p0), w1 = *reinterpret_cast<const float4*>(wc + r * F + p1);
           a_cls += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
         } else {
-          const int cc = c - F;
-          const float4 p0 = *reinterpret_cast<const float4*>(wb + r * F + cc), p1 = *reinterpret_cast<const float4*>(wb + r * F + cc + 4);
-          const float4 q0 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + cc), q1 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + cc + 4);
-          a_b0 += v[0] * p0.x + v[1] * p0.y + v[2] * p0.z + v[3] * p0.w + v[4] * p1.x + v[5] * p1.y + v[6] * p1.z + v[7] * p1.w;
+          const float4 u0 = *reinterpret_cast<const float4*>(wb + r * F + p0), u1 = *reinterpret_cast<const float4*>(wb + r * F + p1);
+          const float4 q0 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + p0), q1 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + p1);
+          a_b0 += v[0] * u0.x + v[1] * u0.y + v[2] * u0.z + v[3] * u0.w + v[4] * u1.x + v[5] * u1.y + v[6] * u1.z + v[7] * u1.w;
           a_b1 += v[0] * q0.x + v[1] * q0.y + v[2] * q0.z + v[3] * q0.w + v[4] * q1.x + v[5] * q1.y + v[6] * q1.z + v[7] * q1.w;
         }
       }
@@ -630,6 +636,7 @@ extern "C" int drn_head_proj_fwd(const drn_head_levels_t* h, const float* Wc, co
   if (P < 0) return P;
   const long long total = static_cast<long long>(g.B) * P;
   const size_t smem = (9 * g.F + g.F / 2) * sizeof(float);
+  if (g.F % 256) return fail(DRN_EINVAL, "drn_head_proj_fwd: tower channels per branch must be a multiple of 256 (F=%d)", g.F);
   if (smem > 48 * 1024) return fail(DRN_EINVAL, "drn_head_proj_fwd: F=%d too large for the weight stage", g.F);
   long long ctas = (total + 7) / 8;
   if (ctas > 148 * 4) ctas = 148 * 4;

@@ -187,7 +187,14 @@ class mainModel(nn.Module):
         pse = props_start_end.to(dev, dtype=torch.float64, non_blocking=True).contiguous()
         gt = gt_start_end.to(dev, non_blocking=True).float().contiguous()  # `.float()` as at main_model.py:74
         B, T = feats.shape[0], feats.shape[1]
-        path = self._path(B, T, tokens.shape[1], dev)
+        # the reference collate pads queries to the longest of the batch (dataset.py:186,198), so the token width varies from
+        # batch to batch; every (B, T, L) owns ~2 GB of buffers and two CUDA graphs, so L is bucketed (zero = padding tokens,
+        # masked by the lengths: results are unchanged)
+        Lq = tokens.shape[1]
+        Lb = max(10, (Lq + 3) // 4 * 4) if Lq > 10 else 10
+        if Lb != Lq:
+            tokens = torch.nn.functional.pad(tokens, (0, Lb - Lq))
+        path = self._path(B, T, Lb, dev)
         names, tensors = self._dense_trainable()
         self._trainable_names = names
         training = self.training

@@ -260,3 +260,30 @@ def test_eval_forward_sweep_sizes(B, T):
     for k, v in sd.items():
         if "running_" in k or "num_batches" in k:
             assert torch.equal(msd[k].cpu(), v), k
+
+
+@pytest.mark.parametrize("L", [7, 14])
+def test_token_width_buckets(L):
+    """The reference collate pads queries to the longest of the batch (dataset.py:186,198), so the token width changes from
+    batch to batch; mainModel pads it up to a bucket (zero tokens beyond the lengths are masked).  Losses and head gradients
+    must be those of the oracle run on the UNPADDED tokens, and widths of one bucket must share one DensePath."""
+    torch.set_num_threads(os.cpu_count())
+    cfg, sd, batch, stage, training = _build(B=4, T=64, L=L)
+    assert batch["query_tokens"].shape[1] == L
+    model = _cuda_model(sd, 1, True)
+    _, ld = _run_cuda(model, batch)
+    sum(ld.values()).backward()
+    _, old, _, cap, grads = _oracle(sd, cfg, batch, 1, True)
+    for k in ("loss_cls", "loss_reg"):
+        assert _maxrel(ld[k].detach().cpu(), old[k].detach()) <= FWD_TOL, k
+    params = dict(model.named_parameters())
+    for k in ("fcos.head.cls_logits.weight", "fcos.head.bbox_pred.weight", "query_encoder.embedding.weight"):
+        g, r = params[k].grad.cpu(), grads[k]
+        assert float((g - r).norm() / r.norm()) <= 2e-3, k
+    # a narrower batch of the same bucket reuses the buffers and graphs
+    n_paths = len(model._paths)
+    b2 = dict(batch)
+    b2["query_tokens"] = batch["query_tokens"][:, :L - 1].contiguous()
+    b2["query_length"] = batch["query_length"].clamp(max=L - 1)
+    _run_cuda(model, b2)
+    assert len(model._paths) == n_paths
