@@ -250,18 +250,116 @@ __global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const 
 
 // backward of cls_logits (blockIdx.x = 0: channels [0,F)) and bbox_pred (blockIdx.x = 1: channels [F,2F)) on every level
 // (blockIdx.z); blockIdx.y = chunk of rows
-__global__ void __launch_bounds__(256) head_proj_bwd_kernel(HeadLevels g, const float* __restrict__ dcls,
+// backward of the N = 1 / 2 projections on all levels in one launch: d_tower[b,t,c] = sum_{o,r} d[b,t+1-r,o] W[o][c][r] and
+// dW[o][c][r] += sum_{b,t} tower[b,t,c] d[b,t+1-r,o].  Memory-bound (planes read once, fp32 gradient written once: 8 bytes
+// per (location, channel)).  blockIdx.y = branch (0: cls_logits on channels [0,F), 1: bbox_pred on [F,2F)); a CTA walks row
+// blocks (HB_ROWS consecutive locations of ONE sample, so no per-row index arithmetic) round-robin over all levels with the
+// weights and the dW partial sums in registers; a thread owns 4 channels (8-byte plane loads, 16-byte stores) of every
+// rsub-th row; the upstream gradients of a row block (+1 halo row each side, zero outside the sample) sit in shared memory.
+// dW leaves the CTA once: partials of the row sub-groups are folded through shared memory, one atomic per weight per CTA.
+constexpr int HB_ROWS = 32;
+template <int NOUT, int HB_U>
+__device__ __forceinline__ void head_bwd_branch(const HeadLevels& g, const float* __restrict__ dall, const float* __restrict__ W,
+                                                float* __restrict__ dW, int c0, int nblk_total, float* dsm, float* wred) {
+  const int F = g.F, nq = F >> 2;
+  const int cq = threadIdx.x % nq, rs = threadIdx.x / nq, rsub = blockDim.x / nq;
+  const int c = cq * 4;
+  float w[4][NOUT][3], gw[4][NOUT][3];
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        w[h][o][r] = __ldg(W + (static_cast<long long>(o) * F + c + h) * 3 + r);
+        gw[h][o][r] = 0.f;
+      }
+  for (int blk = blockIdx.x; blk < nblk_total; blk += gridDim.x) {
+    int lvl = 0, rem = blk;
+#pragma unroll
+    for (int l = 0; l < MAX_LEVELS - 1; ++l) {
+      const int nb = g.B * ((g.T[l] + HB_ROWS - 1) / HB_ROWS);
+      if (lvl == l && l + 1 < g.nlevels && rem >= nb) {
+        rem -= nb;
+        lvl = l + 1;
+      }
+    }
+    const int T = g.T[lvl], bps = (T + HB_ROWS - 1) / HB_ROWS;
+    const int b = rem / bps, t0 = (rem - b * bps) * HB_ROWS;
+    const int nrow = min(HB_ROWS, T - t0);
+    const long long row0 = static_cast<long long>(b) * T + t0;
+    const float* __restrict__ dl = dall + static_cast<long long>(g.B) * g.off[lvl] * NOUT;
+    __syncthreads();  // the previous row block's readers are done with dsm
+    for (int i = threadIdx.x; i < (HB_ROWS + 2) * NOUT; i += blockDim.x) {
+      const int j = i / NOUT, o = i % NOUT;
+      const int t = t0 - 1 + j;  // dsm row j = time t0 - 1 + j
+      dsm[i] = (t >= 0 && t < T) ? __ldg(dl + (static_cast<long long>(b) * T + t) * NOUT + o) : 0.f;
+    }
+    __syncthreads();
+    const __nv_bfloat16* __restrict__ xb = g.tw[lvl] + row0 * (2 * F) + c0 + c;
+    const long long ps = g.tw_ps[lvl];
+    float* __restrict__ dxb = g.dtw[lvl] + row0 * (2 * F) + c0 + c;
+    for (int i0 = rs; i0 < nrow; i0 += rsub * HB_U) {
+      uint2 xh[HB_U], xl[HB_U];
+#pragma unroll
+      for (int u = 0; u < HB_U; ++u) {  // all plane loads of HB_U rows are issued before any of them is used
+        const int i = i0 + u * rsub;
+        xh[u] = xl[u] = make_uint2(0u, 0u);
+        if (i < nrow) {
+          const __nv_bfloat16* xp = xb + static_cast<long long>(i) * (2 * F);
+          xh[u] = __ldg(reinterpret_cast<const uint2*>(xp));
+          xl[u] = __ldg(reinterpret_cast<const uint2*>(xp + ps));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < HB_U; ++u) {
+        const int i = i0 + u * rsub;
+        if (i < nrow) {
+          const float xv[4] = {__uint_as_float(xh[u].x << 16) + __uint_as_float(xl[u].x << 16),
+                               __uint_as_float(xh[u].x & 0xffff0000u) + __uint_as_float(xl[u].x & 0xffff0000u),
+                               __uint_as_float(xh[u].y << 16) + __uint_as_float(xl[u].y << 16),
+                               __uint_as_float(xh[u].y & 0xffff0000u) + __uint_as_float(xl[u].y & 0xffff0000u)};
+          float ga[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {
+              const float e = dsm[(i + 2 - r) * NOUT + o];  // d[t + 1 - r]
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                ga[h] = fmaf(e, w[h][o][r], ga[h]);
+                gw[h][o][r] = fmaf(e, xv[h], gw[h][o][r]);
+              }
+            }
+          *reinterpret_cast<float4*>(dxb + static_cast<long long>(i) * (2 * F)) = make_float4(ga[0], ga[1], ga[2], ga[3]);
+        }
+      }
+    }
+  }
+  if (!dW) return;
+  const int nw = F * NOUT * 3;
+#pragma unroll
+  for (int h = 0; h < 4; ++h)
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o)
+#pragma unroll
+      for (int r = 0; r < 3; ++r) wred[rs * nw + (o * F + c + h) * 3 + r] = gw[h][o][r];
+  __syncthreads();
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+    float v = wred[i];
+    for (int q = 1; q < rsub; ++q) v += wred[q * nw + i];
+    atomicAdd(dW + i, v);
+  }
+}
+__global__ void __launch_bounds__(256, 3) head_proj_bwd_kernel(HeadLevels g, const float* __restrict__ dcls,
                                                             const float* __restrict__ dbox, const float* __restrict__ Wc,
-                                                            const float* __restrict__ Wb, int rows_per_block,
+                                                            const float* __restrict__ Wb, int nblk_total,
                                                             float* __restrict__ dWc, float* __restrict__ dWb) {
-  const int lvl = blockIdx.z, F = g.F;
-  const long long o = static_cast<long long>(g.B) * g.off[lvl];
-  if (blockIdx.x == 0)
-    skinny_bwd_body<1, 3>(dcls + o, g.tw[lvl], g.tw_ps[lvl], 2 * F, 0, F, g.B, g.T[lvl], Wc, rows_per_block, g.dtw[lvl], 2 * F, 0, dWc,
-                          0, blockIdx.y);
-  else
-    skinny_bwd_body<2, 3>(dbox + 2 * o, g.tw[lvl], g.tw_ps[lvl], 2 * F, F, F, g.B, g.T[lvl], Wb, rows_per_block, g.dtw[lvl], 2 * F, 0,
-                          dWb, 0, blockIdx.y);
+  extern __shared__ __align__(16) float hb_sm[];  // [(HB_ROWS + 2) * 2] upstream gradients, then [rsub][F * NOUT * 3] dW partials
+  float* dsm = hb_sm;
+  float* wred = hb_sm + (HB_ROWS + 2) * 2 + 4;
+  if (blockIdx.y == 0) head_bwd_branch<1, 4>(g, dcls, Wc, dWc, 0, nblk_total, dsm, wred);
+  else head_bwd_branch<2, 2>(g, dbox, Wb, dWb, g.F, nblk_total, dsm, wred);
 }
 
 // ---- loss ---------------------------------------------------------------------------------------------------------------
@@ -650,23 +748,18 @@ extern "C" int drn_head_proj_bwd(const drn_head_levels_t* h, const float* dcls, 
   const int P = make_head_levels(&g, h, "drn_head_proj_bwd");
   if (P < 0) return P;
   if (g.F > 512) return fail(DRN_EINVAL, "drn_head_proj_bwd: at most 512 tower channels per branch (F=%d)", g.F);
-  long long rows_max = 0;
-  for (int l = 0; l < g.nlevels; ++l) {
+  for (int l = 0; l < g.nlevels; ++l)
     if (!g.dtw[l]) return fail(DRN_EINVAL, "drn_head_proj_bwd: d_tower[%d] missing", l);
-    const long long r = static_cast<long long>(g.B) * g.T[l];
-    rows_max = r > rows_max ? r : rows_max;
-  }
-  int rpb = 16;
-  while (rpb < 32 && static_cast<long long>(g.B) * P / rpb > 148) rpb *= 2;  // A/B-measured: 16..128 within noise, 32 marginally best
-  {
-    static int forced = -1;  // DRN_HEAD_RPB: tuning override
-    if (forced < 0) {
-      const char* e = getenv("DRN_HEAD_RPB");
-      forced = e ? atoi(e) : 0;
-    }
-    if (forced > 0) rpb = forced;
-  }
-  dim3 grid(2, static_cast<unsigned>((rows_max + rpb - 1) / rpb), g.nlevels);
-  head_proj_bwd_kernel<<<grid, 256, 0, ST(stream)>>>(g, dcls, dbox, Wc, Wb, rpb, dWc, dWb);
+  if (g.F != 256 && g.F != 512) return fail(DRN_EINVAL, "drn_head_proj_bwd: tower channels per branch must be 256 or 512 (F=%d)", g.F);
+  long long nblk = 0;
+  for (int l = 0; l < g.nlevels; ++l) nblk += static_cast<long long>(g.B) * ((g.T[l] + HB_ROWS - 1) / HB_ROWS);
+  // 3 CTAs per SM over the two branches; whole rounds of row blocks per CTA (448 blocks at B = 32, T = 256 -> 150 CTAs x 3 rounds)
+  const long long gmax = 148 * 3 / 2;
+  const long long rounds = (nblk + gmax - 1) / gmax;
+  const long long gx = (nblk + rounds - 1) / rounds;
+  const int rsub = 256 / (g.F / 4);
+  const size_t smem = ((HB_ROWS + 2) * 2 + 4 + static_cast<size_t>(rsub) * g.F * 2 * 3) * sizeof(float);
+  dim3 grid(static_cast<unsigned>(gx), 2, 1);
+  head_proj_bwd_kernel<<<grid, 256, smem, ST(stream)>>>(g, dcls, dbox, Wc, Wb, static_cast<int>(nblk), dWc, dWb);
   return check_launch("head_proj_bwd");
 }

@@ -243,12 +243,18 @@ static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, 
 // ------------------------------------------------------------------------------------------------------------------------
 // Deterministic small-batch nn.Linear forward: out[b][n] = act(bias[n] + sum_k x[b][k] W[n][k]).  The forward of the path must
 // be run-to-run reproducible (train-mode BatchNorm amplifies 1e-7 input noise ~100x into the early-layer gradients): every
-// output is ONE thread's sequential sum over k -- no atomics, no split.  This is a weight-streaming problem (B <= 32 rows of x
-// against N x K weights): a CTA stages a 32-sample chunk of x transposed in shared memory ([k][sample], K in chunks of 1024)
-// and each of its 16 warps owns LIN_NT output rows; lane = sample, the weights are read with 16-byte broadcast loads straight
-// from global memory (each weight is used exactly once per CTA, so staging it would buy nothing).
+// output is a FIXED-order sum -- no atomics.  This is a weight-streaming problem (B <= 32 rows of x against N x K weights,
+// 30 MB per step for the command and gate linears) whose fp32-FMA form was issue-bound (32 FMAs per weight element, 117 us per
+// step); it now runs on the warp-level tensor cores with the same split-BF16 products as the dense path
+// (hi*hi + hi*lo + lo*hi, fp32 accumulate: ~2^-17 relative per product), 0.4 instructions per weight element:
+//   * a CTA owns LIN_ROWS = 16 output rows (one m16 tile, W = the row-major A operand) x one 32-sample chunk (four n8 tiles,
+//     x = the col-major B operand); its 8 warps split K into contiguous slices and the 8 partial tiles are folded through
+//     shared memory in warp order;
+//   * fragments are loaded straight from global memory with 16-byte loads: the contraction index inside a k16 block is
+//     permuted (logical k {2t, 2t+1, 2t+8, 2t+9} <- physical {4t .. 4t+3}, the same for both operands), so a thread's four
+//     A (or B) values of one row are ONE float4; fp32 -> (hi, lo) bf16x2 happens in registers.
 // ------------------------------------------------------------------------------------------------------------------------
-constexpr int LIN_NT = 4, LIN_WARPS = 8, LIN_KC = 256;  // 32 rows per 256-thread CTA, 66 KB of shared memory: 3 CTAs per SM
+constexpr int LIN_WARPS = 8, LIN_ROWS = 16, LIN_RED_LD = 33;
 struct LinP {
   const float* x; long long ldx;
   const float* W; long long ldw;
@@ -263,6 +269,27 @@ struct LinJobs {
   int gx[LIN_MAX_JOBS];
   LinP p[LIN_MAX_JOBS];
 };
+// (a, b) -> hi = {bf16(b) : bf16(a)} (a in the low half = the lower contraction index), lo = the bf16 of the remainders
+__device__ __forceinline__ void lin_split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
+}
+__device__ __forceinline__ void lin_mma(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four consecutive values p[k .. k+3] of one operand row, zero beyond kend; 16-byte load when the whole k16 block is inside
+__device__ __forceinline__ float4 lin_load4(const float* __restrict__ p, int k, int kend, bool fast) {
+  if (fast) return __ldg(reinterpret_cast<const float4*>(p + k));
+  float4 v;
+  v.x = (k + 0 < kend) ? __ldg(p + k + 0) : 0.f;
+  v.y = (k + 1 < kend) ? __ldg(p + k + 1) : 0.f;
+  v.z = (k + 2 < kend) ? __ldg(p + k + 2) : 0.f;
+  v.w = (k + 3 < kend) ? __ldg(p + k + 3) : 0.f;
+  return v;
+}
 __global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const LinJobs jobs) {
   int jb = 0;
 #pragma unroll
@@ -271,101 +298,74 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const LinJ
   const LinP& P = jobs.p[jb];
   const int local = blockIdx.x - jobs.cta_start[jb];
   const int bxx = local % jobs.gx[jb], byy = local / jobs.gx[jb];
-  const float* __restrict__ x = P.x;
-  const float* __restrict__ W = P.W;
   const int Bn = P.Bn, N = P.N, K = P.K;
-  extern __shared__ __align__(16) float xs[];  // [LIN_KC + 4][33] staged samples, then [LIN_WARPS][LIN_NT][LIN_KC] weight strips
-  float* wbuf = xs + (LIN_KC + 4) * 33;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  const int b0 = byy * 32;
-  const int n0 = (bxx * LIN_WARPS + w) * LIN_NT;
-  float acc[LIN_NT];
+  __shared__ float red[LIN_WARPS][LIN_ROWS][LIN_RED_LD];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int b0 = byy * 32, n0 = bxx * LIN_ROWS;
+  const int kslice = (K + LIN_WARPS * 16 - 1) / (LIN_WARPS * 16) * 16;  // per-warp K slice, whole k16 blocks
+  const int kbeg = w * kslice, kend = min(K, kbeg + kslice);
+  const bool vec = (P.ldw % 4 == 0) && (P.ldx % 4 == 0) && (((reinterpret_cast<uintptr_t>(P.W) | reinterpret_cast<uintptr_t>(P.x)) & 15) == 0);
+  // rows / samples beyond the problem are clamped for the loads and dropped at the store
+  const float* __restrict__ wr0 = P.W + static_cast<long long>(min(n0 + g, N - 1)) * P.ldw;
+  const float* __restrict__ wr1 = P.W + static_cast<long long>(min(n0 + g + 8, N - 1)) * P.ldw;
+  const float* __restrict__ xr[4];
 #pragma unroll
-  for (int j = 0; j < LIN_NT; ++j) acc[j] = 0.f;
-  const bool vec = (P.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  for (int kc = 0; kc < K; kc += LIN_KC) {
-    const int kn = min(LIN_KC, K - kc);
-    __syncthreads();
-    if (n0 < N) {  // request this warp's weight strip [LIN_NT][kn] (zero-filled up to a multiple of 4 columns)
-      float* wb = wbuf + w * (LIN_NT * LIN_KC);
+  for (int j = 0; j < 4; ++j) xr[j] = P.x + static_cast<long long>(min(b0 + 8 * j + g, Bn - 1)) * P.ldx;
+  float c[4][4];
 #pragma unroll
-      for (int j = 0; j < LIN_NT; ++j) {
-        const float* wr = W + static_cast<long long>(min(n0 + j, N - 1)) * P.ldw + kc;
-        for (int k = lane * 4; k < kn; k += 128) {
-          if (vec && k + 4 <= kn) {
-            cp_async16(wb + j * LIN_KC + k, wr + k);
-          } else {
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) wb[j * LIN_KC + k + i] = (k + i < kn) ? __ldg(wr + k + i) : 0.f;
-          }
-        }
-      }
-    }
-    {  // stage x[b0 .. b0+32)[kc .. kc+kn) transposed into [k][sample]: warp w owns 32 / LIN_WARPS samples, 16-byte loads along
-       // k (no index divisions: they were half of this kernel's instructions)
-      const bool xvec = (P.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (kn % 4 == 0);
-      constexpr int SPW = 32 / LIN_WARPS;
-#pragma unroll
-      for (int sb = 0; sb < SPW; ++sb) {
-        const int b = w * SPW + sb;
-        const bool live = b0 + b < Bn;
-        const float* xr = x + (b0 + b) * P.ldx + kc;
-        if (xvec) {
+    for (int i = 0; i < 4; ++i) c[j][i] = 0.f;
 #pragma unroll 2
-          for (int k4 = lane; k4 * 4 < kn; k4 += 32) {
-            const float4 v = live ? __ldg(reinterpret_cast<const float4*>(xr) + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const int k = k4 * 4;
-            xs[(k + 0) * 33 + b] = v.x;
-            xs[(k + 1) * 33 + b] = v.y;
-            xs[(k + 2) * 33 + b] = v.z;
-            xs[(k + 3) * 33 + b] = v.w;
-          }
-        } else {
-          for (int k = lane; k < kn; k += 32) xs[k * 33 + b] = live ? __ldg(xr + k) : 0.f;
-        }
-      }
-    }
-    if (tid < 4 * 32) xs[(kn + (tid >> 5)) * 33 + (tid & 31)] = 0.f;  // zero rows behind a ragged K tail
-    cp_async_wait_all();
-    __syncthreads();
-    // weights: every warp's LIN_NT x kn strip was requested with cp.async BEFORE the x staging above (all of a chunk's
-    // weight bytes are in flight at once: the kernel is a latency-bound weight stream otherwise); read back as broadcast float4s
-    if (n0 < N) {
-      const float* wb = wbuf + w * (LIN_NT * LIN_KC);
-#pragma unroll 4
-      for (int kk = 0; kk < kn; kk += 4) {  // columns beyond kn hold zero weights; xs rows kn..kn+3 are zero
-        const float x0 = xs[(kk + 0) * 33 + lane], x1 = xs[(kk + 1) * 33 + lane], x2 = xs[(kk + 2) * 33 + lane],
-                    x3 = xs[(kk + 3) * 33 + lane];
+  for (int k0 = kbeg; k0 < kend; k0 += 16) {
+    const bool fast = vec && (k0 + 16 <= kend);
+    const int k = k0 + 4 * t;
+    const float4 wa = lin_load4(wr0, k, kend, fast), wb = lin_load4(wr1, k, kend, fast);
+    float4 xv[4];
 #pragma unroll
-        for (int j = 0; j < LIN_NT; ++j) {
-          const float4 wv = *reinterpret_cast<const float4*>(wb + j * LIN_KC + kk);
-          acc[j] = fmaf(x0, wv.x, acc[j]);
-          acc[j] = fmaf(x1, wv.y, acc[j]);
-          acc[j] = fmaf(x2, wv.z, acc[j]);
-          acc[j] = fmaf(x3, wv.w, acc[j]);
-        }
-      }
+    for (int j = 0; j < 4; ++j) xv[j] = lin_load4(xr[j], k, kend, fast);
+    uint32_t ah[4], al[4];
+    lin_split_pack(wa.x, wa.y, ah[0], al[0]);  // (row g,     logical k 2t, 2t+1)
+    lin_split_pack(wb.x, wb.y, ah[1], al[1]);  // (row g + 8, logical k 2t, 2t+1)
+    lin_split_pack(wa.z, wa.w, ah[2], al[2]);  // (row g,     logical k 2t+8, 2t+9)
+    lin_split_pack(wb.z, wb.w, ah[3], al[3]);  // (row g + 8, logical k 2t+8, 2t+9)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t bh0, bl0, bh1, bl1;
+      lin_split_pack(xv[j].x, xv[j].y, bh0, bl0);
+      lin_split_pack(xv[j].z, xv[j].w, bh1, bl1);
+      lin_mma(c[j], al, bh0, bh1);  // small terms first
+      lin_mma(c[j], ah, bl0, bl1);
+      lin_mma(c[j], ah, bh0, bh1);
     }
   }
-  if (b0 + lane < Bn) {
+  // accumulator fragment: c[j][0..1] = (row g, samples 8j + 2t, +1), c[j][2..3] = (row g + 8, same samples)
 #pragma unroll
-    for (int j = 0; j < LIN_NT; ++j) {
-      if (n0 + j >= N) continue;
-      float v = acc[j] + (P.bias ? __ldg(P.bias + n0 + j) : 0.f);
-      P.out[(b0 + lane) * P.ldo + n0 + j] = P.relu ? fmaxf(v, 0.f) : v;
+  for (int j = 0; j < 4; ++j) {
+    red[w][g][8 * j + 2 * t] = c[j][0];
+    red[w][g][8 * j + 2 * t + 1] = c[j][1];
+    red[w][g + 8][8 * j + 2 * t] = c[j][2];
+    red[w][g + 8][8 * j + 2 * t + 1] = c[j][3];
+  }
+  __syncthreads();
+  const int row = tid & (LIN_ROWS - 1);
+  if (n0 + row < N) {
+    const float bv = P.bias ? __ldg(P.bias + n0 + row) : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int sm = (tid >> 4) + 16 * h;
+      if (b0 + sm >= Bn) continue;
+      float v = red[0][row][sm];
+#pragma unroll
+      for (int q = 1; q < LIN_WARPS; ++q) v += red[q][row][sm];
+      v += bv;
+      P.out[static_cast<long long>(b0 + sm) * P.ldo + n0 + row] = P.relu ? fmaxf(v, 0.f) : v;
     }
   }
 }
 static int linear_launch(cudaStream_t st, LinJobs& jobs) {
-  constexpr size_t smem = ((LIN_KC + 4) * 33 + LIN_WARPS * LIN_NT * LIN_KC) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(linear_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(linear_small): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
   for (int i = jobs.n; i < LIN_MAX_JOBS; ++i) jobs.cta_start[i + 1] = jobs.cta_start[jobs.n];
-  linear_small_kernel<<<jobs.cta_start[jobs.n], LIN_WARPS * 32, smem, st>>>(jobs);
+  linear_small_kernel<<<jobs.cta_start[jobs.n], LIN_WARPS * 32, 0, st>>>(jobs);
   return check_launch("linear_small");
 }
 static int linear_add(LinJobs& jobs, const float* x, long long ldx, const float* W, long long ldw, const float* bias, float* out,
@@ -375,7 +375,7 @@ static int linear_add(LinJobs& jobs, const float* x, long long ldx, const float*
   const int i = jobs.n++;
   if (i == 0) jobs.cta_start[0] = 0;
   jobs.p[i] = LinP{x, ldx, W, ldw, bias, out, ldo, Bn, N, K, relu};
-  jobs.gx[i] = ceil_div(N, LIN_NT * LIN_WARPS);
+  jobs.gx[i] = ceil_div(N, LIN_ROWS);
   jobs.cta_start[i + 1] = jobs.cta_start[i] + jobs.gx[i] * ceil_div(Bn, 32);
   return 0;
 }
@@ -1037,11 +1037,15 @@ extern "C" size_t drn_qe_workspace_bytes(int B, int L, int H, int E) {
   return carve(&a, nullptr);
 }
 
-extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
+// parts: bit 0 = everything before the recurrence (embedding, W_ih packing, input projection), bit 1 = the recurrence and
+// everything after it.  The split lets the caller fork an independent HBM-bound branch (weight packing) at the point where
+// the latency-bound recurrence starts (drn_b200/dense.py: forward_pre).
+static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
   QeDev q;
   TRY(make_dev(a, &q, "drn_qe_forward"));
   cudaStream_t st = ST(stream);
   const int B = q.B, L = q.L, H = q.H, R = B * L, D = 2 * H;
+  if (parts & 1) {
   cudaError_t e = cudaMemsetAsync(q.cnt, 0, sizeof(unsigned) * 2 * q.BC * (H / 32), st);
   if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_qe_forward memset: %s", cudaGetErrorString(e));
   qe_embed_kernel<<<R, 256, 0, st>>>(q, a->emb);
@@ -1058,6 +1062,8 @@ extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
     g.out = q.xg; g.out_ld = 8 * H; g.bias = q.bias_sum;
     TRY(drn_gemm_group(1, &g, stream));
   }
+  }
+  if (!(parts & 2)) return 0;
   const size_t smem_f = (32 * H + H * 32 + 8 * 4 * 32) * sizeof(float);
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), smem_f, "lstm_fwd"));
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<false>), smem_f, "lstm_fwd"));
@@ -1088,13 +1094,20 @@ extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) {
   qe_attn_fwd_kernel<<<dim3(B, 3), 256, (D + L) * sizeof(float), st>>>(q, a->wa, a->ba, a->cmd[0], a->cmd[1], a->cmd[2]);
   return check_launch("qe_attn_fwd");
 }
+extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) { return qe_forward_parts(a, 3, stream); }
+extern "C" int drn_qe_forward_part(const drn_qe_t* a, int part, void* stream) {
+  if (part != 1 && part != 2) return fail(DRN_EINVAL, "drn_qe_forward_part: part must be 1 or 2 (got %d)", part);
+  return qe_forward_parts(a, part, stream);
+}
 
-extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
+// parts: bit 0 = attention / command / q_vector backward (before the BPTT), bit 1 = the BPTT and everything after it
+static int qe_backward_parts(const drn_qe_t* a, int parts, void* stream) {
   QeDev q;
   TRY(make_dev(a, &q, "drn_qe_backward"));
   cudaStream_t st = ST(stream);
   const int B = q.B, L = q.L, H = q.H, E = q.E, R = B * L, D = 2 * H;
   if (!a->dcmd[0] || !a->dcmd[1] || !a->dcmd[2]) return fail(DRN_EINVAL, "drn_qe_backward: dcmd missing");
+  if (parts & 1) {
   qe_attn_bwd_scalars_kernel<<<dim3(B, 3), 256, 0, st>>>(q, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_ba);
   TRY(check_launch("qe_attn_bwd_scalars"));
   qe_attn_bwd_apply_kernel<<<dim3(B, ceil_div(D, 256)), 256, 0, st>>>(q, a->wa, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_wa);
@@ -1121,6 +1134,8 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
   TRY(sb.launch(st));
   qe_vscatter_kernel<<<B, 256, 0, st>>>(q);
   TRY(check_launch("qe_vscatter"));
+  }
+  if (!(parts & 2)) return 0;
   const size_t smem_b = (2 * H * 32 + (LSTM_THREADS / 32) * 32 * 33) * sizeof(float);
   TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), smem_b, "lstm_bwd"));
   TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<false>), smem_b, "lstm_bwd"));
@@ -1183,4 +1198,9 @@ extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) {
     TRY(check_launch("qe_embed_bwd"));
   }
   return 0;
+}
+extern "C" int drn_qe_backward(const drn_qe_t* a, void* stream) { return qe_backward_parts(a, 3, stream); }
+extern "C" int drn_qe_backward_part(const drn_qe_t* a, int part, void* stream) {
+  if (part != 1 && part != 2) return fail(DRN_EINVAL, "drn_qe_backward_part: part must be 1 or 2 (got %d)", part);
+  return qe_backward_parts(a, part, stream);
 }

@@ -7,6 +7,7 @@ moved by a kernel of the C-ABI library (include/drn_b200.h).  Layouts are channe
 split-BF16 planes (drn_b200/planes.py).
 """
 import ctypes as C
+import contextlib
 import os
 
 import torch
@@ -175,11 +176,29 @@ class DensePath:
         self.iou_branch_on = not cfg["is_first_stage"]
         self.gamma = float(cfg["fcos_loss_gamma"][0] if isinstance(cfg["fcos_loss_gamma"], (list, tuple)) else cfg["fcos_loss_gamma"])
         self.alpha = float(cfg["fcos_loss_alpha"][0] if isinstance(cfg["fcos_loss_alpha"], (list, tuple)) else cfg["fcos_loss_alpha"])
-        self.launches = self.launches_fwd = self.launches_bwd = 0
+        self.launches = self.launches_fwd = self.launches_bwd = self.launches_pre = 0
+        # optional side branch (DRN_SIDE=1): the HBM-bound weight packing / weight-gradient unpacking are forked off where the
+        # latency-bound LSTM recurrences start (their CTAs use no shared memory, so -- unlike a second contraction -- they can
+        # co-reside with the LSTM).  Measured NEUTRAL on B200 (r01 v11 A/B, gpurun_out/ab_v11.log: 3.732 vs 3.737 ms per step:
+        # what the packing gains the recurrence loses to the loaded memory system), so the default is ONE stream.
+        self.side = torch.cuda.Stream(device=dev) if os.environ.get("DRN_SIDE", "0") == "1" else None
 
     # ---------------------------------------------------------------------------------------------------------------
     # small launch helpers
     # ---------------------------------------------------------------------------------------------------------------
+    def _fork(self):
+        """Context manager: the body is enqueued on the side stream, ordered after everything enqueued so far on the current
+        stream (inside a CUDA-graph capture this becomes a parallel branch of the graph).  `_join()` orders the current stream
+        after the side branch.  Without a side stream both are no-ops."""
+        if self.side is None:
+            return contextlib.nullcontext()
+        self.side.wait_stream(torch.cuda.current_stream(self.dev))
+        return torch.cuda.stream(self.side)
+
+    def _join(self):
+        if self.side is not None:
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
+
     def _chk(self, rc, what):
         self.launches += 1
         L.check(rc, what)
@@ -249,8 +268,8 @@ class DensePath:
         items.append(self._pack_item(p[h + "mix_fc.0.weight"], self.wp["mix"]))
         items.append(self._pack_item(p[h + "iou_scores.0.weight"], self.wp["iouc"]))
         arr = (L.PackItem * len(items))(*items)
-        self._chk(_lib().drn_pack_conv_weights(len(items), arr, _st()), "pack_conv_weights")
         torch.cat([p[h + "cls_tower.0.bias"], p[h + "bbox_tower.0.bias"]], out=self.tower_bias)
+        self._chk(_lib().drn_pack_conv_weights(len(items), arr, _st()), "pack_conv_weights")
 
     def _bn_job(self, blk, p, grads=None, da=None, out_a=None, up=None, gate=None, out_qa=None, y2=None):
         """drn_bn_job_t of one conv block (model/basic_blocks.py:22-30): statistics / apply / backward operands."""
@@ -321,15 +340,17 @@ class DensePath:
     # ---------------------------------------------------------------------------------------------------------------
     # forward
     # ---------------------------------------------------------------------------------------------------------------
-    def stage_inputs(self, p, tokens, lengths, feats, pse, gt):
-        """Eager part of the forward: reads the caller's tensors and fills the static operand buffers (query tokens and
-        lengths, split planes of the clip features, position feature, GT).  Everything after this runs on library-owned
-        buffers only, so it can be replayed from a CUDA graph."""
-        lib, B, T = _lib(), self.B, self.T
-        self.launches = 0
+    def stage_query(self, tokens, lengths, gt):
+        """Eager: the caller's query tokens / lengths / ground truth -> the static buffers the replayable parts read."""
         self.gt.copy_(gt)
         self.tokens.copy_(tokens)
         self.lengths.copy_(lengths)
+
+    def stage_feats(self, p, feats, pse):
+        """Eager: reads the caller's clip features and proposal boundaries and fills the static operand buffers (split planes
+        of the clip features, position feature)."""
+        lib, B, T = _lib(), self.B, self.T
+        self.launches = 0
         # position feature -> X0[:, :, D:] (main_model.py:53-55, backbone.py:31-32)
         self._chk(lib.drn_pos_feature(_vp(pse), _vp(p["position_transform.weight"]), _vp(p["position_transform.bias"]),
                                       C.c_int64(B * T), 256, _vp(self.X0.data), C.c_int64(self.C0), self.D,
@@ -337,21 +358,40 @@ class DensePath:
         self._split(feats.view(B * T, self.D), self.f_pl)
         self.launches_stage = self.launches
 
+    def stage_inputs(self, p, tokens, lengths, feats, pse, gt):
+        self.stage_query(tokens, lengths, gt)
+        self.stage_feats(p, feats, pse)
+
     def forward(self, p, tokens, lengths, feats, pse, gt, training):
         """p: name -> parameter/buffer tensor (fp32 on device); tokens [B,L] i64, lengths [B] i64 (device);
-        feats [B,T,D] fp32, pse [B,T,2] f64, gt [B,2] f32.  Fills self.losses / raw head outputs."""
+        feats [B,T,D] fp32, pse [B,T,2] f64, gt [B,2] f32.  Fills self.losses / raw head outputs.  (Single-stream order; the
+        overlapped schedule is model/main_model.py:_run_forward.)"""
         self.stage_inputs(p, tokens, lengths, feats, pse, gt)
-        self.forward_core(p, training)
+        self.forward_pre(p)
+        self.forward_main(p, training)
 
-    def forward_core(self, p, training):
-        lib, B, T = _lib(), self.B, self.T
-        h = "fcos.head."
-        self.launches = self.launches_stage
-        self.pack_weights(p)
-        # query encoder -> three command vectors (model/main_model.py:47, language_module.py:38-62)
-        self._chk(lib.drn_qe_forward(C.byref(self._qe_desc(p)), _st()), "qe_forward")
-        self.launches += lib.drn_qe_launch_count(B, self.L, self.qe_H, 0) - 1  # kernels enqueued inside drn_qe_forward
-        # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50): exact fp32 on CUDA cores (M = B rows only)
+    def forward_pre(self, p):
+        """Replayable, reads parameters and the staged query only: query encoder and gates, with the weight packing (HBM-bound,
+        364 MB of traffic, no dependence on the query) forked off as a side branch at the point where the latency-bound
+        recurrence starts.  The branch begins with a tiny kernel (`torch.cat` of two bias vectors), so that the LSTM's CTAs are
+        resident before the packing grid is dispatched: a grid launched EARLIER than the LSTM would have to be dispatched
+        completely before the LSTM can start, i.e. it would run before it rather than under it."""
+        lib, B = _lib(), self.B
+        self.launches = 0
+        qd = self._qe_desc(p)
+        nq = lib.drn_qe_launch_count(B, self.L, self.qe_H, 0)  # kernels enqueued inside drn_qe_forward
+        if self.side is None:
+            self.pack_weights(p)
+            self._chk(lib.drn_qe_forward(C.byref(qd), _st()), "qe_forward")
+            self.launches += nq - 1
+        else:
+            # query encoder -> three command vectors (model/main_model.py:47, language_module.py:38-62)
+            self._chk(lib.drn_qe_forward_part(C.byref(qd), 1, _st()), "qe_forward[1]")
+            with self._fork():
+                self.pack_weights(p)
+            self._chk(lib.drn_qe_forward_part(C.byref(qd), 2, _st()), "qe_forward[2]")
+            self.launches += nq - 2
+        # gates q_i = qInput_i(cmd_i) (model/main_model.py:48-50): M = B rows only, weight-streaming (drn_linear_fwd_batch)
         K = self.cmd_dim
         jobs = (L.LinearJob * 3)()
         for i in range(3):
@@ -359,10 +399,18 @@ class DensePath:
             j.x, j.ldx, j.W, j.ldw = self.cmd[i].data_ptr(), K, p["qInput%d.weight" % i].data_ptr(), K
             j.bias, j.out, j.ldo, j.B, j.N, j.K, j.relu = p["qInput%d.bias" % i].data_ptr(), self.q[i].data_ptr(), n, B, n, K, 0
         self._chk(lib.drn_linear_fwd_batch(3, jobs, _st()), "gates")
+        self._join()
+        self.launches_pre = self.launches
+
+    def forward_main(self, p, training):
+        """Replayable: prop_fc -> backbone -> FPN -> head -> losses, on the staged planes, packed weights and gates."""
+        lib, B, T = _lib(), self.B, self.T
+        h = "fcos.head."
+        self.launches = self.launches_stage + self.launches_pre
         # prop_fc (main_model.py:59) with the level-0 gate fused in the epilogue: Pre = W f + b (kept for the gate gradient),
-        # X0[:, :, :D] = planes(q0 * Pre) (backbone.py:28-30; the cat with the position channels is the layout).  Running it
-        # beside the query encoder on a second stream was measured to buy nothing (no SM co-residency with the persistent
-        # kernel, scripts/overlap_probe.py), while the separate gating pass cost 39 us.
+        # X0[:, :, :D] = planes(q0 * Pre) (backbone.py:28-30; the cat with the position channels is the layout).  Running
+        # this contraction beside the query encoder was measured to buy nothing (the persistent kernel and the LSTM cannot
+        # share an SM: shared memory, scripts/overlap_probe.py), while the separate gating pass cost 39 us.
         if os.environ.get("DRN_FUSE_GATE", "1") == "1":
             self._gemm(L.GEMM_ROWS, self.f_pl.desc(), self.wp["prop_fc"].desc(), B, T, self.D, K=self.D, bias=p["prop_fc.bias"],
                        out2=self.Pre, rowscale=self.q[0], outp=self.X0)
@@ -554,7 +602,29 @@ class DensePath:
         self._chk(lib.drn_pos_bwd(_vp(self.dX0), C.c_int64(self.C0), self.D, _vp(self.pos_in), C.c_int64(B * self.T), 256,
                                   _vp(grads["position_transform.weight"]), _vp(grads["position_transform.bias"]), _st()),
                   "pos_bwd")
-        # partial sums (K-splits x levels) in tap-major workspaces -> parameter layout [O][C][k], one launch
+        # partial sums (K-splits x levels) in tap-major workspaces -> parameter layout [O][C][k]: here, or (single-GPU schedule)
+        # as a side branch under the BPTT of the tail.  [Forking it beside the prop_fc weight gradient below was measured
+        # 50 us SLOWER than running it first: r01 v11 A/B.]
+        defer = tail and self.side is not None
+        if not defer:
+            self._unpack_wgrads(grads, iou_on)
+        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D], the largest contraction of the backward pass
+        self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
+                   out_ld=self.D, out_tap_stride=0)
+        self.launches_bwd = self.launches
+        if tail:
+            self.backward_tail(p, grads, unpack=(iou_on,) if defer else None)
+
+    def _unpack_wgrads(self, grads, iou_on):
+        """Weight-gradient workspaces [slices][k][O][C] -> parameter layout [O][C][k] (sum of the K-split / level slices), one
+        launch, after the scalar parameter gradients gathered by the loss kernel (tiny copies)."""
+        lib, h, F = _lib(), "fcos.head.", self.F
+        grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
+        grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])
+        if iou_on:
+            grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
+        for l in range(3):
+            grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
         items = []
         for i in range(3):
             items.append(self._unpack_item(grads["backbone_net.forward_conv%d.0.weight" % i], "conv%d" % i))
@@ -567,24 +637,12 @@ class DensePath:
             items.append(self._unpack_item(grads[h + "iou_scores.0.weight"], "iouc"))
         arr = (L.PackItem * len(items))(*items)
         self._chk(lib.drn_unpack_conv_wgrads(len(items), arr, _st()), "unpack_conv_wgrads")
-        # scalar parameter gradients gathered by the loss kernel
-        grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
-        grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])
-        if iou_on:
-            grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
-        for l in range(3):
-            grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
-        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D], the largest contraction of the backward pass
-        self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
-                   out_ld=self.D, out_tap_stride=0)
-        self.launches_bwd = self.launches
-        if tail:
-            self.backward_tail(p, grads)
 
-    def backward_tail(self, p, grads):
+    def backward_tail(self, p, grads, unpack=None):
         """Second part of the backward: the gates and the query encoder -- a latency-bound chain of small kernels (~0.4 ms) that
         leaves most SMs idle, which is where a data-parallel run hides the all-reduce of everything the first part produced
-        (model/main_model.py:_run_backward)."""
+        (model/main_model.py:_run_backward) and where the single-GPU schedule hides the weight-gradient unpacking
+        (`unpack` = (iou_on,): side branch forked where the BPTT starts)."""
         lib, B = _lib(), self.B
         # gates: dW += dq^T cmd, db += colsum(dq), dcmd = dq W  -- nine small contractions, one launch (dcmd is zero-filled
         # together with dq / pgrad at the start of the backward)
@@ -603,6 +661,16 @@ class DensePath:
             jc.C, jc.ldc, jc.M, jc.N, jc.K = self.dcmd[i].data_ptr(), K, B, K, n
         self._chk(lib.drn_sgemm_batch(9, jobs, _st()), "gates_bwd")
         # query encoder backward (BPTT), gradients accumulated into the zeroed buffers
-        self._chk(lib.drn_qe_backward(C.byref(self._qe_desc(p, grads)), _st()), "qe_backward")
-        self.launches += lib.drn_qe_launch_count(B, self.L, self.qe_H, 1) - 1  # kernels enqueued inside drn_qe_backward
+        qd = self._qe_desc(p, grads)
+        nq = lib.drn_qe_launch_count(B, self.L, self.qe_H, 1)  # kernels enqueued inside drn_qe_backward
+        if unpack is None:
+            self._chk(lib.drn_qe_backward(C.byref(qd), _st()), "qe_backward")
+            self.launches += nq - 1
+        else:
+            self._chk(lib.drn_qe_backward_part(C.byref(qd), 1, _st()), "qe_backward[1]")
+            with self._fork():
+                self._unpack_wgrads(grads, unpack[0])
+            self._chk(lib.drn_qe_backward_part(C.byref(qd), 2, _st()), "qe_backward[2]")
+            self._join()
+            self.launches += nq - 2
         self.launches_bwd = self.launches

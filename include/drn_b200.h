@@ -250,7 +250,7 @@ int drn_pool_proposals(const float* feats, const int64_t* win_off, const double*
                        float* out_feats, double* out_pse, void* stream);
 
 /* Language-guided pooling, model/LGP.py:29-51 (dead code in the reference; standalone op `model/LGP.py` of this repo), reference
- * layout: x [B][C][t] channels-first, t even.  Forward: z = query W^T (drn_linear_fwd) -> drn_lgp_bn: BatchNorm1d of the query
+ * layout: x [B][C][t] channels-first, t even.  Forward: z = query W^T (drn_sgemm_batch, store mode: exact fp32) -> drn_lgp_bn: BatchNorm1d of the query
  * tiled over t (statistics over the batch; running variance with n = B*t) -> qn, xhat [B][C], invstd [C] -> drn_lgp_pool_fwd:
  * pair scores, softmax over each pair (att [B][t/2][2]), out [B][C][t/2].  Backward: drn_lgp_pool_bwd (dx, dqn) ->
  * drn_lgp_bn_bwd (dz [B][C]; dgamma / dbeta accumulated) -> d query = dz W, dW += dz^T query (drn_sgemm_batch). */
@@ -289,7 +289,9 @@ int drn_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t 
               int N, int K, const float* bias, int relu, int accumulate, void* stream);
 
 /* Deterministic (fixed reduction order, no atomics) small-batch nn.Linear forward out[b][n] = act(bias[n] + sum_k x[b][k] W[n][k]):
- * query_encoder.qInput / qInput0-2 (model/language_module.py:57-58,30-31) and the gates qInput0-2 (model/main_model.py:49-50). */
+ * query_encoder.qInput / qInput0-2 (model/language_module.py:57-58,30-31) and the gates qInput0-2 (model/main_model.py:49-50).
+ * Weight-streaming on the warp-level tensor cores with the dense path's split-BF16 products (hi*hi + hi*lo + lo*hi, fp32
+ * accumulate: ~1e-5 relative; use drn_sgemm_batch with store = 1 where exact fp32 FMA arithmetic is required). */
 int drn_linear_fwd(const float* x, int64_t ldx, const float* W, int64_t ldw, const float* bias, float* out, int64_t ldo, int B,
                    int N, int K, int relu, void* stream);
 
@@ -342,6 +344,12 @@ size_t drn_qe_workspace_bytes(int B, int L, int H, int E);
 int drn_qe_launch_count(int B, int L, int H, int backward);
 int drn_qe_forward(const drn_qe_t* q, void* stream);
 int drn_qe_backward(const drn_qe_t* q, void* stream);
+/* The same work in two calls, split where the latency-bound recurrence starts, so that the caller can fork an independent
+ * HBM-bound branch there (weight packing beside the forward LSTM, weight-gradient unpacking beside the BPTT):
+ * part 1 = everything before the recurrence, part 2 = the recurrence and everything after it.  part 1 then part 2 on one
+ * stream == drn_qe_forward / drn_qe_backward. */
+int drn_qe_forward_part(const drn_qe_t* q, int part, void* stream);
+int drn_qe_backward_part(const drn_qe_t* q, int part, void* stream);
 
 #ifdef __cplusplus
 }

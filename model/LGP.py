@@ -23,7 +23,13 @@ class _LGPFn(torch.autograd.Function):
         Q = query.shape[1]
         w2 = weight.view(Cn, Q)
         z = torch.empty(B, Cn, device=x.device)
-        L.check(lib.drn_linear_fwd(_p(query), C.c_int64(Q), _p(w2), C.c_int64(Q), None, _p(z), C.c_int64(Cn), B, Cn, Q, 0, st), "lgp linear")
+        # z = query W^T in exact fp32 (store mode: no split, no atomics); the batch statistics of a handful of query vectors
+        # that follow amplify rounding noise, so this one does not go through the split-BF16 drn_linear_fwd
+        fj = (L.SgemmJob * 1)()
+        f = fj[0]
+        f.A, f.sam, f.sak, f.B, f.sbk, f.sbn, f.C, f.ldc, f.M, f.N, f.K = query.data_ptr(), Q, 1, w2.data_ptr(), 1, Q, z.data_ptr(), Cn, B, Cn, Q
+        f.store = 1
+        L.check(lib.drn_sgemm_batch(1, fj, st), "lgp linear")
         qn, xhat, invstd = torch.empty_like(z), torch.empty_like(z), torch.empty(Cn, device=x.device)
         L.check(lib.drn_lgp_bn(_p(z), B, Cn, t, _p(gamma), _p(beta), _p(running_mean), _p(running_var), _p(nbt), C.c_float(momentum),
                                C.c_float(eps), 1 if training else 0, _p(qn), _p(xhat), _p(invstd), st), "lgp_bn")

@@ -22,22 +22,32 @@ def _sig(p):
     return hash(tuple(t.data_ptr() for t in p.values()))
 
 
-def _run_forward_core(path, p, training, use_graphs):
-    """The replayable part of the forward.  First call for a (mode, parameter-storage) signature runs eagerly and records a
-    CUDA graph of the same launch sequence; later calls replay it (~150 kernel launches -> one graph launch)."""
+def _replay(path, key, fn, use_graphs):
+    """First call for a (part, mode, parameter-storage) signature runs `fn` eagerly and records a CUDA graph of the same launch
+    sequence; later calls replay it (~50 kernel launches -> one graph launch)."""
     if not use_graphs:
-        path.forward_core(p, training)
+        fn()
         return
-    key = ("fwd", training, _sig(p))
     g = path.graphs.get(key)
     if g is None:
-        path.forward_core(p, training)
+        fn()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            path.forward_core(p, training)
+            fn()
         path.graphs[key] = g
     else:
         g.replay()
+
+
+def _run_forward(path, p, training, use_graphs, tokens, lengths, feats, pse, gt):
+    """Forward schedule: the eager staging of the caller's tensors, then ONE replayable graph (query encoder + gates with the
+    weight packing as a parallel branch under the recurrence, then prop_fc ... losses)."""
+    path.stage_inputs(p, tokens, lengths, feats, pse, gt)
+
+    def core():
+        path.forward_pre(p)
+        path.forward_main(p, training)
+    _replay(path, ("fwd", training, _sig(p)), core, use_graphs)
 
 
 def _run_backward(path, p, names, upstream, use_graphs, dp=None):
@@ -104,8 +114,7 @@ class _DenseFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, path, training, tokens, lengths, feats, pse, gt, *params):
         p = model._tensor_dict()
-        path.stage_inputs(p, tokens, lengths, feats, pse, gt)
-        _run_forward_core(path, p, training, model.use_graphs)
+        _run_forward(path, p, training, model.use_graphs, tokens, lengths, feats, pse, gt)
         ctx.model, ctx.path = model, path
         ctx.nparams = len(params)
         return path.losses[:3].clone()
@@ -203,8 +212,7 @@ class mainModel(nn.Module):
         else:
             with torch.no_grad():
                 p = self._tensor_dict()
-                path.stage_inputs(p, tokens, lengths, feats, pse, gt)
-                _run_forward_core(path, p, training, self.use_graphs)
+                _run_forward(path, p, training, self.use_graphs, tokens, lengths, feats, pse, gt)
                 losses = path.losses[:3].clone()
         loss_dict = {"loss_cls": losses[0], "loss_reg": losses[1]}
         if self.cfg["is_first_stage"]:

@@ -1,0 +1,182 @@
+"""BASELINE.json configs[2] and configs[4] on one B200 (configs[1] / [3] are bench.py's lines): measured, not asserted.
+
+  * configs[2] -- the full three-stage schedule of the reference driver (main.py:124-140, 216-243), batch 32, T = 256:
+        stage 1  lr 1e-3, iou_scores / mix_fc frozen, loss = cls + reg (+ the zero loss_iou)
+        stage 2  lr 1e-5, optimizer over iou_scores + mix_fc only, loss = loss_iou
+        stage 3  lr 1e-7, everything, loss = cls + reg + iou
+    each stage = a new mainModel built with that stage's flags and loaded from the previous stage's state_dict (the
+    reference's --resume), a fixed number of steps instead of epochs, `clip_grad_norm_(model.parameters(), 0.5)` + Adam exactly
+    as the driver does (stock torch), then the same with the opt-in fused drn_clip_adam.  Time = forward + backward +
+    optimizer per step (CUDA events, device-resident synthetic batch), i.e. the "incl. optimizer" column of SURVEY.md 8(d).
+  * configs[4] -- inference sweep, eval-mode forward + candidate selection (drn_postprocess) + assembly of the reference's
+    result dicts, batch 256, T in {64, 128, 256, 512}; pairs/s and algorithmic TFLOP/s from SURVEY.md 8(d)
+    F_fwd(T) = 53.69e6 T + 0.086e9 FLOP per pair.
+
+    python scripts/configs_bench.py [--steps 20] [--warmup 5] [--skip-train] [--skip-sweep]
+Prints one JSON object per line."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from torch.nn.utils import clip_grad_norm_  # noqa: E402
+
+from drn_b200 import spec as spec_mod  # noqa: E402
+from drn_b200 import synthetic as S  # noqa: E402
+
+
+def build(stage, sd, dev):
+    from model.main_model import mainModel
+    model = mainModel(1301, S.config_namespace(stage=stage))
+    model.load_state_dict(sd)
+    return model.to(dev).train()
+
+
+def stage_setup(model, stage):
+    """main.py:124-138: which parameters learn, and at which rate."""
+    lr = 1e-3
+    if stage == 1:
+        for name, value in model.named_parameters():
+            if "iou_scores" in name or "mix_fc" in name:
+                value.requires_grad = False
+        learned = [p for p in model.parameters() if p.requires_grad]
+    elif stage == 2:
+        learned = list(model.fcos.head.iou_scores.parameters()) + list(model.fcos.head.mix_fc.parameters())
+        lr /= 100
+    else:
+        learned = list(model.parameters())
+        lr /= 10000
+    return learned, lr
+
+
+def run_stage(stage, sd, batch, dev, steps, warmup, fused):
+    model = build(stage, sd, dev)
+    learned, lr = stage_setup(model, stage)
+    if fused:
+        from drn_b200.optim import FusedClipAdam
+        opt = FusedClipAdam(learned, lr=lr, clip_params=list(model.parameters()), max_norm=0.5)
+    else:
+        opt = torch.optim.Adam(learned, lr)
+    b = {k: v.to(dev) for k, v in batch.items()}
+    b["query_length"] = batch["query_length"]
+    log = []
+
+    def step():
+        _, ld = model(b["query_tokens"], b["query_length"], b["props_features"], b["props_start_end"], b["gt_start_end"], None, None)
+        loss = ld["loss_iou"] if stage == 2 else sum(v for v in ld.values())  # main.py:221-224
+        if loss.requires_grad:  # `if loss != 0` (main.py:236) without the host sync: the integer constant has no graph
+            loss.backward()
+        if fused:
+            opt.step()
+        else:
+            clip_grad_norm_(model.parameters(), 0.5)
+            opt.step()
+        for p in model.parameters():
+            p.grad = None
+        return ld
+
+    for _ in range(warmup):
+        ld = step()
+    first = {k: float(v.reshape(-1)[0]) for k, v in ld.items()}
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ld = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    last = {k: float(v.reshape(-1)[0]) for k, v in ld.items()}
+    path = list(model._paths.values())[0]
+    log = {"stage": stage, "optimizer": "fused drn_clip_adam" if fused else "torch clip_grad_norm_ + Adam (main.py:239-243)",
+           "lr": lr, "ms_per_step_incl_optimizer": round(ms, 4), "pairs_per_s": round(batch["props_features"].shape[0] / ms * 1e3, 1),
+           "loss_after_warmup": first, "loss_last": last, "iou_branch_positives_last_step": int(path.losses[4].item()),
+           "trainable_tensors": len(learned)}
+    out_sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    del model, opt
+    torch.cuda.empty_cache()
+    return log, out_sd
+
+
+def three_stage(dev, steps, warmup):
+    cfg = S.default_config(stage=1)
+    sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
+    batch = S.synth_batch(32, 256, max_len=10, embedding=sd["query_encoder.embedding.weight"])
+    for fused in (False, True):
+        cur = sd
+        for stage in (1, 2, 3):
+            log, cur = run_stage(stage, cur, batch, dev, steps, warmup, fused)
+            log.update({"config": "configs[2]: three-stage schedule, batch 32, T=256, 1xB200", "steps": steps, "warmup": warmup})
+            print(json.dumps(log), flush=True)
+
+
+def sweep(dev, steps, warmup):
+    from model.main_model import mainModel
+    cfg = S.default_config(stage=1)
+    sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
+    for T in (64, 128, 256, 512):
+        B = 256
+        batch = S.synth_batch(B, T, max_len=10, embedding=sd["query_encoder.embedding.weight"])
+        model = mainModel(1301, S.config_namespace(stage=1))
+        model.load_state_dict(sd)
+        model = model.to(dev).eval()
+        b = {k: v.to(dev) for k, v in batch.items()}
+        b["query_length"] = batch["query_length"]
+
+        def fwd():
+            with torch.no_grad():
+                return model(b["query_tokens"], b["query_length"], b["props_features"], b["props_start_end"], b["gt_start_end"], None, None)
+        for _ in range(warmup):
+            boxes, _ = fwd()
+        torch.cuda.synchronize()
+        path = list(model._paths.values())[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            boxes, _ = fwd()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        # device part alone: the forward graph + candidate-selection kernel, without the host-side assembly of the result dicts
+        p = model._tensor_dict()
+        g = [v for k, v in path.graphs.items() if k[0] == "fwd"][0]
+        e0.record()
+        for _ in range(steps):
+            path.stage_inputs(p, b["query_tokens"], b["query_length"].to(dev), b["props_features"], b["props_start_end"], b["gt_start_end"].float())
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_dev = e0.elapsed_time(e1) / steps
+        flop = 53.69e6 * T + 0.086e9
+        print(json.dumps({
+            "config": "configs[4]: inference sweep, batch 256, 1xB200", "T": T, "B": B, "steps": steps, "warmup": warmup,
+            "ms_per_batch_forward_plus_postprocess": round(ms, 4), "pairs_per_s": round(B / ms * 1e3, 1),
+            "ms_per_batch_device_forward_only": round(ms_dev, 4), "pairs_per_s_device_forward_only": round(B / ms_dev * 1e3, 1),
+            "algorithmic_tflops_per_s_device_forward_only": round(B * flop / (ms_dev * 1e-3) / 1e12, 1),
+            "detections_first_sample": int(boxes[0]["detections"].shape[0]),
+            "device_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}), flush=True)
+        del model, path, g
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--skip-train", action="store_true")
+    ap.add_argument("--skip-sweep", action="store_true")
+    a = ap.parse_args()
+    torch.set_num_threads(os.cpu_count())
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    if not a.skip_train:
+        three_stage(dev, a.steps, a.warmup)
+    if not a.skip_sweep:
+        sweep(dev, a.steps, a.warmup)
+
+
+if __name__ == "__main__":
+    main()
