@@ -159,14 +159,28 @@ struct HeadLevels {
   float* dtw[MAX_LEVELS];         // backward: gradient w.r.t. the tower tensor, fp32 [B*T][2F]
 };
 
-// forward: one warp per location; weights staged tap-major in shared memory once per CTA
+// forward: one warp per location; weights staged tap-major in shared memory once per CTA.  NCH = 2F / 256 chunks of 256
+// channels per row (a lane owns 8 consecutive channels of every chunk): compile-time, so that the plane loads of a whole tap
+// (2 x NCH 16-byte loads per lane) are in flight together and the cls / bbox branch of a chunk is resolved statically.
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float (&v)[8]) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[2 * k] = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+    v[2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ float dot8(const float (&v)[8], const float4& w0, const float4& w1) {
+  return v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+}
+template <int NCH>
 __global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const float* __restrict__ Wc, const float* __restrict__ bc,
                                                             const float* __restrict__ Wb, const float* __restrict__ bb,
                                                             const float* __restrict__ Wi, const float* __restrict__ bi,
                                                             float* __restrict__ cls_raw, float* __restrict__ box_raw,
                                                             float* __restrict__ iou_raw, long long total) {
   extern __shared__ __align__(16) float hsm[];
-  const int F = g.F;
+  constexpr int F = NCH * 128;
   float* wc = hsm;              // [3][F]
   float* wb = hsm + 3 * F;      // [2][3][F]
   float* wi = hsm + 9 * F;      // [F/2]
@@ -189,51 +203,51 @@ __global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const 
 #pragma unroll
     for (int l = 1; l < MAX_LEVELS; ++l)
       if (l < g.nlevels && i >= static_cast<long long>(g.B) * g.off[l]) lvl = l;
-    const long long j = i - static_cast<long long>(g.B) * g.off[lvl];
+    const int j = static_cast<int>(i - static_cast<long long>(g.B) * g.off[lvl]);  // row inside the level (< B * T)
     const int T = g.T[lvl];
-    const int t = static_cast<int>(j % T);
+    const int t = j % T;
+    const long long ps = g.tw_ps[lvl];
     float a_cls = 0.f, a_b0 = 0.f, a_b1 = 0.f, a_iou = 0.f;
+    const bool has_iou = g.hi[lvl] != nullptr;
+    uint4 ih = make_uint4(0u, 0u, 0u, 0u), il = ih;
+    const bool iou_lane = has_iou && lane * 8 < F / 2;  // F/2 <= 256 channels: one chunk
+    if (iou_lane) {
+      const __nv_bfloat16* row = g.hi[lvl] + static_cast<long long>(j) * (F / 2) + lane * 8;
+      ih = __ldg(reinterpret_cast<const uint4*>(row));
+      il = __ldg(reinterpret_cast<const uint4*>(row + g.hi_ps[lvl]));
+    }
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int ts = t + r - 1;
       if (ts < 0 || ts >= T) continue;
-      const __nv_bfloat16* row = g.tw[lvl] + (j + r - 1) * (2 * F);
-      for (int c = lane * 8; c < 2 * F; c += 256) {
-        const uint4 h = *reinterpret_cast<const uint4*>(row + c);
-        const uint4 l = *reinterpret_cast<const uint4*>(row + c + g.tw_ps[lvl]);
-        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
-        float v[8];
+      const __nv_bfloat16* row = g.tw[lvl] + (static_cast<long long>(j) + r - 1) * (2 * F) + lane * 8;
+      uint4 h[NCH], l[NCH];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          v[2 * k] = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
-          v[2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
-        }
-        const int cl = (c < F) ? c : c - F;               // channel inside its branch
-        const int p0 = ((cl >> 8) * 2) * 128 + lane * 4;  // permuted offsets of the lane's two float4s
+      for (int k = 0; k < NCH; ++k) {
+        h[k] = __ldg(reinterpret_cast<const uint4*>(row + k * 256));
+        l[k] = __ldg(reinterpret_cast<const uint4*>(row + k * 256 + ps));
+      }
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        float v[8];
+        unpack8(h[k], l[k], v);
+        constexpr int HALF = NCH / 2;               // chunks [0, HALF) = cls tower, [HALF, NCH) = bbox tower
+        const int kk = k < HALF ? k : k - HALF;     // chunk inside its branch
+        const int p0 = (kk * 2) * 128 + lane * 4;   // permuted offsets of the lane's two float4s
         const int p1 = p0 + 128;
-        if (c < F) {
-          const float4 w0 = *reinterpret_cast<const float4*>(wc + r * F + p0), w1 = *reinterpret_cast<const float4*>(wc + r * F + p1);
-          a_cls += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+        if (k < HALF) {
+          a_cls += dot8(v, *reinterpret_cast<const float4*>(wc + r * F + p0), *reinterpret_cast<const float4*>(wc + r * F + p1));
         } else {
-          const float4 u0 = *reinterpret_cast<const float4*>(wb + r * F + p0), u1 = *reinterpret_cast<const float4*>(wb + r * F + p1);
-          const float4 q0 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + p0), q1 = *reinterpret_cast<const float4*>(wb + (3 + r) * F + p1);
-          a_b0 += v[0] * u0.x + v[1] * u0.y + v[2] * u0.z + v[3] * u0.w + v[4] * u1.x + v[5] * u1.y + v[6] * u1.z + v[7] * u1.w;
-          a_b1 += v[0] * q0.x + v[1] * q0.y + v[2] * q0.z + v[3] * q0.w + v[4] * q1.x + v[5] * q1.y + v[6] * q1.z + v[7] * q1.w;
+          a_b0 += dot8(v, *reinterpret_cast<const float4*>(wb + r * F + p0), *reinterpret_cast<const float4*>(wb + r * F + p1));
+          a_b1 += dot8(v, *reinterpret_cast<const float4*>(wb + (3 + r) * F + p0), *reinterpret_cast<const float4*>(wb + (3 + r) * F + p1));
         }
       }
     }
-    if (g.hi[lvl]) {
-      const __nv_bfloat16* row = g.hi[lvl] + j * (F / 2);
-      for (int c = lane * 8; c < F / 2; c += 256) {
-        const uint4 h = *reinterpret_cast<const uint4*>(row + c);
-        const uint4 l = *reinterpret_cast<const uint4*>(row + c + g.hi_ps[lvl]);
-        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+    if (iou_lane) {
+      float v[8];
+      unpack8(ih, il, v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          a_iou += (__uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16)) * wi[c + 2 * k];
-          a_iou += (__uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u)) * wi[c + 2 * k + 1];
-        }
-      }
+      for (int k = 0; k < 8; ++k) a_iou = fmaf(v[k], wi[lane * 8 + k], a_iou);
     }
     a_cls = warp_sum(a_cls);
     a_b0 = warp_sum(a_b0);
@@ -243,7 +257,7 @@ __global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const 
       cls_raw[i] = a_cls + bc[0];
       box_raw[2 * i] = a_b0 + bb[0];
       box_raw[2 * i + 1] = a_b1 + bb[1];
-      if (g.hi[lvl]) iou_raw[i] = a_iou + bi[0];
+      if (has_iou) iou_raw[i] = a_iou + bi[0];
     }
   }
 }
@@ -734,11 +748,13 @@ extern "C" int drn_head_proj_fwd(const drn_head_levels_t* h, const float* Wc, co
   if (P < 0) return P;
   const long long total = static_cast<long long>(g.B) * P;
   const size_t smem = (9 * g.F + g.F / 2) * sizeof(float);
-  if (g.F % 256) return fail(DRN_EINVAL, "drn_head_proj_fwd: tower channels per branch must be a multiple of 256 (F=%d)", g.F);
-  if (smem > 48 * 1024) return fail(DRN_EINVAL, "drn_head_proj_fwd: F=%d too large for the weight stage", g.F);
+  if (g.F != 256 && g.F != 512) return fail(DRN_EINVAL, "drn_head_proj_fwd: tower channels per branch must be 256 or 512 (F=%d)", g.F);
   long long ctas = (total + 7) / 8;
-  if (ctas > 148 * 4) ctas = 148 * 4;
-  head_proj_fwd_kernel<<<static_cast<unsigned>(ctas), 256, smem, ST(stream)>>>(g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
+  if (ctas > 148 * 3) ctas = 148 * 3;  // 70 registers x 256 threads: three CTAs per SM, one wave (grid-stride loop over locations)
+  if (g.F == 512)
+    head_proj_fwd_kernel<4><<<static_cast<unsigned>(ctas), 256, smem, ST(stream)>>>(g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
+  else
+    head_proj_fwd_kernel<2><<<static_cast<unsigned>(ctas), 256, smem, ST(stream)>>>(g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
   return check_launch("head_proj_fwd");
 }
 

@@ -424,19 +424,21 @@ __global__ void __launch_bounds__(256) qe_embed_kernel(QeDev q, const float* __r
 __global__ void __launch_bounds__(256) qe_pack_wih_kernel(QeDev q, const float* __restrict__ w0, const float* __restrict__ w1,
                                                           const float* __restrict__ bi0, const float* __restrict__ bh0,
                                                           const float* __restrict__ bi1, const float* __restrict__ bh1) {
-  const int H4 = 4 * q.H;
-  const long long total = 2LL * H4 * q.EP, ps = total;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
-    const int e = static_cast<int>(i % q.EP);
-    const long long row = i / q.EP;
-    const float* w = row < H4 ? w0 : w1;
-    const long long rr = row < H4 ? row : row - H4;
+  // one warp per packed row (8H rows): 32-bit indexing, no divisions (a flat 64-bit-indexed grid-stride loop over 148 CTAs was a
+  // 25 us latency chain for 5 MB)
+  const int H4 = 4 * q.H, EP = q.EP, E = q.E;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= 2 * H4) return;
+  const int rr = row < H4 ? row : row - H4;
+  const float* __restrict__ w = (row < H4 ? w0 : w1) + static_cast<long long>(rr) * E;
+  const long long ps = 2LL * H4 * EP, o = static_cast<long long>(row) * EP;
+  for (int e = lane; e < EP; e += 32) {
     __nv_bfloat16 h, l;
-    split_bf16(e < q.E ? w[rr * q.E + e] : 0.f, h, l);
-    q.Wih_pl[i] = h;
-    q.Wih_pl[ps + i] = l;
-    if (e == 0) q.bias_sum[row] = row < H4 ? bi0[rr] + bh0[rr] : bi1[rr] + bh1[rr];
+    split_bf16(e < E ? __ldg(w + e) : 0.f, h, l);
+    q.Wih_pl[o + e] = h;
+    q.Wih_pl[ps + o + e] = l;
   }
+  if (lane == 0) q.bias_sum[row] = row < H4 ? bi0[rr] + bh0[rr] : bi1[rr] + bh1[rr];
 }
 __global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __restrict__ g_emb) {
   const int r = blockIdx.x;
@@ -477,9 +479,15 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_fwd_kernel(QeDev q, int s0,
   const bool inb = b < q.B;
   const int len = inb ? static_cast<int>(q.lengths[b]) : 0;
   bool w_loaded = false;
+  float c_carry = 0.f;  // cell state of (sample, unit) written by the previous step of THIS launch (same thread every step)
   for (int s = s0; s < s1; ++s) {
     const int t = dir == 0 ? s : L - 1 - s;
     const int tp = dir == 0 ? t - 1 : t + 1;
+    // input projection of this step (independent of the recurrence): issued before the wait on the staged state below
+    const long long r = static_cast<long long>(inb ? b : 0) * L + t;
+    float acc[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) acc[g] = (inb && kh == 0) ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
     if (s > 0) {
       if (!w_loaded) {
         const float* W = q.w_hh[dir];
@@ -496,10 +504,6 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_fwd_kernel(QeDev q, int s0,
       cp_async_wait_all();
       __syncthreads();
     }
-    const long long r = static_cast<long long>(inb ? b : 0) * L + t;
-    float acc[4];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) acc[g] = (inb && kh == 0) ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;
     if (s > 0) {
       const float* wr = ws + (ul * 4) * H;
       const int kbeg = kh * (H / 2), kend = kbeg + H / 2;
@@ -534,10 +538,13 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_fwd_kernel(QeDev q, int s0,
         gf = sigmoidf_(acc[1]);
         gg = tanhf(acc[2]);
         go = sigmoidf_(acc[3]);
-        const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+        // previous cell state: zero at non-live positions, so the register copy is exact for both directions
+        const float cp = (s > s0) ? c_carry
+                                  : ((tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f);
         c = gf * cp + gi * gg;
         h = go * tanhf(c);
       }
+      c_carry = c;
       q.HT[(s & 1) * ht_sz + ((static_cast<long long>(dir) * q.BC + bc) * H + unit) * 32 + lane] = h;
       if (inb) {
         float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
@@ -585,6 +592,10 @@ __global__ void __launch_bounds__(256) qe_hprev_kernel(QeDev q) {
 //     jq = 0 CTA of each unit group runs Phase B.
 // dG is also kept transposed ([gate row][32 samples], double-buffered) so Phase A stages both operands with cp.async.
 constexpr int BWD_JQ = 4;
+struct BwdIn {
+  float gi, gf, gg, go, c, cp, dh;
+  bool live;
+};
 template <bool PERSIST>
 __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0, int s1, int nq_launch) {
   extern __shared__ __align__(16) float smem[];
@@ -601,11 +612,36 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
   constexpr int NW = LSTM_THREADS / 32;
   __shared__ bool is_last;
   bool w_loaded = false;
+  float carry_reg[2] = {0.f, 0.f};
   for (int s = s0; s < s1; ++s) {
     const int t = dir == 0 ? L - 1 - s : s;
     const int tp = dir == 0 ? t - 1 : t + 1;  // recurrence predecessor (source of c_prev)
     const int nq = PERSIST ? (s == 0 ? 1 : BWD_JQ) : nq_launch;
     bool do_b = PERSIST ? (jq == 0) : true;
+    // Phase B operands that do not depend on Phase A (gates, cell states, upstream dH of this time step): the persistent
+    // kernel's Phase-B CTAs request them BEFORE Phase A and its grid barrier, which hides one global-memory round trip per step
+    auto load_in = [&](int idx) -> BwdIn {
+      BwdIn in;
+      in.live = false;
+      in.gi = in.gf = in.gg = in.go = in.c = in.cp = in.dh = 0.f;
+      const int b = b0 + (idx >> 5), unit = ug * 32 + (idx & 31);
+      if (b < q.B && t < q.lengths[b]) {
+        const long long r = static_cast<long long>(b) * L + t;
+        const float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+        in.live = true;
+        in.gi = G[0]; in.gf = G[H]; in.gg = G[2 * H]; in.go = G[3 * H];
+        in.c = q.Cst[(r * 2 + dir) * H + unit];
+        in.cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
+        in.dh = q.dH[r * 2 * H + dir * H + unit];
+      }
+      return in;
+    };
+    BwdIn pre[2];
+    const bool prefetched = PERSIST && do_b;
+    if (prefetched) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) pre[e] = load_in(tid + e * LSTM_THREADS);
+    }
     if (nq > 1) {
       const float* src = q.dGT + ((s - 1) & 1) * gt_sz + ((static_cast<long long>(dir) * q.BC + bc) * 4 * H + jq * H) * 32;
       for (int idx = tid; idx < H * 8; idx += LSTM_THREADS) cp_async16(dgs + idx * 4, src + idx * 4);
@@ -658,7 +694,9 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
       }
     }
     if (do_b) {
-      for (int idx = tid; idx < 1024; idx += LSTM_THREADS) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {  // 1024 (sample, unit) pairs, two per thread -- the same two in every step
+        const int idx = tid + e * LSTM_THREADS;
         const int bl = idx >> 5, u = idx & 31;
         const int b = b0 + bl, unit = ug * 32 + u;
         float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f, carry = 0.f;
@@ -669,17 +707,16 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
             for (int qq = 0; qq < BWD_JQ; ++qq) dhrec += __ldcg(part + qq * 1024 + idx);
           }
           const long long r = static_cast<long long>(b) * L + t;
-          if (t < q.lengths[b]) {
-            const float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
-            const float gi = G[0], gf = G[H], gg = G[2 * H], go = G[3 * H];
-            const float c = q.Cst[(r * 2 + dir) * H + unit];
-            const float cp = (tp >= 0 && tp < L) ? q.Cst[((static_cast<long long>(b) * L + tp) * 2 + dir) * H + unit] : 0.f;
-            const float dh = q.dH[r * 2 * H + dir * H + unit] + dhrec;
-            const float tc = tanhf(c);
+          const BwdIn in = prefetched ? pre[e] : load_in(idx);
+          if (in.live) {
+            const float gi = in.gi, gf = in.gf, gg = in.gg, go = in.go;
+            const float dh = in.dh + dhrec;
+            const float tc = tanhf(in.c);
             float dc = dh * go * (1.f - tc * tc);
-            if (s > 0) dc += q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit];
+            // cell-state gradient carried from the previous step: a register in the persistent kernel
+            if (s > 0) dc += PERSIST ? carry_reg[e] : q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit];
             d_i = dc * gg * gi * (1.f - gi);
-            d_f = dc * cp * gf * (1.f - gf);
+            d_f = dc * in.cp * gf * (1.f - gf);
             d_g = dc * gi * (1.f - gg * gg);
             d_o = dh * tc * go * (1.f - go);
             carry = dc * gf;
@@ -696,8 +733,9 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
             q.dG_pl[go_ + g4 * H] = hh;
             q.dG_pl[gps + go_ + g4 * H] = ll;
           }
-          q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit] = carry;
+          if (!PERSIST) q.dcarry[(static_cast<long long>(dir) * q.B + b) * H + unit] = carry;
         }
+        carry_reg[e] = carry;
         red[(0 * 32 + u) * 33 + bl] = d_i;
         red[(1 * 32 + u) * 33 + bl] = d_f;
         red[(2 * 32 + u) * 33 + bl] = d_g;
@@ -1052,7 +1090,7 @@ static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
   TRY(check_launch("qe_embed"));
   // xg = E [W_ih ; W_ih_reverse]^T + b_ih + b_hh for all time steps and both directions: ONE tensor-core contraction
   // (split-BF16, deterministic) on the persistent CTA-pair kernel
-  qe_pack_wih_kernel<<<148, 256, 0, st>>>(q, a->w_ih[0], a->w_ih[1], a->b_ih[0], a->b_hh[0], a->b_ih[1], a->b_hh[1]);
+  qe_pack_wih_kernel<<<ceil_div(8 * H, 8), 256, 0, st>>>(q, a->w_ih[0], a->w_ih[1], a->b_ih[0], a->b_hh[0], a->b_ih[1], a->b_hh[1]);
   TRY(check_launch("qe_pack_wih"));
   {
     drn_gemm_t g = qe_gemm_base(DRN_GEMM_ROWS, R);
