@@ -48,6 +48,7 @@ __device__ __forceinline__ void store8_planes(__nv_bfloat16* hi, long long plane
 __global__ void __launch_bounds__(EW_THREADS) split_planes_kernel(const float* __restrict__ src, long long rows, int C8,
                                                                   long long src_ld, __nv_bfloat16* __restrict__ dst,
                                                                   long long dst_ld, int dst_col0, long long plane_stride) {
+  pdl_sync();
   const long long total = rows * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(EW_THREADS) split_planes_kernel(const float* _
 __global__ void __launch_bounds__(EW_THREADS) gate_planes_kernel(const float* __restrict__ x, const float* __restrict__ q, int T,
                                                                  int C8, long long total, __nv_bfloat16* __restrict__ dst,
                                                                  long long dst_ld, int dst_col0, long long plane_stride) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / C8;
@@ -94,6 +96,7 @@ struct PackTable {
 };
 
 __global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const PackTable tab) {
+  pdl_sync();
   const PackItem& e = tab.it[blockIdx.y];
   const long long total = static_cast<long long>(e.O) * e.C;
   if (e.k == 1) {  // nn.Linear / 1x1 conv: straight split, 8 elements per thread
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const Pack
 // (the K-splits of drn_gemm WGRAD and the three pyramid levels of a shared head conv store their partial sums side by side:
 // deterministic, no atomics, no zero-fill).  Reads are coalesced over C; gridDim.y = table item.
 __global__ void __launch_bounds__(EW_THREADS) unpack_conv_wgrad_kernel(const PackTable tab) {
+  pdl_sync();
   const PackItem& e = tab.it[blockIdx.y];
   const long long total = static_cast<long long>(e.O) * e.C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(EW_THREADS) pos_feature_kernel(const double* _
                                                                  __nv_bfloat16* __restrict__ dst, long long dst_ld,
                                                                  int dst_col0, long long plane_stride,
                                                                  float* __restrict__ pos_in) {
+  pdl_sync();
   const long long total = rows * Cp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -229,6 +234,7 @@ __device__ __forceinline__ void bn_coef_from_stats(double mean, double var, floa
 template <int MODE>  // 0: sum y, sum y^2 ; 1: BN backward sums (sum g, sum g*xhat) with g = relu-masked da
 __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float momentum, float eps, int update_running,
                                                         int STAT_ROWS) {
+  pdl_sync();
   __shared__ float red[2][8][128];
   __shared__ bool is_last;
   const BnJob& J = jobs.j[blockIdx.z];
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
 // ---- ordered running-statistics update of jobs that SHARE BatchNorm modules (the head applied to three pyramid levels,
 // model/fcos.py:93-102): running <- (1-m) running + m stat, job after job, exactly the order of the reference's level loop.
 __global__ void bn_running_update_kernel(const BnJobs jobs, float momentum) {
+  pdl_sync();
   const int p = blockIdx.y;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jobs.j[0].parts.n[p]; i += gridDim.x * blockDim.x) {
     for (int k = 0; k < jobs.n; ++k) {
@@ -377,6 +384,7 @@ __global__ void bn_running_update_kernel(const BnJobs jobs, float momentum) {
 
 // ---- eval-mode BN: coefficients from the running statistics ----------------------------------------------------------------
 __global__ void bn_eval_coef_kernel(const BnJobs jobs, float eps) {
+  pdl_sync();
   const BnJob& J = jobs.j[blockIdx.y];
   const int C = J.C;
   const BnParts& parts = J.parts;
@@ -389,6 +397,7 @@ __global__ void bn_eval_coef_kernel(const BnJobs jobs, float eps) {
 
 // ---- BN apply + ReLU (+ nearest x2 upsample add, + query gate) -> planes ---------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) bn_relu_apply_kernel(const BnJobs jobs) {
+  pdl_sync();
   const BnJob& J = jobs.j[blockIdx.y];
   const float* __restrict__ y = J.y;
   const int B = J.B, T = J.T, C = J.C;
@@ -432,6 +441,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_relu_apply_kernel(const BnJobs 
 
 // ---- BN backward apply: dy = scale * (g - mean(g) - xhat * mean(g*xhat)) -> planes ------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const BnJobs jobs) {
+  pdl_sync();
   const BnJob& J = jobs.j[blockIdx.y];
   const float* __restrict__ da = J.da;
   const float* __restrict__ y = J.y;
@@ -485,6 +495,7 @@ __device__ __forceinline__ RowWalk row_walk(int C, int rpt) {
   return w;
 }
 __global__ void __launch_bounds__(EW_THREADS, 3) bn_relu_apply_rows_kernel(const BnJobs jobs, int rpt) {
+  pdl_sync();
   const BnJob& J = jobs.j[blockIdx.y];
   const int T = J.T, C = J.C;
   const long long rows = static_cast<long long>(J.B) * T;
@@ -541,6 +552,7 @@ __global__ void __launch_bounds__(EW_THREADS, 3) bn_relu_apply_rows_kernel(const
   }
 }
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_rows_kernel(const BnJobs jobs, int rpt) {
+  pdl_sync();
   const BnJob& J = jobs.j[blockIdx.y];
   const int C = J.C;
   const long long rows = J.rows;
@@ -607,6 +619,7 @@ static int rows_walk_plan(const BnJobs& t, unsigned* gx) {
 // ---- FPN backward of nearest x2 upsample: dst[b,j,:] += src[b,2j,:] + src[b,2j+1,:] ------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) pair_sum_add_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                                                   long long rows_half, int C) {
+  pdl_sync();
   const int C4 = C >> 2;
   const long long total = rows_half * C4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -629,6 +642,7 @@ __global__ void __launch_bounds__(256) gate_reduce_kernel(const float* __restric
                                                           int C, int t_chunk, float* __restrict__ dq,
                                                           const float* __restrict__ q, __nv_bfloat16* __restrict__ dp,
                                                           long long dp_ps, float* __restrict__ dbias) {
+  pdl_sync();
   __shared__ float red[2][8][128];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 128 + tx * 4;
@@ -699,6 +713,7 @@ __global__ void __launch_bounds__(256) gate_reduce_kernel(const float* __restric
 __global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ dx, long long dx_ld, int col0,
                                                       const float* __restrict__ pos_in, long long rows, int Cp,
                                                       int rows_per_block, float* __restrict__ dWp, float* __restrict__ dbp) {
+  pdl_sync();
   const int c = threadIdx.x;  // Cp <= 256 threads
   if (c >= Cp) return;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
@@ -730,6 +745,7 @@ __global__ void __launch_bounds__(256) pos_bwd_kernel(const float* __restrict__ 
 // ---- column sums (bias gradients of the small Linear layers): out[c] += sum_rows x[row,c] ------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, int C, long long ld,
                                                      float* __restrict__ out) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float acc = 0.f;
@@ -753,7 +769,7 @@ extern "C" int drn_split_planes(const float* src, int64_t rows, int C, int64_t s
                                 int dst_col0, int64_t dst_plane_stride, void* stream) {
   if (C % 8 || src_ld % 4 || dst_ld % 8 || dst_col0 % 8 || dst_plane_stride % 8) return fail(DRN_EINVAL, "drn_split_planes: alignment (C=%d)", C);
   if (rows <= 0) return 0;
-  split_planes_kernel<<<ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream)>>>(src, rows, C / 8, src_ld, static_cast<__nv_bfloat16*>(dst),
+  launch_k(split_planes_kernel, ew_grid(rows * (C / 8)), EW_THREADS, 0, ST(stream), src, rows, C / 8, src_ld, static_cast<__nv_bfloat16*>(dst),
                                                                               dst_ld, dst_col0, dst_plane_stride);
   return check_launch("split_planes");
 }
@@ -763,7 +779,7 @@ extern "C" int drn_gate_planes(const float* x, const float* q, int B, int T, int
   if (C % 8 || dst_ld % 8 || dst_col0 % 8 || dst_plane_stride % 8) return fail(DRN_EINVAL, "drn_gate_planes: alignment (C=%d)", C);
   const long long total = static_cast<long long>(B) * T * (C / 8);
   if (total <= 0) return 0;
-  gate_planes_kernel<<<ew_grid(total), EW_THREADS, 0, ST(stream)>>>(x, q, T, C / 8, total, static_cast<__nv_bfloat16*>(dst), dst_ld,
+  launch_k(gate_planes_kernel, ew_grid(total), EW_THREADS, 0, ST(stream), x, q, T, C / 8, total, static_cast<__nv_bfloat16*>(dst), dst_ld,
                                                                     dst_col0, dst_plane_stride);
   return check_launch("gate_planes");
 }
@@ -784,7 +800,7 @@ extern "C" int drn_pack_conv_weights(int n, const drn_pack_item_t* items, void* 
   PackTable t;
   int rc = fill_table(&t, n, items);
   if (rc) return rc;
-  pack_conv_weight_kernel<<<dim3(148, n), EW_THREADS, 0, ST(stream)>>>(t);
+  launch_k(pack_conv_weight_kernel, dim3(148, n), EW_THREADS, 0, ST(stream), t);
   return check_launch("pack_conv_weights");
 }
 
@@ -792,13 +808,13 @@ extern "C" int drn_unpack_conv_wgrads(int n, const drn_pack_item_t* items, void*
   PackTable t;
   int rc = fill_table(&t, n, items);
   if (rc) return rc;
-  unpack_conv_wgrad_kernel<<<dim3(148 * 2, n), EW_THREADS, 0, ST(stream)>>>(t);
+  launch_k(unpack_conv_wgrad_kernel, dim3(148 * 2, n), EW_THREADS, 0, ST(stream), t);
   return check_launch("unpack_conv_wgrads");
 }
 
 extern "C" int drn_pos_feature(const double* pse, const float* Wp, const float* bp, int64_t rows, int Cp, void* dst,
                                int64_t dst_ld, int dst_col0, int64_t plane_stride, float* pos_in, void* stream) {
-  pos_feature_kernel<<<ew_grid(rows * Cp), EW_THREADS, 0, ST(stream)>>>(pse, Wp, bp, rows, Cp, static_cast<__nv_bfloat16*>(dst),
+  launch_k(pos_feature_kernel, ew_grid(rows * Cp), EW_THREADS, 0, ST(stream), pse, Wp, bp, rows, Cp, static_cast<__nv_bfloat16*>(dst),
                                                                         dst_ld, dst_col0, plane_stride, pos_in);
   return check_launch("pos_feature");
 }
@@ -879,12 +895,12 @@ extern "C" int drn_bn_stats_multi(int n, const drn_bn_job_t* jobs, float momentu
   if (!training) {
     int cmax = 0;
     for (int i = 0; i < n; ++i) cmax = t.j[i].C > cmax ? t.j[i].C : cmax;
-    bn_eval_coef_kernel<<<dim3(ceil_div(cmax, 256), n), 256, 0, ST(stream)>>>(t, eps);
+    launch_k(bn_eval_coef_kernel, dim3(ceil_div(cmax, 256), n), 256, 0, ST(stream), t, eps);
     return check_launch("bn_eval_coef");
   }
   dim3 grid;
   const int sr = stats_grid(t, &grid);
-  col_stats_kernel<0><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, momentum, eps, training == 1 ? 1 : 0, sr);
+  launch_k(col_stats_kernel<0>, grid, dim3(32, 8), 0, ST(stream), t, momentum, eps, training == 1 ? 1 : 0, sr);
   return check_launch("bn_stats");
 }
 
@@ -896,7 +912,7 @@ extern "C" int drn_bn_running_update(int n, const drn_bn_job_t* jobs, float mome
     if (t.j[i].parts.nparts != t.j[0].parts.nparts) return fail(DRN_EINVAL, "drn_bn_running_update: jobs must share their BatchNorm modules");
   int nmax = 0;
   for (int p = 0; p < t.j[0].parts.nparts; ++p) nmax = t.j[0].parts.n[p] > nmax ? t.j[0].parts.n[p] : nmax;
-  bn_running_update_kernel<<<dim3(ceil_div(nmax, 256), t.j[0].parts.nparts), 256, 0, ST(stream)>>>(t, momentum);
+  launch_k(bn_running_update_kernel, dim3(ceil_div(nmax, 256), t.j[0].parts.nparts), 256, 0, ST(stream), t, momentum);
   return check_launch("bn_running_update");
 }
 
@@ -910,8 +926,8 @@ extern "C" int drn_bn_relu_apply_multi(int n, const drn_bn_job_t* jobs, void* st
   }
   unsigned gx = 0;
   const int rpt = rows_walk_plan(t, &gx);
-  if (rpt) bn_relu_apply_rows_kernel<<<dim3(gx, n), EW_THREADS, 0, ST(stream)>>>(t, rpt);
-  else bn_relu_apply_kernel<<<dim3(ew_grid_jobs(t), n), EW_THREADS, 0, ST(stream)>>>(t);
+  if (rpt) launch_k(bn_relu_apply_rows_kernel, dim3(gx, n), EW_THREADS, 0, ST(stream), t, rpt);
+  else launch_k(bn_relu_apply_kernel, dim3(ew_grid_jobs(t), n), EW_THREADS, 0, ST(stream), t);
   return check_launch("bn_relu_apply");
 }
 
@@ -921,7 +937,7 @@ extern "C" int drn_bn_bwd_reduce_multi(int n, const drn_bn_job_t* jobs, void* st
   if (rc) return rc;
   dim3 grid;
   const int sr = stats_grid(t, &grid);
-  col_stats_kernel<1><<<grid, dim3(32, 8), 0, ST(stream)>>>(t, 0.f, 0.f, 0, sr);
+  launch_k(col_stats_kernel<1>, grid, dim3(32, 8), 0, ST(stream), t, 0.f, 0.f, 0, sr);
   return check_launch("bn_bwd_reduce");
 }
 
@@ -931,8 +947,8 @@ extern "C" int drn_bn_bwd_apply_multi(int n, const drn_bn_job_t* jobs, void* str
   if (rc) return rc;
   unsigned gx = 0;
   const int rpt = rows_walk_plan(t, &gx);
-  if (rpt) bn_bwd_apply_rows_kernel<<<dim3(gx, n), EW_THREADS, 0, ST(stream)>>>(t, rpt);
-  else bn_bwd_apply_kernel<<<dim3(ew_grid_jobs(t), n), EW_THREADS, 0, ST(stream)>>>(t);
+  if (rpt) launch_k(bn_bwd_apply_rows_kernel, dim3(gx, n), EW_THREADS, 0, ST(stream), t, rpt);
+  else launch_k(bn_bwd_apply_kernel, dim3(ew_grid_jobs(t), n), EW_THREADS, 0, ST(stream), t);
   return check_launch("bn_bwd_apply");
 }
 
@@ -982,7 +998,7 @@ extern "C" int drn_bn_bwd_apply(const float* da, const float* y, int64_t rows, i
 
 extern "C" int drn_pair_sum_add(float* dst, const float* src, int64_t rows_half, int C, void* stream) {
   if (C % 4) return fail(DRN_EINVAL, "drn_pair_sum_add: C %% 4");
-  pair_sum_add_kernel<<<ew_grid(rows_half * (C / 4)), EW_THREADS, 0, ST(stream)>>>(dst, src, rows_half, C);
+  launch_k(pair_sum_add_kernel, ew_grid(rows_half * (C / 4)), EW_THREADS, 0, ST(stream), dst, src, rows_half, C);
   return check_launch("pair_sum_add");
 }
 
@@ -993,10 +1009,10 @@ extern "C" int drn_gate_reduce(const float* g, int64_t g_ld, const void* a, int6
   const int t_chunk = 64;
   dim3 grid(ceil_div(C, 128), ceil_div(T, t_chunk), B);
   if (a_is_planes)
-    gate_reduce_kernel<true><<<grid, dim3(32, 8), 0, ST(stream)>>>(g, g_ld, a, a_ld, a_plane_stride, T, C, t_chunk, dq, q,
+    launch_k(gate_reduce_kernel<true>, grid, dim3(32, 8), 0, ST(stream), g, g_ld, a, a_ld, a_plane_stride, T, C, t_chunk, dq, q,
                                                                   static_cast<__nv_bfloat16*>(dp), dp_plane_stride, dbias);
   else
-    gate_reduce_kernel<false><<<grid, dim3(32, 8), 0, ST(stream)>>>(g, g_ld, a, a_ld, a_plane_stride, T, C, t_chunk, dq, q,
+    launch_k(gate_reduce_kernel<false>, grid, dim3(32, 8), 0, ST(stream), g, g_ld, a, a_ld, a_plane_stride, T, C, t_chunk, dq, q,
                                                                    static_cast<__nv_bfloat16*>(dp), dp_plane_stride, dbias);
   return check_launch("gate_reduce");
 }
@@ -1005,13 +1021,13 @@ extern "C" int drn_pos_bwd(const float* dx, int64_t dx_ld, int col0, const float
                            float* dbp, void* stream) {
   if (Cp > 256) return fail(DRN_EINVAL, "drn_pos_bwd: Cp > 256");
   const int rpb = 32;
-  pos_bwd_kernel<<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, 0, ST(stream)>>>(dx, dx_ld, col0, pos_in, rows, Cp, rpb, dWp,
+  launch_k(pos_bwd_kernel, static_cast<unsigned>((rows + rpb - 1) / rpb), 256, 0, ST(stream), dx, dx_ld, col0, pos_in, rows, Cp, rpb, dWp,
                                                                                        dbp);
   return check_launch("pos_bwd");
 }
 
 extern "C" int drn_colsum(const float* x, int64_t rows, int C, int64_t ld, float* out, void* stream) {
   dim3 grid(ceil_div(C, 256), static_cast<unsigned>(rows < 64 ? rows : 64));
-  colsum_kernel<<<grid, 256, 0, ST(stream)>>>(x, rows, C, ld, out);
+  launch_k(colsum_kernel, grid, 256, 0, ST(stream), x, rows, C, ld, out);
   return check_launch("colsum");
 }

@@ -23,6 +23,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CUtensorMap tma_a,
                const __grid_constant__ CUtensorMap tma_b) {
+  pdl_trigger();
   using Cfg = TileCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[Cfg::STAGES];
@@ -78,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ GemmKParams p, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();  // barriers initialised, TMEM allocated: only now wait for the kernel before this one (its output = our operands)
   const uint32_t tmem_base = tmem_base_holder;
 
   if (warp == 0) {
@@ -211,6 +213,7 @@ __device__ __forceinline__ float fetch(const PlanesView& v, int b, int t, int pa
 }
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmKParams p) {
+  pdl_sync();
   __shared__ float As[16][65];
   __shared__ float Bs[16][65];
   const bool wgrad = (p.form == DRN_GEMM_WGRAD);
@@ -351,7 +354,7 @@ static int launch_tc(const GemmKParams& kp, const CUtensorMap& ma, const CUtenso
     if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  gemm_tc_kernel<BLOCK_N><<<grid, GEMM_THREADS, Cfg::SMEM, st>>>(kp, ma, mb);
+  launch_k(gemm_tc_kernel<BLOCK_N>, grid, GEMM_THREADS, Cfg::SMEM, st, kp, ma, mb);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -525,7 +528,7 @@ extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
     if (kp.out_split_stride != 0 && kp.split_k > 1) return fail(DRN_EINVAL, "drn_gemm: the checker engine has no K-split");
     const int Mtot = wgrad ? g->M : g->B * g->T;
     dim3 grid(ceil_div(Mtot, 64), ceil_div(g->N, 64), wgrad ? g->ntaps : 1);
-    gemm_simt_kernel<<<grid, 256, 0, st>>>(kp);
+    launch_k(gemm_simt_kernel, grid, 256, 0, st, kp);
     return check_launch("gemm_simt_kernel");
   }
 

@@ -88,6 +88,7 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ GroupMaps gm, int num_tiles) {
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[P2_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[P2_STAGES];
@@ -126,6 +127,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  pdl_wait();  // prologue done (barriers, TMEM, descriptor prefetch): wait here for the kernel that produces our operands
 
   if (warp == 0) {
     // ===== TMA producer (one thread per CTA; completion is signalled on the LEADER's full barrier) =====
@@ -301,7 +303,7 @@ int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaS
   if (cap > 0 && clusters > cap) clusters = cap;
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
-  gemm_pair_kernel<<<2 * clusters, P2_THREADS, P2_SMEM, st>>>(gp, gm, num_tiles);
+  launch_k(gemm_pair_kernel, 2 * clusters, P2_THREADS, P2_SMEM, st, gp, gm, num_tiles);
   return check_launch("gemm_pair_kernel");
 }
 

@@ -26,6 +26,7 @@ template <int NOUT, int K>
 __global__ void __launch_bounds__(256) skinny_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long x_ps, int x_ld, int c0,
                                                          int Cw, int B, int T, const float* __restrict__ W,
                                                          const float* __restrict__ bias, float* __restrict__ out) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B * T) return;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(256) skinny_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ W, int rows_per_block,
                                                          float* __restrict__ dx, int dx_ld, int dx_accumulate,
                                                          float* __restrict__ dW) {
+  pdl_sync();
   skinny_bwd_body<NOUT, K>(d, x, x_ps, x_ld, c0, Cw, B, T, W, rows_per_block, dx, dx_ld, dx_accumulate, dW, blockIdx.x, blockIdx.y);
 }
 
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(256) head_proj_fwd_kernel(HeadLevels g, const 
                                                             const float* __restrict__ Wi, const float* __restrict__ bi,
                                                             float* __restrict__ cls_raw, float* __restrict__ box_raw,
                                                             float* __restrict__ iou_raw, long long total) {
+  pdl_sync();
   extern __shared__ __align__(16) float hsm[];
   constexpr int F = NCH * 128;
   float* wc = hsm;              // [3][F]
@@ -369,6 +372,7 @@ __global__ void __launch_bounds__(256, 3) head_proj_bwd_kernel(HeadLevels g, con
                                                             const float* __restrict__ dbox, const float* __restrict__ Wc,
                                                             const float* __restrict__ Wb, int nblk_total,
                                                             float* __restrict__ dWc, float* __restrict__ dWb) {
+  pdl_sync();
   extern __shared__ __align__(16) float hb_sm[];  // [(HB_ROWS + 2) * 2] upstream gradients, then [rsub][F * NOUT * 3] dW partials
   float* dsm = hb_sm;
   float* wred = hb_sm + (HB_ROWS + 2) * 2 + 4;
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(256) fcos_loss_fwd_kernel(LevelGeom g, const f
                                                             const float* __restrict__ scales, const float* __restrict__ gt,
                                                             float gamma, float alpha, int iou_branch_on,
                                                             float* __restrict__ bbox_out, double* __restrict__ acc) {
+  pdl_sync();
   __shared__ double red[5][8];
   const long long total = static_cast<long long>(g.B) * g.P;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -483,6 +488,7 @@ __global__ void __launch_bounds__(256) fcos_loss_fwd_kernel(LevelGeom g, const f
 
 // losses: [0] loss_cls, [1] loss_reg, [2] loss_iou, [3] n_pos, [4] IoU-branch count
 __global__ void fcos_loss_finalize_kernel(const double* __restrict__ acc, int B, float* __restrict__ losses) {
+  pdl_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double npos = acc[1], cnt = acc[4];
   losses[0] = static_cast<float>(acc[0] / (npos + B));          // model/loss.py:210-213
@@ -501,6 +507,7 @@ __global__ void __launch_bounds__(256) fcos_loss_bwd_kernel(LevelGeom g, const f
                                                             const double* __restrict__ acc, const float* __restrict__ upstream,
                                                             float* __restrict__ dcls, float* __restrict__ dbox,
                                                             float* __restrict__ diou, float* __restrict__ pgrad) {
+  pdl_sync();
   __shared__ float red[4 + MAX_LEVELS][8];
   const long long total = static_cast<long long>(g.B) * g.P;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -583,6 +590,7 @@ __global__ void __launch_bounds__(256) postprocess_kernel(LevelGeom g, const flo
                                                           float thr, int top_n, int use_iou, float* __restrict__ out_det,
                                                           float* __restrict__ out_score, float* __restrict__ out_loc,
                                                           int* __restrict__ out_count) {
+  pdl_sync();
   __shared__ float sc[POST_MAX_T];
   __shared__ unsigned char keep[POST_MAX_T];
   __shared__ int ncand_s;
@@ -655,9 +663,9 @@ extern "C" int drn_skinny_conv_fwd(const void* x, int64_t x_plane_stride, int x_
   const long long warps = static_cast<long long>(B) * T;
   const unsigned grid = static_cast<unsigned>((warps * 32 + 255) / 256);
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
-  if (nout == 1 && k == 3) skinny_fwd_kernel<1, 3><<<grid, 256, 0, ST(stream)>>>(xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
-  else if (nout == 2 && k == 3) skinny_fwd_kernel<2, 3><<<grid, 256, 0, ST(stream)>>>(xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
-  else if (nout == 1 && k == 1) skinny_fwd_kernel<1, 1><<<grid, 256, 0, ST(stream)>>>(xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
+  if (nout == 1 && k == 3) launch_k(skinny_fwd_kernel<1, 3>, grid, 256, 0, ST(stream), xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
+  else if (nout == 2 && k == 3) launch_k(skinny_fwd_kernel<2, 3>, grid, 256, 0, ST(stream), xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
+  else if (nout == 1 && k == 1) launch_k(skinny_fwd_kernel<1, 1>, grid, 256, 0, ST(stream), xp, x_plane_stride, x_ld, c0, Cw, B, T, W, bias, out);
   else return fail(DRN_EINVAL, "drn_skinny_conv_fwd: unsupported (nout=%d,k=%d)", nout, k);
   return check_launch("skinny_conv_fwd");
 }
@@ -671,9 +679,9 @@ extern "C" int drn_skinny_conv_bwd(const float* d, const void* x, int64_t x_plan
   while (rpb < 64 && rows_total / rpb > 2 * 148) rpb *= 2;
   dim3 grid(ceil_div(Cw, 512), static_cast<unsigned>((rows_total + rpb - 1) / rpb));
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
-  if (nout == 1 && k == 3) skinny_bwd_kernel<1, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
-  else if (nout == 2 && k == 3) skinny_bwd_kernel<2, 3><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
-  else if (nout == 1 && k == 1) skinny_bwd_kernel<1, 1><<<grid, 256, 0, ST(stream)>>>(d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
+  if (nout == 1 && k == 3) launch_k(skinny_bwd_kernel<1, 3>, grid, 256, 0, ST(stream), d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
+  else if (nout == 2 && k == 3) launch_k(skinny_bwd_kernel<2, 3>, grid, 256, 0, ST(stream), d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
+  else if (nout == 1 && k == 1) launch_k(skinny_bwd_kernel<1, 1>, grid, 256, 0, ST(stream), d, xp, x_plane_stride, x_ld, c0, Cw, B, T, W, rpb, dx, dx_ld, dx_accumulate, dW);
   else return fail(DRN_EINVAL, "drn_skinny_conv_bwd: unsupported (nout=%d,k=%d)", nout, k);
   return check_launch("skinny_conv_bwd");
 }
@@ -687,9 +695,9 @@ extern "C" int drn_fcos_loss_fwd(int nlevels, int B, const int* T, const float* 
   cudaError_t e = cudaMemsetAsync(acc, 0, 8 * sizeof(double), ST(stream));
   if (e != cudaSuccess) return fail(static_cast<int>(e), "memset: %s", cudaGetErrorString(e));
   const long long total = static_cast<long long>(B) * g.P;
-  fcos_loss_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ST(stream)>>>(g, cls_raw, box_raw, iou_raw, scales, gt, gamma,
+  launch_k(fcos_loss_fwd_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, ST(stream), g, cls_raw, box_raw, iou_raw, scales, gt, gamma,
                                                                                          alpha, iou_branch_on, bbox_out, acc);
-  fcos_loss_finalize_kernel<<<1, 32, 0, ST(stream)>>>(acc, B, losses);
+  launch_k(fcos_loss_finalize_kernel, 1, 32, 0, ST(stream), acc, B, losses);
   return check_launch("fcos_loss_fwd");
 }
 
@@ -701,7 +709,7 @@ extern "C" int drn_fcos_loss_bwd(int nlevels, int B, const int* T, const float* 
   int rc = make_geom(&g, nlevels, B, T, strides);
   if (rc) return rc;
   const long long total = static_cast<long long>(B) * g.P;
-  fcos_loss_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ST(stream)>>>(
+  launch_k(fcos_loss_bwd_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, ST(stream), 
       g, cls_raw, box_raw, iou_raw, scales, gt, gamma, alpha, iou_branch_on, acc, upstream, dcls, dbox, diou, pgrad);
   return check_launch("fcos_loss_bwd");
 }
@@ -715,7 +723,7 @@ extern "C" int drn_postprocess(int nlevels, int B, const int* T, const float* st
   if (top_n < 1) return fail(DRN_EINVAL, "drn_postprocess: top_n must be positive");
   for (int l = 0; l < nlevels; ++l)
     if (T[l] > POST_MAX_T) return fail(DRN_EINVAL, "drn_postprocess: at most %d locations per level (got %d)", POST_MAX_T, T[l]);
-  postprocess_kernel<<<dim3(nlevels, B), 256, 0, ST(stream)>>>(g, cls_raw, bbox, iou_raw, thr, top_n, use_iou, out_det, out_score,
+  launch_k(postprocess_kernel, dim3(nlevels, B), 256, 0, ST(stream), g, cls_raw, bbox, iou_raw, thr, top_n, use_iou, out_det, out_score,
                                                              out_loc, out_count);
   return check_launch("postprocess");
 }
@@ -752,9 +760,9 @@ extern "C" int drn_head_proj_fwd(const drn_head_levels_t* h, const float* Wc, co
   long long ctas = (total + 7) / 8;
   if (ctas > 148 * 3) ctas = 148 * 3;  // 70 registers x 256 threads: three CTAs per SM, one wave (grid-stride loop over locations)
   if (g.F == 512)
-    head_proj_fwd_kernel<4><<<static_cast<unsigned>(ctas), 256, smem, ST(stream)>>>(g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
+    launch_k(head_proj_fwd_kernel<4>, static_cast<unsigned>(ctas), 256, smem, ST(stream), g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
   else
-    head_proj_fwd_kernel<2><<<static_cast<unsigned>(ctas), 256, smem, ST(stream)>>>(g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
+    launch_k(head_proj_fwd_kernel<2>, static_cast<unsigned>(ctas), 256, smem, ST(stream), g, Wc, bc, Wb, bb, Wi, bi, cls_raw, box_raw, iou_raw, total);
   return check_launch("head_proj_fwd");
 }
 
@@ -776,6 +784,6 @@ extern "C" int drn_head_proj_bwd(const drn_head_levels_t* h, const float* dcls, 
   const int rsub = 256 / (g.F / 4);
   const size_t smem = ((HB_ROWS + 2) * 2 + 4 + static_cast<size_t>(rsub) * g.F * 2 * 3) * sizeof(float);
   dim3 grid(static_cast<unsigned>(gx), 2, 1);
-  head_proj_bwd_kernel<<<grid, 256, smem, ST(stream)>>>(g, dcls, dbox, Wc, Wb, static_cast<int>(nblk), dWc, dWb);
+  launch_k(head_proj_bwd_kernel, grid, 256, smem, ST(stream), g, dcls, dbox, Wc, Wb, static_cast<int>(nblk), dWc, dWb);
   return check_launch("head_proj_bwd");
 }

@@ -18,6 +18,7 @@ __global__ void lgp_bn_kernel(const float* __restrict__ z, int B, int C, int t, 
                               const float* __restrict__ beta, float* running_mean, float* running_var, long long* nbt,
                               float momentum, float eps, int training, float* __restrict__ qn, float* __restrict__ xhat,
                               float* __restrict__ invstd_out) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, var;
@@ -53,6 +54,7 @@ __global__ void lgp_bn_kernel(const float* __restrict__ z, int B, int C, int t, 
 // grid (ceil(t/2 / 128), B), block 128: thread = pair j
 __global__ void __launch_bounds__(128) lgp_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ qn, int C, int t,
                                                            float* __restrict__ att, float* __restrict__ out) {
+  pdl_sync();
   extern __shared__ float qs[];  // [C]
   const int b = blockIdx.y, h = t >> 1;
   for (int c = threadIdx.x; c < C; c += blockDim.x) qs[c] = qn[static_cast<long long>(b) * C + c];
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(128) lgp_pool_fwd_kernel(const float* __restri
 __global__ void __launch_bounds__(128) lgp_pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ qn,
                                                            const float* __restrict__ att, const float* __restrict__ dout, int C,
                                                            int t, float* __restrict__ dx, float* __restrict__ dqn) {
+  pdl_sync();
   extern __shared__ float qs[];  // [C]
   __shared__ float red[4];
   const int b = blockIdx.y, h = t >> 1;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(128) lgp_pool_bwd_kernel(const float* __restri
 __global__ void lgp_bn_bwd_kernel(const float* __restrict__ dqn, const float* __restrict__ xhat, const float* __restrict__ invstd,
                                   const float* __restrict__ gamma, int B, int C, int training, float* __restrict__ dz,
                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float s = 0.f, sx = 0.f;
@@ -157,7 +161,7 @@ extern "C" int drn_lgp_bn(const float* z, int B, int C, int t, const float* gamm
                           float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int training, float* qn,
                           float* xhat, float* invstd, void* stream) {
   if (B < 1 || C < 1 || t < 2) return fail(DRN_EINVAL, "drn_lgp_bn: bad shape");
-  lgp_bn_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(z, B, C, t, gamma, beta, running_mean, running_var,
+  launch_k(lgp_bn_kernel, ceil_div(C, 128), 128, 0, ST(stream), z, B, C, t, gamma, beta, running_mean, running_var,
                                                          reinterpret_cast<long long*>(num_batches_tracked), momentum, eps, training, qn,
                                                          xhat, invstd);
   return check_launch("lgp_bn");
@@ -166,7 +170,7 @@ extern "C" int drn_lgp_bn(const float* z, int B, int C, int t, const float* gamm
 extern "C" int drn_lgp_pool_fwd(const float* x, const float* qn, int B, int C, int t, float* att, float* out, void* stream) {
   if (B < 1 || C < 1 || t < 2 || t % 2) return fail(DRN_EINVAL, "drn_lgp_pool_fwd: t must be even (t=%d)", t);
   if (C * sizeof(float) > 48 * 1024) return fail(DRN_EINVAL, "drn_lgp_pool_fwd: at most 12288 channels");
-  lgp_pool_fwd_kernel<<<dim3(ceil_div(t / 2, 128), B), 128, C * sizeof(float), ST(stream)>>>(x, qn, C, t, att, out);
+  launch_k(lgp_pool_fwd_kernel, dim3(ceil_div(t / 2, 128), B), 128, C * sizeof(float), ST(stream), x, qn, C, t, att, out);
   return check_launch("lgp_pool_fwd");
 }
 
@@ -176,13 +180,13 @@ extern "C" int drn_lgp_pool_bwd(const float* x, const float* qn, const float* at
   if (C * sizeof(float) > 48 * 1024) return fail(DRN_EINVAL, "drn_lgp_pool_bwd: at most 12288 channels");
   cudaError_t e = cudaMemsetAsync(dqn, 0, sizeof(float) * B * C, ST(stream));
   if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_lgp_pool_bwd memset: %s", cudaGetErrorString(e));
-  lgp_pool_bwd_kernel<<<dim3(ceil_div(t / 2, 128), B), 128, C * sizeof(float), ST(stream)>>>(x, qn, att, dout, C, t, dx, dqn);
+  launch_k(lgp_pool_bwd_kernel, dim3(ceil_div(t / 2, 128), B), 128, C * sizeof(float), ST(stream), x, qn, att, dout, C, t, dx, dqn);
   return check_launch("lgp_pool_bwd");
 }
 
 extern "C" int drn_lgp_bn_bwd(const float* dqn, const float* xhat, const float* invstd, const float* gamma, int B, int C, int training,
                               float* dz, float* dgamma, float* dbeta, void* stream) {
   if (B < 1 || C < 1) return fail(DRN_EINVAL, "drn_lgp_bn_bwd: bad shape");
-  lgp_bn_bwd_kernel<<<ceil_div(C, 128), 128, 0, ST(stream)>>>(dqn, xhat, invstd, gamma, B, C, training, dz, dgamma, dbeta);
+  launch_k(lgp_bn_bwd_kernel, ceil_div(C, 128), 128, 0, ST(stream), dqn, xhat, invstd, gamma, B, C, training, dz, dgamma, dbeta);
   return check_launch("lgp_bn_bwd");
 }

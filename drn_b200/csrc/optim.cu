@@ -22,6 +22,7 @@ struct AdamItemDev {
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const AdamItemDev* __restrict__ items, const int* __restrict__ chunk_item,
                                                           const long long* __restrict__ chunk_off, double* __restrict__ scratch,
                                                           int* __restrict__ steps) {
+  pdl_sync();
   const AdamItemDev it = items[chunk_item[blockIdx.x]];
   if (!it.grad) return;
   const long long o = chunk_off[blockIdx.x];
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) clip_adam_kernel(const AdamItemDev* __res
                                                         const long long* __restrict__ chunk_off, double* __restrict__ scratch,
                                                         float max_norm, float lr, float beta1, float beta2, float eps,
                                                         const int* __restrict__ steps) {
+  pdl_sync();
   const AdamItemDev it = items[chunk_item[blockIdx.x]];
   // torch.nn.utils.clip_grad_norm_: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1
   const float total_norm = static_cast<float>(sqrt(scratch[0]));
@@ -97,10 +99,10 @@ extern "C" int drn_clip_adam(int nchunks, const void* items, const int32_t* chun
   cudaError_t e = cudaMemsetAsync(scratch, 0, 3 * sizeof(double), st);
   if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_clip_adam memset: %s", cudaGetErrorString(e));
   const AdamItemDev* it = static_cast<const AdamItemDev*>(items);
-  grad_sqnorm_kernel<<<nchunks, 256, 0, st>>>(it, chunk_item, reinterpret_cast<const long long*>(chunk_off), scratch, steps);
+  launch_k(grad_sqnorm_kernel, nchunks, 256, 0, st, it, chunk_item, reinterpret_cast<const long long*>(chunk_off), scratch, steps);
   int rc = check_launch("grad_sqnorm");
   if (rc) return rc;
-  clip_adam_kernel<<<nchunks, 256, 0, st>>>(it, chunk_item, reinterpret_cast<const long long*>(chunk_off), scratch, max_norm, lr,
+  launch_k(clip_adam_kernel, nchunks, 256, 0, st, it, chunk_item, reinterpret_cast<const long long*>(chunk_off), scratch, max_norm, lr,
                                             beta1, beta2, eps, steps);
   return check_launch("clip_adam");
 }

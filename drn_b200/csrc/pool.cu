@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) pool_proposals_kernel(const float* __rest
                                                              const int* __restrict__ nprops, const int* __restrict__ num_frames,
                                                              int P, int D, int window, int interval, float* __restrict__ out,
                                                              double* __restrict__ pse) {
+  pdl_sync();
   const int p = blockIdx.x, b = blockIdx.y;
   float* o = out + (static_cast<long long>(b) * P + p) * D;
   const int D4 = D >> 2;
@@ -61,7 +62,7 @@ extern "C" int drn_pool_proposals(const float* feats, const int64_t* win_off, co
   if (window < 1 || interval < 1) return fail(DRN_EINVAL, "drn_pool_proposals: window / interval must be positive");
   if (reinterpret_cast<uintptr_t>(feats) % 16 || reinterpret_cast<uintptr_t>(out_feats) % 16)
     return fail(DRN_EINVAL, "drn_pool_proposals: feature buffers must be 16-byte aligned");
-  pool_proposals_kernel<<<dim3(P, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pool_proposals_kernel, dim3(P, B), 256, 0, static_cast<cudaStream_t>(stream), 
       feats, reinterpret_cast<const long long*>(win_off), p_start, p_end, nprops, num_frames, P, D, window, interval, out_feats,
       out_pse);
   return check_launch("pool_proposals");

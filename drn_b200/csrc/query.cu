@@ -150,6 +150,7 @@ static void prefer_max_smem(F* fn) {
 
 template <int BM>
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmP p) {
+  pdl_sync();
   sgemm_body<BM>(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
@@ -163,6 +164,7 @@ struct SgemmJobs {
   SgemmP p[SG_MAX_JOBS];
 };
 __global__ void __launch_bounds__(256) sgemm_multi_kernel(const SgemmJobs jobs) {
+  pdl_sync();
   int j = 0;
 #pragma unroll
   for (int i = 1; i < SG_MAX_JOBS; ++i)
@@ -204,7 +206,7 @@ struct SgemmBatch {
   int launch(cudaStream_t st) {
     if (jobs.n == 0) return 0;
     for (int i = jobs.n; i < SG_MAX_JOBS; ++i) jobs.cta_start[i + 1] = jobs.cta_start[jobs.n];
-    sgemm_multi_kernel<<<jobs.cta_start[jobs.n], 256, 0, st>>>(jobs);
+    launch_k(sgemm_multi_kernel, jobs.cta_start[jobs.n], 256, 0, st, jobs);
     jobs.n = 0;
     jobs.cta_start[0] = 0;
     return check_launch("sgemm_multi");
@@ -238,8 +240,8 @@ static int sgemm(cudaStream_t st, const float* A, long long sam, long long sak, 
     carve = true;
   }
   dim3 grid(ceil_div(M, bm), ceil_div(N, 64), splits);
-  if (bm == 32) sgemm_kernel<32><<<grid, 256, 0, st>>>(p);
-  else sgemm_kernel<64><<<grid, 256, 0, st>>>(p);
+  if (bm == 32) launch_k(sgemm_kernel<32>, grid, 256, 0, st, p);
+  else launch_k(sgemm_kernel<64>, grid, 256, 0, st, p);
   return check_launch("sgemm");
 }
 
@@ -294,6 +296,7 @@ __device__ __forceinline__ float4 lin_load4(const float* __restrict__ p, int k, 
   return v;
 }
 __global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const LinJobs jobs) {
+  pdl_sync();
   int jb = 0;
 #pragma unroll
   for (int i = 1; i < LIN_MAX_JOBS; ++i)
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) linear_small_kernel(const LinJ
 }
 static int linear_launch(cudaStream_t st, LinJobs& jobs) {
   for (int i = jobs.n; i < LIN_MAX_JOBS; ++i) jobs.cta_start[i + 1] = jobs.cta_start[jobs.n];
-  linear_small_kernel<<<jobs.cta_start[jobs.n], LIN_WARPS * 32, 0, st>>>(jobs);
+  launch_k(linear_small_kernel, jobs.cta_start[jobs.n], LIN_WARPS * 32, 0, st, jobs);
   return check_launch("linear_small");
 }
 static int linear_add(LinJobs& jobs, const float* x, long long ldx, const float* W, long long ldw, const float* bias, float* out,
@@ -411,6 +414,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 // ---- embedding gather (language_module.py:41) / scatter-add of its gradient (row 0 = padding_idx gets none) ------------
 __global__ void __launch_bounds__(256) qe_embed_kernel(QeDev q, const float* __restrict__ emb) {
+  pdl_sync();
   const int r = blockIdx.x;
   const int b = r / q.L, t = r % q.L;
   const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
@@ -427,6 +431,7 @@ __global__ void __launch_bounds__(256) qe_embed_kernel(QeDev q, const float* __r
 __global__ void __launch_bounds__(256) qe_pack_wih_kernel(QeDev q, const float* __restrict__ w0, const float* __restrict__ w1,
                                                           const float* __restrict__ bi0, const float* __restrict__ bh0,
                                                           const float* __restrict__ bi1, const float* __restrict__ bh1) {
+  pdl_sync();
   // one warp per packed row (8H rows): 32-bit indexing, no divisions (a flat 64-bit-indexed grid-stride loop over 148 CTAs was a
   // 25 us latency chain for 5 MB)
   const int H4 = 4 * q.H, EP = q.EP, E = q.E;
@@ -444,6 +449,7 @@ __global__ void __launch_bounds__(256) qe_pack_wih_kernel(QeDev q, const float* 
   if (lane == 0) q.bias_sum[row] = row < H4 ? bi0[rr] + bh0[rr] : bi1[rr] + bh1[rr];
 }
 __global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __restrict__ g_emb) {
+  pdl_sync();
   const int r = blockIdx.x;
   const int b = r / q.L, t = r % q.L;
   const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
@@ -468,6 +474,7 @@ __global__ void __launch_bounds__(256) qe_embed_bwd_kernel(QeDev q, float* __res
 constexpr int LSTM_THREADS = 512;  // 16 warps: two per hidden unit (each takes half of the contraction), 8 units per CTA
 template <bool PERSIST>
 __global__ void __launch_bounds__(LSTM_THREADS) lstm_fwd_kernel(QeDev q, int s0, int s1) {
+  pdl_sync();
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
   float* ws = smem;                 // [32][H]   rows (unit, gate) -> unit*4+g
@@ -567,6 +574,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_fwd_kernel(QeDev q, int s0,
 
 // Hprev planes [dir][b][t] = hidden state the recurrence consumed at step t (operand of the W_hh weight gradient)
 __global__ void __launch_bounds__(256) qe_hprev_kernel(QeDev q) {
+  pdl_sync();
   const int H = q.H, L = q.L;
   const long long total = 2LL * q.B * L * H, ps = total;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += 256LL * gridDim.x) {
@@ -601,6 +609,7 @@ struct BwdIn {
 };
 template <bool PERSIST>
 __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0, int s1, int nq_launch) {
+  pdl_sync();
   extern __shared__ __align__(16) float smem[];
   const int H = q.H, L = q.L;
   const int ug = blockIdx.x, jq = blockIdx.y, dir = blockIdx.z / q.BC, bc = blockIdx.z % q.BC, b0 = bc * 32;
@@ -762,6 +771,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
 
 // ---- q_vector = [H[b,0] | H[b,len-1]] (language_module.py:50-55) and the scatter of its gradient ------------------------
 __global__ void __launch_bounds__(256) qe_vgather_kernel(QeDev q) {
+  pdl_sync();
   const int b = blockIdx.x, D = 2 * q.H;
   const long long last = q.lengths[b] - 1;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -770,6 +780,7 @@ __global__ void __launch_bounds__(256) qe_vgather_kernel(QeDev q) {
   }
 }
 __global__ void __launch_bounds__(256) qe_vscatter_kernel(QeDev q) {
+  pdl_sync();
   const int b = blockIdx.x, D = 2 * q.H;
   const long long last = q.lengths[b] - 1;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
@@ -779,6 +790,7 @@ __global__ void __launch_bounds__(256) qe_vscatter_kernel(QeDev q) {
 }
 // ReLU backward from the activation itself (relu(x) > 0 <=> x > 0)
 __global__ void relu_mask_kernel(const float* __restrict__ g, const float* __restrict__ act, float* __restrict__ y, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = act[i] > 0.f ? g[i] : 0.f;
 }
@@ -787,6 +799,7 @@ __global__ void relu_mask_kernel(const float* __restrict__ g, const float* __res
 constexpr int QE_MAX_L = 64;
 __global__ void __launch_bounds__(256) qe_attn_fwd_kernel(QeDev q, const float* __restrict__ wa, const float* __restrict__ ba,
                                                           float* cmd0, float* cmd1, float* cmd2) {
+  pdl_sync();
   extern __shared__ __align__(16) float smem[];
   const int D = 2 * q.H, L = q.L;
   float* wc = smem;       // [D]
@@ -842,6 +855,7 @@ __global__ void __launch_bounds__(256) qe_attn_fwd_kernel(QeDev q, const float* 
 // alpha_i dalpha_i), dalpha_j = dcmd . H[b,j]; zero at masked positions (alpha = 0).
 __global__ void __launch_bounds__(256) qe_attn_bwd_scalars_kernel(QeDev q, const float* dcmd0, const float* dcmd1,
                                                                   const float* dcmd2, float* __restrict__ g_ba) {
+  pdl_sync();
   __shared__ float da[QE_MAX_L];
   const int D = 2 * q.H, L = q.L;
   const int b = blockIdx.x, t = blockIdx.y;
@@ -881,6 +895,7 @@ __global__ void __launch_bounds__(256) qe_attn_bwd_scalars_kernel(QeDev q, const
 __global__ void __launch_bounds__(256) qe_attn_bwd_apply_kernel(QeDev q, const float* __restrict__ wa, const float* dcmd0,
                                                                 const float* dcmd1, const float* dcmd2,
                                                                 float* __restrict__ g_wa) {
+  pdl_sync();
   __shared__ float al[3][QE_MAX_L], dr[3][QE_MAX_L];
   const int D = 2 * q.H, L = q.L;
   const int b = blockIdx.x, d = blockIdx.y * 256 + threadIdx.x;
@@ -1101,11 +1116,11 @@ static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
   if (parts & 1) {
   cudaError_t e = cudaMemsetAsync(q.cnt, 0, sizeof(unsigned) * 2 * q.BC * (H / 32), st);
   if (e != cudaSuccess) return fail(static_cast<int>(e), "drn_qe_forward memset: %s", cudaGetErrorString(e));
-  qe_embed_kernel<<<R, 256, 0, st>>>(q, a->emb);
+  launch_k(qe_embed_kernel, R, 256, 0, st, q, a->emb);
   TRY(check_launch("qe_embed"));
   // xg = E [W_ih ; W_ih_reverse]^T + b_ih + b_hh for all time steps and both directions: ONE tensor-core contraction
   // (split-BF16, deterministic) on the persistent CTA-pair kernel
-  qe_pack_wih_kernel<<<ceil_div(8 * H, 8), 256, 0, st>>>(q, a->w_ih[0], a->w_ih[1], a->b_ih[0], a->b_hh[0], a->b_ih[1], a->b_hh[1]);
+  launch_k(qe_pack_wih_kernel, ceil_div(8 * H, 8), 256, 0, st, q, a->w_ih[0], a->w_ih[1], a->b_ih[0], a->b_hh[0], a->b_ih[1], a->b_hh[1]);
   TRY(check_launch("qe_pack_wih"));
   {
     drn_gemm_t g = qe_gemm_base(DRN_GEMM_ROWS, R);
@@ -1128,13 +1143,13 @@ static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "lstm_fwd (cooperative): %s", cudaGetErrorString(ce));
   } else {
     for (int s = 0; s < L; ++s) {
-      lstm_fwd_kernel<false><<<grid_f, LSTM_THREADS, smem_f, st>>>(q, s, s + 1);
+      launch_k(lstm_fwd_kernel<false>, grid_f, LSTM_THREADS, smem_f, st, q, s, s + 1);
       TRY(check_launch("lstm_fwd_step"));
     }
   }
-  qe_hprev_kernel<<<148, 256, 0, st>>>(q);
+  launch_k(qe_hprev_kernel, 148, 256, 0, st, q);
   TRY(check_launch("qe_hprev"));
-  qe_vgather_kernel<<<B, 256, 0, st>>>(q);
+  launch_k(qe_vgather_kernel, B, 256, 0, st, q);
   TRY(check_launch("qe_vgather"));
   TRY(linear_small(st, q.v, 4 * H, a->w1, 4 * H, a->b1, q.hid, H, B, H, 4 * H, 1));
   {
@@ -1144,7 +1159,7 @@ static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
       TRY(linear_add(lj, q.hid, H, a->w2[t], H, a->b2[t], q.c3 + static_cast<long long>(t) * B * D, D, B, D, H, 0));
     TRY(linear_launch(st, lj));
   }
-  qe_attn_fwd_kernel<<<dim3(B, 3), 256, (D + L) * sizeof(float), st>>>(q, a->wa, a->ba, a->cmd[0], a->cmd[1], a->cmd[2]);
+  launch_k(qe_attn_fwd_kernel, dim3(B, 3), 256, (D + L) * sizeof(float), st, q, a->wa, a->ba, a->cmd[0], a->cmd[1], a->cmd[2]);
   return check_launch("qe_attn_fwd");
 }
 extern "C" int drn_qe_forward(const drn_qe_t* a, void* stream) { return qe_forward_parts(a, 3, stream); }
@@ -1161,9 +1176,9 @@ static int qe_backward_parts(const drn_qe_t* a, int parts, void* stream) {
   const int B = q.B, L = q.L, H = q.H, E = q.E, R = B * L, D = 2 * H;
   if (!a->dcmd[0] || !a->dcmd[1] || !a->dcmd[2]) return fail(DRN_EINVAL, "drn_qe_backward: dcmd missing");
   if (parts & 1) {
-  qe_attn_bwd_scalars_kernel<<<dim3(B, 3), 256, 0, st>>>(q, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_ba);
+  launch_k(qe_attn_bwd_scalars_kernel, dim3(B, 3), 256, 0, st, q, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_ba);
   TRY(check_launch("qe_attn_bwd_scalars"));
-  qe_attn_bwd_apply_kernel<<<dim3(B, ceil_div(D, 256)), 256, 0, st>>>(q, a->wa, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_wa);
+  launch_k(qe_attn_bwd_apply_kernel, dim3(B, ceil_div(D, 256)), 256, 0, st, q, a->wa, a->dcmd[0], a->dcmd[1], a->dcmd[2], a->g_wa);
   TRY(check_launch("qe_attn_bwd_apply"));
   // dhid / dv accumulate from several contractions: one zero-fill of the contiguous [dhid | dhid_pre | dv] scratch
   {
@@ -1179,13 +1194,13 @@ static int qe_backward_parts(const drn_qe_t* a, int parts, void* stream) {
     if (a->g_b2[t]) TRY(sb.add(dc, 1, D, q.one, 0, 0, a->g_b2[t], 1, D, 1, B));
   }
   TRY(sb.launch(st));
-  relu_mask_kernel<<<ceil_div(B * H, 256), 256, 0, st>>>(q.dhid, q.hid, q.dhid_pre, B * H);
+  launch_k(relu_mask_kernel, ceil_div(B * H, 256), 256, 0, st, q.dhid, q.hid, q.dhid_pre, B * H);
   TRY(check_launch("qe relu_mask"));
   TRY(sb.add(q.dhid_pre, H, 1, a->w1, 4 * H, 1, q.dv, 4 * H, B, 4 * H, H));
   if (a->g_w1) TRY(sb.add(q.dhid_pre, 1, H, q.v, 4 * H, 1, a->g_w1, 4 * H, H, 4 * H, B));
   if (a->g_b1) TRY(sb.add(q.dhid_pre, 1, H, q.one, 0, 0, a->g_b1, 1, H, 1, B));
   TRY(sb.launch(st));
-  qe_vscatter_kernel<<<B, 256, 0, st>>>(q);
+  launch_k(qe_vscatter_kernel, B, 256, 0, st, q);
   TRY(check_launch("qe_vscatter"));
   }
   if (!(parts & 2)) return 0;
@@ -1201,7 +1216,7 @@ static int qe_backward_parts(const drn_qe_t* a, int parts, void* stream) {
   } else {
     for (int s = 0; s < L; ++s) {
       const int nq = s == 0 ? 1 : BWD_JQ;
-      lstm_bwd_kernel<false><<<dim3(H / 32, nq, 2 * q.BC), LSTM_THREADS, smem_b, st>>>(q, s, s + 1, nq);
+      launch_k(lstm_bwd_kernel<false>, dim3(H / 32, nq, 2 * q.BC), LSTM_THREADS, smem_b, st, q, s, s + 1, nq);
       TRY(check_launch("lstm_bwd_step"));
     }
   }
@@ -1247,7 +1262,7 @@ static int qe_backward_parts(const drn_qe_t* a, int parts, void* stream) {
     TRY(cb.launch(st));
   }
   if (a->g_emb) {
-    qe_embed_bwd_kernel<<<R, 256, 0, st>>>(q, a->g_emb);
+    launch_k(qe_embed_bwd_kernel, R, 256, 0, st, q, a->g_emb);
     TRY(check_launch("qe_embed_bwd"));
   }
   return 0;
