@@ -214,6 +214,8 @@ struct BnJob {
   long long qa_ps;
   __nv_bfloat16* dy;
   long long dy_ps;
+  const float* partials;  // MODE 2: [prows][2][C] partial column sums written by the contraction epilogue
+  long long prows;
 };
 struct BnJobs {
   int n;
@@ -231,7 +233,9 @@ __device__ __forceinline__ void bn_coef_from_stats(double mean, double var, floa
   coef[3 * C + c] = invstd;
 }
 
-template <int MODE>  // 0: sum y, sum y^2 ; 1: BN backward sums (sum g, sum g*xhat) with g = relu-masked da
+// MODE 0: sum y, sum y^2 ; 1: BN backward sums (sum g, sum g*xhat) with g = relu-masked da ; 2: as 0, but reduced from the
+// per-32-row partial sums the contraction epilogue wrote (J.partials: 1/16 of the bytes of y)
+template <int MODE>
 __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float momentum, float eps, int update_running,
                                                         int STAT_ROWS) {
   pdl_sync();
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
   const BnJob& J = jobs.j[blockIdx.z];
   float* __restrict__ y = J.y;
   const float* __restrict__ da = J.da;
-  const long long rows = J.rows;
+  const long long rows = (MODE == 2) ? J.prows : J.rows;  // rows this kernel walks (MODE 2: rows of the partial-sum buffer)
   const int C = J.C;
   float* __restrict__ coef = J.coef;
   double* __restrict__ sums = J.sums;
@@ -273,7 +277,10 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
         ok[u] = (i0 + 8 * u < STAT_ROWS) && (r < rows);
         v4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         g4[u] = v4[u];
-        if (ok[u]) {
+        if (ok[u] && MODE == 2) {
+          v4[u] = *reinterpret_cast<const float4*>(J.partials + r * 2 * C + c);
+          g4[u] = *reinterpret_cast<const float4*>(J.partials + r * 2 * C + C + c);
+        } else if (ok[u]) {
           v4[u] = *reinterpret_cast<const float4*>(y + r * C + c);
           if (MODE == 0 && J.y2) {  // y <- y + y2 (K-split slices of the contraction), summed once, here
             const float4 w4 = *reinterpret_cast<const float4*>(J.y2 + r * C + c);
@@ -287,7 +294,10 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
       for (int u = 0; u < U; ++u) {
         if (!ok[u]) continue;
         const float v[4] = {v4[u].x, v4[u].y, v4[u].z, v4[u].w};
-        if (MODE == 0) {
+        if (MODE == 2) {
+          s0[0] += v4[u].x; s0[1] += v4[u].y; s0[2] += v4[u].z; s0[3] += v4[u].w;
+          s1[0] += g4[u].x; s1[1] += g4[u].y; s1[2] += g4[u].z; s1[3] += g4[u].w;
+        } else if (MODE == 0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             s0[j] += v[j];
@@ -329,18 +339,19 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const double n = static_cast<double>(rows);
+  const double n = static_cast<double>(J.rows);
+  const long long nrows = J.rows;
   for (int p = 0; p < parts.nparts; ++p) {
     for (int i = t; i < parts.n[p]; i += 256) {
       const int cc = parts.c0[p] + i;
       const double a0 = __ldcg(sums + cc), a1 = __ldcg(sums + C + cc);
       sums[cc] = 0.0;
       sums[C + cc] = 0.0;
-      if (MODE == 0) {
+      if (MODE != 1) {
         const double mean = a0 / n;
         double var = a1 / n - mean * mean;
         if (var < 0) var = 0;
-        const double unbiased = (rows > 1) ? var * n / (n - 1.0) : var;
+        const double unbiased = (nrows > 1) ? var * n / (n - 1.0) : var;
         if (update_running) {
           parts.running_mean[p][i] = (1.f - momentum) * parts.running_mean[p][i] + momentum * static_cast<float>(mean);
           parts.running_var[p][i] = (1.f - momentum) * parts.running_var[p][i] + momentum * static_cast<float>(unbiased);
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(256) col_stats_kernel(const BnJobs jobs, float
         }
       }
     }
-    if (MODE == 0 && update_running && t == 0 && parts.nbt[p]) parts.nbt[p][0] += 1;
+    if (MODE != 1 && update_running && t == 0 && parts.nbt[p]) parts.nbt[p][0] += 1;
   }
   if (t == 0) *counter = 0u;
 }
@@ -854,6 +865,7 @@ static int fill_jobs(BnJobs* t, int n, const drn_bn_job_t* jobs, const char* who
     d.out_a = static_cast<__nv_bfloat16*>(s.out_a); d.a_ps = s.a_plane_stride;
     d.out_qa = static_cast<__nv_bfloat16*>(s.out_qa); d.qa_ps = s.qa_plane_stride;
     d.dy = static_cast<__nv_bfloat16*>(s.dy); d.dy_ps = s.dy_plane_stride;
+    d.partials = s.partials; d.prows = s.partial_rows;
   }
   return 0;
 }
@@ -897,6 +909,22 @@ extern "C" int drn_bn_stats_multi(int n, const drn_bn_job_t* jobs, float momentu
     for (int i = 0; i < n; ++i) cmax = t.j[i].C > cmax ? t.j[i].C : cmax;
     launch_k(bn_eval_coef_kernel, dim3(ceil_div(cmax, 256), n), 256, 0, ST(stream), t, eps);
     return check_launch("bn_eval_coef");
+  }
+  int with_partials = 0;
+  for (int i = 0; i < n; ++i) with_partials += t.j[i].partials ? 1 : 0;
+  if (with_partials) {  // statistics from the partial sums of the contraction epilogue (drn_gemm_t.stats): y is not read
+    if (with_partials != n) return fail(DRN_EINVAL, "drn_bn_stats_multi: partial sums must be given for all jobs of a launch or for none");
+    int cmax = 0;
+    long long pmax = 0;
+    for (int i = 0; i < n; ++i) {
+      if (t.j[i].y2 || t.j[i].prows < 1) return fail(DRN_EINVAL, "drn_bn_stats_multi: job %d: partial sums exclude y2 and need partial_rows >= 1", i);
+      cmax = t.j[i].C > cmax ? t.j[i].C : cmax;
+      pmax = t.j[i].prows > pmax ? t.j[i].prows : pmax;
+    }
+    const int sr = 64;
+    launch_k(col_stats_kernel<2>, dim3(ceil_div(cmax, 128), static_cast<unsigned>((pmax + sr - 1) / sr), n), dim3(32, 8), 0, ST(stream), t,
+             momentum, eps, training == 1 ? 1 : 0, sr);
+    return check_launch("bn_stats(partials)");
   }
   dim3 grid;
   const int sr = stats_grid(t, &grid);

@@ -413,6 +413,9 @@ static int prepare(const drn_gemm_t* g, Prepared* out) {
   kp.a = PlanesView{static_cast<const __nv_bfloat16*>(g->a.ptr), g->a.plane_stride, g->a.B, g->a.T, g->a.P, g->a.C};
   kp.b = PlanesView{static_cast<const __nv_bfloat16*>(g->b.ptr), g->b.plane_stride, g->b.B, g->b.T, g->b.P, g->b.C};
   kp.dbg_lbo = g->dbg_lbo; kp.dbg_sbo = g->dbg_sbo; kp.dbg_kadv = g->dbg_kadv;
+  kp.stats = g->stats;
+  if (kp.stats && (wgrad || kp.split_k > 1))
+    return fail(DRN_EINVAL, "drn_gemm: stats (fused BatchNorm partial sums) need the ROWS form without a K-split");
   if (!wgrad && kp.split_k > 1 && kp.out_split_stride == 0)
     return fail(DRN_EINVAL, "drn_gemm: a ROWS problem splits K only into slices (out_split_stride)");
   if (kp.split_k > 1 && kp.out_split_stride == 0 && kp.out_mode != DRN_OUT_ATOMIC)
@@ -516,10 +519,19 @@ extern "C" int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream) {
   return launch_group(gp, gm, sm_count_cached(), static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int drn_gemm_stats_rows(const drn_gemm_t* g) {
+  Prepared pr;
+  int rc = prepare(g, &pr);
+  if (rc) return rc;
+  if (pr.wgrad) return fail(DRN_EINVAL, "drn_gemm_stats_rows: ROWS form only");
+  return 8 * pr.pair_m_tiles;  // 2 CTAs x 4 epilogue warps x 32 rows per 256-row pair tile
+}
+
 extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
   Prepared pr;
   int rc = prepare(g, &pr);
   if (rc) return rc;
+  if (g->stats && g->engine != 2) return fail(DRN_EINVAL, "drn_gemm: stats are written by the CTA-pair kernel only (engine 2 / drn_gemm_group)");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GemmKParams& kp = pr.kp;
   const bool wgrad = pr.wgrad;

@@ -29,6 +29,7 @@ constexpr int P2_TILE = 256;
 struct PairTile {
   int prob;       // problem of the group
   int b0, t0;     // ROWS: first (sample, time slot) of this CTA's 128 rows
+  int ms;         // ROWS: index of this CTA's 128-row sub-tile
   int m0;         // WGRAD: first A channel (= output row) of this CTA
   int nb;         // first column of B staged by this CTA
   int n0;         // first output column of the pair's tile
@@ -66,6 +67,7 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
   if (!wgrad) {
     t.split = z;                     // K-split of a ROWS problem (conv0 forward: few tiles, very long K)
     const int ms = 2 * mt + rank;    // 128-row sub-tile of this CTA
+    t.ms = ms;
     if (p.Bbm == 1) {
       t.b0 = ms / p.tiles_per_sample;
       t.t0 = (ms % p.tiles_per_sample) * p.Rm;
@@ -268,13 +270,14 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         if (out_base) out_base += p.tap_w[t.tap] * p.out_tap_stride + t.split * p.out_split_stride;
       }
       const uint32_t taddr = tmem_base + as * P2_TILE + (static_cast<uint32_t>(q * 32) << 16);
+      const int stats_blk = (!wgrad && p.stats) ? t.ms * 4 + q : -1;  // 32-row block of the output (BatchNorm partial sums)
 #pragma unroll 1
       for (int c0 = 0; c0 < P2_TILE; c0 += 32) {
         if (t.n0 + c0 >= p.N) break;
         float v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
-        epilogue_chunk(p, v, valid, orow, bb, t.n0 + c0, out_base);
+        epilogue_chunk(p, v, valid, orow, bb, t.n0 + c0, out_base, stats_blk);
       }
       tc_fence_before();
       __syncwarp();

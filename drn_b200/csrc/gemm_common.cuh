@@ -37,6 +37,7 @@ struct GemmKParams {
   long long outp_ld;
   int outp_col0;
   long long outp_plane_stride;
+  float* stats;  // ROWS, optional: per 32-row block partial column sums [blk][2][N] (BatchNorm statistics, see drn_gemm_t)
   int vec_ok;   // 16-byte vector accesses are aligned
   int vec8_ok;  // 32-byte (full-sector) stores are aligned
   PlanesView a, b;
@@ -81,9 +82,24 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
 // ------------------------------------------------------------------------------------------------
 // Epilogue for one 32-column chunk held in registers (one row per thread).
 // ------------------------------------------------------------------------------------------------
+// Column sums over the 32 lanes of a warp of 32 per-lane values: lane j ends up with sum_lanes a[j] in a[0].  Recursive
+// halving -- 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_col_reduce(float (&a)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? a[i] : a[i + s];
+      const float keep = up ? a[i + s] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+// `stats_blk` = index of this warp's 32-row block in p.stats (< 0: no statistics).  Must be called by all 32 lanes.
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, bool valid, long long orow, int bb,
-                                               int ncol0, float* out_base) {
-  if (!valid) return;
+                                               int ncol0, float* out_base, int stats_blk = -1) {
   const int nleft = p.N - ncol0;
   const bool full = nleft >= 32;
   const int cnt = full ? 32 : nleft;
@@ -92,6 +108,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, b
     for (int j = 0; j < 32; ++j)
       if (j < cnt) v[j] += __ldg(p.bias + ncol0 + j);
   }
+  if (stats_blk >= 0) {  // warp-uniform: BatchNorm statistics of the conv output, padding rows excluded
+    float s1[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      s1[j] = valid ? v[j] : 0.f;
+      s2[j] = s1[j] * s1[j];
+    }
+    const int lane = threadIdx.x & 31;
+    warp_col_reduce(s1, lane);
+    warp_col_reduce(s2, lane);
+    if (lane < cnt) {
+      float* st = p.stats + static_cast<long long>(stats_blk) * 2 * p.N + ncol0 + lane;
+      st[0] = s1[0];
+      st[p.N] = s2[0];
+    }
+  }
+  if (!valid) return;
   if (p.out2) {
     float* o2 = p.out2 + orow * p.out2_ld + ncol0;
     if (full && p.vec8_ok) {

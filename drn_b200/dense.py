@@ -46,6 +46,8 @@ class ConvBN:
         self.rows = B * self.t_out
         self.y = torch.empty(B, self.t_out, cout, device=dev)
         self.y2 = None  # second K-split slice of the forward contraction (conv0 only)
+        self.stats = None  # [stats_rows][2][cout] BatchNorm partial sums written by the contraction epilogue (fused_stats)
+        self.stats_rows = 0
         self.coef = torch.empty(5, cout, device=dev)
         self.sums = torch.zeros(2, cout, dtype=torch.float64, device=dev)   # kept zero between uses by the kernels
         self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -173,6 +175,19 @@ class DensePath:
         ws_alloc("towers", self.tower)
         ws_alloc("mix", self.mix)
         ws_alloc("iouc", self.iouc)
+        # BatchNorm statistics fused into the contraction epilogue (drn_gemm_t.stats) for every conv that runs through the grouped
+        # CTA-pair launches without a K-split: the statistics pass then reduces [rows/32][2][C] partial sums instead of re-reading
+        # the conv output.  DRN_FUSED_STATS=0: statistics pass over y (A/B).
+        self.fused_stats = os.environ.get("DRN_FUSED_STATS", "1") == "1"
+        if self.fused_stats:
+            for i in range(3):
+                for blk, a_pl, w in ((self.inner[i], self.Cact[i], self.wp["inner%d" % i]), (self.layer[i], self.I[i], self.wp["layer%d" % i]),
+                                     (self.tower[i], self.Pf[i], self.wp["towers"]), (self.mix[i], self.TW[i], self.wp["mix"]),
+                                     (self.iouc[i], self.MX[i], self.wp["iouc"])):
+                    rows = int(_lib().drn_gemm_stats_rows(C.byref(self._conv_desc(blk, a_pl, w, engine=2))))
+                    if rows < 1:
+                        raise RuntimeError("drn_gemm_stats_rows: " + _lib().drn_last_error().decode())
+                    blk.stats, blk.stats_rows = torch.zeros(rows, 2, blk.cout, device=dev), rows
         self.iou_branch_on = not cfg["is_first_stage"]
         self.gamma = float(cfg["fcos_loss_gamma"][0] if isinstance(cfg["fcos_loss_gamma"], (list, tuple)) else cfg["fcos_loss_gamma"])
         self.alpha = float(cfg["fcos_loss_alpha"][0] if isinstance(cfg["fcos_loss_alpha"], (list, tuple)) else cfg["fcos_loss_alpha"])
@@ -271,12 +286,15 @@ class DensePath:
         torch.cat([p[h + "cls_tower.0.bias"], p[h + "bbox_tower.0.bias"]], out=self.tower_bias)
         self._chk(_lib().drn_pack_conv_weights(len(items), arr, _st()), "pack_conv_weights")
 
-    def _bn_job(self, blk, p, grads=None, da=None, out_a=None, up=None, gate=None, out_qa=None, y2=None):
-        """drn_bn_job_t of one conv block (model/basic_blocks.py:22-30): statistics / apply / backward operands."""
+    def _bn_job(self, blk, p, grads=None, da=None, out_a=None, up=None, gate=None, out_qa=None, y2=None, partials=False):
+        """drn_bn_job_t of one conv block (model/basic_blocks.py:22-30): statistics / apply / backward operands.
+        partials: the statistics come from the partial sums the contraction epilogue wrote into blk.stats."""
         j = L.BnJob()
         j.y, j.B, j.T, j.C = blk.y.data_ptr(), self.B, blk.t_out, blk.cout
         if y2 is not None:
             j.y2 = y2.data_ptr()
+        if partials:
+            j.partials, j.partial_rows = blk.stats.data_ptr(), blk.stats_rows
         j.nparts = len(blk.bn_parts)
         for i, (pre, c0, n) in enumerate(blk.bn_parts):
             a = j.parts[i]
@@ -326,11 +344,14 @@ class DensePath:
         self._chk(_lib().drn_bn_bwd_reduce_multi(len(jobs), arr, _st()), "bn_bwd_reduce")
         self._chk(_lib().drn_bn_bwd_apply_multi(len(jobs), arr, _st()), "bn_bwd_apply")
 
-    def _conv_desc(self, blk, a_pl, w_pl, bias=None, engine=None):
+    def _conv_desc(self, blk, a_pl, w_pl, bias=None, engine=None, stats=False):
         par = blk.stride
         taps = K1 if blk.k == 1 else (K3 if blk.stride == 1 else K3S2)
-        return ops.desc(L.GEMM_ROWS, a_pl.desc(par), w_pl.desc(), self.B, blk.t_out, blk.cout, K=blk.cin, taps=taps,
-                        out=blk.y, bias=bias, engine=engine)
+        g = ops.desc(L.GEMM_ROWS, a_pl.desc(par), w_pl.desc(), self.B, blk.t_out, blk.cout, K=blk.cin, taps=taps,
+                     out=blk.y, bias=bias, engine=engine)
+        if stats:
+            g.stats = blk.stats.data_ptr()
+        return g
 
     def _conv(self, blk, a_pl, w_pl, bias=None):
         self.launches += 1
@@ -441,22 +462,26 @@ class DensePath:
         # FPN top-down (FPN.py:54-69).  The three lateral 1x1 convs are independent -> one grouped launch; their applies run
         # top-down (the upsample-add needs the level above); then the three 3-tap output convs, again one launch.  Every FPN
         # block owns its BatchNorm module, so the order of the running-statistics updates is immaterial here.
-        self._group([self._conv_desc(self.inner[i], self.Cact[i], self.wp["inner%d" % i], engine=2) for i in range(3)])
-        jobs = [self._bn_job(self.inner[i], p, out_a=self.I[i], up=self.I[i + 1] if i < 2 else None) for i in range(3)]
+        fs = training and self.fused_stats  # BatchNorm partial sums from the contraction epilogues (train mode only)
+        self._group([self._conv_desc(self.inner[i], self.Cact[i], self.wp["inner%d" % i], engine=2, stats=fs) for i in range(3)])
+        jobs = [self._bn_job(self.inner[i], p, out_a=self.I[i], up=self.I[i + 1] if i < 2 else None, partials=fs) for i in range(3)]
         self._bn_stats(jobs, training)
         for i in (2, 1, 0):  # the upsample-add reads the level above: applies run top-down
             self._bn_apply([jobs[i]])
-        self._group([self._conv_desc(self.layer[i], self.I[i], self.wp["layer%d" % i], engine=2) for i in range(3)])
-        self._bn_fwd([self._bn_job(self.layer[i], p, out_a=self.Pf[i]) for i in range(3)], training)
+        self._group([self._conv_desc(self.layer[i], self.I[i], self.wp["layer%d" % i], engine=2, stats=fs) for i in range(3)])
+        self._bn_fwd([self._bn_job(self.layer[i], p, out_a=self.Pf[i], partials=fs) for i in range(3)], training)
         # head (fcos.py:93-102): shared weights, per-level batch statistics.  Each shared conv runs its three levels in ONE
         # grouped launch; the BatchNorm statistics kernels follow in level order, which keeps the order of the three
         # running-statistics updates of every shared module (levels ascending) exactly as in the reference.
-        self._group([self._conv_desc(self.tower[l], self.Pf[l], self.wp["towers"], bias=self.tower_bias, engine=2) for l in range(3)])
-        self._bn_fwd([self._bn_job(self.tower[l], p, out_a=self.TW[l]) for l in range(3)], training, shared=True)
-        self._group([self._conv_desc(self.mix[l], self.TW[l], self.wp["mix"], bias=p[h + "mix_fc.0.bias"], engine=2) for l in range(3)])
-        self._bn_fwd([self._bn_job(self.mix[l], p, out_a=self.MX[l]) for l in range(3)], training, shared=True)
-        self._group([self._conv_desc(self.iouc[l], self.MX[l], self.wp["iouc"], bias=p[h + "iou_scores.0.bias"], engine=2) for l in range(3)])
-        self._bn_fwd([self._bn_job(self.iouc[l], p, out_a=self.HI[l]) for l in range(3)], training, shared=True)
+        self._group([self._conv_desc(self.tower[l], self.Pf[l], self.wp["towers"], bias=self.tower_bias, engine=2, stats=fs)
+                     for l in range(3)])
+        self._bn_fwd([self._bn_job(self.tower[l], p, out_a=self.TW[l], partials=fs) for l in range(3)], training, shared=True)
+        self._group([self._conv_desc(self.mix[l], self.TW[l], self.wp["mix"], bias=p[h + "mix_fc.0.bias"], engine=2, stats=fs)
+                     for l in range(3)])
+        self._bn_fwd([self._bn_job(self.mix[l], p, out_a=self.MX[l], partials=fs) for l in range(3)], training, shared=True)
+        self._group([self._conv_desc(self.iouc[l], self.MX[l], self.wp["iouc"], bias=p[h + "iou_scores.0.bias"], engine=2, stats=fs)
+                     for l in range(3)])
+        self._bn_fwd([self._bn_job(self.iouc[l], p, out_a=self.HI[l], partials=fs) for l in range(3)], training, shared=True)
         # cls_logits / bbox_pred / iou_scores.3 on every level: one launch (fcos.py:95-102)
         self._chk(lib.drn_head_proj_fwd(C.byref(self._head_levels()), _vp(p[h + "cls_logits.weight"]), _vp(p[h + "cls_logits.bias"]),
                                         _vp(p[h + "bbox_pred.weight"]), _vp(p[h + "bbox_pred.bias"]),

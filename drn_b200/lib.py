@@ -37,6 +37,7 @@ class GemmDesc(C.Structure):
         ("outp", C.c_void_p), ("outp_ld", C.c_int64), ("outp_col0", C.c_int32), ("outp_plane_stride", C.c_int64),
         ("engine", C.c_int32),
         ("dbg_lbo", C.c_int32), ("dbg_sbo", C.c_int32), ("dbg_kadv", C.c_int32),
+        ("stats", C.c_void_p),
     ]
 
 
@@ -53,7 +54,8 @@ class BnJob(C.Structure):
                 ("coef", C.c_void_p), ("sums", C.c_void_p), ("counter", C.c_void_p), ("bcoef", C.c_void_p),
                 ("up", C.c_void_p), ("up_plane_stride", C.c_int64), ("gate", C.c_void_p),
                 ("out_a", C.c_void_p), ("a_plane_stride", C.c_int64), ("out_qa", C.c_void_p), ("qa_plane_stride", C.c_int64),
-                ("da", C.c_void_p), ("dy", C.c_void_p), ("dy_plane_stride", C.c_int64)]
+                ("da", C.c_void_p), ("dy", C.c_void_p), ("dy_plane_stride", C.c_int64),
+                ("partials", C.c_void_p), ("partial_rows", C.c_int64)]
 
 
 class HeadLevels(C.Structure):

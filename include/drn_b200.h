@@ -102,6 +102,12 @@ typedef struct {
   /* engine: 0 = tcgen05 tensor cores (product path), 1 = fp32 CUDA-core checker kernel (tests only) */
   int32_t engine;
   int32_t dbg_lbo, dbg_sbo, dbg_kadv; /* 0 = defaults; descriptor overrides used by the bring-up sweep test */
+  /* Optional, ROWS form through drn_gemm_group only (split_k == 1): BatchNorm statistics of the conv output fused into the
+   * epilogue.  Every 32-row block of the output writes the partial column sums of v (after the bias) over its valid rows:
+   *   stats[(blk * 2 + 0) * N + n] = sum v,   stats[(blk * 2 + 1) * N + n] = sum v^2,   blk < drn_gemm_stats_rows(g)
+   * (plain stores, deterministic; blocks made of padding rows write zeros).  drn_bn_stats_multi reduces them
+   * (drn_bn_job_t.partials) instead of re-reading the whole tensor. */
+  float* stats;
 } drn_gemm_t;
 
 int drn_gemm(const drn_gemm_t* g, void* stream);
@@ -109,6 +115,8 @@ int drn_gemm(const drn_gemm_t* g, void* stream);
  * the three pyramid levels of a shared head / FPN conv, or the data- and weight-gradients of one layer.  Small problems
  * launched one by one leave most of the 148 SMs idle and each pay pipeline fill and drain. */
 int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream);
+/* number of 32-row blocks (rows of the `stats` buffer, each 2*N floats) a drn_gemm_group launch writes for this problem */
+int drn_gemm_stats_rows(const drn_gemm_t* g);
 
 /* ------------------------------------------------------------------------------------------------
  * HBM-bound kernels (drn_b200/csrc/elementwise.cu).  "planes" arguments are the hi plane pointer of a
@@ -178,6 +186,9 @@ typedef struct {
   const void* up; int64_t up_plane_stride; const float* gate;                  /* apply: FPN upsample-add source, query gate */
   void* out_a; int64_t a_plane_stride; void* out_qa; int64_t qa_plane_stride;  /* apply outputs (planes) */
   const float* da; void* dy; int64_t dy_plane_stride;                          /* backward */
+  /* drn_bn_stats_multi, training: partial column sums written by the contraction epilogue (drn_gemm_t.stats),
+   * [partial_rows][2][C]; when set (for ALL jobs of a launch) the statistics are reduced from them and y is not read */
+  const float* partials; int64_t partial_rows;
 } drn_bn_job_t;
 /* training: 0 = eval (coef from the running statistics); 1 = batch statistics, each job's finaliser also updates its running
  * statistics (jobs must own DISTINCT modules); 2 = batch statistics only -- the caller follows with drn_bn_running_update,
