@@ -135,7 +135,7 @@ def time_dominant_kernel(path, p, reps=10):
     from drn_b200 import ops
     D = path.D
 
-    def launch():  # exactly the call DensePath.forward_core makes for prop_fc (model/main_model.py:59)
+    def launch():  # exactly the call DensePath.forward_main makes for prop_fc (model/main_model.py:59)
         ops.gemm(L.GEMM_ROWS, path.f_pl.desc(), path.wp["prop_fc"].desc(), path.B, path.T, D, K=D, bias=p["prop_fc.bias"],
                  out2=path.Pre, rowscale=path.q[0], outp=path.X0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

@@ -101,7 +101,7 @@ class DensePath:
         self.conv = [ConvBN("backbone_net.forward_conv0", self.C0, c1, 3, 1, B, T, dev),
                      ConvBN("backbone_net.forward_conv1", c1, 2 * c1, 3, 2, B, T, dev),
                      ConvBN("backbone_net.forward_conv2", 2 * c1, 4 * c1, 3, 2, B, T // 2, dev)]
-        if B * T >= 4096:  # enough rows for the K-split of conv0 to pay (see forward_core)
+        if B * T >= 4096:  # enough rows for the K-split of conv0 to pay (see forward_main)
             ys = torch.empty(2, B, T, c1, device=dev)
             self.conv[0].y, self.conv[0].y2 = ys[0], ys[1]
         self.Cact = [Planes.empty(B, self.Tl[i], self.c[i], dev) for i in range(3)]
@@ -507,13 +507,13 @@ class DensePath:
 
     def postprocess(self):
         """Eval only (fcos.py:172-191 -> inference.py:49-136): candidate selection for every (sample, level) in one launch.
-        Returns CPU tensors (det, score, loc, count) after a single device->host copy each."""
+        Returns the device tensors (det [B,3,K,2], score, loc [B,3,K], count [B,3]); model/inference.py:assemble compacts them."""
         cfg = self.cfg
         self._chk(_lib().drn_postprocess(3, self.B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.bbox), _vp(self.iou_raw),
                                          C.c_float(float(cfg["fcos_inference_thr"])), self.top_n,
                                          0 if cfg["is_first_stage"] else 1, _vp(self.post_det), _vp(self.post_score),
                                          _vp(self.post_loc), _vp(self.post_count), _st()), "postprocess")
-        return self.post_det.cpu(), self.post_score.cpu(), self.post_loc.cpu(), self.post_count.cpu()
+        return self.post_det, self.post_score, self.post_loc, self.post_count
 
     # ---------------------------------------------------------------------------------------------------------------
     # backward

@@ -223,8 +223,4 @@ class mainModel(nn.Module):
             loss_dict["loss_iou"] = losses[2]
         if training:
             return None, loss_dict
-        boxes = assemble(*path.postprocess())
-        for d in boxes:
-            for k in ("detections", "scores", "locations"):
-                d[k] = d[k].to(dev)
-        return boxes, loss_dict
+        return assemble(*path.postprocess()), loss_dict

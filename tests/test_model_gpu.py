@@ -225,6 +225,8 @@ def test_postprocess_kernel_matches_oracle(first):
     path.bbox.copy_(torch.cat([x.permute(0, 2, 1).reshape(-1, 2) for x in bbox]))
     path.iou_raw.copy_(torch.cat([x.permute(0, 2, 1).reshape(-1) for x in iou]))
     got = assemble(*path.postprocess())
+    assert all(d["detections"].is_cuda for d in got)  # inference.py:193-196 returns CUDA tensors
+    got = [{k: (v.cpu() if torch.is_tensor(v) else v) for k, v in d.items()} for d in got]
     assert max(len(x) for r in ref for x in r["level"]) == 32  # the top-k branch is exercised
     for g, r in zip(got, ref):
         assert g["detections"].shape == r["detections"].shape
