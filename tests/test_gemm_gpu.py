@@ -231,3 +231,55 @@ def test_rows_k_split_slices():
     assert not torch.isnan(ys).any()
     assert float(ys[1].abs().max()) > 0
     assert (ys.double().sum(0) - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("B,T,N", [(4, 256, 512), (3, 96, 256), (5, 32, 512), (2, 200, 256)])
+def test_fused_batchnorm_partial_sums(B, T, N):
+    """drn_gemm_t.stats: the epilogue's per-32-row partial column sums (after the bias, padding rows excluded) add up to the
+    column sums / sums of squares of the conv output -- ragged last tiles (T = 96, 200), several samples per tile (T = 32) and an
+    odd number of 128-row sub-tiles -- and drn_bn_stats_multi reduces them to the same BatchNorm coefficients and running
+    statistics as its pass over y."""
+    import ctypes as C
+    Cin = 256
+    a = Planes.from_float(_rand(B, T, Cin, seed=51))
+    w = Planes.from_float(_rand(3, N, Cin, seed=52, scale=(3 * Cin) ** -0.5))
+    bias = _rand(N, seed=53)
+    out = torch.full((B, T, N), float("nan"), device=DEV)
+    d = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=out, bias=bias, engine=2)
+    lib = L.load()
+    rows = lib.drn_gemm_stats_rows(C.byref(d))
+    assert rows >= (B * T + 31) // 32
+    stats = torch.full((rows, 2, N), float("nan"), device=DEV)
+    d.stats = stats.data_ptr()
+    assert ops.gemm_group([d]) == 1
+    torch.cuda.synchronize()
+    assert not torch.isnan(stats).any()
+    y = out.double().view(-1, N)
+    s = stats.double().sum(0)
+    assert (s[0] - y.sum(0)).abs().max().item() <= 1e-5 * y.abs().sum(0).max().item()
+    assert (s[1] - (y * y).sum(0)).abs().max().item() <= 1e-5 * (y * y).sum(0).max().item()
+    # the statistics finaliser: partial sums vs a pass over y (same module state before each)
+    def job(partials):
+        j = L.BnJob()
+        j.y, j.B, j.T, j.C, j.nparts = out.data_ptr(), B, T, N, 1
+        st = dict(gamma=_rand(N, seed=54), beta=_rand(N, seed=55), rm=torch.zeros(N, device=DEV), rv=torch.ones(N, device=DEV),
+                  nbt=torch.zeros(1, dtype=torch.int64, device=DEV), coef=torch.zeros(5, N, device=DEV),
+                  sums=torch.zeros(2, N, dtype=torch.float64, device=DEV), cnt=torch.zeros(1, dtype=torch.int32, device=DEV))
+        p = j.parts[0]
+        p.c0, p.n, p.gamma, p.beta = 0, N, st["gamma"].data_ptr(), st["beta"].data_ptr()
+        p.running_mean, p.running_var, p.num_batches_tracked = st["rm"].data_ptr(), st["rv"].data_ptr(), st["nbt"].data_ptr()
+        j.coef, j.sums, j.counter = st["coef"].data_ptr(), st["sums"].data_ptr(), st["cnt"].data_ptr()
+        if partials:
+            j.partials, j.partial_rows = stats.data_ptr(), rows
+        arr = (L.BnJob * 1)(j)
+        L.check(lib.drn_bn_stats_multi(1, arr, C.c_float(0.1), C.c_float(1e-5), 1, L.stream_ptr()), "bn_stats")
+        torch.cuda.synchronize()
+        return st
+    ref, got = job(False), job(True)
+    for k in ("coef", "rm", "rv"):
+        assert (got[k] - ref[k]).abs().max().item() <= 2e-6 * max(ref[k].abs().max().item(), 1.0), k
+    assert int(got["nbt"]) == 1 and float(got["sums"].abs().max()) == 0.0 and int(got["cnt"]) == 0
+    # wrong use is rejected: statistics with a K-split / through the one-tile-per-CTA engine
+    d3 = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=out, engine=3)
+    d3.stats = stats.data_ptr()
+    assert lib.drn_gemm(C.byref(d3), L.stream_ptr()) == -1
