@@ -519,6 +519,9 @@ extern "C" int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream) {
   return launch_group(gp, gm, sm_count_cached(), static_cast<cudaStream_t>(stream));
 }
 
+namespace drn { void set_pair_clusters(int n); }
+extern "C" void drn_set_pair_clusters(int n) { drn::set_pair_clusters(n); }
+
 extern "C" int drn_gemm_stats_rows(const drn_gemm_t* g) {
   Prepared pr;
   int rc = prepare(g, &pr);

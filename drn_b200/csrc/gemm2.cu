@@ -289,6 +289,11 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
 }
 
+// Process-wide cap on the SM pairs the persistent kernel occupies (0 = none), set by the caller around individual launches:
+// the data-parallel schedule leaves 4 of the 74 pairs to NCCL while the prop_fc weight gradient runs (drn_b200/dense.py).
+static int g_pair_clusters = 0;
+void set_pair_clusters(int n) { g_pair_clusters = n > 0 ? n : 0; }
+
 int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -304,6 +309,7 @@ int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaS
     cap = e ? atoi(e) : 0;
   }
   if (cap > 0 && clusters > cap) clusters = cap;
+  if (g_pair_clusters > 0 && clusters > g_pair_clusters) clusters = g_pair_clusters;
   if (clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
   launch_k(gemm_pair_kernel, 2 * clusters, P2_THREADS, P2_SMEM, st, gp, gm, num_tiles);

@@ -561,9 +561,11 @@ class DensePath:
         """Gradients produced by `backward_tail` (everything else is final when `backward(..., tail=False)` returns)."""
         return {n for n in names if n.startswith("qInput") or n.startswith("query_encoder.")}
 
-    def backward(self, p, grads, upstream, tail=True):
+    def backward(self, p, grads, upstream, tail=True, propfc=True):
         """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
-        upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou).  tail=False stops before `backward_tail`."""
+        upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou).  tail=False stops before `backward_tail`;
+        propfc=False also leaves out the prop_fc weight gradient (`backward_propfc`): the data-parallel schedule runs the three
+        parts as separate graphs with an all-reduce started after each."""
         lib, B = _lib(), self.B
         h = "fcos.head."
         F = self.F
@@ -633,12 +635,26 @@ class DensePath:
         defer = tail and self.side is not None
         if not defer:
             self._unpack_wgrads(grads, iou_on)
-        # prop_fc weight gradient: [D x (B*T)] x [(B*T) x D], the largest contraction of the backward pass
-        self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
-                   out_ld=self.D, out_tap_stride=0)
+        if propfc:
+            self.backward_propfc(grads)
         self.launches_bwd = self.launches
         if tail:
             self.backward_tail(p, grads, unpack=(iou_on,) if defer else None)
+
+    def backward_propfc(self, grads, pair_clusters=0):
+        """prop_fc weight gradient: [D x (B*T)] x [(B*T) x D], the largest contraction of the backward pass.  pair_clusters > 0
+        confines the persistent kernel to that many SM pairs (data parallel: the rest run the NCCL all-reduce of the gradients
+        that are already complete)."""
+        B = self.B
+        if pair_clusters:
+            _lib().drn_set_pair_clusters(pair_clusters)
+        try:
+            self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
+                       out_ld=self.D, out_tap_stride=0)
+        finally:
+            if pair_clusters:
+                _lib().drn_set_pair_clusters(0)
+        self.launches_bwd = self.launches
 
     def _unpack_wgrads(self, grads, iou_on):
         """Weight-gradient workspaces [slices][k][O][C] -> parameter layout [O][C][k] (sum of the K-split / level slices), one

@@ -4,9 +4,9 @@ NVLink/NVSwitch.  BatchNorm statistics and the loss norma
 reference's own (nominal) multi-GPU mode, nn.DataParallel at main.py:99, computes.
 
 The path (query encoder included) produces all of its gradients in one flat buffer (model/main_model.py:
-_run_backward).  The backward runs in two parts: when the first (head, FPN, backbone) ends, its gradients -- a contiguous
-region of the buffer -- are all-reduced on NCCL's stream WHILE the tail (prop_fc weight gradient, gates, query encoder: ~0.9 ms)
-runs; the tail's two regions follow.  Gradients
+_run_backward).  The backward runs in three parts, each followed by the all-reduce of the contiguous region it completed, on
+NCCL's stream: head / FPN / backbone gradients are reduced WHILE the prop_fc weight gradient (0.53 ms) runs, prop_fc.weight's
+WHILE the tail (gates, query encoder: ~0.35 ms) runs; the tail's region follows.  Gradients
 that autograd produced outside that buffer (none for the reference model; kept for wrapped modules that add their own
 parameters) are all-reduced in `finish_gradient_sync()` after `loss.backward()`.
 """

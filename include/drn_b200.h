@@ -115,6 +115,10 @@ int drn_gemm(const drn_gemm_t* g, void* stream);
  * the three pyramid levels of a shared head / FPN conv, or the data- and weight-gradients of one layer.  Small problems
  * launched one by one leave most of the 148 SMs idle and each pay pipeline fill and drain. */
 int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream);
+/* Cap (0 = none) on the SM pairs the persistent CTA-pair kernel occupies in the launches that follow (process-wide; one host
+ * thread per process).  The data-parallel schedule confines the prop_fc weight gradient to 70 of the 74 pairs so that the
+ * NCCL all-reduce of the gradients already complete runs beside it. */
+void drn_set_pair_clusters(int n);
 /* number of 32-row blocks (rows of the `stats` buffer, each 2*N floats) a drn_gemm_group launch writes for this problem */
 int drn_gemm_stats_rows(const drn_gemm_t* g);
 

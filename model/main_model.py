@@ -53,18 +53,24 @@ def _run_forward(path, p, training, use_graphs, tokens, lengths, feats, pse, gt)
 def _run_backward(path, p, names, upstream, use_graphs, dp=None):
     """Backward of the path into ONE flat gradient buffer.  Layout:
         [A: accumulated, produced by the tail (gates, query encoder)][B: accumulated, first part][C: stored, first part]
-    A+B are zero-filled every backward (atomics / += land there); C (conv weights, prop_fc.weight) is fully overwritten by its
-    kernels.  Every slot starts on a 32-byte boundary (full-sector vector stores in the contraction epilogues).
-    Data parallel (dp = drn_b200.parallel.DataParallelDRN): the backward runs as TWO graphs.  When the first (head, FPN,
-    backbone, prop_fc) ends, its gradients B+C -- 77 % of the bytes, one contiguous region -- are all-reduced on NCCL's stream
-    WHILE the tail runs: a ~0.4 ms latency-bound chain of small kernels that leaves most SMs free for the collective.  The
-    tail's region A follows."""
+        [D: prop_fc.weight]
+    A+B are zero-filled every backward (atomics / += land there); C (conv weights) and D are fully overwritten by their kernels.
+    Every slot starts on a 32-byte boundary (full-sector vector stores in the contraction epilogues).
+    Data parallel (dp = drn_b200.parallel.DataParallelDRN): the backward runs as THREE graphs with an all-reduce on NCCL's
+    stream started behind each of them:
+        head, FPN, backbone                 -> B+C (51 MB) reduced WHILE the prop_fc weight gradient runs
+                                               (DRN_DP_PAIR_CLUSTERS=n confines that contraction to n of the 74 SM pairs so that
+                                               NCCL's CTAs find room at once: measured neutral at 2 and 8 GPUs, default off)
+        prop_fc weight gradient (0.53 ms)   -> D (67 MB) reduced WHILE the tail runs: a ~0.35 ms latency-bound chain of small
+                                               kernels that leaves most SMs free
+        tail (gates, query encoder)         -> A (35 MB)."""
     key = ("bwd", _sig(p), tuple(names), dp is not None)
     ent = path.graphs.get(key)
     if ent is None:
         stored, tailn = path.stored_grad_names(names), path.part2_grad_names(names)
+        last = {"prop_fc.weight"} & set(names)
         groups = [[n for n in names if n in tailn], [n for n in names if n not in tailn and n not in stored],
-                  [n for n in names if n not in tailn and n in stored]]
+                  [n for n in names if n not in tailn and n in stored and n not in last], [n for n in names if n in last]]
         pad = lambda k: (k + 7) // 8 * 8  # noqa: E731
         bounds = [0]
         for g_ in groups:
@@ -75,32 +81,41 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
             for n in g_:
                 grads[n] = flat[o:o + p[n].numel()].view_as(p[n])
                 o += pad(p[n].numel())
-        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:], "tail": flat[:bounds[1]]}
+        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:bounds[3]], "propfc": flat[bounds[3]:], "tail": flat[:bounds[1]]}
+        pc = int(os.environ.get("DRN_DP_PAIR_CLUSTERS", "0"))
         path.upstream.copy_(upstream)
         path.backward(p, grads, path.upstream)
-        g1 = g2 = None
+        g1 = g1b = g2 = None
         if use_graphs:
             g1 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 regions["zero"].zero_()
-                path.backward(p, grads, path.upstream, tail=dp is None)
+                path.backward(p, grads, path.upstream, tail=dp is None, propfc=dp is None)
             if dp is not None:
+                g1b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1b):
+                    path.backward_propfc(grads, pair_clusters=pc)
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2):
                     path.backward_tail(p, grads)
         if dp is not None:  # the eager run above produced a complete local gradient: reduce it in one go
             dp.reduce_regions([flat])
-        path.graphs[key] = (g1, g2, flat, grads, regions)
+        path.graphs[key] = (g1, g1b, g2, flat, grads, regions, pc)
         return flat, grads
-    g1, g2, flat, grads, regions = ent
+    g1, g1b, g2, flat, grads, regions, pc = ent
     path.upstream.copy_(upstream)
     if g1 is not None:
         g1.replay()
     else:
         regions["zero"].zero_()
-        path.backward(p, grads, path.upstream, tail=dp is None)
+        path.backward(p, grads, path.upstream, tail=dp is None, propfc=dp is None)
     if dp is not None:
-        work = dp.reduce_regions([regions["first"]], wait=False)  # overlaps the tail below
+        work = dp.reduce_regions([regions["first"]], wait=False)  # overlaps the prop_fc weight gradient below
+        if g1b is not None:
+            g1b.replay()
+        else:
+            path.backward_propfc(grads, pair_clusters=pc)
+        work += dp.reduce_regions([regions["propfc"]], wait=False)  # overlaps the tail below
         if g2 is not None:
             g2.replay()
         else:
