@@ -295,7 +295,8 @@ int drn_clip_adam_chunk(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Query encoder (drn_b200/csrc/query.cu): model/language_module.py:27-62 (QueryEncoder.forward +
- * extract_textual_command) with model/ops.py:16-25,74-85, forward and backward, exact fp32 FMA arithmetic.
+ * extract_textual_command) with model/ops.py:16-25,74-85, forward and backward (recurrence, attention and backward
+ * contractions in exact fp32 FMA arithmetic; input projection and forward linears in split-BF16 products).
  * ---------------------------------------------------------------------------------------------- */
 /* Small fp32 contraction on CUDA cores: C[m][n] (= | +=) sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias[n]), optional ReLU.
  * accumulate = 1 adds into C.  Serves nn.Linear forward (x W^T), data gradient (dy W) and weight gradient (dy^T x) of the
