@@ -22,6 +22,7 @@ sys.path.insert(0, REPO)
 import torch  # noqa: E402
 
 B_PER_GPU, T, MAX_LEN = 32, 256, 10
+METRIC = "video-query pairs/sec (fwd+bwd) at T=256 C3D-4096"
 WORKLOAD = "configs[1]: first-stage training fwd+bwd, batch 32/GPU, T=256, C3D-4096, 10-word GloVe-300 queries"
 FLOP_PER_PAIR = 31.3e9  # algorithmic fp32 FLOPs fwd+bwd stage 1 at T=256
 
@@ -118,7 +119,7 @@ def run_reference(args):
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     v = B_PER_GPU / (ms / 1e3)
-    line = {"impl": "reference", "metric": "video-query pairs/sec (fwd+bwd)", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch": B_PER_GPU, "T": T},
@@ -310,7 +311,7 @@ def run_ours(args):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     value = world * B_PER_GPU / (ms * 1e-3)
     line = {
-        "metric": "video-query pairs/sec (fwd+bwd) at T=256 C3D-4096", "value": value, "unit": "pairs/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (split-BF16 x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "T": T, "stage": 1,
