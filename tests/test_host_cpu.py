@@ -49,6 +49,7 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(drn_planes_t), sizeof(drn_gemm_t), offsetof(drn_gemm_t, b), offsetof(drn_gemm_t, tap_w),
          offsetof(drn_gemm_t, out_split_stride), offsetof(drn_gemm_t, outp_plane_stride), offsetof(drn_gemm_t, dbg_kadv),
          sizeof(drn_bn_part_t), offsetof(drn_bn_part_t, dbeta), sizeof(drn_pack_item_t), offsetof(drn_pack_item_t, slice_stride));
+  printf("%zu %zu %zu\n", offsetof(drn_gemm_t, stats), offsetof(drn_bn_job_t, partials), offsetof(drn_bn_job_t, partial_rows));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -63,7 +64,8 @@ int main(void) {
     from drn_b200.optim import _Item
     mine = [ctypes.sizeof(_Item), _Item.update.offset, ctypes.sizeof(L.SgemmJob), L.SgemmJob.bias.offset, ctypes.sizeof(L.LinearJob), L.LinearJob.relu.offset, ctypes.sizeof(HL), HL.tower.offset, HL.d_tower.offset, ctypes.sizeof(J), J.coef.offset, J.out_qa.offset, J.dy_plane_stride.offset, ctypes.sizeof(L.Qe), L.Qe.tokens.offset, L.Qe.g_w2.offset, L.Qe.workspace_bytes.offset, ctypes.sizeof(L.Planes), ctypes.sizeof(G), G.b.offset, G.tap_w.offset, G.out_split_stride.offset,
             G.outp_plane_stride.offset, G.dbg_kadv.offset, ctypes.sizeof(L.BnPart), L.BnPart.dbeta.offset,
-            ctypes.sizeof(L.PackItem), L.PackItem.slice_stride.offset]
+            ctypes.sizeof(L.PackItem), L.PackItem.slice_stride.offset,
+            G.stats.offset, J.partials.offset, J.partial_rows.offset]
     assert [int(x) for x in out] == mine
 
 
@@ -162,3 +164,23 @@ def test_reference_checkpoint_round_trip():
     bad = {"state_dict": {"module.prop_fc.bias": torch.zeros(7)}}
     with pytest.raises(RuntimeError, match="shape"):
         load_reference_checkpoint(m, bad)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference algorithm on the host cores: the one place besides tests / smoke where the
+    oracle may run) prints ONE JSON line with the own arm's metric / unit / workload and the keys the driver reads."""
+    import json
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()))
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, check=True, env=env, cwd=REPO, timeout=600).stdout.strip().splitlines()
+    assert len(out) == 1
+    d = json.loads(out[0])
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(REPO, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    assert d["impl"] == "reference" and d["metric"] == b.METRIC and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["config"]["workload"] == b.WORKLOAD and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
