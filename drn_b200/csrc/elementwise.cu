@@ -614,7 +614,12 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_rows_kernel(const BnJ
 // rows per thread of the row-walking kernels (0: some job's channel count does not fit them -> flat kernels); *gx = grid.x
 static int rows_walk_plan(const BnJobs& t, unsigned* gx) {
   long long gmax = 0;
-  const int rpt = 8;
+  static int rpt_env = -1;  // DRN_BN_RPT: rows per thread (tuning; cold-cache ncu favours fewer rows = more CTAs, r01 v17)
+  if (rpt_env < 0) {
+    const char* e = getenv("DRN_BN_RPT");
+    rpt_env = e ? atoi(e) : 0;
+  }
+  const int rpt = (rpt_env >= 1 && rpt_env <= 64) ? rpt_env : 8;
   for (int i = 0; i < t.n; ++i) {
     const int C8 = t.j[i].C / 8;
     if (t.j[i].C % 8 || C8 < 1 || C8 > EW_THREADS || (C8 & (C8 - 1))) return 0;
