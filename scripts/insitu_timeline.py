@@ -5,6 +5,10 @@ L2-resident inside a real step.  Here the step runs eagerly (DRN_NO_GRAPHS=1) wi
 call (drn_b200.lib.check is the single choke point); the host stays ahead of the GPU, so the interval between two consecutive
 events is the GPU time of the call in between (one call = one kernel, except the query encoder's two multi-kernel calls).
 
+CAVEAT (measured, r01 v15): the eager step is host-bound around the small kernels (4.9 ms against 3.7 ms replayed from the
+graphs: a ctypes call + event record costs ~10 us), so only the intervals of calls longer than ~20 us are GPU time; for the
+small kernels use the ncu section captures (scripts/gpu_ncu_small.sh), which have the opposite bias (cold caches).
+
     DRN_NO_GRAPHS=1 python scripts/insitu_timeline.py [--steps 5]
 Prints per-call medians over the steps, aggregated by call name, as one JSON object."""
 import argparse
