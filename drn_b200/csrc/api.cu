@@ -20,6 +20,20 @@ bool pdl_enabled() {
 
 using namespace drn;
 
+// One thread writes the GPU's nanosecond global timer: enqueued between the kernels of a step (also inside a CUDA-graph
+// capture) it gives their in-situ durations -- warm caches, back to back -- which neither ncu (cold, serialised) nor host
+// events around eager launches (host-bound) can (scripts/insitu_timeline.py).
+__global__ void timestamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+extern "C" int drn_timestamp(uint64_t* slot, void* stream) {
+  if (!slot) return fail(DRN_EINVAL, "drn_timestamp: null slot");
+  timestamp_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
+  return check_launch("timestamp");
+}
+
 extern "C" int drn_version(void) { return DRN_VERSION; }
 
 extern "C" const char* drn_last_error(void) { return err_buf(); }

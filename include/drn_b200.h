@@ -115,6 +115,9 @@ int drn_gemm(const drn_gemm_t* g, void* stream);
  * the three pyramid levels of a shared head / FPN conv, or the data- and weight-gradients of one layer.  Small problems
  * launched one by one leave most of the 148 SMs idle and each pay pipeline fill and drain. */
 int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream);
+/* Profiling aid: a one-thread kernel that stores the GPU's %globaltimer (ns) into *slot (device memory).  Enqueued between
+ * the kernels of a step -- also inside a CUDA-graph capture -- it yields their in-situ durations (scripts/insitu_timeline.py). */
+int drn_timestamp(uint64_t* slot, void* stream);
 /* Cap (0 = none) on the SM pairs the persistent CTA-pair kernel occupies in the launches that follow (process-wide; one host
  * thread per process).  The data-parallel schedule confines the prop_fc weight gradient to 70 of the 74 pairs so that the
  * NCCL all-reduce of the gradients already complete runs beside it. */

@@ -76,6 +76,9 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         for g_ in groups:
             bounds.append(bounds[-1] + sum(pad(p[n].numel()) for n in g_))
         flat = torch.zeros(bounds[-1], device=upstream.device, dtype=torch.float32)
+        if not hasattr(path, "flat_storages"):
+            path.flat_storages = set()
+        path.flat_storages.add(flat.untyped_storage().data_ptr())
         grads, o = {}, 0
         for g_ in groups:
             for n in g_:
@@ -140,11 +143,31 @@ class _DenseFn(torch.autograd.Function):
         names = model._trainable_names
         assert len(names) == ctx.nparams
         p = model._tensor_dict()
-        # gradients are produced in ONE flat static buffer (graph-replayable, and the unit of the data-parallel all-reduce);
-        # autograd copies the returned views into param.grad, so the buffer can be reused by the next step.
+        # Gradients are produced in ONE flat static buffer (graph-replayable, and the unit of the data-parallel all-reduce).
+        # They are handed to the parameters as VIEWS of that buffer (param.grad = view) instead of being returned to autograd,
+        # whose AccumulateGrad would clone every one of them: ~60 copy kernels, 153 MB read + written, 0.29 ms of a 3.67 ms step
+        # (in-graph timestamps, profiles/r01_insitu_v17.json).  The views stay valid until the next backward of this path; a
+        # gradient that is still attached to its parameter then (no zero_grad in between: gradient accumulation, which the
+        # reference driver never does, main.py:236-244) is detached from the buffer first and accumulated into afterwards.
+        # DRN_GRAD_VIEWS=0: return the gradients to autograd (copies).
         # data parallel: model._dp (drn_b200/parallel.py) all-reduces the flat gradient buffer, overlapped with the tail
+        views = os.environ.get("DRN_GRAD_VIEWS", "1") == "1"
+        if views:
+            owned = getattr(path, "flat_storages", ())
+            for n in names:
+                old = p[n].grad
+                if old is not None and old.untyped_storage().data_ptr() in owned:
+                    p[n].grad = old.clone()
         flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs, dp=model._dp)
-        return (None,) * 8 + tuple(grads[n] for n in names)
+        if not views:
+            return (None,) * 8 + tuple(grads[n] for n in names)
+        for n in names:
+            prm = p[n]
+            if prm.grad is None:
+                prm.grad = grads[n]
+            else:
+                prm.grad.add_(grads[n])
+        return (None,) * (8 + len(names))
 
 
 class mainModel(nn.Module):
