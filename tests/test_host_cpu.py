@@ -184,3 +184,53 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["config"]["workload"] == b.WORKLOAD and d["value"] > 0 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_gradients_are_attached_as_views_and_still_accumulate(monkeypatch):
+    """_DenseFn.backward hands the path's gradients to the parameters as views of the flat buffer (no autograd clone).  With
+    CPU stand-ins for the two device schedules: the view is attached, zero_grad/None + a new backward overwrites it, and a
+    backward WITHOUT zeroing in between accumulates old + new (the buffer is overwritten by every backward, so the old
+    gradient must have been detached from it first)."""
+    import types
+    from model import main_model as MM
+
+    w = torch.nn.Parameter(torch.arange(6.0).view(2, 3))
+    v = torch.nn.Parameter(torch.ones(4))
+    model = types.SimpleNamespace(_trainable_names=["w", "v"], use_graphs=False, _dp=None, _tensor_dict=lambda: {"w": w, "v": v})
+    flat = torch.zeros(16)
+    grads = {"w": flat[0:6].view(2, 3), "v": flat[8:12]}
+    path = types.SimpleNamespace(losses=torch.zeros(8), flat_storages={flat.untyped_storage().data_ptr()})
+    scale = {"k": 1.0}
+
+    def fake_forward(path_, p, training, use_graphs, *inputs):
+        path_.losses[:3] = torch.tensor([1.0, 2.0, 3.0])
+
+    def fake_backward(path_, p, names, upstream, use_graphs, dp=None):
+        flat.zero_()                       # what every real backward does: the buffer is rewritten
+        grads["w"].copy_(scale["k"] * upstream[0] * torch.ones(2, 3))
+        grads["v"].copy_(scale["k"] * upstream[1] * torch.full((4,), 2.0))
+        return flat, grads
+    monkeypatch.setattr(MM, "_run_forward", fake_forward)
+    monkeypatch.setattr(MM, "_run_backward", fake_backward)
+    dummy = torch.zeros(1)
+
+    def step():
+        losses = MM._DenseFn.apply(model, path, True, dummy, dummy, dummy, dummy, dummy, w, v)
+        (losses[0] + 3.0 * losses[1]).backward()
+    step()
+    assert w.grad.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()   # a view, not a clone
+    assert torch.equal(w.grad, torch.ones(2, 3)) and torch.equal(v.grad, torch.full((4,), 6.0))
+    w.grad = v.grad = None
+    scale["k"] = 2.0
+    step()
+    assert torch.equal(w.grad, torch.full((2, 3), 2.0)) and torch.equal(v.grad, torch.full((4,), 12.0))
+    scale["k"] = 5.0
+    step()                                  # no zeroing in between: 2 + 5, 12 + 30
+    assert torch.equal(w.grad, torch.full((2, 3), 7.0)) and torch.equal(v.grad, torch.full((4,), 42.0))
+    assert w.grad.untyped_storage().data_ptr() != flat.untyped_storage().data_ptr()
+    # DRN_GRAD_VIEWS=0: autograd receives the gradients and clones them
+    monkeypatch.setenv("DRN_GRAD_VIEWS", "0")
+    w.grad = v.grad = None
+    scale["k"] = 1.0
+    step()
+    assert torch.equal(w.grad, torch.ones(2, 3)) and w.grad.untyped_storage().data_ptr() != flat.untyped_storage().data_ptr()
