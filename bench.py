@@ -101,30 +101,63 @@ def build_inputs(world_rank):
     return cfg, sd, batch
 
 
-def run_reference(args):
-    """The reference algorithm on the host CPU (oracle port of the reference's PyTorch code; the reference package itself
-    lives only in the build container).  A bounded sample: `steps` fwd+bwd steps of the same B=32 batch."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import drn_oracle as O
+def workload_config(world):
+    """The `config` object of BOTH arms (identical by construction: the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "T": T, "stage": 1, "parallelism": "dp%d" % world,
+            "l2": "per-step working set ~1.9 GB >> 126 MB L2 (no explicit flush needed)"}
+
+
+def time_reference_cpu(steps, warmup):
+    """Forward + backward of the same B=32, T=256 batch on the host cores.  kind "reference": the UNMODIFIED reference package
+    from oracle/_ref/drn_reference.zip (packed by build(); a subprocess with no GPU visible, oracle/time_reference.py);
+    kind "port": the oracle restatement, when the archive is absent.  Returns (ms_per_step, cores, kind, description)."""
     cores = os.cpu_count()
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable, os.path.join(REPO, "oracle", "time_reference.py"), "--steps", str(steps), "--warmup", str(warmup),
+                            "--B", str(B_PER_GPU), "--T", str(T)], capture_output=True, text=True, timeout=1200, env=env)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        if "ms_per_step" in d:
+            return d["ms_per_step"], d["cores"], "reference", d["impl"]
+        why = d.get("unavailable", "no timing")
+    except Exception as e:  # noqa: BLE001
+        why = "reference subprocess failed: %r" % (e,)
+    sys.stderr.write("bench: reference package not usable (%s); timing the oracle port instead\n" % why)
+    from oracle import drn_oracle as O
     torch.set_num_threads(cores)
     cfg, sd, batch = build_inputs(0)
     times = []
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         t0 = time.perf_counter()
         O.forward_backward(sd, cfg, batch, stage=1)
-        if i >= args.warmup:
+        if i >= warmup:
             times.append(time.perf_counter() - t0)
-    ms = 1e3 * sum(times) / len(times)
+    return 1e3 * sum(times) / len(times), cores, "port", "oracle/drn_oracle.py restatement (CPU, torch fp32)"
+
+
+def run_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores, all threads, same config / metric / unit as
+    our arm.  Each step is a full B=32, T=256 forward + backward (~0.6 s): the requested steps are capped so the arm stays
+    bounded, and the line says so (`steps_requested`, `steps_capped`)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    steps, warmup = min(args.steps, 10), min(max(args.warmup, 1), 2)
+    ms, cores, kind, what = time_reference_cpu(steps, warmup)
     v = B_PER_GPU / (ms / 1e3)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "steps_requested": args.steps, "warmup_requested": args.warmup,
+            "steps_capped": steps != args.steps or warmup != args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch": B_PER_GPU, "T": T},
-            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": "%d fwd+bwd steps of one B=32,T=256 batch, torch CPU fp32, %d threads" % (args.steps, cores)},
+            "config": workload_config(world),
+            "note": "CPU arm: ONE process on the host cores runs one B=32 batch per step whatever n_gpus is (the reference has no "
+                    "multi-process mode); value = 32 / step time",
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind,
+                             "sample": "%d fwd+bwd steps of one B=32,T=256 batch after %d warm-up, %s, %d threads" % (steps, warmup, what, cores)},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -293,10 +326,28 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    # ---- sustained leg: >= 3 s of back-to-back steps (device-resident inputs) with its own clock samples, so that step-level
+    # ---- roofline fractions can be quoted against the peak measured in the same regime (burst for the short run above)
+    sus_steps = max(args.steps, int(args.sustain_seconds * 1e3 / max(ms, 1e-3)) + 1) if args.sustain_seconds > 0 else 0
+    sustained = None
+    if sus_steps:
+        s2 = ClockSampler(local)
+        s2.start()
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for _ in range(sus_steps):
+            step(dev_batch)
+        e5.record()
+        barrier()
+        s2.stop_flag = True
+        s2.join(timeout=2)
+        sustained = (e4.elapsed_time(e5) / sus_steps, sus_steps, s2.summary())
+
+    t = torch.tensor([ms, ms_e2e, sustained[0] if sustained else 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_sus = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -314,10 +365,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (split-BF16 x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "T": T, "stage": 1,
-                   "parallelism": "dp%d" % world, "l2": "per-step working set ~1.9 GB >> 126 MB L2 (no explicit flush needed)",
-                   "algorithmic_tflops_per_s": value * FLOP_PER_PAIR / 1e12,
-                   "fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3)},
+        "config": workload_config(world),
+        "diag": {"algorithmic_tflops_per_s": value * FLOP_PER_PAIR / 1e12, "fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3)},
         "clocks": sampler.summary(),
         "e2e": {"value": world * B_PER_GPU / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
@@ -330,22 +379,37 @@ def run_ours(args):
                              "product (hi*hi + hi*lo + lo*hi), so the issued-MMA rate is 3x achieved and frac_issued = 3x frac",
                      "frac_issued": 3.0 * achieved / pk["bf16_tflops"], "ms_per_launch": k_ms,
                      "step_algorithmic_tflops_per_gpu": value / world * FLOP_PER_PAIR / 1e12,
-                     "step_frac_of_sustained_peak_issued": 3.0 * value / world * FLOP_PER_PAIR / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"])},
+                     # whole step, issued BF16 MMAs (3 per algorithmic product) against the peak of the SAME regime
+                     "step_frac_of_burst_peak_issued": 3.0 * value / world * FLOP_PER_PAIR / 1e12 / pk["bf16_tflops"]},
     }
+    if sustained:
+        v_sus = world * B_PER_GPU / (ms_sus * 1e-3)
+        line["sustained"] = {"ms_per_step": ms_sus, "steps": sustained[1], "seconds": ms_sus * sustained[1] * 1e-3, "value": v_sus,
+                             "unit": "pairs/s", "clocks": sustained[2],
+                             "step_frac_of_sustained_peak_issued": 3.0 * v_sus / world * FLOP_PER_PAIR / 1e12 / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                             "note": "device-resident inputs, max over ranks; fraction = issued BF16 MMA rate / cuBLAS bf16 rate measured back to back for 4 s"}
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same workload on the host cores
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import drn_oracle as O
-        cores = os.cpu_count()
-        torch.set_num_threads(cores)
-        cpu_sd = {k: v for k, v in sd.items()}
-        O.forward_backward(cpu_sd, cfg, batch, stage=1)
-        t0 = time.perf_counter()
-        n = 2
-        for _ in range(n):
-            O.forward_backward(cpu_sd, cfg, batch, stage=1)
-        dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": B_PER_GPU / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                "sample": "%d fwd+bwd steps of the same B=32,T=256 batch after 1 warm-up (torch CPU fp32 oracle)" % n}
+        n = 3
+        ms_cpu, cores, kind, what = time_reference_cpu(n, 1)
+        line["cpu_baseline"] = {"value": B_PER_GPU / (ms_cpu * 1e-3), "unit": "pairs/s", "cores": cores, "kind": kind,
+                                "sample": "%d fwd+bwd steps of the same B=32,T=256 batch after 1 warm-up, %s" % (n, what)}
+    # the other BASELINE configs as short driver-visible runs (N=1 only): configs[2] three-stage schedule incl. optimizer,
+    # configs[4] inference sweep at batch 256 (scripts/configs_bench.py documents each field)
+    if world == 1 and not args.no_extra:
+        del model, core, path
+        torch.cuda.empty_cache()
+        import importlib.util
+        sp = importlib.util.spec_from_file_location("_configs_bench", os.path.join(REPO, "scripts", "configs_bench.py"))
+        cb = importlib.util.module_from_spec(sp)
+        sp.loader.exec_module(cb)
+        extra = {}
+        try:
+            extra["configs[2]"] = cb.three_stage(dev, 10, 3, fused_modes=(False,))
+            extra["configs[4]"] = cb.sweep(dev, 5, 2)
+        except Exception as e:  # noqa: BLE001
+            extra["error"] = repr(e)
+        line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -358,10 +422,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-extra", dest="no_extra", action="store_true", help="skip the configs[2] / configs[4] blocks")
+    ap.add_argument("--sustain-seconds", dest="sustain_seconds", type=float, default=3.0,
+                    help="length of the sustained leg (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
-        args.steps = min(args.steps, 10)  # each CPU step is ~3 s of 100 % of the host cores; keep the arm bounded
-        args.warmup = min(args.warmup, 1)
         run_reference(args)
     else:
         run_ours(args)

@@ -358,7 +358,8 @@ static int launch_tc(const GemmKParams& kp, const CUtensorMap& ma, const CUtenso
   return check_launch("gemm_tc_kernel");
 }
 
-int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaStream_t st);  // gemm2.cu
+int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int sm_count, void* ws, size_t ws_bytes,
+                 cudaStream_t st);  // gemm2.cu
 
 static int sm_count_cached() {
   static int sm_count = 0;
@@ -375,6 +376,7 @@ struct Prepared {
   int m_sub;                                 // 128-row sub-tiles (ROWS) / 128-channel sub-tiles (WGRAD)
   int pair_n_tiles, pair_m_tiles, pair_tiles;  // 256 x 256 tiling of the CTA-pair kernel
   int cost;                                  // k-iterations per pair tile (load-balance key)
+  int nk_uniform;                            // k-iterations of EVERY tile, or 0 when the K-split does not divide evenly
 };
 
 // Validate a descriptor and derive the kernel-side parameters (no tensor maps yet).
@@ -460,7 +462,9 @@ static int prepare(const drn_gemm_t* g, Prepared* out) {
   out->pair_n_tiles = ceil_div(g->N, 256);
   out->pair_m_tiles = ceil_div(out->m_sub, 2);
   out->pair_tiles = out->pair_m_tiles * out->pair_n_tiles * (wgrad ? g->ntaps * kp.split_k : kp.split_k);
-  out->cost = wgrad ? ceil_div(kp.num_kblocks, kp.split_k) : ceil_div(g->ntaps * (g->K / BLOCK_K), kp.split_k);
+  const int its = wgrad ? kp.num_kblocks : g->ntaps * (g->K / BLOCK_K);
+  out->cost = ceil_div(its, kp.split_k);
+  out->nk_uniform = (its % kp.split_k == 0) ? its / kp.split_k : 0;
   return 0;
 }
 
@@ -480,7 +484,15 @@ using namespace drn;
 
 // One launch for up to GROUP_MAX independent problems (persistent CTA-pair kernel).  Tiles are ordered by decreasing
 // k-iterations per tile so the static round-robin over the 74 SM pairs ends with the cheapest tiles.
+extern "C" size_t drn_gemm_workspace_bytes(void) {
+  return SK_FLAG_BYTES + static_cast<size_t>(sm_count_cached() / 2) * SK_SLOT_FLOATS * sizeof(float);
+}
+
 extern "C" int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream) {
+  return drn_gemm_group_ws(n, descs, nullptr, 0, stream);
+}
+
+extern "C" int drn_gemm_group_ws(int n, const drn_gemm_t* descs, void* workspace, size_t workspace_bytes, void* stream) {
   if (n < 1 || n > GROUP_MAX) return fail(DRN_EINVAL, "drn_gemm_group: 1..%d problems (got %d)", GROUP_MAX, n);
   if (!descs) return fail(DRN_EINVAL, "drn_gemm_group: null descriptors");
   Prepared pr[GROUP_MAX];
@@ -506,9 +518,11 @@ extern "C" int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream) {
     }
     gp.raster_gm = gm > 0 ? gm : 1;  // A/B-measured r01: 1 / 4 / 8 / 16 within noise (DRAM is at ~18 % while the tensor pipe is at ~90 %)
   }
+  int nk_tile[GROUP_MAX];
   gp.tile_start[0] = 0;
   for (int k = 0; k < n; ++k) {
     const int i = order[k];
+    nk_tile[k] = pr[i].nk_uniform;
     gp.p[k] = pr[i].kp;
     gp.n_tiles[k] = pr[i].pair_n_tiles;
     gp.m_tiles[k] = pr[i].pair_m_tiles;
@@ -516,7 +530,8 @@ extern "C" int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream) {
     if ((rc = pair_maps(&descs[i], pr[i], &gm.a[k], &gm.b[k])) != 0) return rc;
   }
   for (int k = n; k < GROUP_MAX; ++k) gp.tile_start[k + 1] = gp.tile_start[n];
-  return launch_group(gp, gm, sm_count_cached(), static_cast<cudaStream_t>(stream));
+  if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 31) != 0) return fail(DRN_EINVAL, "drn_gemm_group_ws: workspace must be 32-byte aligned");
+  return launch_group(gp, gm, nk_tile, sm_count_cached(), workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 namespace drn { void set_pair_clusters(int n); }
@@ -530,7 +545,9 @@ extern "C" int drn_gemm_stats_rows(const drn_gemm_t* g) {
   return 8 * pr.pair_m_tiles;  // 2 CTAs x 4 epilogue warps x 32 rows per 256-row pair tile
 }
 
-extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
+extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) { return drn_gemm_ws(g, nullptr, 0, stream); }
+
+extern "C" int drn_gemm_ws(const drn_gemm_t* g, void* workspace, size_t workspace_bytes, void* stream) {
   Prepared pr;
   int rc = prepare(g, &pr);
   if (rc) return rc;
@@ -552,8 +569,8 @@ extern "C" int drn_gemm(const drn_gemm_t* g, void* stream) {
   bool use_pair = (g->engine == 2) || (g->engine == 0 && pr.pair_tiles >= sm_count / 4);
   if (g->engine == 3) use_pair = false;
   if (g->dbg_lbo || g->dbg_sbo || g->dbg_kadv) use_pair = false;
-  if (use_pair) return drn_gemm_group(1, g, stream);
-  if (kp.split_k > 1 && (kp.out_split_stride != 0 || !wgrad)) return drn_gemm_group(1, g, stream);  // slices: pair kernel only
+  if (use_pair) return drn_gemm_group_ws(1, g, workspace, workspace_bytes, stream);
+  if (kp.split_k > 1 && (kp.out_split_stride != 0 || !wgrad)) return drn_gemm_group_ws(1, g, workspace, workspace_bytes, stream);  // slices: pair kernel only
 
   // one tile per CTA: 128 x 256 tiles unless that leaves most SMs idle, then 128 x 128
   int block_n = (g->N > 128) ? 256 : 128;

@@ -11,6 +11,13 @@
 //     their data- and weight-gradients).  Launched one by one each pays pipeline fill/drain and leaves most of a wave
 //     idle (5-27 % tensor-pipe utilisation measured); as one tile list they fill the waves and share one fill/drain.
 //     ROWS (conv forward / dgrad) and WGRAD problems mix freely in a group.
+//   * stream-K schedule (when the caller supplies a workspace, drn_gemm_group_ws): instead of whole tiles round-robin, the
+//     k-iterations of ALL tiles of the launch form one sequence that is cut into equal contiguous ranges, one per SM pair.
+//     224 tower tiles on 74 pairs are 3.03 waves of tiles but 72.6 (of 73) iterations per pair; 56 long tiles of the conv2
+//     backward are one 32-iteration wave but 20.8 iterations per pair.  At most the first segment of a pair starts inside a
+//     tile: its accumulator goes to the pair's workspace slot (fp32, plain stores) and a flag; the pair that ran the first
+//     iterations of that tile -- always its LAST segment in time, so the partial tiles are long there -- adds them in pair
+//     order (deterministic) and runs the normal epilogue (bias, gate, statistics, planes).
 // Operand forms, tensor maps and epilogue semantics are those of gemm.cu (include/drn_b200.h).
 #include <cuda.h>
 #include <stdlib.h>
@@ -88,6 +95,61 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
   return t;
 }
 
+// Per-role cursor over the work of one SM pair: whole tiles (static round-robin) or the segments of its stream-K range.
+struct PairSched {
+  int tile, stride, num_tiles;  // static
+  int it, it_end;               // stream-K: global k-iteration cursor / end of this pair's range
+  int seg_it;                   // stream-K: global iteration at which the current segment starts
+};
+
+__device__ __forceinline__ PairSched sched_init(const GroupParams& gp, int cluster_id, int num_clusters, int num_tiles) {
+  PairSched s{};
+  s.tile = cluster_id;
+  s.stride = num_clusters;
+  s.num_tiles = num_tiles;
+  if (gp.sk_quota > 0) {
+    const int total = gp.it_start[gp.nprob];
+    s.it = min(total, cluster_id * gp.sk_quota);
+    s.it_end = min(total, s.it + gp.sk_quota);
+  }
+  return s;
+}
+
+// Next segment of this pair: tile `t`, k-iterations [k0, k0 + kn) of the tile's t.nk.  False when the pair is done.
+__device__ __forceinline__ bool next_seg(const GroupParams& gp, PairSched& s, int rank, PairTile& t, int& k0, int& kn) {
+  if (gp.sk_quota <= 0) {
+    if (s.tile >= s.num_tiles) return false;
+    t = decode_tile(gp, s.tile, rank);
+    s.tile += s.stride;
+    k0 = 0;
+    kn = t.nk;
+    return true;
+  }
+  if (s.it >= s.it_end) return false;
+  int pr = 0;
+#pragma unroll
+  for (int i = 1; i < GROUP_MAX; ++i)
+    if (i < gp.nprob && s.it >= gp.it_start[i]) pr = i;
+  const int loc = s.it - gp.it_start[pr];
+  const int nkp = gp.nk_tile[pr];
+  const int local = loc / nkp;
+  k0 = loc - local * nkp;
+  t = decode_tile(gp, gp.tile_start[pr] + local, rank);
+  kn = min(nkp - k0, s.it_end - s.it);
+  s.seg_it = s.it;
+  s.it += kn;
+  return true;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ GroupMaps gm, int num_tiles) {
   pdl_trigger();
@@ -135,8 +197,10 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
     // ===== TMA producer (one thread per CTA; completion is signalled on the LEADER's full barrier) =====
     if (lane == 0) {
       int g = 0;  // global k-iteration counter (pipeline runs across tiles and problems)
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const PairTile t = decode_tile(gp, tile, rank);
+      PairSched sc = sched_init(gp, cluster_id, num_clusters, num_tiles);
+      PairTile t;
+      int k0, kn;
+      while (next_seg(gp, sc, rank, t, k0, kn)) {
         const GemmKParams& p = gp.p[t.prob];
         const CUtensorMap* tma_a = &gm.a[t.prob];
         const CUtensorMap* tma_b = &gm.b[t.prob];
@@ -145,7 +209,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         const int nplanes = (p.nprod == 1) ? 1 : 2;
         const int kpt = wgrad ? 1 : p.K / BLOCK_K;
         const uint32_t tx = 2u * nplanes * 2u * P2_HALF;  // both CTAs' bytes land on the leader's barrier
-        for (int i = 0; i < t.nk; ++i, ++g) {
+        for (int i = 0; i < kn; ++i, ++g) {
           const int s = g % P2_STAGES;
           const uint32_t ph = (g / P2_STAGES) & 1;
           mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
@@ -153,7 +217,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
           const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
           const uint32_t sa = smem_base + s * P2_STAGE;
           const uint32_t sb = sa + 2 * P2_HALF;
-          const int it = t.it_begin + i;
+          const int it = t.it_begin + k0 + i;
           if (!wgrad) {
             const int tap = it / kpt, kb = it % kpt;
             for (int pl = 0; pl < nplanes; ++pl) {
@@ -197,10 +261,12 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer: one thread of the leader CTA =====
     if (leader && lane == 0) {
-      int g = 0, lt = 0;  // lt counts the tiles that actually use an accumulator stage
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const PairTile t = decode_tile(gp, tile, rank);
-        if (t.nk <= 0) continue;
+      int g = 0, lt = 0;  // lt counts the segments that actually use an accumulator stage
+      PairSched sc = sched_init(gp, cluster_id, num_clusters, num_tiles);
+      PairTile t;
+      int k0, kn;
+      while (next_seg(gp, sc, rank, t, k0, kn)) {
+        if (kn <= 0) continue;
         const GemmKParams& p = gp.p[t.prob];
         const bool wgrad = (p.form == DRN_GEMM_WGRAD);
         const bool a_mn = wgrad;
@@ -216,7 +282,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * P2_TILE;
         uint32_t accumulate = 0;
-        for (int i = 0; i < t.nk; ++i, ++g) {
+        for (int i = 0; i < kn; ++i, ++g) {
           const int s = g % P2_STAGES;
           const uint32_t ph = (g / P2_STAGES) & 1;
           mbar_wait(smem_u32(&full_bar[s]), ph);
@@ -244,16 +310,59 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int lt = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const PairTile t = decode_tile(gp, tile, rank);
-      if (t.nk <= 0) continue;
+    PairSched sc = sched_init(gp, cluster_id, num_clusters, num_tiles);
+    PairTile t;
+    int k0, kn;
+    while (next_seg(gp, sc, rank, t, k0, kn)) {
+      if (kn <= 0) continue;
       const GemmKParams& p = gp.p[t.prob];
       const bool wgrad = (p.form == DRN_GEMM_WGRAD);
       const int as = lt & 1;
       const uint32_t aph = (lt >> 1) & 1;
       ++lt;
+      const uint32_t taddr = tmem_base + as * P2_TILE + (static_cast<uint32_t>(q * 32) << 16);
+      // stream-K: partial tiles of this warp's 32 rows live at [pair][rank][chunk][row][32] of the workspace
+      const size_t ws_off = static_cast<size_t>(rank) * (128 * 256) + static_cast<size_t>(row) * 32;
+      int ncontrib = 0;
+      if (k0 == 0 && kn < t.nk) {
+        // owner of a tile other pairs finish: pairs cluster_id+1 ... whose ranges start before the end of this tile
+        const int tile_end = sc.seg_it + t.nk;
+        while ((cluster_id + 1 + ncontrib) * gp.sk_quota < tile_end) ++ncontrib;
+        if (lane == 0) {
+          for (int j = 0; j < ncontrib; ++j) {
+            const unsigned* f = gp.sk_flags + (cluster_id + 1 + j) * 8 + rank * 4 + q;
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(f) == 0u) {
+              if (clock64() - t0 > 4000000000LL) __trap();
+            }
+          }
+        }
+        __syncwarp();
+      }
       mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
       tc_fence_after();
+      if (k0 > 0) {
+        // not the owner: this pair's range starts inside the tile -> partial accumulator to the workspace slot + flag
+        float* slot = gp.sk_ws + static_cast<size_t>(cluster_id) * SK_SLOT_FLOATS + ws_off;
+#pragma unroll 1
+        for (int c0 = 0; c0 < P2_TILE; c0 += 32) {
+          if (t.n0 + c0 >= p.N) break;
+          float v[32];
+          tmem_ld_32x32(taddr + c0, v);
+          tmem_ld_wait();
+          float* d = slot + (c0 >> 5) * (128 * 32);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) st_global_v8(d + j, v + j);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+          __threadfence();
+          st_release_gpu(gp.sk_flags + cluster_id * 8 + rank * 4 + q, 1u);
+        }
+        continue;
+      }
       bool valid;
       long long orow;
       int bb = 0;
@@ -269,7 +378,6 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         orow = t.m0 + row;
         if (out_base) out_base += p.tap_w[t.tap] * p.out_tap_stride + t.split * p.out_split_stride;
       }
-      const uint32_t taddr = tmem_base + as * P2_TILE + (static_cast<uint32_t>(q * 32) << 16);
       const int stats_blk = (!wgrad && p.stats) ? t.ms * 4 + q : -1;  // 32-row block of the output (BatchNorm partial sums)
 #pragma unroll 1
       for (int c0 = 0; c0 < P2_TILE; c0 += 32) {
@@ -277,11 +385,23 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         float v[32];
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
+        for (int j = 0; j < ncontrib; ++j) {  // fold the partial tiles, in pair order
+          const float4* src = reinterpret_cast<const float4*>(gp.sk_ws + static_cast<size_t>(cluster_id + 1 + j) * SK_SLOT_FLOATS +
+                                                              ws_off + (c0 >> 5) * (128 * 32));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 x = __ldcg(src + i);
+            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+          }
+        }
         epilogue_chunk(p, v, valid, orow, bb, t.n0 + c0, out_base, stats_blk);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+      if (lane == 0) {
+        mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
+        for (int j = 0; j < ncontrib; ++j) gp.sk_flags[(cluster_id + 1 + j) * 8 + rank * 4 + q] = 0u;  // re-armed for the next launch
+      }
     }
   }
   tc_fence_before();
@@ -294,7 +414,14 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
 static int g_pair_clusters = 0;
 void set_pair_clusters(int n) { g_pair_clusters = n > 0 ? n : 0; }
 
-int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaStream_t st) {
+// Stream-K runs when the caller passes a workspace (drn_gemm_group_ws).  DRN_SK_MIN (environment, read once) = fewest
+// k-iterations worth giving an SM pair (a range shorter than that costs more in the fold than it saves).
+static int sk_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int sm_count, void* ws, size_t ws_bytes, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
@@ -304,13 +431,41 @@ int launch_group(const GroupParams& gp, const GroupMaps& gm, int sm_count, cudaS
   const int num_tiles = gp.tile_start[gp.nprob];
   int clusters = sm_count / 2;
   static int cap = -1;  // DRN_PAIR_CLUSTERS: leave SM pairs free for kernels of other streams (tuning / probing knob)
+  static int sk_min = 4;
   if (cap < 0) {
-    const char* e = getenv("DRN_PAIR_CLUSTERS");
-    cap = e ? atoi(e) : 0;
+    cap = sk_env("DRN_PAIR_CLUSTERS", 0);
+    sk_min = sk_env("DRN_SK_MIN", 4);
+    if (sk_min < 1) sk_min = 1;
   }
   if (cap > 0 && clusters > cap) clusters = cap;
   if (g_pair_clusters > 0 && clusters > g_pair_clusters) clusters = g_pair_clusters;
-  if (clusters > num_tiles) clusters = num_tiles;
+  if (clusters < 1) clusters = 1;
+  // ---- stream-K: equal contiguous ranges of k-iterations per SM pair (needs uniform tiles inside every problem) ------------
+  gp.sk_quota = 0;
+  gp.sk_ws = nullptr;
+  gp.sk_flags = nullptr;
+  bool uniform = true;
+  long long total = 0;
+  gp.it_start[0] = 0;
+  for (int k = 0; k < gp.nprob; ++k) {
+    if (nk_tile[k] <= 0) uniform = false;
+    gp.nk_tile[k] = nk_tile[k] > 0 ? nk_tile[k] : 1;
+    total += static_cast<long long>(gp.tile_start[k + 1] - gp.tile_start[k]) * gp.nk_tile[k];
+    gp.it_start[k + 1] = static_cast<int>(total);
+  }
+  for (int k = gp.nprob; k < GROUP_MAX; ++k) gp.it_start[k + 1] = gp.it_start[gp.nprob];
+  if (ws && uniform && total > 0 && total < (1ll << 30) &&
+      ws_bytes >= SK_FLAG_BYTES + static_cast<size_t>(clusters) * SK_SLOT_FLOATS * sizeof(float) &&
+      static_cast<size_t>(clusters) * 8 * sizeof(unsigned) <= SK_FLAG_BYTES) {
+    int quota = static_cast<int>((total + clusters - 1) / clusters);
+    if (quota < sk_min) quota = sk_min;
+    gp.sk_quota = quota;
+    gp.sk_flags = static_cast<unsigned*>(ws);
+    gp.sk_ws = reinterpret_cast<float*>(static_cast<char*>(ws) + SK_FLAG_BYTES);
+    clusters = static_cast<int>((total + quota - 1) / quota);
+  } else if (clusters > num_tiles) {
+    clusters = num_tiles;
+  }
   if (clusters < 1) clusters = 1;
   launch_k(gemm_pair_kernel, 2 * clusters, P2_THREADS, P2_SMEM, st, gp, gm, num_tiles);
   return check_launch("gemm_pair_kernel");

@@ -51,8 +51,19 @@ struct GroupParams {
   int raster_gm;                  // tile-rows per rasterisation group (1 = plain row-major tile order)
   int tile_start[GROUP_MAX + 1];  // prefix sums of the per-problem 256 x 256 tile counts
   int n_tiles[GROUP_MAX], m_tiles[GROUP_MAX];
+  // stream-K schedule (gemm2.cu): the k-iterations of all tiles form one sequence (tile-major); SM pair c runs iterations
+  // [c*sk_quota, (c+1)*sk_quota).  A pair whose range starts inside a tile stores that partial accumulator in its workspace
+  // slot; the pair that ran the tile's first iterations folds the partial tiles in (in pair order: deterministic) and runs
+  // the epilogue.  sk_quota == 0: static round-robin over whole tiles.
+  int sk_quota;
+  int it_start[GROUP_MAX + 1];    // prefix sums of tiles x k-iterations per problem
+  int nk_tile[GROUP_MAX];         // k-iterations of one tile (uniform inside a problem)
+  float* sk_ws;                   // [pairs][2 CTAs][8 column chunks][128 rows][32] fp32
+  unsigned* sk_flags;             // [pairs][2 CTAs][4 epilogue warps], zero between launches
   GemmKParams p[GROUP_MAX];
 };
+constexpr size_t SK_SLOT_FLOATS = 2 * 128 * 256;  // one 256 x 256 fp32 partial tile per SM pair
+constexpr size_t SK_FLAG_BYTES = 4096;
 struct GroupMaps {
   CUtensorMap a[GROUP_MAX];
   CUtensorMap b[GROUP_MAX];

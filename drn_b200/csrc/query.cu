@@ -1272,3 +1272,53 @@ extern "C" int drn_qe_backward_part(const drn_qe_t* a, int part, void* stream) {
   if (part != 1 && part != 2) return fail(DRN_EINVAL, "drn_qe_backward_part: part must be 1 or 2 (got %d)", part);
   return qe_backward_parts(a, part, stream);
 }
+
+
+// ---- staging of the caller's query tensors into the static buffers the graphs read, with validation -----------------------
+// The kernels index the embedding table with the token ids and the LSTM output with length-1 (qe_embed_kernel,
+// qe_embed_bwd_kernel's atomicAdd into the gradient buffer, qe_vgather / qe_vscatter): an id outside [0, vocab) or a length
+// outside [1, L] must never reach them.  The reference raises (IndexError in nn.Embedding, pack_padded_sequence's length check:
+// language_module.py:41-42); here an invalid id is staged as 0 (= padding: zero embedding row semantics aside, no gradient), an
+// invalid length is clamped, `err` gets the sticky bits 1 (token) / 2 (length) and `poison` = NaN for THIS batch (else 0): the
+// caller adds it to the losses, so a bad batch is loud without a device synchronisation.  One CTA: B * L <= a few thousand.
+__global__ void __launch_bounds__(256) qe_stage_kernel(const long long* __restrict__ tok, long long tok_ld, int ncols,
+                                                       const long long* __restrict__ len, int B, int L, int vocab,
+                                                       long long* __restrict__ tok_out, long long* __restrict__ len_out,
+                                                       int* __restrict__ err, float* __restrict__ poison) {
+  pdl_sync();
+  int bad = 0;
+  for (int i = threadIdx.x; i < B * L; i += blockDim.x) {
+    const int b = i / L, t = i % L;
+    long long v = (t < ncols) ? tok[static_cast<long long>(b) * tok_ld + t] : 0;
+    if (v < 0 || v >= vocab) {
+      bad |= 1;
+      v = 0;
+    }
+    tok_out[i] = v;
+  }
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    long long v = len[b];
+    if (v < 1 || v > L || v > ncols) {
+      bad |= 2;
+      v = v < 1 ? 1 : (L < ncols ? L : ncols);
+    }
+    len_out[b] = v;
+  }
+  const int any1 = __syncthreads_or(bad & 1), any2 = __syncthreads_or(bad & 2);
+  if (threadIdx.x == 0) {
+    const int e = (any1 ? 1 : 0) | (any2 ? 2 : 0);
+    if (e) atomicOr(err, e);
+    poison[0] = e ? __int_as_float(0x7fc00000) : 0.f;
+  }
+}
+
+extern "C" int drn_qe_stage(const int64_t* tokens, int64_t tok_ld, int ncols, const int64_t* lengths, int B, int L, int vocab,
+                            int64_t* tokens_out, int64_t* lengths_out, int32_t* err, float* poison, void* stream) {
+  if (!tokens || !lengths || !tokens_out || !lengths_out || !err || !poison) return fail(DRN_EINVAL, "drn_qe_stage: null pointer");
+  if (B < 1 || L < 1 || ncols < 1 || tok_ld < ncols || vocab < 1)
+    return fail(DRN_EINVAL, "drn_qe_stage: bad shape (B=%d L=%d ncols=%d tok_ld=%lld vocab=%d)", B, L, ncols, (long long)tok_ld, vocab);
+  launch_k(qe_stage_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(tokens),
+           static_cast<long long>(tok_ld), ncols, reinterpret_cast<const long long*>(lengths), B, L, vocab,
+           reinterpret_cast<long long*>(tokens_out), reinterpret_cast<long long*>(lengths_out), reinterpret_cast<int*>(err), poison);
+  return check_launch("qe_stage_kernel");
+}

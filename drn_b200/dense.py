@@ -77,6 +77,10 @@ class DensePath:
         # query encoder (drn_qe_forward / drn_qe_backward): static token / length buffers, commands, workspace
         self.tokens = torch.zeros(B, L, dtype=torch.int64, device=dev)
         self.lengths = torch.ones(B, dtype=torch.int64, device=dev)
+        # drn_qe_stage: sticky error bits (1 = token id outside the vocabulary, 2 = length outside [1, L]) and the per-batch
+        # poison (0 or NaN) that the model adds to the losses
+        self.input_err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.poison = torch.zeros(1, device=dev)
         self.cmd_dim = 2 * qe_hidden
         self.cmd = [e(B, self.cmd_dim) for _ in range(3)]
         self.qe_ws = torch.zeros(int(_lib().drn_qe_workspace_bytes(B, L, qe_hidden, qe_embed)), dtype=torch.uint8, device=dev)
@@ -142,6 +146,8 @@ class DensePath:
         self.post_loc = z(B, 3, self.top_n)
         self.post_count = torch.zeros(B, 3, dtype=torch.int32, device=dev)
         self.graphs = {}
+        if ops.STREAMK:
+            ops.workspace(dev)  # stream-K workspace of the contraction kernel: allocated here, not inside a graph capture
         self.launches_stage = 0
         self.Tl_c = (C.c_int * 3)(*self.Tl)
         self.strides_c = (C.c_float * 3)(*self.strides)
@@ -356,16 +362,23 @@ class DensePath:
     def _conv(self, blk, a_pl, w_pl, bias=None):
         self.launches += 1
         g = self._conv_desc(blk, a_pl, w_pl, bias)
-        L.check(_lib().drn_gemm(C.byref(g), _st()), "drn_gemm")
+        ws, nb = ops._ws_args(None)
+        L.check(_lib().drn_gemm_ws(C.byref(g), ws, nb, _st()), "drn_gemm")
 
     # ---------------------------------------------------------------------------------------------------------------
     # forward
     # ---------------------------------------------------------------------------------------------------------------
-    def stage_query(self, tokens, lengths, gt):
-        """Eager: the caller's query tokens / lengths / ground truth -> the static buffers the replayable parts read."""
+    def stage_query(self, tokens, lengths, gt, vocab=None):
+        """Eager: the caller's query tokens [B, <= L] / lengths / ground truth -> the static buffers the replayable parts read.
+        Token ids and lengths are validated on the way (drn_qe_stage): the kernels index the embedding table, its gradient and
+        the LSTM output with them."""
         self.gt.copy_(gt)
-        self.tokens.copy_(tokens)
-        self.lengths.copy_(lengths)
+        ncols = tokens.shape[1]
+        if ncols > self.L or tokens.stride(1) != 1:
+            raise ValueError("stage_query: tokens [B, %d] do not fit the path's query width L = %d" % (ncols, self.L))
+        self._chk(_lib().drn_qe_stage(_vp(tokens), C.c_int64(tokens.stride(0)), ncols, _vp(lengths), self.B, self.L,
+                                      int(vocab) if vocab is not None else (1 << 30), _vp(self.tokens), _vp(self.lengths),
+                                      _vp(self.input_err), _vp(self.poison), _st()), "qe_stage")
 
     def stage_feats(self, p, feats, pse):
         """Eager: reads the caller's clip features and proposal boundaries and fills the static operand buffers (split planes
@@ -380,7 +393,7 @@ class DensePath:
         self.launches_stage = self.launches
 
     def stage_inputs(self, p, tokens, lengths, feats, pse, gt):
-        self.stage_query(tokens, lengths, gt)
+        self.stage_query(tokens, lengths, gt, vocab=p["query_encoder.embedding.weight"].shape[0])
         self.stage_feats(p, feats, pse)
 
     def forward(self, p, tokens, lengths, feats, pse, gt, training):

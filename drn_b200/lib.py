@@ -118,6 +118,7 @@ def load():
         lib.drn_last_error.restype = C.c_char_p
         lib.drn_version.restype = C.c_int
         lib.drn_qe_workspace_bytes.restype = C.c_size_t
+        lib.drn_gemm_workspace_bytes.restype = C.c_size_t
         _lib = lib
     return _lib
 

@@ -53,21 +53,53 @@ def desc(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=
     return g
 
 
-def gemm(*a, **k):
+import os
+
+# Stream-K schedule of the persistent contraction kernel (drn_gemm_group_ws): OPT-IN.  Measured on B200 (r02,
+# profiles/r02_ab_streamk.log, profiles/r02_insitu_{static,streamk}.json): 3.86 ms per step against 3.45 ms with the static
+# tile round-robin -- contiguous per-pair tile ranges lose the L2 sharing of operand tiles between neighbouring SM pairs
+# (prop_fc forward 514 -> 624 us) and every extra segment pays a full TMEM -> global epilogue (conv1 backward 48 -> 79 us).
+STREAMK = os.environ.get("DRN_STREAMK", "0") == "1"
+_WS = {}
+
+
+def workspace(device=None):
+    """Stream-K workspace of the persistent contraction kernel (drn_gemm_workspace_bytes, include/drn_b200.h): one per device,
+    zero-filled once, owned by the caller as every other buffer.  All contractions of a process run on one stream at a time
+    (model/main_model.py), so one workspace per device is enough; DRN_STREAMK=0 in the environment disables the schedule."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(L.load().drn_gemm_workspace_bytes()), dtype=torch.uint8, device=torch.device("cuda", key))
+        _WS[key] = ws
+    return ws
+
+
+def _ws_args(streamk):
+    if not (STREAMK if streamk is None else streamk):
+        return None, C.c_size_t(0)
+    ws = workspace()
+    return C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel())
+
+
+def gemm(*a, streamk=None, **k):
     """One contraction, one launch (engine chosen by the library)."""
     g = desc(*a, **k)
-    L.check(L.load().drn_gemm(C.byref(g), L.stream_ptr()), "drn_gemm")
+    ws, nb = _ws_args(streamk)
+    L.check(L.load().drn_gemm_ws(C.byref(g), ws, nb, L.stream_ptr()), "drn_gemm")
 
 
 GROUP_MAX = 6
 
 
-def gemm_group(descs):
+def gemm_group(descs, streamk=None):
     """Independent contractions in ONE launch of the persistent CTA-pair kernel (drn_gemm_group).  Returns the launch count."""
     n = 0
+    ws, nb = _ws_args(streamk)
     for i in range(0, len(descs), GROUP_MAX):
         chunk = descs[i:i + GROUP_MAX]
         arr = (L.GemmDesc * len(chunk))(*chunk)
-        L.check(L.load().drn_gemm_group(len(chunk), arr, L.stream_ptr()), "drn_gemm_group")
+        L.check(L.load().drn_gemm_group_ws(len(chunk), arr, ws, nb, L.stream_ptr()), "drn_gemm_group")
         n += 1
     return n

@@ -115,6 +115,15 @@ int drn_gemm(const drn_gemm_t* g, void* stream);
  * the three pyramid levels of a shared head / FPN conv, or the data- and weight-gradients of one layer.  Small problems
  * launched one by one leave most of the 148 SMs idle and each pay pipeline fill and drain. */
 int drn_gemm_group(int n, const drn_gemm_t* descs, void* stream);
+/* The same launches with a caller-owned workspace (drn_gemm_workspace_bytes() bytes, 32-byte aligned, ZERO-FILLED ONCE by the
+ * caller, never shared by launches that may run concurrently): switches the persistent kernel from whole tiles round-robin
+ * to a stream-K schedule -- the k-iterations of all tiles are cut into equal contiguous ranges, one per SM pair; a range that
+ * starts inside a tile leaves its fp32 partial accumulator in the workspace and the pair that owns the tile folds the
+ * partials in a fixed order before the epilogue (deterministic).  Removes the tile-wave quantisation of the small layers
+ * (224 tower tiles on 74 pairs = 3.03 waves -> 72.6 of 73 iterations per pair).  workspace == NULL: static schedule. */
+size_t drn_gemm_workspace_bytes(void);
+int drn_gemm_ws(const drn_gemm_t* g, void* workspace, size_t workspace_bytes, void* stream);
+int drn_gemm_group_ws(int n, const drn_gemm_t* descs, void* workspace, size_t workspace_bytes, void* stream);
 /* Profiling aid: a one-thread kernel that stores the GPU's %globaltimer (ns) into *slot (device memory).  Enqueued between
  * the kernels of a step -- also inside a CUDA-graph capture -- it yields their in-situ durations (scripts/insitu_timeline.py). */
 int drn_timestamp(uint64_t* slot, void* stream);
@@ -359,6 +368,14 @@ typedef struct {
 } drn_qe_t;
 
 size_t drn_qe_workspace_bytes(int B, int L, int H, int E);
+/* Staging of the caller's query tensors (tokens [B][tok_ld], first `ncols` columns used; lengths [B]; both int64, device) into
+ * the static [B][L] / [B] buffers drn_qe_t points at, WITH VALIDATION: the kernels index the embedding table (and its gradient)
+ * by token id and the LSTM output by length-1.  A token id outside [0, vocab) is staged as 0 (padding), a length outside
+ * [1, min(L, ncols)] is clamped; *err gets the sticky bits 1 (token) / 2 (length) and *poison = NaN for this batch, else 0 --
+ * the caller adds *poison to the losses, so a bad batch is loud without a device synchronisation (the reference raises:
+ * nn.Embedding IndexError / pack_padded_sequence, model/language_module.py:41-42). */
+int drn_qe_stage(const int64_t* tokens, int64_t tok_ld, int ncols, const int64_t* lengths, int B, int L, int vocab,
+                 int64_t* tokens_out, int64_t* lengths_out, int32_t* err, float* poison, void* stream);
 /* number of kernels one drn_qe_forward (backward = 0) / drn_qe_backward (backward = 1) call launches for this shape */
 int drn_qe_launch_count(int B, int L, int H, int backward);
 int drn_qe_forward(const drn_qe_t* q, void* stream);

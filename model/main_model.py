@@ -32,7 +32,7 @@ def _replay(path, key, fn, use_graphs):
     if g is None:
         fn()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):  # a DataLoader's pin-memory thread may call CUDA meanwhile
             fn()
         path.graphs[key] = g
     else:
@@ -91,15 +91,15 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         g1 = g1b = g2 = None
         if use_graphs:
             g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
+            with torch.cuda.graph(g1, capture_error_mode="thread_local"):
                 regions["zero"].zero_()
                 path.backward(p, grads, path.upstream, tail=dp is None, propfc=dp is None)
             if dp is not None:
                 g1b = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1b):
+                with torch.cuda.graph(g1b, capture_error_mode="thread_local"):
                     path.backward_propfc(grads, pair_clusters=pc)
                 g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2):
+                with torch.cuda.graph(g2, capture_error_mode="thread_local"):
                     path.backward_tail(p, grads)
         if dp is not None:  # the eager run above produced a complete local gradient: reduce it in one go
             dp.reduce_regions([flat])
@@ -134,14 +134,21 @@ class _DenseFn(torch.autograd.Function):
         p = model._tensor_dict()
         _run_forward(path, p, training, model.use_graphs, tokens, lengths, feats, pse, gt)
         ctx.model, ctx.path = model, path
-        ctx.nparams = len(params)
-        return path.losses[:3].clone()
+        ctx.names = tuple(model._trainable_names)
+        # the backward reads the activations from the path's static buffers: stamp which forward filled them
+        path.generation = getattr(path, "generation", 0) + 1
+        ctx.generation = path.generation
+        return path.losses[:3] + path.poison  # poison = NaN when drn_qe_stage rejected a token id / length of this batch
 
     @staticmethod
     def backward(ctx, g):
         model, path = ctx.model, ctx.path
-        names = model._trainable_names
-        assert len(names) == ctx.nparams
+        names = list(ctx.names)
+        if path.generation != ctx.generation:
+            raise RuntimeError("mainModel: another forward of the same (batch, T, query-length) shape ran between this forward and "
+                               "its backward; the activations live in static per-shape buffers (CUDA-graph replay), so the "
+                               "backward would differentiate the wrong batch.  Call backward() before the next forward of that "
+                               "shape (the reference driver does: main.py:217-236)")
         p = model._tensor_dict()
         # Gradients are produced in ONE flat static buffer (graph-replayable, and the unit of the data-parallel all-reduce).
         # They are handed to the parameters as VIEWS of that buffer (param.grad = view) instead of being returned to autograd,
@@ -149,7 +156,9 @@ class _DenseFn(torch.autograd.Function):
         # (in-graph timestamps, profiles/r01_insitu_v17.json).  The views stay valid until the next backward of this path; a
         # gradient that is still attached to its parameter then (no zero_grad in between: gradient accumulation, which the
         # reference driver never does, main.py:236-244) is detached from the buffer first and accumulated into afterwards.
-        # DRN_GRAD_VIEWS=0: return the gradients to autograd (copies).
+        # DRN_GRAD_VIEWS=0: return the gradients to autograd (copies).  With views (the default) autograd sees no gradient for
+        # the parameters, so per-parameter hooks (register_hook / register_post_accumulate_grad_hook: DDP, gradient scalers,
+        # loggers) do NOT fire; use DRN_GRAD_VIEWS=0 with such tools, and drn_b200.parallel for data parallelism.
         # data parallel: model._dp (drn_b200/parallel.py) all-reduces the flat gradient buffer, overlapped with the tail
         views = os.environ.get("DRN_GRAD_VIEWS", "1") == "1"
         if views:
@@ -194,7 +203,10 @@ class mainModel(nn.Module):
             setattr(self, "qInput%d" % t, nn.Linear(1024, channels_list[t - 1][1] if t > 0 else self.feature_dim))
         self._paths = {}
         self._trainable_names = []
-        self._dp = None  # set by drn_b200.parallel.DataParallelDRN
+        # gradient reducer (drn_b200.parallel.GradReducer, a plain object): set by DataParallelDRN, or -- the reference's main.py
+        # has no process-group code (main.py:52-53,99) -- by the first CUDA forward when WORLD_SIZE > 1 (`torchrun main.py`)
+        self._dp = None
+        self._dp_checked = False
         # CUDA graphs over the dense path (static shapes, library-owned buffers); DRN_NO_GRAPHS=1 launches kernel by kernel
         self.use_graphs = os.environ.get("DRN_NO_GRAPHS", "0") != "1"
 
@@ -215,21 +227,61 @@ class mainModel(nn.Module):
         return names, tensors
 
     def _path(self, B, T, L, device):
+        """Buffers + CUDA graphs of one (B, T, L) shape: ~2.3 GB at B=32, T=256.  Kept in a small LRU (DRN_MAX_PATHS, default 6:
+        a training run sees the full batch, the last ragged batch and a few query-length buckets, in train and eval mode)."""
         key = (B, T, L, device.index, bool(self.cfg["is_first_stage"]))
-        if key not in self._paths:
+        path = self._paths.pop(key, None)
+        if path is None:
+            cap = max(1, int(os.environ.get("DRN_MAX_PATHS", "6")))
+            while len(self._paths) >= cap:
+                old = self._paths.pop(next(iter(self._paths)))
+                old.graphs.clear()
+                del old
             qe = self.query_encoder
-            self._paths[key] = DensePath(self.cfg, B, T, device, L=L, qe_hidden=qe.hidden_dim, qe_embed=qe.embed_dim)
-        return self._paths[key]
+            path = DensePath(self.cfg, B, T, device, L=L, qe_hidden=qe.hidden_dim, qe_embed=qe.embed_dim)
+        self._paths[key] = path  # most recently used last
+        return path
+
+    def input_error(self):
+        """Synchronising check of the sticky input-validation flags of every path (drn_qe_stage): None, or a message naming
+        what was rejected since the last call.  A rejected batch has NaN losses (no synchronisation needed to notice)."""
+        bits = 0
+        for path in self._paths.values():
+            bits |= int(path.input_err.item())
+            path.input_err.zero_()
+        if not bits:
+            return None
+        what = [w for b, w in ((1, "token id outside the vocabulary (staged as padding)"), (2, "query length outside [1, L] (clamped)")) if bits & b]
+        return "mainModel input validation: " + "; ".join(what)
 
     # ---- forward -------------------------------------------------------------------------------------------------
     def forward(self, query_tokens, query_length, props_features, props_start_end, gt_start_end, props_num, num_frames):
         dev = self.prop_fc.weight.device
+        if getattr(self, "_is_replica", False):
+            raise RuntimeError("mainModel was replicated by nn.DataParallel over several devices: replicas have no parameters of "
+                               "their own, so no gradient would reach the model.  Run one process per GPU instead (torchrun "
+                               "main.py ... --gpu $LOCAL_RANK): mainModel then all-reduces its gradients over NCCL itself "
+                               "(INTEGRATION.md section 3)")
         if dev.type != "cuda":
             raise RuntimeError("mainModel runs on a B200 through libdrn_sm100.so only (no CPU / torch fallback): call .cuda()")
+        if self._dp is None and not self._dp_checked:
+            self._dp_checked = True
+            from drn_b200.parallel import auto_reducer
+            self._dp = auto_reducer(self, dev)
         # non_blocking: a synchronous host->device copy would drain the stream every step (the host could then never run ahead
         # of the GPU); pageable sources are staged by the runtime, pinned ones are the caller's to keep unchanged until used
-        tokens = torch.as_tensor(query_tokens).to(dev, dtype=torch.int64, non_blocking=True).contiguous()
-        lengths = torch.as_tensor(query_length).to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+        query_tokens, query_length = torch.as_tensor(query_tokens), torch.as_tensor(query_length)
+        if query_tokens.device.type == "cpu" and query_length.device.type == "cpu" and query_tokens.numel():
+            # host tensors: validate for free, with the reference's exceptions (nn.Embedding / pack_padded_sequence,
+            # language_module.py:41-42).  Device tensors are validated by drn_qe_stage (NaN losses + input_error()).
+            vocab = self.query_encoder.embedding.weight.shape[0]
+            if int(query_tokens.min()) < 0 or int(query_tokens.max()) >= vocab:
+                raise IndexError("index out of range in self (token id outside [0, %d))" % vocab)
+            if int(query_length.min()) < 1 or int(query_length.max()) > query_tokens.shape[1]:
+                raise RuntimeError("query lengths must lie in [1, %d] (got %d .. %d)"
+                                   % (query_tokens.shape[1], int(query_length.min()), int(query_length.max())))
+        tokens = query_tokens.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+        lengths = query_length.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
         feats = props_features.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
         pse = props_start_end.to(dev, dtype=torch.float64, non_blocking=True).contiguous()
         gt = gt_start_end.to(dev, non_blocking=True).float().contiguous()  # `.float()` as at main_model.py:74
@@ -238,9 +290,7 @@ class mainModel(nn.Module):
         # batch to batch; every (B, T, L) owns ~2 GB of buffers and two CUDA graphs, so L is bucketed (zero = padding tokens,
         # masked by the lengths: results are unchanged)
         Lq = tokens.shape[1]
-        Lb = max(10, (Lq + 3) // 4 * 4) if Lq > 10 else 10
-        if Lb != Lq:
-            tokens = torch.nn.functional.pad(tokens, (0, Lb - Lq))
+        Lb = max(10, (Lq + 3) // 4 * 4) if Lq > 10 else 10  # the staging kernel pads the token columns Lq .. Lb with zeros
         path = self._path(B, T, Lb, dev)
         names, tensors = self._dense_trainable()
         self._trainable_names = names
@@ -251,7 +301,8 @@ class mainModel(nn.Module):
             with torch.no_grad():
                 p = self._tensor_dict()
                 _run_forward(path, p, training, self.use_graphs, tokens, lengths, feats, pse, gt)
-                losses = path.losses[:3].clone()
+                path.generation = getattr(path, "generation", 0) + 1  # a pending backward of this shape is now stale
+                losses = path.losses[:3] + path.poison
         loss_dict = {"loss_cls": losses[0], "loss_reg": losses[1]}
         if self.cfg["is_first_stage"]:
             loss_dict["loss_iou"] = torch.zeros(1, device=dev)  # torch.FloatTensor([0]).cuda(), loss.py:239

@@ -100,23 +100,29 @@ def run_stage(stage, sd, batch, dev, steps, warmup, fused):
     return log, out_sd
 
 
-def three_stage(dev, steps, warmup):
+def three_stage(dev, steps, warmup, fused_modes=(False, True), emit=None):
+    """Returns the per-stage records (and passes each to `emit` as it is produced)."""
     cfg = S.default_config(stage=1)
     sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
     batch = S.synth_batch(32, 256, max_len=10, embedding=sd["query_encoder.embedding.weight"])
-    for fused in (False, True):
+    out = []
+    for fused in fused_modes:
         cur = sd
         for stage in (1, 2, 3):
             log, cur = run_stage(stage, cur, batch, dev, steps, warmup, fused)
             log.update({"config": "configs[2]: three-stage schedule, batch 32, T=256, 1xB200", "steps": steps, "warmup": warmup})
-            print(json.dumps(log), flush=True)
+            out.append(log)
+            if emit:
+                emit(log)
+    return out
 
 
-def sweep(dev, steps, warmup):
+def sweep(dev, steps, warmup, Ts=(64, 128, 256, 512), emit=None):
     from model.main_model import mainModel
     cfg = S.default_config(stage=1)
     sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
-    for T in (64, 128, 256, 512):
+    out = []
+    for T in Ts:
         B = 256
         batch = S.synth_batch(B, T, max_len=10, embedding=sd["query_encoder.embedding.weight"])
         model = mainModel(1301, S.config_namespace(stage=1))
@@ -150,16 +156,20 @@ def sweep(dev, steps, warmup):
         torch.cuda.synchronize()
         ms_dev = e0.elapsed_time(e1) / steps
         flop = 53.69e6 * T + 0.086e9
-        print(json.dumps({
+        rec = ({
             "config": "configs[4]: inference sweep, batch 256, 1xB200", "T": T, "B": B, "steps": steps, "warmup": warmup,
             "ms_per_batch_forward_plus_postprocess": round(ms, 4), "pairs_per_s": round(B / ms * 1e3, 1),
             "ms_per_batch_device_forward_only": round(ms_dev, 4), "pairs_per_s_device_forward_only": round(B / ms_dev * 1e3, 1),
             "algorithmic_tflops_per_s_device_forward_only": round(B * flop / (ms_dev * 1e-3) / 1e12, 1),
             "detections_first_sample": int(boxes[0]["detections"].shape[0]),
-            "device_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}), flush=True)
+            "device_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)})
+        out.append(rec)
+        if emit:
+            emit(rec)
         del model, path, g
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
+    return out
 
 
 def main():
@@ -172,10 +182,11 @@ def main():
     torch.set_num_threads(os.cpu_count())
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
+    emit = lambda r: print(json.dumps(r), flush=True)  # noqa: E731
     if not a.skip_train:
-        three_stage(dev, a.steps, a.warmup)
+        three_stage(dev, a.steps, a.warmup, emit=emit)
     if not a.skip_sweep:
-        sweep(dev, a.steps, a.warmup)
+        sweep(dev, a.steps, a.warmup, emit=emit)
 
 
 if __name__ == "__main__":

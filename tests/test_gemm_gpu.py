@@ -283,3 +283,130 @@ def test_fused_batchnorm_partial_sums(B, T, N):
     d3 = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=out, engine=3)
     d3.stats = stats.data_ptr()
     assert lib.drn_gemm(C.byref(d3), L.stream_ptr()) == -1
+
+
+# ---- stream-K schedule (drn_gemm_group_ws; opt-in, DRN_STREAMK=1 in the product path): many partial tiles per owner, every
+# ---- epilogue option behind a fold, static-schedule agreement, determinism, flags re-armed
+def _group_static(descs):
+    arr = (L.GemmDesc * len(descs))(*descs)
+    L.check(L.load().drn_gemm_group(len(descs), arr, L.stream_ptr()), "drn_gemm_group (static schedule)")
+
+
+def _flags_clear():
+    torch.cuda.synchronize()
+    return int(ops.workspace()[:4096].max()) == 0
+
+
+def test_streamk_long_tiles_many_contributors():
+    """Two 256 x 256 tiles of 96 k-iterations each (3 taps x 2048 channels): stream-K cuts them into ~48 ranges of 4 iterations,
+    so each owner folds ~23 partial tiles -- against fp64, against the static schedule, bit-exact on a repeat, flags re-armed."""
+    B, T, Cin, N = 2, 256, 2048, 256
+    a = Planes.from_float(_rand(B, T, Cin, seed=61))
+    w = Planes.from_float(_rand(3, N, Cin, seed=62, scale=(3 * Cin) ** -0.5))
+    out = torch.full((B, T, N), float("nan"), device=DEV)
+    d = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=out, engine=2)
+    ops.gemm_group([d], streamk=True)
+    assert _flags_clear()
+    ref = ref_rows(a, w, K3, 1, B, T, N, Cin, 0)
+    assert (out.double() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+    first = out.clone()
+    ops.gemm_group([d], streamk=True)
+    assert _flags_clear() and torch.equal(first, out)
+    stat = torch.full_like(out, float("nan"))
+    d.out = stat.data_ptr()
+    _group_static([d])
+    torch.cuda.synchronize()
+    # one accumulator over all 96 iterations (1152 dependent tensor-core accumulations): measurably less accurate than the sum
+    # of short partial tiles folded in fp32 round-to-nearest
+    assert (stat.double() - ref).abs().max().item() / ref.abs().max().item() < 6e-5
+    assert (stat - first).abs().max().item() / ref.abs().max().item() < 6e-5
+
+
+def test_streamk_ragged_remainder_mixed_group():
+    """The shape class of the head backward: three pyramid levels of data gradients (K = 3 x 512 -> 24 iterations a tile) and
+    weight gradients with K-split slices, tile counts that do not divide by the 74 SM pairs, ragged N and ragged rows."""
+    descs, checks, keep = [], [], []
+    w = Planes.from_float(_rand(3, 320, 512, seed=71, scale=(3 * 320) ** -0.5))       # [tap][K][N] for the data gradient
+    wf = Planes.from_float(_rand(3, 1000, 320, seed=72, scale=(3 * 320) ** -0.5))     # [tap][N][K], ragged N = 1000
+    for i, (B, T) in enumerate(((9, 200), (7, 100), (5, 52))):
+        dy = Planes.from_float(_rand(B, T, 320, seed=80 + i))
+        keep.append(dy)
+        o1 = torch.full((B, T, 512), float("nan"), device=DEV)
+        descs.append(ops.desc(L.GEMM_ROWS, dy.desc(), w.desc(), B, T, 512, K=320, taps=K3, b_mn=1, out=o1, engine=2))
+        checks.append((o1, ref_rows(dy, w, K3, 1, B, T, 512, 320, 1)))
+        if i < 2:
+            o2 = torch.full((B, T, 1000), float("nan"), device=DEV)
+            descs.append(ops.desc(L.GEMM_ROWS, dy.desc(), wf.desc(), B, T, 1000, K=320, taps=K3, out=o2, engine=2))
+            checks.append((o2, ref_rows(dy, wf, K3, 1, B, T, 1000, 320, 0)))
+    B, T, Co, Ci = 10, 128, 320, 448
+    dy, x = Planes.from_float(_rand(B, T, Co, seed=91)), Planes.from_float(_rand(B, T, Ci, seed=92))
+    ws = torch.full((4, 3, Co, Ci), float("nan"), device=DEV)
+    descs.append(ops.desc(L.GEMM_WGRAD, dy.desc(), x.desc(), B, T, Ci, M=Co, taps=K3, out=ws[0], out_ld=Ci,
+                          out_tap_stride=Co * Ci, out_split_stride=ws.stride(0), split_k=4, engine=2))
+    DY, X = dy.to_float().double(), x.to_float().double()
+    ref_w = torch.zeros(3, Co, Ci, dtype=torch.float64, device=DEV)
+    for (sh, par, wt) in K3:
+        src = torch.zeros(B, T, Ci, dtype=torch.float64, device=DEV)
+        lo, hi = max(0, -sh), min(T, T - sh)
+        src[:, lo:hi] = X[:, lo + sh:hi + sh]
+        ref_w[wt] = torch.einsum("bto,btc->oc", DY, src)
+    assert len(descs) == 6 and ops.gemm_group(descs, streamk=True) == 1
+    assert _flags_clear()
+    for out, ref in checks:
+        assert not torch.isnan(out).any()
+        assert (out.double() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+    assert not torch.isnan(ws).any()
+    assert (ws.double().sum(0) - ref_w).abs().max().item() / ref_w.abs().max().item() < 2e-5
+    snap = [o.clone() for o, _ in checks] + [ws.clone()]
+    ops.gemm_group(descs, streamk=True)
+    assert _flags_clear()
+    for s, t in zip(snap, [o for o, _ in checks] + [ws]):
+        assert torch.equal(s, t)
+
+
+def test_streamk_epilogue_options_behind_a_fold():
+    """bias, second output, row gate, accumulate mode, plane output and BatchNorm partial sums all run AFTER the fold: 6 tiles of
+    48 iterations on 74 pairs -> every tile is folded from several partial tiles."""
+    import ctypes as C
+    B, T, Cin, N = 3, 256, 1024, 512
+    a = Planes.from_float(_rand(B, T, Cin, seed=101))
+    w = Planes.from_float(_rand(3, N, Cin, seed=102, scale=(3 * Cin) ** -0.5))
+    bias, q = _rand(N, seed=103), _rand(B, N, seed=104)
+    base = _rand(B, T, N, seed=105)
+    out, pre, pl = base.clone(), torch.empty(B, T, N, device=DEV), Planes.zeros(B, T, N, DEV)
+    d = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=out, out_mode=L.OUT_ADD, bias=bias, rowscale=q,
+                 out2=pre, outp=pl, engine=2)
+    ops.gemm_group([d], streamk=True)
+    assert _flags_clear()
+    ref_pre = ref_rows(a, w, K3, 1, B, T, N, Cin, 0) + bias.double()
+    ref = ref_pre * q.double()[:, None, :]
+    s = ref.abs().max().item()
+    assert (pre.double() - ref_pre).abs().max().item() / s < 2e-5
+    assert (out.double() - base.double() - ref).abs().max().item() / s < 4e-5
+    assert (pl.to_float().double() - ref).abs().max().item() / s < 3e-5
+    y = torch.full((B, T, N), float("nan"), device=DEV)
+    d2 = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=y, bias=bias, engine=2)
+    rows = L.load().drn_gemm_stats_rows(C.byref(d2))
+    stats = torch.full((rows, 2, N), float("nan"), device=DEV)
+    d2.stats = stats.data_ptr()
+    ops.gemm_group([d2], streamk=True)
+    assert _flags_clear() and not torch.isnan(stats).any()
+    yy = y.double().view(-1, N)
+    st = stats.double().sum(0)
+    assert (st[0] - yy.sum(0)).abs().max().item() <= 1e-5 * yy.abs().sum(0).max().item()
+    assert (st[1] - (yy * yy).sum(0)).abs().max().item() <= 1e-5 * (yy * yy).sum(0).max().item()
+
+
+def test_streamk_matches_static_on_full_size_layers():
+    """prop_fc-forward and prop_fc-wgrad shape classes at a size with several tiles per SM pair: stream-K and the static
+    schedule agree to fp32 summation-order noise."""
+    old = ops.STREAMK
+    ops.STREAMK = True
+    try:
+        err, out, ref = run_rows(8, 256, 1024, 2048, ((0, 0, 0),), engine=2)
+        assert err < 2e-5, err
+        err = run_wgrad(16, 256, 1024, 1536, ((0, 0, 0),), engine=2)
+        assert err < 2e-5, err
+    finally:
+        ops.STREAMK = old
+    assert _flags_clear()

@@ -181,8 +181,12 @@ def test_bench_reference_arm_prints_the_contract_line():
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
     assert d["impl"] == "reference" and d["metric"] == b.METRIC and d["unit"] == "pairs/s" and d["higher_is_better"] is True
-    assert d["config"]["workload"] == b.WORKLOAD and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"] == b.workload_config(1) and d["value"] > 0 and d["vs_baseline"] is None  # the own arm emits the same dict
+    assert d["steps_requested"] == 1 and d["steps"] == 1 and isinstance(d["steps_capped"], bool)
+    # kind "reference" when build() has packed oracle/_ref/drn_reference.zip (the unmodified reference runs), else the port
+    packed = os.path.isfile(os.path.join(REPO, "oracle", "_ref", "drn_reference.zip"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if packed else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
@@ -199,7 +203,7 @@ def test_gradients_are_attached_as_views_and_still_accumulate(monkeypatch):
     model = types.SimpleNamespace(_trainable_names=["w", "v"], use_graphs=False, _dp=None, _tensor_dict=lambda: {"w": w, "v": v})
     flat = torch.zeros(16)
     grads = {"w": flat[0:6].view(2, 3), "v": flat[8:12]}
-    path = types.SimpleNamespace(losses=torch.zeros(8), flat_storages={flat.untyped_storage().data_ptr()})
+    path = types.SimpleNamespace(losses=torch.zeros(8), poison=torch.zeros(1), flat_storages={flat.untyped_storage().data_ptr()})
     scale = {"k": 1.0}
 
     def fake_forward(path_, p, training, use_graphs, *inputs):
@@ -234,3 +238,23 @@ def test_gradients_are_attached_as_views_and_still_accumulate(monkeypatch):
     scale["k"] = 1.0
     step()
     assert torch.equal(w.grad, torch.ones(2, 3)) and w.grad.untyped_storage().data_ptr() != flat.untyped_storage().data_ptr()
+
+
+def test_backward_after_another_forward_of_the_same_shape_raises(monkeypatch):
+    """The backward reads the activations of its forward from the path's static buffers: a second forward of the same shape
+    in between (eval pass, two losses) must raise instead of silently differentiating the wrong batch."""
+    import types
+    from model import main_model as MM
+
+    w = torch.nn.Parameter(torch.ones(3))
+    model = types.SimpleNamespace(_trainable_names=["w"], use_graphs=False, _dp=None, _tensor_dict=lambda: {"w": w})
+    flat = torch.zeros(8)
+    path = types.SimpleNamespace(losses=torch.zeros(8), poison=torch.zeros(1), flat_storages=set())
+    monkeypatch.setattr(MM, "_run_forward", lambda path_, p, *a: path_.losses.__setitem__(slice(0, 3), torch.ones(3)))
+    monkeypatch.setattr(MM, "_run_backward", lambda path_, p, names, up, ug, dp=None: (flat, {"w": flat[:3]}))
+    dummy = torch.zeros(1)
+    l1 = MM._DenseFn.apply(model, path, True, dummy, dummy, dummy, dummy, dummy, w)
+    l2 = MM._DenseFn.apply(model, path, True, dummy, dummy, dummy, dummy, dummy, w)
+    l2.sum().backward()  # the latest forward: fine
+    with pytest.raises(RuntimeError, match="another forward"):
+        l1.sum().backward()

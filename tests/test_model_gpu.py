@@ -295,3 +295,105 @@ def test_token_width_buckets(L):
     b2["query_length"] = batch["query_length"].clamp(max=L - 1)
     _run_cuda(model, b2)
     assert len(model._paths) == n_paths
+
+
+def _summary(t):
+    """oracle/make_goldens.py:summarize -- [norm, sum, 16 sampled values] of a tensor in the reference's layout."""
+    t = t.detach().to(torch.float64).reshape(-1).cpu()
+    idx = torch.from_numpy(S.sample_indices(t.numel()))
+    return torch.cat([torch.tensor([float(t.norm()), float(t.sum())], dtype=torch.float64), t[idx]]), float(t.abs().sum())
+
+
+@pytest.mark.parametrize("name", list(S.GOLDEN_CASES))
+def test_intermediates_match_reference_golden(name, golden_dir):
+    """The goldens hold summaries of thirteen intermediates captured by forward hooks on the UNMODIFIED reference (gates, prop_fc
+    output, backbone C1-C3, FPN laterals / outputs): the CUDA path's buffers must reproduce them -- a wrong layer cannot hide
+    behind a matching loss."""
+    cfg, sd, batch, stage, training = _build(name)
+    model = _cuda_model(sd, stage, training)
+    with torch.no_grad():
+        _run_cuda(model, batch)
+    path = list(model._paths.values())[-1]
+    bct = lambda pl: pl.to_float().permute(0, 2, 1)  # noqa: E731  planes [B,T,C] -> reference layout [B,C,T]
+    I = [bct(path.I[i]) for i in range(3)]
+    mine = {"q0": path.q[0], "q1": path.q[1], "q2": path.q[2], "P_btd": path.Pre,
+            "C1": bct(path.Cact[0]), "C2": bct(path.Cact[1]), "C3": bct(path.Cact[2]),
+            "I3": I[2], "P3": bct(path.Pf[2]), "P2": bct(path.Pf[1]), "P1": bct(path.Pf[0]),
+            # fused upsample-add (FPN.py:63-68): the lateral before the add is I_l - up2(I_{l+1})
+            "L2": I[1] - I[2].repeat_interleave(2, dim=2), "L1": I[0] - I[1].repeat_interleave(2, dim=2)}
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    for k, v in mine.items():
+        ref = torch.from_numpy(g["cap/" + k])
+        got, l1 = _summary(v)
+        scale = float(ref[2:].abs().max())
+        assert abs(float(got[0] - ref[0])) <= 1e-3 * float(ref[0]), (k, "norm", float(got[0]), float(ref[0]))
+        assert abs(float(got[1] - ref[1])) <= 1e-3 * l1, (k, "sum")
+        assert float((got[2:] - ref[2:]).abs().max()) <= 1e-3 * max(scale, float(ref[0]) / v.numel() ** 0.5), (k, "samples")
+
+
+def test_eval_parity_at_sweep_batch_256():
+    """BASELINE configs[4] is quoted at batch 256: eval-mode forward + candidate selection at B=256, T=64 against the oracle
+    (head outputs 1e-3; detections per sample after the ordering-free canonicalisation; at most a threshold flip or two)."""
+    torch.set_num_threads(os.cpu_count())
+    B, T = 256, 64
+    cfg, sd, batch, stage, _ = _build(B=B, T=T)
+    model = _cuda_model(sd, 1, False)
+    with torch.no_grad():
+        boxes, ld = _run_cuda(model, batch)
+    oboxes, old, _, cap, _ = _oracle(sd, cfg, batch, 1, False)
+    mine = _head_outputs(model, B)
+    for k, v in mine.items():
+        assert _maxrel(v, cap[k]) <= FWD_TOL, (k, _maxrel(v, cap[k]))
+    for k in ("loss_cls", "loss_reg"):
+        assert _maxrel(ld[k].detach().cpu(), old[k].detach()) <= FWD_TOL, k
+    assert len(boxes) == len(oboxes) == B
+    same = 0
+    for d, od in zip(boxes, oboxes):
+        if d["detections"].shape != od["detections"].shape:
+            continue
+        o1 = np.lexsort((d["detections"][:, 0].cpu().numpy(), d["scores"].cpu().numpy()))
+        o2 = np.lexsort((od["detections"][:, 0].numpy(), od["scores"].numpy()))
+        if _maxrel(d["detections"].cpu()[o1], od["detections"][o2]) <= FWD_TOL and _maxrel(d["scores"].cpu()[o1], od["scores"][o2]) <= FWD_TOL:
+            same += 1
+    assert same >= B - 2, same
+
+
+def test_invalid_tokens_and_lengths_are_rejected_not_dereferenced():
+    """token ids index the embedding table (and its gradient) and lengths index the LSTM output.  Host tensors raise
+    like the reference (nn.Embedding IndexError / pack_padded_sequence); device tensors are sanitised by drn_qe_stage: the batch's
+    losses are NaN, input_error() names the problem, nothing outside the buffers is touched and the next valid batch is exact."""
+    cfg, sd, batch, stage, _ = _build(B=4, T=32, L=8)
+    model = _cuda_model(sd, 1, True)
+    _, ld = _run_cuda(model, batch)
+    sum(ld.values()).backward()
+    good = {k: float(v) for k, v in ld.items()}
+    gemb = model.query_encoder.embedding.weight.grad.clone()
+    assert model.input_error() is None
+    bad_tok = batch["query_tokens"].clone()
+    bad_tok[1, 0] = 1302          # one past the table
+    bad_tok[2, 1] = -5
+    with pytest.raises(IndexError):
+        model(bad_tok, batch["query_length"], batch["props_features"], batch["props_start_end"], batch["gt_start_end"], None, None)
+    bad_len = batch["query_length"].clone()
+    bad_len[3] = 0
+    with pytest.raises(RuntimeError):
+        model(batch["query_tokens"], bad_len, batch["props_features"], batch["props_start_end"], batch["gt_start_end"], None, None)
+    for tok, ln, what in ((bad_tok.cuda(), batch["query_length"].cuda(), "token"), (batch["query_tokens"].cuda(), bad_len.cuda(), "length"),
+                          (batch["query_tokens"].cuda(), torch.full_like(bad_len, 99).cuda(), "length")):
+        for p in model.parameters():
+            p.grad = None
+        _, ld2 = model(tok, ln, batch["props_features"], batch["props_start_end"], batch["gt_start_end"], None, None)
+        assert all(torch.isnan(v).all() for k, v in ld2.items() if k != "loss_iou")
+        (ld2["loss_cls"] + ld2["loss_reg"]).backward()   # must not fault: sanitised ids / lengths
+        torch.cuda.synchronize()
+        msg = model.input_error()
+        assert msg is not None and what in msg, msg
+        assert model.input_error() is None  # flags are cleared by the read
+    for p in model.parameters():
+        p.grad = None
+    _, ld3 = model(batch["query_tokens"].cuda(), batch["query_length"].cuda(), batch["props_features"], batch["props_start_end"],
+                   batch["gt_start_end"], None, None)
+    sum(ld3.values()).backward()
+    assert {k: float(v) for k, v in ld3.items()} == good
+    assert torch.equal(model.query_encoder.embedding.weight.grad, gemb) or \
+        float((model.query_encoder.embedding.weight.grad - gemb).abs().max()) <= 1e-6 * float(gemb.abs().max())

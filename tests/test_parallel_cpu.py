@@ -38,7 +38,16 @@ def _worker(rank, world, port, q):
     dp = DataParallelDRN(toy)
     ok = all(bool((p == 1.0).all()) for p in toy.parameters()) and bool((toy.running == 0.0).all())  # replica 0 wins
     flat = torch.arange(6, dtype=torch.float32) * (rank + 1)
-    ok = ok and toy._dp is dp
+    ok = ok and toy._dp is dp.reducer and "_dp" not in toy._modules  # a plain object: no cycle in the module tree
+    # with the wrapper registered as a submodule of the model it wraps these recursed for ever
+    from drn_b200.checkpoint import reference_checkpoint
+    dp.eval()
+    dp.train()
+    toy.eval()
+    toy.train()
+    ok = ok and sorted(dp.state_dict()) == sorted("module." + k for k in toy.state_dict())
+    ok = ok and sorted(reference_checkpoint(dp)["state_dict"]) == sorted(dp.state_dict())
+    dp.to("cpu")
     work = dp.reduce_regions([flat[:4]], wait=False)  # what _run_backward does: first region async, tail regions, then wait
     dp.reduce_regions([flat[4:], flat[:0]])
     dp.wait(work)
@@ -58,6 +67,38 @@ def test_data_parallel_wrapper_two_ranks_gloo():
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def _auto_worker(rank, world, port, q):
+    """The `torchrun main.py` route: WORLD_SIZE in the environment, no process group yet -> auto_reducer creates it (gloo on a
+    CPU device), broadcasts rank 0's tensors and returns the reducer; with WORLD_SIZE=1 or DRN_AUTO_DP=0 it returns None."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from drn_b200.parallel import auto_reducer
+    toy = _Toy(rank)
+    os.environ["DRN_AUTO_DP"] = "0"
+    ok = auto_reducer(toy, torch.device("cpu")) is None and not dist.is_initialized()
+    os.environ["DRN_AUTO_DP"] = "1"
+    red = auto_reducer(toy, torch.device("cpu"))
+    ok = ok and red is not None and red.world == world and dist.is_initialized()
+    ok = ok and all(bool((p == 1.0).all()) for p in toy.parameters()) and bool((toy.running == 0.0).all())
+    flat = torch.full((5,), float(rank + 1))
+    red.reduce_regions([flat])
+    ok = ok and torch.allclose(flat, torch.full((5,), 1.5))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_auto_reducer_from_environment_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_auto_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
