@@ -155,11 +155,29 @@ def sweep(dev, steps, warmup, Ts=(64, 128, 256, 512), emit=None):
         e1.record()
         torch.cuda.synchronize()
         ms_dev = e0.elapsed_time(e1) / steps
+        # forward + candidate selection + the metric (temporal NMS, R@1 / R@5 at tIoU 0.5) entirely on the device: what an
+        # evaluation loop needs when it does not ask for the per-sample lists (drn_b200/metric.py:recall_from_candidates)
+        from drn_b200 import metric as M
+        gt_dev = b["gt_start_end"]
+        tot = torch.zeros(2, dtype=torch.int32, device=dev)
+        e0.record()
+        for _ in range(steps):
+            path.stage_inputs(p, b["query_tokens"], b["query_length"].to(dev), b["props_features"], b["props_start_end"], b["gt_start_end"].float())
+            g.replay()
+            det, score, _, count = path.postprocess()
+            tot += M.recall_from_candidates(det, score, count, gt_dev, iou=0.5, topk=(1, 5), sync=False)["correct"]
+        e1.record()
+        torch.cuda.synchronize()
+        ms_metric = e0.elapsed_time(e1) / steps
+        r1, r5 = (tot.float() / (B * steps)).tolist()
         flop = 53.69e6 * T + 0.086e9
         rec = ({
             "config": "configs[4]: inference sweep, batch 256, 1xB200", "T": T, "B": B, "steps": steps, "warmup": warmup,
             "ms_per_batch_forward_plus_postprocess": round(ms, 4), "pairs_per_s": round(B / ms * 1e3, 1),
             "ms_per_batch_device_forward_only": round(ms_dev, 4), "pairs_per_s_device_forward_only": round(B / ms_dev * 1e3, 1),
+            "ms_per_batch_forward_postprocess_metric_on_device": round(ms_metric, 4),
+            "pairs_per_s_forward_postprocess_metric_on_device": round(B / ms_metric * 1e3, 1),
+            "recall_at_1_5_random_weights": [round(r1, 4), round(r5, 4)],
             "algorithmic_tflops_per_s_device_forward_only": round(B * flop / (ms_dev * 1e-3) / 1e12, 1),
             "detections_first_sample": int(boxes[0]["detections"].shape[0]),
             "device_memory_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)})

@@ -60,7 +60,7 @@ def _train_cuda(sd, stage, batches, kind, lr, opt_filter=None, clip=0.5):
     return model, losses, norms
 
 
-def _train_oracle(sd, cfg, stage, batches, kind, lr, opt_filter=None, clip=0.5, perturb=0.0):
+def _train_oracle(sd, cfg, stage, batches, kind, lr, opt_filter=None, clip=0.5, perturb=0.0, zero_all=False):
     leaf = {}
     for k, v in sd.items():
         v = v.detach().clone()
@@ -84,6 +84,9 @@ def _train_oracle(sd, cfg, stage, batches, kind, lr, opt_filter=None, clip=0.5, 
         norms.append(float(torch.nn.utils.clip_grad_norm_(every, clip)))
         opt.step()
         opt.zero_grad()
+        if zero_all:
+            for v in every:
+                v.grad = None
         with torch.no_grad():
             for k, v in newbuf.items():
                 leaf[k] = v.detach().clone()
@@ -106,12 +109,15 @@ def test_five_optimizer_steps_stage1(kind, lr):
     msd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     # step 0 is a pure forward/backward comparison
     assert abs(lc[0] - lo[0]) <= 1e-4 * abs(lo[0]) and abs(nc[0] - no[0]) <= 2e-3 * no[0]
+    ctl_gap = 0.0
     for i in range(5):
-        ctl_gap = abs(lp[i] - lo[i])
-        bound = (1e-3 if kind == "sgd" else 0.0) * abs(lo[i]) + 4.0 * ctl_gap + 1e-4 * abs(lo[i])
-        assert abs(lc[i] - lo[i]) <= bound, "step %d: loss %.6f vs oracle %.6f (control gap %.2e)" % (i, lc[i], lo[i], ctl_gap)
+        ctl_gap = max(ctl_gap, abs(lp[i] - lo[i]))  # the control's divergence so far
+        bound = (1e-3 if kind == "sgd" else 2e-4) * abs(lo[i]) + 4.0 * ctl_gap
+        assert abs(lc[i] - lo[i]) <= bound, "step %d: loss %.6f vs oracle %.6f (control gap %.2e); losses %s | %s | %s" % (
+            i, lc[i], lo[i], ctl_gap, lc, lo, lp)
     # BatchNorm: five updates of every running statistic, num_batches_tracked exact (shared head modules: 3 levels x 5 steps)
     worst_w = worst_ctl = 0.0
+    tot_e = tot_c = tot_u = 0.0
     for k, v in ref.items():
         if k.endswith("num_batches_tracked"):
             assert int(msd[k]) == int(v), k
@@ -123,8 +129,13 @@ def test_five_optimizer_steps_stage1(kind, lr):
             e = float((msd[k].double() - v.detach().double()).norm()) / upd
             c = float((ctl[k].detach().double() - v.detach().double()).norm()) / upd
             worst_w, worst_ctl = max(worst_w, e), max(worst_ctl, c)
-            assert e <= (5e-3 if kind == "sgd" else 0.0) + 4.0 * c + 1e-3, "%s: update error %.2e (control %.2e)" % (k, e, c)
-    print("five steps (%s): worst update error %.2e, control %.2e" % (kind, worst_w, worst_ctl))
+            tot_e, tot_c, tot_u = tot_e + (e * upd) ** 2, tot_c + (c * upd) ** 2, tot_u + upd ** 2
+            # per tensor: SGD is proportional to the gradient (plain bound); under Adam both e and c are chaotic, so the
+            # per-tensor bound is loose and the aggregate below carries the comparison
+            assert e <= (5e-3 + 4.0 * c if kind == "sgd" else 2e-2 + 10.0 * c), "%s: update error %.2e (control %.2e)" % (k, e, c)
+    E, Cc = (tot_e / tot_u) ** 0.5, (tot_c / tot_u) ** 0.5
+    print("five steps (%s): update error over all tensors %.2e (control %.2e); worst tensor %.2e (control %.2e)" % (kind, E, Cc, worst_w, worst_ctl))
+    assert E <= 3.0 * Cc + 2e-3, "all tensors: update error %.2e vs control %.2e" % (E, Cc)
 
 
 def test_stage2_stale_gradients_accumulate_like_the_reference():
@@ -144,7 +155,9 @@ def test_stage2_stale_gradients_accumulate_like_the_reference():
     for i in range(3):
         assert abs(lc[i] - lo[i]) <= 1e-3 * abs(lo[i]), (i, lc[i], lo[i])
         assert abs(nc[i] - no[i]) <= 5e-3 * no[i], (i, nc[i], no[i])
-    assert no[2] > 1.5 * no[0]  # the stale gradients really did pile up
+    # the quirk is live: with every gradient zeroed each step (what the reference does NOT do) the clipped norms differ
+    _, _, nz = _train_oracle(sd, cfg, 2, batches, "sgd", 1e-3, opt_filter=flt, zero_all=True)
+    assert abs(nz[0] - no[0]) <= 1e-6 * no[0] and abs(nz[2] - no[2]) > 5e-3 * no[2], (nz, no)
     params = dict(model.named_parameters())
     for k in ("fcos.head.bbox_pred.weight", "fcos.head.bbox_tower.0.weight", "fpn.fpn_layer1.0.weight"):
         g, r = params[k].grad.cpu(), ref[k].grad  # accumulated over 3 steps, clipped in place each step
