@@ -92,6 +92,27 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe root), BEFORE the pinned
+    input buffers are allocated (first touch places their pages on that node).  Best effort: returns a small report."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 16)
+        local = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(local & allowed)
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            return {"bound": True, "cpus": len(use), "of_allowed": len(allowed)}
+        return {"bound": False, "cpus": len(allowed), "gpu_local_cpus_visible": len(use)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "error": repr(e)[:80]}
+
+
 def build_inputs(world_rank):
     from drn_b200 import spec as spec_mod
     from drn_b200 import synthetic as S
@@ -195,7 +216,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local) if world > 1 and os.environ.get("DRN_BIND_NUMA", "1") == "1" else {"bound": False}
     if world > 1:
+        if os.environ.get("DRN_NCCL_MAX_CTAS"):  # fewer NCCL CTAs = more SMs left to the contraction the collective runs beside
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DRN_NCCL_MAX_CTAS"])
         dist.init_process_group("nccl", device_id=dev)
     cfg, sd, batch = build_inputs(rank)
     model = mainModel(1301, S.config_namespace(stage=1))
@@ -323,6 +347,15 @@ def run_ours(args):
     barrier()
     assert len(loss_log) == args.steps and all(x == x for x in loss_log)
     ms_e2e = e2.elapsed_time(e3) / args.steps
+    # host->device bandwidth each rank gets while ALL ranks upload at once (what bounds e2e at N > 1: GPUs share PCIe uplinks)
+    barrier()
+    e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e6.record()
+    for _ in range(5):
+        bufs[0]["props_features"].copy_(pinned["props_features"], non_blocking=True)
+    e7.record()
+    barrier()
+    h2d_gbs = 5 * pinned["props_features"].numel() * 4 / (e6.elapsed_time(e7) * 1e-3) / 1e9
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -344,10 +377,11 @@ def run_ours(args):
         s2.join(timeout=2)
         sustained = (e4.elapsed_time(e5) / sus_steps, sus_steps, s2.summary())
 
-    t = torch.tensor([ms, ms_e2e, sustained[0] if sustained else 0.0], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, sustained[0] if sustained else 0.0, -h2d_gbs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_sus = t.tolist()
+    ms, ms_e2e, ms_sus, h2d_min = t.tolist()
+    h2d_min = -h2d_min
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -369,7 +403,8 @@ def run_ours(args):
         "diag": {"algorithmic_tflops_per_s": value * FLOP_PER_PAIR / 1e12, "fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3)},
         "clocks": sampler.summary(),
         "e2e": {"value": world * B_PER_GPU / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e},
+                "ms_per_step": ms_e2e, "h2d_gbs_per_rank_all_ranks_uploading": {"rank0": h2d_gbs, "min_over_ranks": h2d_min},
+                "host_affinity_rank0": affinity},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": "gemm_pair_kernel (prop_fc forward, M=8192 N=K=4096: 27 % of the step's FLOPs; "
                      "the same kernel runs every contraction of the path)",

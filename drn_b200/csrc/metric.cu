@@ -25,7 +25,7 @@ constexpr int NMS_WARPS = 4;
 
 __global__ void __launch_bounds__(NMS_WARPS * 32) nms_recall_kernel(
     const float* __restrict__ det, const float* __restrict__ score, const int* __restrict__ count, const double* __restrict__ gt,
-    int Q, int G, int K, double overlap, double iou_thr, const int* __restrict__ topk, int ntopk, int empty_fallback,
+    int Q, int G, int K, int nms, double overlap, double iou_thr, const int* __restrict__ topk, int ntopk, int empty_fallback,
     int* __restrict__ picks, int* __restrict__ npicks, int* __restrict__ hits, int* __restrict__ correct) {
   pdl_sync();
   __shared__ double sx1[NMS_WARPS][NMS_MAX_N], sx2[NMS_WARPS][NMS_MAX_N];
@@ -62,20 +62,23 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_recall_kernel(
   int np = 0, first_hit = 0x7fffffff;
   int* my_picks = picks ? picks + static_cast<long long>(q) * N : nullptr;
   while (true) {
-    // argmax over the live candidates of (score, index)
+    // best live candidate: highest score; among equal scores the LATER one with NMS (nms_temporal takes the last element of a
+    // stable ascending sort), the EARLIER one without (picks = the stable descending order itself, evaluate_utils.py:97,165)
     float bs = -CUDART_INF_F;
     int bi = -1;
 #pragma unroll
-    for (int r = 0; r < NMS_PER_LANE; ++r)
-      if (alive[r] && (s[r] > bs || (s[r] == bs && r * 32 + lane > bi))) {
+    for (int r = 0; r < NMS_PER_LANE; ++r) {
+      const int i = r * 32 + lane;
+      if (alive[r] && (bi < 0 || s[r] > bs || (s[r] == bs && (nms ? i > bi : i < bi)))) {
         bs = s[r];
-        bi = r * 32 + lane;
+        bi = i;
       }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float os = __shfl_xor_sync(0xffffffffu, bs, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && oi > bi))) {
+      if (oi >= 0 && (bi < 0 || os > bs || (os == bs && (nms ? oi > bi : oi < bi)))) {
         bs = os;
         bi = oi;
       }
@@ -93,6 +96,7 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_recall_kernel(
         alive[r] = false;
         continue;
       }
+      if (!nms) continue;
       const double inter = fmax(0.0, fmin(px2, x2[r]) - fmax(px1, x1[r]));
       const double o = inter / (plen + (x2[r] - x1[r]) - inter);
       if (!(o <= overlap)) alive[r] = false;
@@ -115,13 +119,13 @@ __global__ void __launch_bounds__(NMS_WARPS * 32) nms_recall_kernel(
 using namespace drn;
 
 extern "C" int drn_nms_recall(const float* det, const float* score, const int32_t* count, const double* gt, int Q, int G, int K,
-                              double overlap, double iou_thr, const int32_t* topk, int ntopk, int empty_fallback, int32_t* picks,
+                              int nms, double overlap, double iou_thr, const int32_t* topk, int ntopk, int empty_fallback, int32_t* picks,
                               int32_t* npicks, int32_t* hits, int32_t* correct, void* stream) {
   if (!det || !score || !count || !gt || !topk) return fail(DRN_EINVAL, "drn_nms_recall: null input");
   if (Q < 1 || G < 1 || K < 1 || G * K > NMS_MAX_N)
     return fail(DRN_EINVAL, "drn_nms_recall: need Q >= 1 and 1 <= groups x slots <= %d (G=%d, K=%d)", NMS_MAX_N, G, K);
   if (ntopk < 1 || ntopk > 8) return fail(DRN_EINVAL, "drn_nms_recall: 1..8 top-k values (got %d)", ntopk);
   launch_k(nms_recall_kernel, (Q + NMS_WARPS - 1) / NMS_WARPS, NMS_WARPS * 32, 0, static_cast<cudaStream_t>(stream), det, score,
-           count, gt, Q, G, K, overlap, iou_thr, topk, ntopk, empty_fallback, picks, npicks, hits, correct);
+           count, gt, Q, G, K, nms ? 1 : 0, overlap, iou_thr, topk, ntopk, empty_fallback, picks, npicks, hits, correct);
   return check_launch("nms_recall_kernel");
 }

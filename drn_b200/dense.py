@@ -654,16 +654,25 @@ class DensePath:
         if tail:
             self.backward_tail(p, grads, unpack=(iou_on,) if defer else None)
 
-    def backward_propfc(self, grads, pair_clusters=0):
+    def backward_propfc(self, grads, pair_clusters=0, chunk=None):
         """prop_fc weight gradient: [D x (B*T)] x [(B*T) x D], the largest contraction of the backward pass.  pair_clusters > 0
-        confines the persistent kernel to that many SM pairs (data parallel: the rest run the NCCL all-reduce of the gradients
-        that are already complete)."""
+        confines the persistent kernel to that many SM pairs.  chunk = (i, n): only output rows [i*D/n, (i+1)*D/n) of the
+        gradient (data parallel: the chunks are all-reduced as they complete; at D = 4096, n = 4 a chunk is 64
+        tiles = one wave on 64 of the 74 SM pairs -- the whole gradient is 4 waves either way -- which leaves 20 SMs to NCCL)."""
         B = self.B
         if pair_clusters:
             _lib().drn_set_pair_clusters(pair_clusters)
         try:
-            self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=grads["prop_fc.weight"],
-                       out_ld=self.D, out_tap_stride=0)
+            gw = grads["prop_fc.weight"]
+            if chunk is None:
+                self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=self.D, out=gw, out_ld=self.D,
+                           out_tap_stride=0)
+            else:
+                i, n = chunk
+                rows = self.D // n
+                assert rows * n == self.D and rows % 8 == 0
+                self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=rows, a_c0=i * rows,
+                           out=gw[i * rows:(i + 1) * rows], out_ld=self.D, out_tap_stride=0, engine=2)
         finally:
             if pair_clusters:
                 _lib().drn_set_pair_clusters(0)

@@ -28,9 +28,8 @@ def _launch(det, score, count, gt, G, K, iou, topk, nms, empty_fallback, want_pi
     npicks = torch.empty(Q, dtype=torch.int32, device=dev)
     hits = torch.empty(Q, len(topk), dtype=torch.int32, device=dev)
     correct = torch.zeros(len(topk), dtype=torch.int32, device=dev)
-    # without NMS every candidate is a pick, best first (compute_IoU_recall_top_n_ours, nms=False): overlap = +inf suppresses none
-    overlap = float(iou) - 0.05 if nms else float("inf")
-    L.check(L.load().drn_nms_recall(L.ptr(det), L.ptr(score), L.ptr(count), L.ptr(gt), Q, G, K, C.c_double(overlap),
+    overlap = float(iou) - 0.05  # evaluate_utils.py:152
+    L.check(L.load().drn_nms_recall(L.ptr(det), L.ptr(score), L.ptr(count), L.ptr(gt), Q, G, K, 1 if nms else 0, C.c_double(overlap),
                                     C.c_double(float(iou)), L.ptr(topk_t), len(topk), 1 if empty_fallback else 0, L.ptr(picks),
                                     L.ptr(npicks), L.ptr(hits), L.ptr(correct), L.stream_ptr()), "nms_recall")
     return picks, npicks, hits, correct
@@ -66,7 +65,7 @@ def nms_temporal(x1, x2, s, overlap, device="cuda"):
     topk = torch.tensor([1], dtype=torch.int32, device=dev)
     picks = torch.empty(1, n, dtype=torch.int32, device=dev)
     npicks = torch.empty(1, dtype=torch.int32, device=dev)
-    L.check(L.load().drn_nms_recall(L.ptr(det), L.ptr(sc), L.ptr(cnt), L.ptr(gt), 1, 1, n, C.c_double(float(overlap)), C.c_double(2.0),
+    L.check(L.load().drn_nms_recall(L.ptr(det), L.ptr(sc), L.ptr(cnt), L.ptr(gt), 1, 1, n, 1, C.c_double(float(overlap)), C.c_double(2.0),
                                     L.ptr(topk), 1, 0, L.ptr(picks), L.ptr(npicks), None, None, L.stream_ptr()), "nms_recall")
     return picks[0, :int(npicks[0])].tolist()
 

@@ -396,12 +396,13 @@ int drn_qe_backward_part(const drn_qe_t* q, int part, void* stream);
  *   count[q*G+g] valid entries at its front (the layout drn_postprocess writes; a plain list is G = 1, K = list capacity);
  *   gt [Q][2] f64; overlap = NMS threshold (the reference passes iou - 0.05); topk [ntopk] int32 (device).
  * Candidate order = (group, slot); among equal scores the later candidate is picked first (stable ascending sort, best last:
- * evaluate_utils.py:200).  Zero-length candidates are dropped (the reference raises ZeroDivisionError on them);
+ * evaluate_utils.py:200).  nms == 0: no suppression, picks = all candidates by descending score, among equal scores the EARLIER
+ * first (the reference's stable descending sort, evaluate_utils.py:97,165); `overlap` is ignored.  Zero-length candidates are dropped (the reference raises ZeroDivisionError on them);
  * empty_fallback != 0: a query without candidates is given the detection (0, 1), score 1 (model/inference.py:192-197).
  * Outputs (each optional): picks [Q][G*K] candidate indices in pick order, -1 padded; npicks [Q]; hits [Q][ntopk] 0/1;
  * correct [ntopk] += number of hit queries (caller zeroes).  G*K <= 256, ntopk <= 8. */
 int drn_nms_recall(const float* det, const float* score, const int32_t* count, const double* gt, int Q, int G, int K,
-                   double overlap, double iou_thr, const int32_t* topk, int ntopk, int empty_fallback, int32_t* picks,
+                   int nms, double overlap, double iou_thr, const int32_t* topk, int ntopk, int empty_fallback, int32_t* picks,
                    int32_t* npicks, int32_t* hits, int32_t* correct, void* stream);
 
 #ifdef __cplusplus

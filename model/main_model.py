@@ -56,15 +56,21 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         [D: prop_fc.weight]
     A+B are zero-filled every backward (atomics / += land there); C (conv weights) and D are fully overwritten by their kernels.
     Every slot starts on a 32-byte boundary (full-sector vector stores in the contraction epilogues).
-    Data parallel (dp = drn_b200.parallel.DataParallelDRN): the backward runs as THREE graphs with an all-reduce on NCCL's
-    stream started behind each of them:
-        head, FPN, backbone                 -> B+C (51 MB) reduced WHILE the prop_fc weight gradient runs
-                                               (DRN_DP_PAIR_CLUSTERS=n confines that contraction to n of the 74 SM pairs so that
-                                               NCCL's CTAs find room at once: measured neutral at 2 and 8 GPUs, default off)
-        prop_fc weight gradient (0.53 ms)   -> D (67 MB) reduced WHILE the tail runs: a ~0.35 ms latency-bound chain of small
-                                               kernels that leaves most SMs free
-        tail (gates, query encoder)         -> A (35 MB)."""
-    key = ("bwd", _sig(p), tuple(names), dp is not None)
+    Data parallel (dp = drn_b200.parallel.GradReducer): the prop_fc weight gradient -- 44 % of the gradient bytes and, in the
+    single-GPU order, the last-but-one thing produced -- moves to the END and is cut into DRN_DP_CHUNKS (4) row chunks, so that
+    every all-reduce but the last runs under a contraction that leaves SMs free:
+        head, FPN, backbone (graph 1)       -> B+C complete
+        tail: gates, query encoder (graph 2)-> A complete.  Nothing is reduced beside the tail: its LSTM kernels are
+                                               cooperative launches that need their whole grid resident, so a collective
+                                               occupying SMs would serialise with them instead of overlapping
+        all-reduce A+B+C (86 MB, one call)     runs WHILE chunks 0.. of the prop_fc weight gradient are computed: a chunk is 64
+        prop_fc wgrad chunk i (graphs 3..)     tiles = one wave on 64 of the 74 SM pairs, 20 SMs stay free for NCCL's CTAs
+        all-reduce chunk i (17 MB)             queued behind it on NCCL's stream, under chunk i+1; only the last one is exposed.
+    DRN_DP_ORDER=r01 keeps the round-1 order (first part -> all-reduce B+C || whole prop_fc wgrad -> all-reduce D || tail ->
+    all-reduce A) for A/B runs."""
+    order = os.environ.get("DRN_DP_ORDER", "tail_first") if dp is not None else "single"
+    nchunk = max(1, int(os.environ.get("DRN_DP_CHUNKS", "4"))) if order == "tail_first" else 1
+    key = ("bwd", _sig(p), tuple(names), order, nchunk)
     ent = path.graphs.get(key)
     if ent is None:
         stored, tailn = path.stored_grad_names(names), path.part2_grad_names(names)
@@ -84,48 +90,79 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
             for n in g_:
                 grads[n] = flat[o:o + p[n].numel()].view_as(p[n])
                 o += pad(p[n].numel())
-        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:bounds[3]], "propfc": flat[bounds[3]:], "tail": flat[:bounds[1]]}
+        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:bounds[3]], "propfc": flat[bounds[3]:], "tail": flat[:bounds[1]],
+                   "all_but_propfc": flat[:bounds[3]]}
+        if last and nchunk > 1 and p["prop_fc.weight"].shape[0] % (8 * nchunk) == 0:
+            rows = p["prop_fc.weight"].shape[0] // nchunk
+            per = rows * p["prop_fc.weight"].shape[1]
+            regions["propfc_chunks"] = [flat[bounds[3] + i * per:bounds[3] + (i + 1) * per] for i in range(nchunk)]
+        else:
+            nchunk = 1
+            regions["propfc_chunks"] = [regions["propfc"]]
         pc = int(os.environ.get("DRN_DP_PAIR_CLUSTERS", "0"))
         path.upstream.copy_(upstream)
         path.backward(p, grads, path.upstream)
-        g1 = g1b = g2 = None
-        if use_graphs:
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1, capture_error_mode="thread_local"):
-                regions["zero"].zero_()
-                path.backward(p, grads, path.upstream, tail=dp is None, propfc=dp is None)
-            if dp is not None:
-                g1b = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1b, capture_error_mode="thread_local"):
-                    path.backward_propfc(grads, pair_clusters=pc)
-                g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2, capture_error_mode="thread_local"):
-                    path.backward_tail(p, grads)
+        cap = lambda fn: _capture(fn) if use_graphs else None  # noqa: E731
+        split = dp is not None
+
+        def first_part():
+            regions["zero"].zero_()
+            path.backward(p, grads, path.upstream, tail=not split, propfc=not split)
+        g1 = cap(first_part)
+        g_tail = cap(lambda: path.backward_tail(p, grads)) if split else None
+        g_chunks = []
+        if split:
+            for i in range(nchunk):
+                ch = (i, nchunk) if nchunk > 1 and last else None
+                g_chunks.append((cap(lambda ch=ch: path.backward_propfc(grads, pair_clusters=pc, chunk=ch)), ch))
         if dp is not None:  # the eager run above produced a complete local gradient: reduce it in one go
             dp.reduce_regions([flat])
-        path.graphs[key] = (g1, g1b, g2, flat, grads, regions, pc)
+        ent = (g1, g_tail, g_chunks, flat, grads, regions, pc, first_part)
+        path.graphs[key] = ent
         return flat, grads
-    g1, g1b, g2, flat, grads, regions, pc = ent
+    g1, g_tail, g_chunks, flat, grads, regions, pc, first_part = ent
     path.upstream.copy_(upstream)
     if g1 is not None:
         g1.replay()
     else:
-        regions["zero"].zero_()
-        path.backward(p, grads, path.upstream, tail=dp is None, propfc=dp is None)
-    if dp is not None:
-        work = dp.reduce_regions([regions["first"]], wait=False)  # overlaps the prop_fc weight gradient below
-        if g1b is not None:
-            g1b.replay()
-        else:
-            path.backward_propfc(grads, pair_clusters=pc)
-        work += dp.reduce_regions([regions["propfc"]], wait=False)  # overlaps the tail below
-        if g2 is not None:
-            g2.replay()
+        first_part()
+    if dp is None:
+        return flat, grads
+
+    def run_tail():
+        if g_tail is not None:
+            g_tail.replay()
         else:
             path.backward_tail(p, grads)
+
+    def run_chunk(i):
+        g, ch = g_chunks[i]
+        if g is not None:
+            g.replay()
+        else:
+            path.backward_propfc(grads, pair_clusters=pc, chunk=ch)
+    if order == "r01":
+        work = dp.reduce_regions([regions["first"]], wait=False)  # overlaps the prop_fc weight gradient below
+        run_chunk(0)
+        work += dp.reduce_regions([regions["propfc"]], wait=False)  # overlaps the tail below
+        run_tail()
         dp.reduce_regions([regions["tail"]])
         dp.wait(work)
+        return flat, grads
+    run_tail()
+    work = dp.reduce_regions([regions["all_but_propfc"]], wait=False)
+    for i in range(len(g_chunks)):
+        run_chunk(i)
+        work += dp.reduce_regions([regions["propfc_chunks"][i]], wait=False)
+    dp.wait(work)
     return flat, grads
+
+
+def _capture(fn):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        fn()
+    return g
 
 
 class _DenseFn(torch.autograd.Function):

@@ -13,10 +13,12 @@ from drn_b200 import synthetic as S  # noqa: E402
 from drn_b200.parallel import DataParallelDRN  # noqa: E402
 from model.main_model import mainModel  # noqa: E402
 
+AUTO = "--auto" in sys.argv  # no wrapper, no init_process_group: mainModel's WORLD_SIZE hook must do both (torchrun main.py)
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("nccl", device_id=dev)
+if not AUTO:
+    dist.init_process_group("nccl", device_id=dev)
 cfg = S.default_config(stage=1)
 sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
 B, T = 8, 64
@@ -41,17 +43,30 @@ def step(m):
     return {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
 
 
+os.environ["DRN_AUTO_DP"] = "0"  # the single-rank reference gradients come from an unsynchronised replica
 local_model = make()
 g_local = step(local_model)
+os.environ["DRN_AUTO_DP"] = "1"
+if AUTO:
+    dp_model = make()
+    with torch.no_grad():  # ranks start from different weights: the hook must broadcast rank 0's
+        dp_model.prop_fc.bias.add_(float(rank))
+    step(dp_model)  # first forward: creates the process group, broadcasts, installs the reducer
+    assert dist.is_initialized() and dp_model._dp is not None and dp_model._dp.world == world
+    t = dp_model.prop_fc.bias.detach().clone()
+    dist.broadcast(t, 0)
+    assert torch.equal(t, dp_model.prop_fc.bias.detach()), "rank-0 broadcast missing"
+    with torch.no_grad():
+        dp_model.prop_fc.bias.copy_(sd["prop_fc.bias"])
 expected = {}
 for k, g in g_local.items():
     t = g.clone()
     dist.all_reduce(t)
     expected[k] = t / world
-dp = DataParallelDRN(make())
+dp_module = dp_model if AUTO else DataParallelDRN(make()).module
 worst = 0.0
-for it in range(3):  # eager first call, then the two-graph replay path twice
-    g_dp = step(dp.module)
+for it in range(3):  # eager first call, then the graph replay path twice
+    g_dp = step(dp_module)
     for k, e in expected.items():
         n = float(e.norm())
         if n < 1e-6:
@@ -60,6 +75,6 @@ for it in range(3):  # eager first call, then the two-graph replay path twice
 t = torch.tensor([worst], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("dp_check world=%d max rel-L2 deviation of DP gradients from the mean of single-rank gradients: %.3e" % (world, float(t)))
+    print("dp_check%s order=%s world=%d max rel-L2 deviation of DP gradients from the mean of single-rank gradients: %.3e" % (" (auto hook)" if AUTO else "", os.environ.get("DRN_DP_ORDER", "tail_first"), world, float(t)))
     assert float(t) < 1e-3
 dist.destroy_process_group()
