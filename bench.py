@@ -117,8 +117,11 @@ def build_inputs(world_rank):
     from drn_b200 import spec as spec_mod
     from drn_b200 import synthetic as S
     cfg = S.default_config(stage=1)
-    sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
-    batch = S.synth_batch(B_PER_GPU, T, max_len=MAX_LEN, embedding=sd["query_encoder.embedding.weight"], seed=S.SEED + world_rank)
+    # SURVEY.md 8d inputs: real Charades-STA queries through Charades_word2id.json, embedding = the shipped GloVe-300 table
+    # (tests/golden/charades_queries.npz, written from the reference's data files by oracle/make_query_fixture.py)
+    sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg), glove=True)
+    batch = S.synth_batch(B_PER_GPU, T, max_len=MAX_LEN, embedding=sd["query_encoder.embedding.weight"], seed=S.SEED + world_rank,
+                          queries="charades")
     return cfg, sd, batch
 
 
@@ -442,6 +445,7 @@ def run_ours(args):
         try:
             extra["configs[2]"] = cb.three_stage(dev, 10, 3, fused_modes=(False,))
             extra["configs[4]"] = cb.sweep(dev, 5, 2)
+            extra["fast_mode"] = cb.fast_mode(dev, 10, 3)
         except Exception as e:  # noqa: BLE001
             extra["error"] = repr(e)
         line["extra"] = extra

@@ -6,8 +6,14 @@ import torch
 from . import lib as L
 from .planes import Planes
 
-# numeric mode of the tensor-core contraction: 3 = split-BF16 parity mode (default), 1 = single BF16 pass, 4 = + lo*lo
-NPROD = 3
+import os
+
+# numeric mode of the tensor-core contraction: 3 = split-BF16 parity mode (default: fp32-equivalent, every reported number),
+# 1 = single BF16 pass (OPT-IN fast mode, DRN_NPROD=1: ~3x fewer tensor-core FLOPs, BF16-level error -- bench.py's
+# extra.fast_mode reports its speed and its error against the oracle), 4 = + lo*lo
+NPROD = int(os.environ.get("DRN_NPROD", "3"))
+if NPROD not in (1, 3, 4):
+    raise ValueError("DRN_NPROD must be 1, 3 or 4")
 ENGINE = 0  # 0 = tcgen05 (product), 1 = fp32 CUDA-core checker (tests only)
 
 
@@ -52,8 +58,6 @@ def desc(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=
     g.dbg_lbo, g.dbg_sbo, g.dbg_kadv = dbg
     return g
 
-
-import os
 
 # Stream-K schedule of the persistent contraction kernel (drn_gemm_group_ws): OPT-IN.  Measured on B200 (r02,
 # profiles/r02_ab_streamk.log, profiles/r02_insitu_{static,streamk}.json): 3.86 ms per step against 3.45 ms with the static

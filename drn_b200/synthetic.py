@@ -118,9 +118,31 @@ def synth_tensor(name, shape, seed=SEED):
     raise ValueError("no rule for %s %s" % (name, shape))
 
 
-def synth_state_dict(spec, seed=SEED):
-    """spec: iterable of (name, shape) (e.g. from model.state_dict()).  Returns name->tensor."""
-    return {name: synth_tensor(name, shape, seed) for name, shape in spec}
+_CHARADES = None
+
+
+def charades_fixture():
+    """tests/golden/charades_queries.npz (written by oracle/make_query_fixture.py from the data files the reference ships):
+    real Charades-STA queries tokenised through Charades_word2id.json and the GloVe-300 embedding table of data/glove_weights
+    (SURVEY.md section 8d).  Used by bench.py / tests / scripts for their inputs; never by the product path."""
+    global _CHARADES
+    if _CHARADES is None:
+        import os
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "charades_queries.npz")
+        z = np.load(path)
+        _CHARADES = {k: z[k] for k in z.files}
+    return _CHARADES
+
+
+def synth_state_dict(spec, seed=SEED, glove=False):
+    """spec: iterable of (name, shape) (e.g. from model.state_dict()).  Returns name->tensor.  glove=True: the embedding table is
+    the reference's data/glove_weights (what main.py:94 copies in), not a random stand-in."""
+    sd = {name: synth_tensor(name, shape, seed) for name, shape in spec}
+    if glove:
+        g = torch.from_numpy(charades_fixture()["glove"].copy())
+        assert tuple(sd["query_encoder.embedding.weight"].shape) == tuple(g.shape)
+        sd["query_encoder.embedding.weight"] = g
+    return sd
 
 
 def load_synth_weights(model, seed=SEED):
@@ -132,19 +154,31 @@ def load_synth_weights(model, seed=SEED):
 
 
 def synth_batch(B, T, max_len=10, feature_dim=4096, vocab_size=1301, seed=SEED, embedding=None,
-                sorted_lengths=True):
-    """One synthetic batch in the dtypes dataset.py:180-224 produces.
+                sorted_lengths=True, queries="random", split="train"):
+    """One synthetic batch in the dtypes dataset.py:180-224 produces.  queries="charades": real Charades-STA queries drawn from
+    the fixture (`split` = train | test for held-out evaluation), padded to the longest of the batch like collate_data.
 
     returns dict(query_tokens i64 [B,L], query_length i64 [B] (descending), props_features f32
     [B,T,D], props_start_end f64 [B,T,2], gt_start_end f64 [B,2])."""
     g = _rng(seed, "batch/%d/%d/%d" % (B, T, max_len))
-    lengths = g.integers(2, max_len + 1, size=B)
-    lengths[0] = max_len
-    if sorted_lengths:
-        lengths = np.sort(lengths)[::-1].copy()
-    tokens = np.zeros((B, max_len), dtype=np.int64)
-    for b in range(B):
-        tokens[b, : lengths[b]] = g.integers(1, vocab_size + 1, size=lengths[b])
+    if queries == "charades":
+        fx = charades_fixture()
+        pool_t, pool_l = fx[split + "_tokens"], fx[split + "_len"]
+        ok = np.nonzero(pool_l <= max_len)[0]
+        pick = ok[g.integers(0, len(ok), size=B)]
+        lengths = pool_l[pick].astype(np.int64)
+        order = np.argsort(-lengths, kind="stable") if sorted_lengths else np.arange(B)  # dataset.py:183
+        pick, lengths = pick[order], lengths[order]
+        max_len = int(lengths.max())  # collate_data pads to the longest query of the batch (dataset.py:186)
+        tokens = pool_t[pick, :max_len].astype(np.int64)
+    else:
+        lengths = g.integers(2, max_len + 1, size=B)
+        lengths[0] = max_len
+        if sorted_lengths:
+            lengths = np.sort(lengths)[::-1].copy()
+        tokens = np.zeros((B, max_len), dtype=np.int64)
+        for b in range(B):
+            tokens[b, : lengths[b]] = g.integers(1, vocab_size + 1, size=lengths[b])
     c = g.uniform(0.2, 0.8, size=B)
     w = g.uniform(0.05, 0.35, size=B)
     gt = np.stack([np.clip(c - w, 0.0, 1.0), np.clip(c + w, 0.0, 1.0)], axis=1)  # f64
@@ -195,6 +229,8 @@ GOLDEN_CASES = {
     "s3_train_b4_t32_crafted": (4, 32, 7, 3, True, True),
     "s2_train_b4_t32_crafted": (4, 32, 7, 2, True, True),
     "s3_eval_b3_t64_crafted": (3, 64, 9, 3, False, True),
+    # real Charades-STA queries + the GloVe-300 table (tests/golden/charades_queries.npz), SURVEY.md section 8d
+    "s1_train_b4_t32_charades": (4, 32, 10, 1, True, False),
 }
 
 
@@ -202,8 +238,9 @@ def golden_case(name, spec):
     """Rebuild (cfg, state_dict, batch) of a golden case from the seed alone."""
     B, T, L, stage, training, crafted = GOLDEN_CASES[name]
     cfg = default_config(stage=stage)
-    sd = synth_state_dict(spec)
-    batch = synth_batch(B, T, max_len=L, embedding=sd["query_encoder.embedding.weight"])
+    real = name.endswith("_charades")
+    sd = synth_state_dict(spec, glove=real)
+    batch = synth_batch(B, T, max_len=L, embedding=sd["query_encoder.embedding.weight"], queries="charades" if real else "random")
     if crafted:
         sd, batch = craft_stage23(sd, batch)
     return cfg, sd, batch, stage, training

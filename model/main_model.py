@@ -18,6 +18,19 @@ from model.language_module import QueryEncoder
 from model.modules import FPN, Backbone, FCOSModule
 
 
+# Optional per-phase CUDA-event trace of the data-parallel backward (scripts/dp_timeline.py sets it to a list): (name, event)
+# pairs recorded on the compute stream; `wait:` entries are recorded right after the stream was made to wait for a collective,
+# i.e. they carry the time at which that all-reduce had finished.
+DP_TRACE = None
+
+
+def _mark(name):
+    if DP_TRACE is not None:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        DP_TRACE.append((name, e))
+
+
 def _sig(p):
     return hash(tuple(t.data_ptr() for t in p.values()))
 
@@ -122,10 +135,12 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         return flat, grads
     g1, g_tail, g_chunks, flat, grads, regions, pc, first_part = ent
     path.upstream.copy_(upstream)
+    _mark("backward start")
     if g1 is not None:
         g1.replay()
     else:
         first_part()
+    _mark("head+FPN+backbone done")
     if dp is None:
         return flat, grads
 
@@ -144,17 +159,25 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
     if order == "r01":
         work = dp.reduce_regions([regions["first"]], wait=False)  # overlaps the prop_fc weight gradient below
         run_chunk(0)
+        _mark("prop_fc wgrad done")
         work += dp.reduce_regions([regions["propfc"]], wait=False)  # overlaps the tail below
         run_tail()
-        dp.reduce_regions([regions["tail"]])
-        dp.wait(work)
+        _mark("tail done")
+        work += dp.reduce_regions([regions["tail"]], wait=False)
+        for i, w in enumerate(work):
+            dp.wait([w])
+            _mark("wait: all-reduce %d done" % i)
         return flat, grads
     run_tail()
+    _mark("tail done")
     work = dp.reduce_regions([regions["all_but_propfc"]], wait=False)
     for i in range(len(g_chunks)):
         run_chunk(i)
+        _mark("prop_fc wgrad chunk %d done" % i)
         work += dp.reduce_regions([regions["propfc_chunks"][i]], wait=False)
-    dp.wait(work)
+    for i, w in enumerate(work):
+        dp.wait([w])
+        _mark("wait: all-reduce %d done" % i)
     return flat, grads
 
 

@@ -45,10 +45,10 @@ def main():
     from oracle import ref_loader
     cfg = S.default_config(stage=1)
     model = ref_loader.build_reference_model(cfg)
-    sd = S.synth_state_dict([(k, tuple(v.shape)) for k, v in model.state_dict().items()])
+    sd = S.synth_state_dict([(k, tuple(v.shape)) for k, v in model.state_dict().items()], glove=True)  # as bench.build_inputs
     model.load_state_dict(sd)
     model.train()
-    batch = S.synth_batch(a.B, a.T, max_len=10, embedding=sd["query_encoder.embedding.weight"])
+    batch = S.synth_batch(a.B, a.T, max_len=10, embedding=sd["query_encoder.embedding.weight"], queries="charades")
     times, loss_v = [], None
     for i in range(a.warmup + a.steps):
         t0 = time.perf_counter()

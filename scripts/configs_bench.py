@@ -190,12 +190,80 @@ def sweep(dev, steps, warmup, Ts=(64, 128, 256, 512), emit=None):
     return out
 
 
+def fast_mode(dev, steps, warmup):
+    """SURVEY.md section 7, hard part 1: the single-pass BF16 mode (DRN_NPROD=1; one tensor-core product instead of three) as an
+    OPT-IN throughput mode with its error reported: configs[1] step time, and losses / head outputs / every gradient against the
+    fp32 CPU oracle on the same batch.  Never the default, never the headline."""
+    from drn_b200 import ops
+    from model.main_model import mainModel
+    from oracle import drn_oracle as O
+    cfg = S.default_config(stage=1)
+    sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
+    batch = S.synth_batch(32, 256, max_len=10, embedding=sd["query_encoder.embedding.weight"])
+    old = ops.NPROD
+    ops.NPROD = 1
+    try:
+        model = mainModel(1301, S.config_namespace(stage=1))
+        model.load_state_dict(sd)
+        for k, p in model.named_parameters():
+            if O.frozen_in_stage1(k):
+                p.requires_grad = False
+        model = model.to(dev).train()
+        b = {k: v.to(dev) for k, v in batch.items()}
+        b["query_length"] = batch["query_length"]
+
+        def step():
+            for p in model.parameters():
+                p.grad = None
+            _, ld = model(b["query_tokens"], b["query_length"], b["props_features"], b["props_start_end"], b["gt_start_end"], None, None)
+            (ld["loss_cls"] + ld["loss_reg"] + ld["loss_iou"]).backward()
+            return ld
+        model.load_state_dict(sd)  # BatchNorm buffers as the oracle sees them
+        ld = step()
+        torch.cuda.synchronize()
+        grads = {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters() if p.grad is not None}
+        losses = {k: float(v.reshape(-1)[0]) for k, v in ld.items()}
+        for _ in range(warmup):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+    finally:
+        ops.NPROD = old
+    torch.set_num_threads(os.cpu_count())
+    old_l, ograds, _ = O.forward_backward(sd, cfg, batch, stage=1)
+    errs = {}
+    for k, r in ograds.items():
+        n = float(r.norm())
+        if n > 1e-6 and k in grads:
+            errs[k] = float((grads[k].double() - r.double()).norm()) / n
+    srt = sorted(errs.values())
+    rec = {"config": "configs[1] in the opt-in single-pass BF16 mode (DRN_NPROD=1)", "ms_per_step": round(ms, 4),
+           "pairs_per_s": round(32 / ms * 1e3, 1), "steps": steps, "warmup": warmup,
+           "loss_rel_err_vs_oracle": {k: abs(losses[k] - float(old_l[k])) / max(abs(float(old_l[k])), 1e-30) for k in ("loss_cls", "loss_reg")},
+           "grad_rel_l2_vs_oracle": {"max": srt[-1], "median": srt[len(srt) // 2], "min": srt[0], "tensors": len(srt),
+                                     "prop_fc.weight": errs.get("prop_fc.weight"), "backbone_net.forward_conv0.0.weight": errs.get("backbone_net.forward_conv0.0.weight"),
+                                     "fcos.head.cls_logits.weight": errs.get("fcos.head.cls_logits.weight"),
+                                     "query_encoder.embedding.weight": errs.get("query_encoder.embedding.weight")},
+           "note": "parity mode (3 BF16 products) on the same batch: profiles/r02_grad_errors.json (max 1.1e-2, the oracle's own "
+                   "2^-16 sensitivity); this mode is outside the 1e-3 contract and is never used for a reported number"}
+    del model
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-sweep", action="store_true")
+    ap.add_argument("--fast-mode", action="store_true", help="also run the opt-in single-pass BF16 mode with its error table")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     dev = torch.device("cuda", 0)
@@ -205,6 +273,8 @@ def main():
         three_stage(dev, a.steps, a.warmup, emit=emit)
     if not a.skip_sweep:
         sweep(dev, a.steps, a.warmup, emit=emit)
+    if a.fast_mode:
+        emit(fast_mode(dev, a.steps, a.warmup))
 
 
 if __name__ == "__main__":

@@ -40,17 +40,24 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--B", type=int, default=32)
     ap.add_argument("--T", type=int, default=256)
+    ap.add_argument("--golden", action="store_true", help="the small training cases of tests/golden instead of the B x T size")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     from model.main_model import mainModel
     out = {"B": a.B, "T": a.T, "note": "err = ||g_cuda - g_oracle|| / ||g_oracle||; sens = the oracle's own response to a 2^-16 relative "
            "perturbation of weights and features (max of 3 draws); tol = the bound of tests/test_model_gpu.py", "stages": {}}
-    for stage in (1, 2, 3):
+    cases = [(str(st), st, None) for st in (1, 2, 3)]
+    if a.golden:
+        cases = [(n, c[3], n) for n, c in S.GOLDEN_CASES.items() if c[4]]
+    for label, stage, gname in cases:
         cfg = S.default_config(stage=stage)
-        sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
-        batch = S.synth_batch(a.B, a.T, max_len=10, embedding=sd["query_encoder.embedding.weight"])
-        if stage > 1:
-            sd, batch = S.craft_stage23(sd, batch)
+        if gname:
+            cfg, sd, batch, _, _ = S.golden_case(gname, spec_mod.state_dict_spec(cfg))
+        else:
+            sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg))
+            batch = S.synth_batch(a.B, a.T, max_len=10, embedding=sd["query_encoder.embedding.weight"])
+            if stage > 1:
+                sd, batch = S.craft_stage23(sd, batch)
         model = mainModel(1301, S.config_namespace(stage=stage))
         model.load_state_dict(sd)
         if stage == 1:
@@ -77,9 +84,11 @@ def main():
             sens = max(float((pt[k].double() - gref.double()).norm()) / n for pt in perts)
             rows[k] = {"err": err, "sens": sens, "tol": 2e-3 + 8.0 * sens, "ref_norm": n, "err_over_sens": err / max(sens, 1e-30)}
         live = [r for r in rows.values() if "err" in r]
-        out["stages"][str(stage)] = {
+        out["stages"][label] = {
             "losses_cuda": {k: float(v.reshape(-1)[0]) for k, v in ld.items()}, "losses_oracle": old,
             "tensors": len(rows), "max_err": max(r["err"] for r in live), "max_err_over_tol": max(r["err"] / r["tol"] for r in live),
+            "max_err_over_sens": max(r["err_over_sens"] for r in live),
+            "max_err_minus_4sens": max(r["err"] - 4.0 * r["sens"] for r in live),
             "n_err_below_1e-3": sum(1 for r in live if r["err"] <= 1e-3), "n_live": len(live), "per_tensor": rows}
         del model
         torch.cuda.empty_cache()
