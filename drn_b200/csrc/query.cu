@@ -141,6 +141,81 @@ __device__ __forceinline__ void sgemm_body(const SgemmP& p, int bx, int by, int 
   }
 }
 
+// Rank-K update with K <= 32 (the weight gradients of every nn.Linear of the query encoder and of the gates: K = the batch):
+// C[M][N] (=, +=) sum_k A(m,k) B(k,n).  The general body above walks K in 16-deep tiles behind a global-memory round trip each
+// and writes a 64 x 64 tile per CTA: for K = 32 it is pure latency (50 us for the 17 MB of gate weight gradients, ncu r01).
+// Here both operand slices (32 x 64 and 32 x 128) are staged ONCE, a thread owns a 4 x 8 patch and the CTA streams out a
+// 64 x 128 tile with 16-byte stores: HBM-write bound.
+constexpr int OU_BM = 64, OU_BN = 128, OU_K = 32;
+__device__ __forceinline__ void outer_body(const SgemmP& p, int bx, int by) {
+  __shared__ __align__(16) float As[OU_K][OU_BM];
+  __shared__ __align__(16) float Bs[OU_K][OU_BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = bx * OU_BM, n0 = by * OU_BN;
+  const bool a_kfast = (p.sak == 1), b_nfast = (p.sbn == 1);
+#pragma unroll
+  for (int e = 0; e < (OU_BM * OU_K) / 256; ++e) {
+    const int idx = tid + e * 256;
+    int m, k;
+    if (a_kfast) { k = idx % OU_K; m = idx / OU_K; }
+    else { m = idx % OU_BM; k = idx / OU_BM; }
+    As[k][m] = (m0 + m < p.M && k < p.K) ? __ldg(p.A + (m0 + m) * p.sam + k * p.sak) : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < (OU_BN * OU_K) / 256; ++e) {
+    const int idx = tid + e * 256;
+    int n, k;
+    if (b_nfast) { n = idx % OU_BN; k = idx / OU_BN; }
+    else { k = idx % OU_K; n = idx / OU_K; }
+    Bs[k][n] = (n0 + n < p.N && k < p.K) ? __ldg(p.B + k * p.sbk + (n0 + n) * p.sbn) : 0.f;
+  }
+  __syncthreads();
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+#pragma unroll 8
+  for (int k = 0; k < OU_K; ++k) {
+    const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+    const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+    const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+  }
+  const bool vec = (p.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(p.C) % 16 == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= p.M) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gn = n0 + h * 64 + tx * 4;
+      float* o = p.C + gm * p.ldc + gn;
+      float v[4] = {acc[i][4 * h], acc[i][4 * h + 1], acc[i][4 * h + 2], acc[i][4 * h + 3]};
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gn + j < p.N) v[j] += __ldg(p.bias + gn + j);
+      }
+      if (!p.atomic && vec && gn + 3 < p.N) {
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gn + j < p.N) {
+            if (p.atomic) atomicAdd(o + j, v[j]);
+            else o[j] = v[j];
+          }
+      }
+    }
+  }
+}
+
 // The query-encoder kernels are meant to run BESIDE the persistent tcgen05 GEMM (which configures every SM for the maximum
 // shared-memory carve-out); a kernel preferring a different L1/shared split cannot become co-resident on such an SM.
 template <typename F>
@@ -173,7 +248,8 @@ __global__ void __launch_bounds__(256) sgemm_multi_kernel(const SgemmJobs jobs) 
   const int bx = local % jobs.gx[j];
   const int by = (local / jobs.gx[j]) % jobs.gy[j];
   const int bz = local / (jobs.gx[j] * jobs.gy[j]);
-  if (jobs.bm[j] == 32) sgemm_body<32>(jobs.p[j], bx, by, bz);
+  if (jobs.bm[j] == 0) outer_body(jobs.p[j], bx, by);
+  else if (jobs.bm[j] == 32) sgemm_body<32>(jobs.p[j], bx, by, bz);
   else sgemm_body<64>(jobs.p[j], bx, by, bz);
 }
 
@@ -187,6 +263,14 @@ struct SgemmBatch {
     if (jobs.n >= SG_MAX_JOBS) return fail(DRN_EINVAL, "sgemm batch: more than %d problems", SG_MAX_JOBS);
     if (M < 1 || N < 1 || K < 1) return fail(DRN_EINVAL, "sgemm batch: empty problem (%d,%d,%d)", M, N, K);
     const int i = jobs.n++;
+    if (K <= OU_K && M >= OU_BM && N >= OU_BN && bias == nullptr) {  // rank-K update: staged once, HBM-write bound (outer_body)
+      jobs.p[i] = SgemmP{A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, nullptr, nullptr, 0, store ? 0 : 1, K};
+      jobs.gx[i] = ceil_div(M, OU_BM);
+      jobs.gy[i] = ceil_div(N, OU_BN);
+      jobs.bm[i] = 0;
+      jobs.cta_start[i + 1] = jobs.cta_start[i] + jobs.gx[i] * jobs.gy[i];
+      return 0;
+    }
     const int bm = (M <= 32) ? 32 : 64;
     const int tiles = ceil_div(M, bm) * ceil_div(N, 64);
     // K-split (atomic accumulation) until the GPU is full.  A CTA walks its k-range as a chain of dependent global-memory round
