@@ -481,6 +481,7 @@ static int linear_small(cudaStream_t st, const float* x, long long ldx, const fl
 // ------------------------------------------------------------------------------------------------------------------------
 // Query encoder device view
 // ------------------------------------------------------------------------------------------------------------------------
+constexpr int QE_MAX_L = 64;
 constexpr int DE_SLICES = 8;  // dE = dG [W_ih ; W_ih_r] contracts over 8H = 4096 gate rows with only 4 output tiles: K-split slices
 struct QeDev {
   int B, L, H, E, tok_ld, BC;  // BC = ceil(B / 32) sample chunks
@@ -492,6 +493,7 @@ struct QeDev {
   __nv_bfloat16 *E_pl, *Wih_pl, *dG_pl, *Hprev_pl;  // split-BF16 planes (hi, lo) of the operands of the big projections
   float *dH, *dc3, *dhid, *dhid_pre, *dv, *dG, *dcarry, *part, *dE, *HT, *dGT, *dr, *one;
   unsigned* cnt;
+  unsigned* bar;  // [2 directions][QE_MAX_L] arrival counters of the per-direction step barrier (lstm_fwd2_kernel), zeroed by qe_embed_kernel
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -504,6 +506,7 @@ __global__ void __launch_bounds__(256) qe_embed_kernel(QeDev q, const float* __r
   const long long tok = q.tokens[static_cast<long long>(b) * q.tok_ld + t];
   const long long ps = static_cast<long long>(q.B) * q.L * q.EP;
   if (r == 0 && threadIdx.x == 0) q.one[0] = 1.f;  // the constant the column-sum contractions multiply by
+  if (r == 0 && threadIdx.x < 2 * QE_MAX_L) q.bar[threadIdx.x] = 0u;  // step-barrier counters of the recurrence that follows
   for (int e = threadIdx.x; e < q.EP; e += blockDim.x) {
     __nv_bfloat16 h, l;
     split_bf16(e < q.E ? emb[tok * q.E + e] : 0.f, h, l);
@@ -653,6 +656,128 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_fwd_kernel(QeDev q, int s0,
     } else if (!PERSIST) {
       __syncthreads();
     }
+  }
+}
+
+// ---- the recurrence, second form (B <= 32, H % 128 == 0: the DRN configuration): W_hh in REGISTERS -------------------------
+// The kernel above keeps both operands of h W_hh^T in shared memory (lane = sample: one broadcast 16-byte load of W per 4
+// FMAs plus four 4-byte loads of h per 16): 8 shared-memory instructions per 16 FMAs, LSU-bound at ~4.3 us of the 11.7 us a
+// step took (r01 ncu: 117 us for L = 10).  Here a warp owns ONE hidden unit and a lane owns a K-SLICE of its four gate rows
+// (k = 4 lane + 128 j: 64 weights in registers for H = 512, loaded once per launch); the previous hidden state is staged
+// sample-major, so one conflict-free 16-byte load feeds 16 FMAs; the 32 lanes' partial sums of (gate, sample) are folded by
+// recursive halving (16 shuffles per gate and 16 samples) which leaves lane l with the four gate pre-activations of sample l --
+// the thread that then runs the cell update and keeps the cell state in a register for the whole sequence.  Steps are separated
+// by a per-DIRECTION barrier (64 CTAs, one arrival counter per step) instead of the grid-wide cooperative barrier.
+// grid (H/8, 2), 8 warps; launched cooperatively (all CTAs must be co-resident for the barrier).
+constexpr int LSTM2_THREADS = 256;
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float fold16(float (&a)[16], int lane) {
+#pragma unroll
+  for (int s = 8; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? a[i] : a[i + s];
+      const float keep = up ? a[i + s] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);  // lane l: sum over all lanes of entry (l & 15)
+}
+__global__ void __launch_bounds__(LSTM2_THREADS, 1) lstm_fwd2_kernel(QeDev q) {
+  pdl_sync();
+  extern __shared__ __align__(16) float hs[];  // [32 samples][H]: hidden state of the previous step
+  const int H = q.H, L = q.L, NJ = H >> 7;
+  const int ug = blockIdx.x, dir = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int unit = ug * 8 + w;
+  const int b = lane;
+  const bool inb = b < q.B;
+  const int len = inb ? static_cast<int>(q.lengths[b]) : 0;
+  float4 wr[4][4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      wr[g][j] = (j < NJ) ? __ldg(reinterpret_cast<const float4*>(q.w_hh[dir] + (static_cast<long long>(g) * H + unit) * H + 4 * lane + 128 * j))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long ht_sz = 2LL * 32 * H;  // one buffer: [2 directions][32][H]
+  float c_carry = 0.f;
+  for (int s = 0; s < L; ++s) {
+    const int t = dir == 0 ? s : L - 1 - s;
+    const long long r = static_cast<long long>(inb ? b : 0) * L + t;
+    float pre[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) pre[g] = inb ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;  // issued before the barrier wait
+    if (s > 0) {
+      if (tid == 0) {  // per-direction barrier: every CTA of this direction has published its h of step s - 1
+        unsigned* cnt = q.bar + dir * QE_MAX_L + (s - 1);
+        __threadfence();
+        atomicAdd(cnt, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_u32(cnt) < gridDim.x) {
+          if (clock64() - t0 > 4000000000LL) __trap();
+        }
+      }
+      __syncthreads();
+      const float* hprev = q.HT + ((s - 1) & 1) * ht_sz + static_cast<long long>(dir) * 32 * H;
+      for (int idx = tid; idx < 8 * H; idx += LSTM2_THREADS) cp_async16(hs + idx * 4, hprev + idx * 4);
+      cp_async_wait_all();
+      __syncthreads();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float acc[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float* hrow = hs + (half * 16 + i) * H + 4 * lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < NJ) {
+              const float4 h4 = *reinterpret_cast<const float4*>(hrow + 128 * j);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                acc[g][i] = fmaf(wr[g][j].x, h4.x, acc[g][i]);
+                acc[g][i] = fmaf(wr[g][j].y, h4.y, acc[g][i]);
+                acc[g][i] = fmaf(wr[g][j].z, h4.z, acc[g][i]);
+                acc[g][i] = fmaf(wr[g][j].w, h4.w, acc[g][i]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float v = fold16(acc[g], lane);
+          if ((lane >> 4) == half) pre[g] += v;  // lane l keeps sample l
+        }
+      }
+    }
+    const bool live = inb && t < len;
+    float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f, c = 0.f, h = 0.f;
+    if (live) {
+      gi = sigmoidf_(pre[0]);
+      gf = sigmoidf_(pre[1]);
+      gg = tanhf(pre[2]);
+      go = sigmoidf_(pre[3]);
+      c = gf * c_carry + gi * gg;  // non-live positions carry c = 0: exact for both directions (packed-sequence semantics)
+      h = go * tanhf(c);
+    }
+    c_carry = c;
+    q.HT[(s & 1) * ht_sz + (static_cast<long long>(dir) * 32 + b) * H + unit] = h;
+    if (inb) {
+      float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
+      G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
+      q.Cst[(r * 2 + dir) * H + unit] = c;
+      q.Hout[r * 2 * H + dir * H + unit] = h;
+    }
+    __syncthreads();  // all of this CTA's h values are written (and hs is free) before thread 0 arrives at the next barrier
   }
 }
 
@@ -880,7 +1005,6 @@ __global__ void relu_mask_kernel(const float* __restrict__ g, const float* __res
 }
 
 // ---- attention over the words (language_module.py:27-36): grid (B, 3) --------------------------------------------------
-constexpr int QE_MAX_L = 64;
 __global__ void __launch_bounds__(256) qe_attn_fwd_kernel(QeDev q, const float* __restrict__ wa, const float* __restrict__ ba,
                                                           float* cmd0, float* cmd1, float* cmd2) {
   pdl_sync();
@@ -1057,6 +1181,7 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
   float* dGT = take(2 * 2 * BC * 4 * H * 32);
   float* dr = take(3 * B * L);
   float* one = take(1);
+  float* bar = take(2 * QE_MAX_L);
   if (q) {
     q->EP = static_cast<int>(EP);
     q->E_pl = reinterpret_cast<__nv_bfloat16*>(E_pl); q->Wih_pl = reinterpret_cast<__nv_bfloat16*>(Wih_pl);
@@ -1065,7 +1190,7 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
     q->xg = xg; q->G = G; q->Cst = Cst; q->Hout = Hout; q->v = v;
     q->hid = hid; q->c3 = c3; q->alpha = alpha; q->dH = dH; q->dc3 = dc3; q->dhid = dhid; q->dhid_pre = dhid_pre; q->dv = dv;
     q->dG = dG; q->dcarry = dcarry; q->part = part; q->dE = dE; q->cnt = reinterpret_cast<unsigned*>(cnt);
-    q->HT = HT; q->dGT = dGT; q->dr = dr; q->one = one;
+    q->HT = HT; q->dGT = dGT; q->dr = dr; q->one = one; q->bar = reinterpret_cast<unsigned*>(bar);
   }
   return off;
 }
@@ -1088,7 +1213,7 @@ static int make_dev(const drn_qe_t* a, QeDev* q, const char* who) {
 }
 
 // A cooperative (grid-barrier) launch needs every CTA resident at once.  DRN_QE_PERSIST=0 forces the per-step launches.
-static bool fits_cooperative(const void* fn, dim3 grid, size_t smem) {
+static bool fits_cooperative(const void* fn, dim3 grid, size_t smem, int threads = 512) {
   static int allow = -1;
   if (allow < 0) {
     const char* e = getenv("DRN_QE_PERSIST");
@@ -1099,7 +1224,7 @@ static bool fits_cooperative(const void* fn, dim3 grid, size_t smem) {
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, LSTM_THREADS, smem) != cudaSuccess) return false;
+  if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess) return false;
   return static_cast<long long>(grid.x) * grid.y * grid.z <= static_cast<long long>(sms) * per_sm;
 }
 
@@ -1220,7 +1345,19 @@ static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), smem_f, "lstm_fwd"));
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<false>), smem_f, "lstm_fwd"));
   const dim3 grid_f(H / 8, 2, q.BC);
-  if (fits_cooperative(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, smem_f)) {
+  static int fwd2 = -1;  // DRN_QE_FWD2=0: the shared-memory form of the recurrence (A/B)
+  if (fwd2 < 0) {
+    const char* e = getenv("DRN_QE_FWD2");
+    fwd2 = e ? atoi(e) : 1;
+  }
+  const size_t smem_f2 = static_cast<size_t>(32) * H * sizeof(float);
+  if (fwd2 && q.BC == 1 && H % 128 == 0 && L <= QE_MAX_L &&
+      set_smem(reinterpret_cast<const void*>(lstm_fwd2_kernel), smem_f2, "lstm_fwd2") == 0 &&
+      fits_cooperative(reinterpret_cast<const void*>(lstm_fwd2_kernel), dim3(H / 8, 2, 1), smem_f2, LSTM2_THREADS)) {
+    void* args[] = {&q};
+    cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd2_kernel), dim3(H / 8, 2, 1), dim3(LSTM2_THREADS), args, smem_f2, st);
+    if (ce != cudaSuccess) return fail(static_cast<int>(ce), "lstm_fwd2 (cooperative): %s", cudaGetErrorString(ce));
+  } else if (fits_cooperative(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, smem_f)) {
     int s0 = 0, s1 = L;
     void* args[] = {&q, &s0, &s1};
     cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), grid_f, dim3(LSTM_THREADS), args, smem_f, st);
