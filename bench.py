@@ -221,8 +221,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     affinity = bind_to_gpu_numa(local) if world > 1 and os.environ.get("DRN_BIND_NUMA", "1") == "1" else {"bound": False}
     if world > 1:
-        if os.environ.get("DRN_NCCL_MAX_CTAS"):  # fewer NCCL CTAs = more SMs left to the contraction the collective runs beside
-            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DRN_NCCL_MAX_CTAS"])
+        from drn_b200.parallel import nccl_env_defaults
+        nccl_env_defaults()  # NCCL_MAX_CTAS=16: leaves the SMs the overlapped backward schedule needs (drn_b200/parallel.py)
         dist.init_process_group("nccl", device_id=dev)
     cfg, sd, batch = build_inputs(rank)
     model = mainModel(1301, S.config_namespace(stage=1))

@@ -24,6 +24,15 @@ import torch.distributed as dist
 from torch import nn
 
 
+def nccl_env_defaults():
+    """Call BEFORE the NCCL communicator is created.  The overlapped schedule runs collectives beside kernels that need most of
+    the GPU: the cooperative LSTM launches of the backward tail (128 CTAs that must be co-resident) and the 64-cluster chunks of
+    the prop_fc weight gradient (128 SMs).  With NCCL capped at 16 CTAs both fit beside it on the 148 SMs; measured on 8 x B200
+    (profiles/r02_dp_timeline8_*.json) the cap costs no all-reduce bandwidth against NCCL's default, 8 CTAs halve it.
+    DRN_NCCL_MAX_CTAS overrides; an NCCL_MAX_CTAS already in the environment wins."""
+    os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("DRN_NCCL_MAX_CTAS", "16"))
+
+
 class GradReducer:
     """Averaging all-reduce of regions of the flat gradient buffer over the ranks of a process group."""
 
@@ -39,6 +48,7 @@ class GradReducer:
         exports them) and makes every rank start from rank 0's parameters and buffers."""
         if not dist.is_initialized():
             if device.type == "cuda":
+                nccl_env_defaults()
                 dist.init_process_group("nccl", device_id=device)
             else:
                 dist.init_process_group("gloo")

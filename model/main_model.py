@@ -81,8 +81,8 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         all-reduce chunk i (17 MB)             queued behind it on NCCL's stream, under chunk i+1; only the last one is exposed.
     DRN_DP_ORDER=r01 keeps the round-1 order (first part -> all-reduce B+C || whole prop_fc wgrad -> all-reduce D || tail ->
     all-reduce A) for A/B runs."""
-    order = os.environ.get("DRN_DP_ORDER", "tail_first") if dp is not None else "single"
-    nchunk = max(1, int(os.environ.get("DRN_DP_CHUNKS", "4"))) if order == "tail_first" else 1
+    order = os.environ.get("DRN_DP_ORDER", "overlap") if dp is not None else "single"
+    nchunk = max(1, int(os.environ.get("DRN_DP_CHUNKS", "4"))) if order in ("tail_first", "overlap") else 1
     key = ("bwd", _sig(p), tuple(names), order, nchunk)
     ent = path.graphs.get(key)
     if ent is None:
@@ -168,9 +168,17 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
             dp.wait([w])
             _mark("wait: all-reduce %d done" % i)
         return flat, grads
-    run_tail()
-    _mark("tail done")
-    work = dp.reduce_regions([regions["all_but_propfc"]], wait=False)
+    if order == "overlap":
+        # B+C is reduced WHILE the tail runs: its cooperative LSTM kernels (128 CTAs) stay co-resident with the collective as
+        # long as NCCL keeps to <= 20 SMs (NCCL_MAX_CTAS=16, set before the communicator is created: drn_b200/parallel.py)
+        work = dp.reduce_regions([regions["first"]], wait=False)
+        run_tail()
+        _mark("tail done")
+        work += dp.reduce_regions([regions["tail"]], wait=False)
+    else:
+        run_tail()
+        _mark("tail done")
+        work = dp.reduce_regions([regions["all_but_propfc"]], wait=False)
     for i in range(len(g_chunks)):
         run_chunk(i)
         _mark("prop_fc wgrad chunk %d done" % i)

@@ -26,8 +26,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("DRN_NCCL_MAX_CTAS"):
-            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DRN_NCCL_MAX_CTAS"])
+        from drn_b200.parallel import nccl_env_defaults
+        if os.environ.get("DRN_NCCL_MAX_CTAS") != "default":
+            nccl_env_defaults()
         dist.init_process_group("nccl", device_id=dev)
     cfg = S.default_config(stage=1)
     sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg), glove=True)
@@ -74,7 +75,7 @@ def main():
     else:
         allt = [mine]
     if rank == 0:
-        print(json.dumps({"world": world, "order": os.environ.get("DRN_DP_ORDER", "tail_first"), "chunks": os.environ.get("DRN_DP_CHUNKS", "4"),
+        print(json.dumps({"world": world, "order": os.environ.get("DRN_DP_ORDER", "overlap"), "chunks": os.environ.get("DRN_DP_CHUNKS", "4"),
                           "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "steps": a.steps,
                           "unit": "ms since the start of the backward (first entry: forward duration)", "phases": names,
                           "per_rank": [[round(x, 4) for x in r] for r in allt],
