@@ -811,6 +811,20 @@ __global__ void __launch_bounds__(256) qe_hprev_kernel(QeDev q) {
 //   PERSIST: one cooperative launch, W_hh tile resident, grid barriers between Phase A, Phase B and the next step; the
 //     jq = 0 CTA of each unit group runs Phase B.
 // dG is also kept transposed ([gate row][32 samples], double-buffered) so Phase A stages both operands with cp.async.
+// Barrier over the CTAs of ONE direction of a cooperative LSTM launch: one arrival counter per use (zeroed before the launch),
+// about a third of the cost of the grid-wide cooperative barrier, and the two directions never wait for each other.
+__device__ __forceinline__ void dir_barrier(unsigned* cnt, unsigned expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(cnt, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(cnt) < expected) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+}
 constexpr int BWD_JQ = 4;
 struct BwdIn {
   float gi, gf, gg, go, c, cp, dh;
@@ -905,7 +919,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
       }
       __threadfence();
       if (PERSIST) {
-        cg::this_grid().sync();
+        dir_barrier(q.bar + 2 * QE_MAX_L + dir * 2 * QE_MAX_L + 2 * s, gridDim.x * gridDim.y * q.BC);
       } else {
         __syncthreads();
         if (tid == 0) is_last = (atomicAdd(q.cnt + slot, 1u) == static_cast<unsigned>(nq - 1));
@@ -973,7 +987,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
     }
     if (PERSIST && s + 1 < s1) {
       __threadfence();
-      cg::this_grid().sync();
+      dir_barrier(q.bar + 2 * QE_MAX_L + dir * 2 * QE_MAX_L + 2 * s + 1, gridDim.x * gridDim.y * q.BC);
     }
   }
 }
@@ -1181,7 +1195,7 @@ static size_t carve(const drn_qe_t* a, QeDev* q) {
   float* dGT = take(2 * 2 * BC * 4 * H * 32);
   float* dr = take(3 * B * L);
   float* one = take(1);
-  float* bar = take(2 * QE_MAX_L);
+  float* bar = take(6 * QE_MAX_L);  // forward: [2][L]; backward: [2][2 L] (two barriers per step)
   if (q) {
     q->EP = static_cast<int>(EP);
     q->E_pl = reinterpret_cast<__nv_bfloat16*>(E_pl); q->Wih_pl = reinterpret_cast<__nv_bfloat16*>(Wih_pl);
@@ -1430,6 +1444,8 @@ static int qe_backward_parts(const drn_qe_t* a, int parts, void* stream) {
   TRY(set_smem(reinterpret_cast<const void*>(lstm_bwd_kernel<false>), smem_b, "lstm_bwd"));
   const dim3 grid_b(H / 32, BWD_JQ, 2 * q.BC);
   if (fits_cooperative(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), grid_b, smem_b)) {
+    cudaError_t me = cudaMemsetAsync(q.bar + 2 * QE_MAX_L, 0, 4 * QE_MAX_L * sizeof(unsigned), st);  // the step barriers' counters
+    if (me != cudaSuccess) return fail(static_cast<int>(me), "drn_qe_backward memset: %s", cudaGetErrorString(me));
     int s0 = 0, s1 = L, nq = BWD_JQ;
     void* args[] = {&q, &s0, &s1, &nq};
     cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_bwd_kernel<true>), grid_b, dim3(LSTM_THREADS), args, smem_b, st);
