@@ -237,7 +237,11 @@ def run_ours(args):
     core = model.module if hasattr(model, "module") else model
 
     dev_batch = {k: v.to(dev) for k, v in batch.items()}
-    dev_batch["query_length"] = batch["query_length"]  # lengths stay on the host (pack_padded_sequence)
+    # `value` = every input resident in HBM, the query lengths included (the path needs no host copy of them).  A pageable
+    # host tensor here makes every step's tiny H2D copy synchronise the stream (CUDA stages pageable sources synchronously), so
+    # the host can no longer run ahead of the GPU; DRN_BENCH_HOST_LENGTHS=1 reproduces that (r01's bench did this).
+    if os.environ.get("DRN_BENCH_HOST_LENGTHS", "0") == "1":
+        dev_batch["query_length"] = batch["query_length"]
     pinned = {k: v.pin_memory() for k, v in batch.items()}
 
     def step(b):

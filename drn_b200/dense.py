@@ -574,16 +574,67 @@ class DensePath:
         """Gradients produced by `backward_tail` (everything else is final when `backward(..., tail=False)` returns)."""
         return {n for n in names if n.startswith("qInput") or n.startswith("query_encoder.")}
 
-    def backward(self, p, grads, upstream, tail=True, propfc=True):
+    @staticmethod
+    def early_grad_name(n):
+        """Gradients that are FINAL once the head and the FPN have been differentiated (`backward(part="early")`): the
+        data-parallel schedule starts their all-reduce while the backbone backward still runs."""
+        return n.startswith("fcos.") or n.startswith("fpn.")
+
+    def backward(self, p, grads, upstream, tail=True, propfc=True, part="all"):
         """grads: name -> zero-initialised fp32 tensor for every parameter that wants a gradient (filled in place).
         upstream: [3] fp32 device tensor = d(total)/d(loss_cls, loss_reg, loss_iou).  tail=False stops before `backward_tail`;
-        propfc=False also leaves out the prop_fc weight gradient (`backward_propfc`): the data-parallel schedule runs the three
-        parts as separate graphs with an all-reduce started after each."""
+        propfc=False also leaves out the prop_fc weight gradient (`backward_propfc`): the data-parallel schedule runs the
+        parts as separate graphs with an all-reduce started after each.  part="early": loss, head and FPN only (their weight
+        gradients unpacked at once); part="late": the backbone, from the activations' gradients the early part left behind."""
         lib, B = _lib(), self.B
         h = "fcos.head."
         F = self.F
         self.launches = 0
         iou_on = self.iou_branch_on and (h + "mix_fc.0.weight") in grads
+        lv = range(3)
+        if part != "late":
+            self._backward_head_fpn(p, grads, upstream, iou_on)
+            if part == "early":
+                self._unpack_wgrads(grads, iou_on, which="early")
+                self.launches_bwd = self.launches
+                return
+        # backbone
+        for i in (2, 1):
+            blk = self.conv[i]
+            self._bn_bwd([self._bn_job(blk, p, grads, da=self.dC[i])])
+            self._group([self._wgrad_desc(blk, self.QC[i - 1], "conv%d" % i)] +
+                        self._dgrad_descs(blk, self.wp["conv%d" % i], self.dC[i - 1], mode=L.OUT_ADD, rowscale=self.q[i],
+                                          out2=self.dQC[i - 1]))
+            a = self.Cact[i - 1]
+            self._chk(lib.drn_gate_reduce(_vp(self.dQC[i - 1]), C.c_int64(a.C), _vp(a.data), C.c_int64(a.C),
+                                          C.c_int64(a.plane_stride), 1, B, self.Tl[i - 1], a.C, _vp(self.dq[i]), None, None,
+                                          C.c_int64(0), None, _st()), "gate_reduce")
+        blk = self.conv[0]
+        self._bn_bwd([self._bn_job(blk, p, grads, da=self.dC[0])])
+        self._group([self._wgrad_desc(blk, self.X0, "conv0")] + self._dgrad_descs(blk, self.wp["conv0"], self.dX0))
+        self._chk(lib.drn_gate_reduce(_vp(self.dX0), C.c_int64(self.C0), _vp(self.Pre), C.c_int64(self.D), C.c_int64(0), 0, B,
+                                      self.T, self.D, _vp(self.dq[0]), _vp(self.q[0]), _vp(self.dP_pl.data),
+                                      C.c_int64(self.dP_pl.plane_stride), _vp(grads["prop_fc.bias"]), _st()), "gate0_bwd")
+        self._chk(lib.drn_pos_bwd(_vp(self.dX0), C.c_int64(self.C0), self.D, _vp(self.pos_in), C.c_int64(B * self.T), 256,
+                                  _vp(grads["position_transform.weight"]), _vp(grads["position_transform.bias"]), _st()),
+                  "pos_bwd")
+        # partial sums (K-splits x levels) in tap-major workspaces -> parameter layout [O][C][k]: here, or (single-GPU schedule)
+        # as a side branch under the BPTT of the tail.  [Forking it beside the prop_fc weight gradient below was measured
+        # 50 us SLOWER than running it first: r01 v11 A/B.]
+        defer = tail and self.side is not None and part == "all"
+        if not defer:
+            self._unpack_wgrads(grads, iou_on, which="late" if part == "late" else "all")
+        if propfc:
+            self.backward_propfc(grads)
+        self.launches_bwd = self.launches
+        if tail:
+            self.backward_tail(p, grads, unpack=(iou_on,) if defer else None)
+
+    def _backward_head_fpn(self, p, grads, upstream, iou_on):
+        """Loss, head and FPN backward (everything above the backbone): leaves dC[0..2] for the backbone part."""
+        lib, B = _lib(), self.B
+        h = "fcos.head."
+        F = self.F
         self.bwd_zero.zero_()
         self._chk(lib.drn_fcos_loss_bwd(3, B, self.Tl_c, self.strides_c, _vp(self.cls_raw), _vp(self.box_raw), _vp(self.iou_raw),
                                         _vp(self.scales), _vp(self.gt), C.c_float(self.gamma), C.c_float(self.alpha),
@@ -622,37 +673,6 @@ class DensePath:
         self._bn_bwd([self._bn_job(self.inner[i], p, grads, da=self.dI[i]) for i in lv])
         self._group([self._wgrad_desc(self.inner[i], self.Cact[i], "inner%d" % i) for i in lv] +
                     [d for i in lv for d in self._dgrad_descs(self.inner[i], self.wp["inner%d" % i], self.dC[i])])
-        # backbone
-        for i in (2, 1):
-            blk = self.conv[i]
-            self._bn_bwd([self._bn_job(blk, p, grads, da=self.dC[i])])
-            self._group([self._wgrad_desc(blk, self.QC[i - 1], "conv%d" % i)] +
-                        self._dgrad_descs(blk, self.wp["conv%d" % i], self.dC[i - 1], mode=L.OUT_ADD, rowscale=self.q[i],
-                                          out2=self.dQC[i - 1]))
-            a = self.Cact[i - 1]
-            self._chk(lib.drn_gate_reduce(_vp(self.dQC[i - 1]), C.c_int64(a.C), _vp(a.data), C.c_int64(a.C),
-                                          C.c_int64(a.plane_stride), 1, B, self.Tl[i - 1], a.C, _vp(self.dq[i]), None, None,
-                                          C.c_int64(0), None, _st()), "gate_reduce")
-        blk = self.conv[0]
-        self._bn_bwd([self._bn_job(blk, p, grads, da=self.dC[0])])
-        self._group([self._wgrad_desc(blk, self.X0, "conv0")] + self._dgrad_descs(blk, self.wp["conv0"], self.dX0))
-        self._chk(lib.drn_gate_reduce(_vp(self.dX0), C.c_int64(self.C0), _vp(self.Pre), C.c_int64(self.D), C.c_int64(0), 0, B,
-                                      self.T, self.D, _vp(self.dq[0]), _vp(self.q[0]), _vp(self.dP_pl.data),
-                                      C.c_int64(self.dP_pl.plane_stride), _vp(grads["prop_fc.bias"]), _st()), "gate0_bwd")
-        self._chk(lib.drn_pos_bwd(_vp(self.dX0), C.c_int64(self.C0), self.D, _vp(self.pos_in), C.c_int64(B * self.T), 256,
-                                  _vp(grads["position_transform.weight"]), _vp(grads["position_transform.bias"]), _st()),
-                  "pos_bwd")
-        # partial sums (K-splits x levels) in tap-major workspaces -> parameter layout [O][C][k]: here, or (single-GPU schedule)
-        # as a side branch under the BPTT of the tail.  [Forking it beside the prop_fc weight gradient below was measured
-        # 50 us SLOWER than running it first: r01 v11 A/B.]
-        defer = tail and self.side is not None
-        if not defer:
-            self._unpack_wgrads(grads, iou_on)
-        if propfc:
-            self.backward_propfc(grads)
-        self.launches_bwd = self.launches
-        if tail:
-            self.backward_tail(p, grads, unpack=(iou_on,) if defer else None)
 
     def backward_propfc(self, grads, pair_clusters=0, chunk=None):
         """prop_fc weight gradient: [D x (B*T)] x [(B*T) x D], the largest contraction of the backward pass.  pair_clusters > 0
@@ -678,26 +698,30 @@ class DensePath:
                 _lib().drn_set_pair_clusters(0)
         self.launches_bwd = self.launches
 
-    def _unpack_wgrads(self, grads, iou_on):
+    def _unpack_wgrads(self, grads, iou_on, which="all"):
         """Weight-gradient workspaces [slices][k][O][C] -> parameter layout [O][C][k] (sum of the K-split / level slices), one
-        launch, after the scalar parameter gradients gathered by the loss kernel (tiny copies)."""
+        launch, after the scalar parameter gradients gathered by the loss kernel (tiny copies).  which = "early": head + FPN
+        only; "late": backbone only (data-parallel schedule: two launches, an all-reduce starts in between)."""
         lib, h, F = _lib(), "fcos.head.", self.F
-        grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
-        grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])
-        if iou_on:
-            grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
-        for l in range(3):
-            grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
         items = []
-        for i in range(3):
-            items.append(self._unpack_item(grads["backbone_net.forward_conv%d.0.weight" % i], "conv%d" % i))
-            items.append(self._unpack_item(grads["fpn.fpn_inner%d.0.weight" % (i + 1)], "inner%d" % i))
-            items.append(self._unpack_item(grads["fpn.fpn_layer%d.0.weight" % (i + 1)], "layer%d" % i))
-        items.append(self._unpack_item(grads[h + "cls_tower.0.weight"], "towers", 0))
-        items.append(self._unpack_item(grads[h + "bbox_tower.0.weight"], "towers", F))
-        if iou_on:
-            items.append(self._unpack_item(grads[h + "mix_fc.0.weight"], "mix"))
-            items.append(self._unpack_item(grads[h + "iou_scores.0.weight"], "iouc"))
+        if which != "late":
+            grads[h + "cls_logits.bias"].copy_(self.pgrad[0:1])
+            grads[h + "bbox_pred.bias"].copy_(self.pgrad[1:3])
+            if iou_on:
+                grads[h + "iou_scores.3.bias"].copy_(self.pgrad[3:4])
+            for l in range(3):
+                grads[h + "scales.%d.scale" % l].copy_(self.pgrad[4 + l:5 + l])
+            for i in range(3):
+                items.append(self._unpack_item(grads["fpn.fpn_inner%d.0.weight" % (i + 1)], "inner%d" % i))
+                items.append(self._unpack_item(grads["fpn.fpn_layer%d.0.weight" % (i + 1)], "layer%d" % i))
+            items.append(self._unpack_item(grads[h + "cls_tower.0.weight"], "towers", 0))
+            items.append(self._unpack_item(grads[h + "bbox_tower.0.weight"], "towers", F))
+            if iou_on:
+                items.append(self._unpack_item(grads[h + "mix_fc.0.weight"], "mix"))
+                items.append(self._unpack_item(grads[h + "iou_scores.0.weight"], "iouc"))
+        if which != "early":
+            for i in range(3):
+                items.append(self._unpack_item(grads["backbone_net.forward_conv%d.0.weight" % i], "conv%d" % i))
         arr = (L.PackItem * len(items))(*items)
         self._chk(lib.drn_unpack_conv_wgrads(len(items), arr, _st()), "unpack_conv_wgrads")
 

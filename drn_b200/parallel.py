@@ -25,12 +25,12 @@ from torch import nn
 
 
 def nccl_env_defaults():
-    """Call BEFORE the NCCL communicator is created.  The overlapped schedule runs collectives beside kernels that need most of
-    the GPU: the cooperative LSTM launches of the backward tail (128 CTAs that must be co-resident) and the 64-cluster chunks of
-    the prop_fc weight gradient (128 SMs).  With NCCL capped at 16 CTAs both fit beside it on the 148 SMs; measured on 8 x B200
-    (profiles/r02_dp_timeline8_*.json) the cap costs no all-reduce bandwidth against NCCL's default, 8 CTAs halve it.
-    DRN_NCCL_MAX_CTAS overrides; an NCCL_MAX_CTAS already in the environment wins."""
-    os.environ.setdefault("NCCL_MAX_CTAS", os.environ.get("DRN_NCCL_MAX_CTAS", "16"))
+    """Call BEFORE the NCCL communicator is created.  DRN_NCCL_MAX_CTAS=n caps NCCL's CTAs (A/B knob).  Measured on 8 x B200
+    (profiles/r02_dp_timeline8_*.json): with 16 CTAs the collectives no longer stretch the kernels they run beside (the
+    cooperative LSTM launches of the tail, the 64-cluster chunks of the prop_fc weight gradient) but lose a third of their
+    bandwidth, with 8 more than half -- a net loss, so NCCL's default stays."""
+    if os.environ.get("DRN_NCCL_MAX_CTAS"):
+        os.environ.setdefault("NCCL_MAX_CTAS", os.environ["DRN_NCCL_MAX_CTAS"])
 
 
 class GradReducer:

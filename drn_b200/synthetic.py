@@ -154,7 +154,7 @@ def load_synth_weights(model, seed=SEED):
 
 
 def synth_batch(B, T, max_len=10, feature_dim=4096, vocab_size=1301, seed=SEED, embedding=None,
-                sorted_lengths=True, queries="random", split="train"):
+                sorted_lengths=True, queries="random", split="train", signal_scale=2.0):
     """One synthetic batch in the dtypes dataset.py:180-224 produces.  queries="charades": real Charades-STA queries drawn from
     the fixture (`split` = train | test for held-out evaluation), padded to the longest of the batch like collate_data.
 
@@ -192,7 +192,7 @@ def synth_batch(B, T, max_len=10, feature_dim=4096, vocab_size=1301, seed=SEED, 
         loc = np.arange(T, dtype=np.float32) + 0.5
         for b in range(B):
             q = emb[tokens[b, : lengths[b]]].mean(0)
-            sig = np.maximum(q @ proj, 0) * np.float32(2.0)
+            sig = np.maximum(q @ proj, 0) * np.float32(signal_scale)  # 2.0: SURVEY 8d; smaller = a harder task (R@1 parity runs)
             inside = (loc > 32 * gt[b, 0]) & (loc < 32 * gt[b, 1])
             feats[b, inside] += sig
     return {

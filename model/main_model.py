@@ -64,10 +64,11 @@ def _run_forward(path, p, training, use_graphs, tokens, lengths, feats, pse, gt)
 
 
 def _run_backward(path, p, names, upstream, use_graphs, dp=None):
-    """Backward of the path into ONE flat gradient buffer.  Layout:
-        [A: accumulated, produced by the tail (gates, query encoder)][B: accumulated, first part][C: stored, first part]
+    """Backward of the path into ONE flat gradient buffer.  Layout (1 = head + FPN, 2 = backbone):
+        [C1: stored][B1: accumulated][B2: accumulated][A: accumulated, produced by the tail (gates, query encoder)][C2: stored]
         [D: prop_fc.weight]
-    A+B are zero-filled every backward (atomics / += land there); C (conv weights) and D are fully overwritten by their kernels.
+    B1+B2+A are zero-filled every backward (atomics / += land there); C (conv weights) and D are fully overwritten by their
+    kernels.  Every all-reduce region of every schedule below is a contiguous slice of this order.
     Every slot starts on a 32-byte boundary (full-sector vector stores in the contraction epilogues).
     Data parallel (dp = drn_b200.parallel.GradReducer): the prop_fc weight gradient -- 44 % of the gradient bytes and, in the
     single-GPU order, the last-but-one thing produced -- moves to the END and is cut into DRN_DP_CHUNKS (4) row chunks, so that
@@ -81,15 +82,21 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         all-reduce chunk i (17 MB)             queued behind it on NCCL's stream, under chunk i+1; only the last one is exposed.
     DRN_DP_ORDER=r01 keeps the round-1 order (first part -> all-reduce B+C || whole prop_fc wgrad -> all-reduce D || tail ->
     all-reduce A) for A/B runs."""
-    order = os.environ.get("DRN_DP_ORDER", "overlap") if dp is not None else "single"
-    nchunk = max(1, int(os.environ.get("DRN_DP_CHUNKS", "4"))) if order in ("tail_first", "overlap") else 1
+    order = os.environ.get("DRN_DP_ORDER", "tail_first") if dp is not None else "single"
+    nchunk = max(1, int(os.environ.get("DRN_DP_CHUNKS", "4"))) if order in ("tail_first", "overlap", "split") else 1
     key = ("bwd", _sig(p), tuple(names), order, nchunk)
     ent = path.graphs.get(key)
     if ent is None:
         stored, tailn = path.stored_grad_names(names), path.part2_grad_names(names)
         last = {"prop_fc.weight"} & set(names)
-        groups = [[n for n in names if n in tailn], [n for n in names if n not in tailn and n not in stored],
-                  [n for n in names if n not in tailn and n in stored and n not in last], [n for n in names if n in last]]
+        early = path.early_grad_name
+        # [C1 stored, head+FPN][B1 accumulated, head+FPN][B2 accumulated, backbone][A accumulated, tail][C2 stored, backbone][D]
+        groups = [[n for n in names if n in stored and n not in tailn and n not in last and early(n)],
+                  [n for n in names if n not in stored and n not in tailn and early(n)],
+                  [n for n in names if n not in stored and n not in tailn and not early(n)],
+                  [n for n in names if n in tailn],
+                  [n for n in names if n in stored and n not in tailn and n not in last and not early(n)],
+                  [n for n in names if n in last]]
         pad = lambda k: (k + 7) // 8 * 8  # noqa: E731
         bounds = [0]
         for g_ in groups:
@@ -103,12 +110,13 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
             for n in g_:
                 grads[n] = flat[o:o + p[n].numel()].view_as(p[n])
                 o += pad(p[n].numel())
-        regions = {"zero": flat[:bounds[2]], "first": flat[bounds[1]:bounds[3]], "propfc": flat[bounds[3]:], "tail": flat[:bounds[1]],
-                   "all_but_propfc": flat[:bounds[3]]}
+        b = bounds
+        regions = {"zero": flat[b[1]:b[4]], "early": flat[:b[2]], "late": flat[b[2]:b[5]], "tail": flat[b[3]:b[4]],
+                   "first": [flat[:b[3]], flat[b[4]:b[5]]], "propfc": flat[b[5]:], "all_but_propfc": flat[:b[5]]}
         if last and nchunk > 1 and p["prop_fc.weight"].shape[0] % (8 * nchunk) == 0:
             rows = p["prop_fc.weight"].shape[0] // nchunk
             per = rows * p["prop_fc.weight"].shape[1]
-            regions["propfc_chunks"] = [flat[bounds[3] + i * per:bounds[3] + (i + 1) * per] for i in range(nchunk)]
+            regions["propfc_chunks"] = [flat[b[5] + i * per:b[5] + (i + 1) * per] for i in range(nchunk)]
         else:
             nchunk = 1
             regions["propfc_chunks"] = [regions["propfc"]]
@@ -120,8 +128,15 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
 
         def first_part():
             regions["zero"].zero_()
-            path.backward(p, grads, path.upstream, tail=not split, propfc=not split)
+            if order == "split":
+                path.backward(p, grads, path.upstream, part="early")
+            else:
+                path.backward(p, grads, path.upstream, tail=not split, propfc=not split)
+
+        def late_part():
+            path.backward(p, grads, path.upstream, tail=False, propfc=False, part="late")
         g1 = cap(first_part)
+        g_late = cap(late_part) if order == "split" else None
         g_tail = cap(lambda: path.backward_tail(p, grads)) if split else None
         g_chunks = []
         if split:
@@ -130,17 +145,17 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
                 g_chunks.append((cap(lambda ch=ch: path.backward_propfc(grads, pair_clusters=pc, chunk=ch)), ch))
         if dp is not None:  # the eager run above produced a complete local gradient: reduce it in one go
             dp.reduce_regions([flat])
-        ent = (g1, g_tail, g_chunks, flat, grads, regions, pc, first_part)
+        ent = (g1, g_tail, g_chunks, flat, grads, regions, pc, first_part, g_late, late_part)
         path.graphs[key] = ent
         return flat, grads
-    g1, g_tail, g_chunks, flat, grads, regions, pc, first_part = ent
+    g1, g_tail, g_chunks, flat, grads, regions, pc, first_part, g_late, late_part = ent
     path.upstream.copy_(upstream)
     _mark("backward start")
     if g1 is not None:
         g1.replay()
     else:
         first_part()
-    _mark("head+FPN+backbone done")
+    _mark("head+FPN done" if order == "split" else "head+FPN+backbone done")
     if dp is None:
         return flat, grads
 
@@ -157,7 +172,7 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         else:
             path.backward_propfc(grads, pair_clusters=pc, chunk=ch)
     if order == "r01":
-        work = dp.reduce_regions([regions["first"]], wait=False)  # overlaps the prop_fc weight gradient below
+        work = dp.reduce_regions(regions["first"], wait=False)  # overlaps the prop_fc weight gradient below
         run_chunk(0)
         _mark("prop_fc wgrad done")
         work += dp.reduce_regions([regions["propfc"]], wait=False)  # overlaps the tail below
@@ -168,10 +183,21 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
             dp.wait([w])
             _mark("wait: all-reduce %d done" % i)
         return flat, grads
-    if order == "overlap":
-        # B+C is reduced WHILE the tail runs: its cooperative LSTM kernels (128 CTAs) stay co-resident with the collective as
-        # long as NCCL keeps to <= 20 SMs (NCCL_MAX_CTAS=16, set before the communicator is created: drn_b200/parallel.py)
-        work = dp.reduce_regions([regions["first"]], wait=False)
+    if order == "split":
+        # head + FPN gradients (C1+B1, ~20 MB) are reduced WHILE the backbone is differentiated; everything else as tail_first
+        work = dp.reduce_regions([regions["early"]], wait=False)
+        if g_late is not None:
+            g_late.replay()
+        else:
+            late_part()
+        _mark("backbone done")
+        run_tail()
+        _mark("tail done")
+        work += dp.reduce_regions([regions["late"]], wait=False)
+    elif order == "overlap":
+        # B+C is reduced WHILE the tail runs: its cooperative LSTM kernels (128 CTAs) stay co-resident with the collective only
+        # if NCCL keeps to <= 20 SMs (NCCL_MAX_CTAS=16), which halves its bandwidth: measured slower (profiles/r02_dp_timeline8_11)
+        work = dp.reduce_regions(regions["first"], wait=False)
         run_tail()
         _mark("tail done")
         work += dp.reduce_regions([regions["tail"]], wait=False)
@@ -310,6 +336,30 @@ class mainModel(nn.Module):
         self._paths[key] = path  # most recently used last
         return path
 
+    def _small_to_device(self, t, dtype, dev):
+        """Host -> device copy of a SMALL tensor (tokens, lengths, ground truth, proposal boundaries: <= 1 MB) that never stalls the host: a `.to(device,
+        non_blocking=True)` from PAGEABLE memory is staged synchronously by the runtime, which synchronises the stream and costs
+        the whole launch-ahead of the step (~0.4 ms measured in bench.py's device-resident leg, where the query lengths used to
+        be a pageable host tensor).  Pageable sources go through a ring of pinned staging buffers (an event per slot guards
+        its reuse); pinned and device sources are passed straight on."""
+        if t.device.type != "cpu" or t.is_pinned() or t.numel() * t.element_size() > (1 << 20):
+            return t.to(dev, dtype=dtype, non_blocking=True).contiguous()
+        ring = self.__dict__.setdefault("_pin_ring", {"slots": [None] * 16, "events": [None] * 16, "next": 0})
+        i = ring["next"]
+        ring["next"] = (i + 1) % 16
+        if ring["events"][i] is not None:
+            ring["events"][i].synchronize()
+        nbytes = max(t.numel(), 1) * torch.empty((), dtype=dtype).element_size()
+        buf = ring["slots"][i]
+        if buf is None or buf.numel() < nbytes:
+            buf = ring["slots"][i] = torch.empty(max(nbytes, 4096), dtype=torch.uint8, pin_memory=True)
+        host = buf[:nbytes].view(dtype)[:t.numel()].view(t.shape)
+        host.copy_(t)
+        out = host.to(dev, non_blocking=True)
+        ev = ring["events"][i] = ring["events"][i] or torch.cuda.Event()
+        ev.record()
+        return out
+
     def input_error(self):
         """Synchronising check of the sticky input-validation flags of every path (drn_qe_stage): None, or a message naming
         what was rejected since the last call.  A rejected batch has NaN losses (no synchronisation needed to notice)."""
@@ -348,11 +398,11 @@ class mainModel(nn.Module):
             if int(query_length.min()) < 1 or int(query_length.max()) > query_tokens.shape[1]:
                 raise RuntimeError("query lengths must lie in [1, %d] (got %d .. %d)"
                                    % (query_tokens.shape[1], int(query_length.min()), int(query_length.max())))
-        tokens = query_tokens.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
-        lengths = query_length.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+        tokens = self._small_to_device(query_tokens, torch.int64, dev)
+        lengths = self._small_to_device(query_length, torch.int64, dev)
         feats = props_features.to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-        pse = props_start_end.to(dev, dtype=torch.float64, non_blocking=True).contiguous()
-        gt = gt_start_end.to(dev, non_blocking=True).float().contiguous()  # `.float()` as at main_model.py:74
+        pse = self._small_to_device(props_start_end, torch.float64, dev)
+        gt = self._small_to_device(gt_start_end, gt_start_end.dtype, dev).float().contiguous()  # `.float()` as at main_model.py:74
         B, T = feats.shape[0], feats.shape[1]
         # the reference collate pads queries to the longest of the batch (dataset.py:186,198), so the token width varies from
         # batch to batch; every (B, T, L) owns ~2 GB of buffers and two CUDA graphs, so L is bucketed (zero = padding tokens,

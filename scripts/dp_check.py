@@ -77,6 +77,6 @@ for it in range(3):  # eager first call, then the graph replay path twice
 t = torch.tensor([worst], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print("dp_check%s order=%s world=%d max rel-L2 deviation of DP gradients from the mean of single-rank gradients: %.3e" % (" (auto hook)" if AUTO else "", os.environ.get("DRN_DP_ORDER", "overlap"), world, float(t)))
+    print("dp_check%s order=%s world=%d max rel-L2 deviation of DP gradients from the mean of single-rank gradients: %.3e" % (" (auto hook)" if AUTO else "", os.environ.get("DRN_DP_ORDER", "tail_first"), world, float(t)))
     assert float(t) < 1e-3
 dist.destroy_process_group()

@@ -75,7 +75,7 @@ def main():
     else:
         allt = [mine]
     if rank == 0:
-        print(json.dumps({"world": world, "order": os.environ.get("DRN_DP_ORDER", "overlap"), "chunks": os.environ.get("DRN_DP_CHUNKS", "4"),
+        print(json.dumps({"world": world, "order": os.environ.get("DRN_DP_ORDER", "tail_first"), "chunks": os.environ.get("DRN_DP_CHUNKS", "4"),
                           "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS"), "steps": a.steps,
                           "unit": "ms since the start of the backward (first entry: forward duration)", "phases": names,
                           "per_rank": [[round(x, 4) for x in r] for r in allt],

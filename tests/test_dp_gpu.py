@@ -23,12 +23,12 @@ def _port():
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("mode", ["overlap", "tail_first", "r01", "auto"])
+@pytest.mark.parametrize("mode", ["tail_first", "split", "overlap", "r01", "auto"])
 def test_dp_gradients_equal_mean_of_single_rank_gradients(mode):
     env = dict(os.environ)
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         env.pop(k, None)
-    if mode in ("r01", "tail_first"):
+    if mode != "auto":
         env["DRN_DP_ORDER"] = mode
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_port()), os.path.join(REPO, "scripts", "dp_check.py")] + (["--auto"] if mode == "auto" else [])
