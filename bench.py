@@ -271,8 +271,10 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_host = time.perf_counter()
     for _ in range(args.steps):
         step(dev_batch)
+    host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps  # host time to ENQUEUE a step (no synchronisation inside)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
@@ -407,7 +409,8 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (split-BF16 x3 tensor-core products, fp32 accumulate)", "data": "synthetic",
         "config": workload_config(world),
-        "diag": {"algorithmic_tflops_per_s": value * FLOP_PER_PAIR / 1e12, "fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3)},
+        "diag": {"algorithmic_tflops_per_s": value * FLOP_PER_PAIR / 1e12, "fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3),
+                 "host_enqueue_ms_per_step": round(host_ms, 3)},
         "clocks": sampler.summary(),
         "e2e": {"value": world * B_PER_GPU / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "h2d_gbs_per_rank_all_ranks_uploading": {"rank0": h2d_gbs, "min_over_ranks": h2d_min},

@@ -36,20 +36,26 @@ def main():
     ap.add_argument("--eval-batches", type=int, default=16)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--T", type=int, default=32)
+    ap.add_argument("--signal-scale", type=float, default=2.0, help="amplitude of the query signal in the features (2.0 = SURVEY 8d; smaller = harder task)")
+    ap.add_argument("--arms", default="cuda,oracle,control", help="which arms to run here (the CPU arms can run in the build container, the cuda arm on the GPU box)")
+    ap.add_argument("--merge", nargs="*", default=None, help="JSON files of earlier --arms runs of the SAME settings to merge into the summary")
     a = ap.parse_args()
+    arms = [x for x in a.arms.split(",") if x]
     torch.set_num_threads(os.cpu_count())
-    from model.main_model import mainModel
     cfg = S.default_config(stage=1)
     sd = S.synth_state_dict(spec_mod.state_dict_spec(cfg), glove=True)
     emb = sd["query_encoder.embedding.weight"]
     B, T = a.batch, a.T
-    evalb = [S.synth_batch(B, T, max_len=10, embedding=emb, seed=S.SEED + 900000 + j, queries="charades", split="test") for j in range(a.eval_batches)]
+    evalb = [S.synth_batch(B, T, max_len=10, embedding=emb, seed=S.SEED + 900000 + j, queries="charades", split="test", signal_scale=a.signal_scale)
+             for j in range(a.eval_batches)]
     gts = [g for b in evalb for g in b["gt_start_end"].tolist()]
 
     def train_batches(seed):
-        return [S.synth_batch(B, T, max_len=10, embedding=emb, seed=S.SEED + 100000 * (seed + 1) + i, queries="charades") for i in range(a.steps)]
+        return [S.synth_batch(B, T, max_len=10, embedding=emb, seed=S.SEED + 100000 * (seed + 1) + i, queries="charades", signal_scale=a.signal_scale)
+                for i in range(a.steps)]
 
     def run_cuda(batches):
+        from model.main_model import mainModel
         model = mainModel(1301, S.config_namespace(stage=1))
         model.load_state_dict(sd)
         for k, p in model.named_parameters():
@@ -121,19 +127,21 @@ def main():
         sys.stderr.write("seed %d: R@1 cuda %.4f oracle %.4f control %.4f  (%.0f s)\\n" % (seed, rc[1], ro[1], rp[1], time.time() - t0))
     mean = lambda arm, k: statistics.mean(r[arm][k] for r in rows)  # noqa: E731
     sdev = lambda arm, k: statistics.pstdev(r[arm][k] for r in rows)  # noqa: E731
-    out = {"steps": a.steps, "B": B, "T": T, "seeds": a.seeds, "eval_pairs": len(gts), "queries": "Charades-STA (train / held-out test split), GloVe-300",
-           "per_seed": rows}
+    out = {"steps": a.steps, "B": B, "T": T, "seeds": a.seeds, "signal_scale": a.signal_scale, "eval_pairs": len(gts),
+           "queries": "Charades-STA (train / held-out test split), GloVe-300", "arms": have, "per_seed": rows}
     for k in ("R@1", "R@5"):
-        out[k] = {"mean_pct": {arm: 100 * mean(arm, k) for arm in ("cuda", "oracle", "control")},
-                  "std_over_seeds_pp": {arm: 100 * sdev(arm, k) for arm in ("cuda", "oracle", "control")},
-                  "mean_cuda_minus_oracle_pp": 100 * (mean("cuda", k) - mean("oracle", k)),
-                  "mean_control_minus_oracle_pp": 100 * (mean("control", k) - mean("oracle", k)),
-                  "mean_abs_pairwise_pp": {"cuda_vs_oracle": 100 * statistics.mean(abs(r["cuda"][k] - r["oracle"][k]) for r in rows),
-                                           "control_vs_oracle": 100 * statistics.mean(abs(r["control"][k] - r["oracle"][k]) for r in rows)}}
-    d, c = abs(out["R@1"]["mean_cuda_minus_oracle_pp"]), abs(out["R@1"]["mean_control_minus_oracle_pp"])
-    sem = 100 * (sdev("oracle", "R@1") ** 2 + sdev("cuda", "R@1") ** 2) ** 0.5 / max(a.seeds, 1) ** 0.5
-    out["verdict"] = {"abs_mean_diff_pp": d, "control_abs_mean_diff_pp": c, "standard_error_of_the_difference_pp": sem,
-                      "within_0.2pp": d <= 0.2, "within_control_or_2_sem": d <= max(0.2, c, 2 * sem)}
+        out[k] = {"mean_pct": {arm: 100 * mean(arm, k) for arm in have}, "std_over_seeds_pp": {arm: 100 * sdev(arm, k) for arm in have}}
+        if "cuda" in have and "oracle" in have:
+            out[k]["mean_cuda_minus_oracle_pp"] = 100 * (mean("cuda", k) - mean("oracle", k))
+            out[k]["mean_abs_cuda_vs_oracle_pp"] = 100 * statistics.mean(abs(r["cuda"][k] - r["oracle"][k]) for r in rows)
+        if "control" in have and "oracle" in have:
+            out[k]["mean_control_minus_oracle_pp"] = 100 * (mean("control", k) - mean("oracle", k))
+            out[k]["mean_abs_control_vs_oracle_pp"] = 100 * statistics.mean(abs(r["control"][k] - r["oracle"][k]) for r in rows)
+    if len(have) == 3:
+        d, c = abs(out["R@1"]["mean_cuda_minus_oracle_pp"]), abs(out["R@1"]["mean_control_minus_oracle_pp"])
+        sem = 100 * (sdev("oracle", "R@1") ** 2 + sdev("cuda", "R@1") ** 2) ** 0.5 / max(a.seeds, 1) ** 0.5
+        out["verdict"] = {"abs_mean_diff_pp": d, "control_abs_mean_diff_pp": c, "standard_error_of_the_difference_pp": sem,
+                          "within_0.2pp": d <= 0.2, "within_control_or_2_sem": d <= max(0.2, c, 2 * sem)}
     print(json.dumps(out))
 
 
