@@ -1,6 +1,9 @@
 // Library-level entry points of libdrn_sm100.so (include/drn_b200.h): version, error text, device check.
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "common.cuh"
 
 namespace drn {
@@ -15,6 +18,19 @@ bool pdl_enabled() {
     on = (e && e[0] == '1') ? 1 : 0;  // measured neutral under graph replay (r01 v14 A/B: 3.71 vs 3.72 ms per step): off
   }
   return on == 1;
+}
+void carveout_once(const void* kernel) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("DRN_CARVEOUT");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!on) return;
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  if (seen.insert(kernel).second)
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 }  // namespace drn
 

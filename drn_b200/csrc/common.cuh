@@ -37,6 +37,10 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // measured neutral on B200 (profiles/r01_ab_pdl_v14.log), so by default kernels are launched without the attribute and the
 // two instructions are no-ops.
 bool pdl_enabled();  // api.cu: reads DRN_PDL once
+// DRN_CARVEOUT=1 (api.cu): every kernel of the library asks for the SAME L1 / shared-memory split as the persistent contraction
+// kernel (maximum shared memory).  An SM has to drain before its split can change, so a step that alternates between a
+// 197 KB-shared-memory contraction and default-split element-wise kernels pays a reconfiguration on every transition.
+void carveout_once(const void* kernel);
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
@@ -49,6 +53,7 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  carveout_once(reinterpret_cast<const void*>(kernel));
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through check_launch (cudaGetLastError)
 }
 #ifdef __CUDACC__

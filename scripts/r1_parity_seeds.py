@@ -115,16 +115,20 @@ def main():
                 res += rb
         return M.recall_at(res, gts), losses
 
-    rows = []
+    rows = [{"seed": seed} for seed in range(a.seeds)]
+    for f in a.merge or []:
+        prev = json.load(open(f))
+        assert (prev["steps"], prev["B"], prev["T"], prev["seeds"], prev.get("signal_scale", 2.0)) == (a.steps, B, T, a.seeds, a.signal_scale), f
+        for r, pr in zip(rows, prev["per_seed"]):
+            r.update({k: v for k, v in pr.items() if k in ("cuda", "oracle", "control")})
     t0 = time.time()
     for seed in range(a.seeds):
         tb = train_batches(seed)
-        rc, lc = run_cuda(tb)
-        ro, lo = run_oracle(tb, 0.0, seed)
-        rp, lp = run_oracle(tb, 2.0 ** -16, seed)
-        rows.append({"seed": seed, "cuda": {"R@1": rc[1], "R@5": rc[5], "final_loss": lc[-1]}, "oracle": {"R@1": ro[1], "R@5": ro[5], "final_loss": lo[-1]},
-                     "control": {"R@1": rp[1], "R@5": rp[5], "final_loss": lp[-1]}, "loss_step0": [lc[0], lo[0], lp[0]]})
-        sys.stderr.write("seed %d: R@1 cuda %.4f oracle %.4f control %.4f  (%.0f s)\\n" % (seed, rc[1], ro[1], rp[1], time.time() - t0))
+        for arm in arms:
+            rec, losses = run_cuda(tb) if arm == "cuda" else run_oracle(tb, 0.0 if arm == "oracle" else 2.0 ** -16, seed)
+            rows[seed][arm] = {"R@1": rec[1], "R@5": rec[5], "final_loss": losses[-1], "loss_step0": losses[0]}
+            sys.stderr.write("seed %d %s: R@1 %.4f R@5 %.4f (%.0f s)\n" % (seed, arm, rec[1], rec[5], time.time() - t0))
+    have = [arm for arm in ("cuda", "oracle", "control") if all(arm in r for r in rows)]
     mean = lambda arm, k: statistics.mean(r[arm][k] for r in rows)  # noqa: E731
     sdev = lambda arm, k: statistics.pstdev(r[arm][k] for r in rows)  # noqa: E731
     out = {"steps": a.steps, "B": B, "T": T, "seeds": a.seeds, "signal_scale": a.signal_scale, "eval_pairs": len(gts),
