@@ -30,7 +30,8 @@ constexpr int P2_STAGES = 3;
 constexpr uint32_t P2_HALF = 128 * 128;                 // one plane of one operand half: 128 rows x 128 B
 constexpr uint32_t P2_STAGE = 4 * P2_HALF;              // A hi, A lo, B hi, B lo
 constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + 1024;
-constexpr int P2_THREADS = 192;
+constexpr int P2_EPI_WARPS = 8;                         // 2 warps per TMEM lane quarter, each drains half of the 256 columns
+constexpr int P2_THREADS = 64 + 32 * P2_EPI_WARPS;
 constexpr int P2_TILE = 256;
 
 struct PairTile {
@@ -179,7 +180,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 2 * P2_EPI_WARPS);  // epilogue warps x 2 CTAs
     }
     fence_mbar_init();
   }
@@ -306,9 +307,13 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ===== epilogue warps 2..5 (both CTAs): TMEM lane quarter = warp % 4 =====
+    // ===== epilogue warps 2.. (both CTAs): TMEM lane quarter = warp % 4 (hardware rule); with 8 warps the two warps of a
+    // quarter split the 256 accumulator columns, which halves the drain time of a tile -- the short-K layers (FPN laterals,
+    // stride-2 data gradients: 4-16 k-iterations a tile) are bound by it, and every launch ends with one exposed drain =====
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    constexpr int COLS_PER_WARP = P2_TILE / (P2_EPI_WARPS / 4);
+    const int cbeg = ((warp - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
     int lt = 0;
     PairSched sc = sched_init(gp, cluster_id, num_clusters, num_tiles);
     PairTile t;
@@ -330,7 +335,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         while ((cluster_id + 1 + ncontrib) * gp.sk_quota < tile_end) ++ncontrib;
         if (lane == 0) {
           for (int j = 0; j < ncontrib; ++j) {
-            const unsigned* f = gp.sk_flags + (cluster_id + 1 + j) * 8 + rank * 4 + q;
+            const unsigned* f = gp.sk_flags + (cluster_id + 1 + j) * 16 + rank * 8 + (warp - 2);
             const long long t0 = clock64();
             while (ld_acquire_gpu(f) == 0u) {
               if (clock64() - t0 > 4000000000LL) __trap();
@@ -345,7 +350,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         // not the owner: this pair's range starts inside the tile -> partial accumulator to the workspace slot + flag
         float* slot = gp.sk_ws + static_cast<size_t>(cluster_id) * SK_SLOT_FLOATS + ws_off;
 #pragma unroll 1
-        for (int c0 = 0; c0 < P2_TILE; c0 += 32) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
           if (t.n0 + c0 >= p.N) break;
           float v[32];
           tmem_ld_32x32(taddr + c0, v);
@@ -359,7 +364,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         if (lane == 0) {
           mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
           __threadfence();
-          st_release_gpu(gp.sk_flags + cluster_id * 8 + rank * 4 + q, 1u);
+          st_release_gpu(gp.sk_flags + cluster_id * 16 + rank * 8 + (warp - 2), 1u);
         }
         continue;
       }
@@ -380,7 +385,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       }
       const int stats_blk = (!wgrad && p.stats) ? t.ms * 4 + q : -1;  // 32-row block of the output (BatchNorm partial sums)
 #pragma unroll 1
-      for (int c0 = 0; c0 < P2_TILE; c0 += 32) {
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
         if (t.n0 + c0 >= p.N) break;
         float v[32];
         tmem_ld_32x32(taddr + c0, v);
@@ -400,7 +405,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
-        for (int j = 0; j < ncontrib; ++j) gp.sk_flags[(cluster_id + 1 + j) * 8 + rank * 4 + q] = 0u;  // re-armed for the next launch
+        for (int j = 0; j < ncontrib; ++j) gp.sk_flags[(cluster_id + 1 + j) * 16 + rank * 8 + (warp - 2)] = 0u;  // re-armed for the next launch
       }
     }
   }
@@ -456,7 +461,7 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
   for (int k = gp.nprob; k < GROUP_MAX; ++k) gp.it_start[k + 1] = gp.it_start[gp.nprob];
   if (ws && uniform && total > 0 && total < (1ll << 30) &&
       ws_bytes >= SK_FLAG_BYTES + static_cast<size_t>(clusters) * SK_SLOT_FLOATS * sizeof(float) &&
-      static_cast<size_t>(clusters) * 8 * sizeof(unsigned) <= SK_FLAG_BYTES) {
+      static_cast<size_t>(clusters) * 16 * sizeof(unsigned) <= SK_FLAG_BYTES) {
     int quota = static_cast<int>((total + clusters - 1) / clusters);
     if (quota < sk_min) quota = sk_min;
     gp.sk_quota = quota;

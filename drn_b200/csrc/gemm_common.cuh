@@ -59,11 +59,11 @@ struct GroupParams {
   int it_start[GROUP_MAX + 1];    // prefix sums of tiles x k-iterations per problem
   int nk_tile[GROUP_MAX];         // k-iterations of one tile (uniform inside a problem)
   float* sk_ws;                   // [pairs][2 CTAs][8 column chunks][128 rows][32] fp32
-  unsigned* sk_flags;             // [pairs][2 CTAs][4 epilogue warps], zero between launches
+  unsigned* sk_flags;             // [pairs][2 CTAs][8 epilogue warps], zero between launches
   GemmKParams p[GROUP_MAX];
 };
 constexpr size_t SK_SLOT_FLOATS = 2 * 128 * 256;  // one 256 x 256 fp32 partial tile per SM pair
-constexpr size_t SK_FLAG_BYTES = 4096;
+constexpr size_t SK_FLAG_BYTES = 8192;
 struct GroupMaps {
   CUtensorMap a[GROUP_MAX];
   CUtensorMap b[GROUP_MAX];

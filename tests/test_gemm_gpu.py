@@ -294,7 +294,7 @@ def _group_static(descs):
 
 def _flags_clear():
     torch.cuda.synchronize()
-    return int(ops.workspace()[:4096].max()) == 0
+    return int(ops.workspace()[:8192].max()) == 0
 
 
 def test_streamk_long_tiles_many_contributors():
