@@ -272,8 +272,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     t_host = time.perf_counter()
+    p2p_before = core._dp.transport_used["p2p"] if world > 1 else 0
     for _ in range(args.steps):
         step(dev_batch)
+    p2p_launches = (core._dp.transport_used["p2p"] - p2p_before) if world > 1 else 0  # peer-memory all-reduce kernels (ours too)
     host_ms = (time.perf_counter() - t_host) * 1e3 / args.steps  # host time to ENQUEUE a step (no synchronisation inside)
     e1.record()
     barrier()
@@ -411,11 +413,13 @@ def run_ours(args):
         "config": workload_config(world),
         "diag": {"algorithmic_tflops_per_s": value * FLOP_PER_PAIR / 1e12, "fwd_ms": round(fwd_ms, 3), "bwd_ms": round(bwd_ms, 3),
                  "host_enqueue_ms_per_step": round(host_ms, 3)},
+        "gradient_exchange": ({"transport": "peer-memory all-reduce kernel (drn_p2p_allreduce_avg)" if core._dp.transport_used["p2p"] else "NCCL all-reduce",
+                               "calls": dict(core._dp.transport_used)} if world > 1 else None),
         "clocks": sampler.summary(),
         "e2e": {"value": world * B_PER_GPU / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "h2d_gbs_per_rank_all_ranks_uploading": {"rank0": h2d_gbs, "min_over_ranks": h2d_min},
                 "host_affinity_rank0": affinity},
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * args.steps + p2p_launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_pair_kernel (prop_fc forward, M=8192 N=K=4096: 27 % of the step's FLOPs; "
                      "the same kernel runs every contraction of the path)",
                      "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_tflops"],

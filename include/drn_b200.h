@@ -405,6 +405,34 @@ int drn_nms_recall(const float* det, const float* score, const int32_t* count, c
                    int nms, double overlap, double iou_thr, const int32_t* topk, int ntopk, int empty_fallback, int32_t* picks,
                    int32_t* npicks, int32_t* hits, int32_t* correct, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Gradient exchange over NVLink peer memory (drn_b200/csrc/p2p.cu): the ONE collective of the data-parallel path
+ * (all-reduce of the fp32 gradients, main.py:99 nn.DataParallel semantics), written as a kernel that
+ * reads and writes the peers' flat gradient buffers directly instead of calling NCCL.
+ *   drn_ipc_export: CUDA IPC handle (64 bytes) of the cudaMalloc allocation that contains `ptr`, and ptr's byte offset in it.
+ *   drn_ipc_open:   maps a peer process's allocation (peer access enabled lazily) and returns base + offset.
+ *   drn_ipc_close:  unmaps what drn_ipc_open returned (pass the same offset).
+ *   drn_p2p_allreduce_avg: buf[r] = rank r's flat fp32 buffer (own pointer at buf[rank], peers' mapped pointers elsewhere),
+ *     flags[r] = rank r's zero-initialised uint32[DRN_P2P_FLAG_WORDS] flag block, mapped the same way.  Elements
+ *     [offset, offset + n) (both multiples of 4) of EVERY rank's buffer are replaced by their mean over the ranks: rank r
+ *     sums slice r of the range from all ranks in rank order (bit-identical result on every rank, deterministic), scales by
+ *     1/world and stores the result into all `world` buffers.  Two flag exchanges (st.release.sys / ld.acquire.sys on the
+ *     peers' flag blocks, an epoch counter in flags[rank][0]) order it: nobody reads before every rank has launched the call
+ *     (its gradients are complete: stream order), nobody returns before every rank's stores have landed.  Every rank must
+ *     issue the same sequence of calls.  `ctas` = CTAs of 512 threads (0 = default).  A peer that never arrives traps the
+ *     kernel after ~4 s instead of hanging the GPU. */
+#define DRN_P2P_MAX_RANKS 8
+#define DRN_P2P_FLAG_WORDS 64
+typedef struct {
+  int32_t world, rank;
+  float* buf[DRN_P2P_MAX_RANKS];
+  uint32_t* flags[DRN_P2P_MAX_RANKS];
+} drn_p2p_t;
+int drn_ipc_export(const void* ptr, unsigned char* handle64, int64_t* offset);
+int drn_ipc_open(const unsigned char* handle64, int64_t offset, void** out);
+int drn_ipc_close(void* ptr, int64_t offset);
+int drn_p2p_allreduce_avg(const drn_p2p_t* comm, int64_t offset, int64_t n, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

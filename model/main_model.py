@@ -63,8 +63,10 @@ def _run_forward(path, p, training, use_graphs, tokens, lengths, feats, pse, gt)
     _replay(path, ("fwd", training, _sig(p)), core, use_graphs)
 
 
-def _run_backward(path, p, names, upstream, use_graphs, dp=None):
-    """Backward of the path into ONE flat gradient buffer.  Layout (1 = head + FPN, 2 = backbone):
+def _run_backward(path, p, names, upstream, use_graphs, dp=None, flat_cache=None):
+    """Backward of the path into ONE flat gradient buffer (one per model and gradient layout, shared by all (B, T, L) shapes --
+    `flat_cache` -- so that in a data-parallel run rank r's gradients always sit in the buffer its peers have mapped, whichever
+    shape each rank happens to run).  Layout (1 = head + FPN, 2 = backbone):
         [C1: stored][B1: accumulated][B2: accumulated][A: accumulated, produced by the tail (gates, query encoder)][C2: stored]
         [D: prop_fc.weight]
     B1+B2+A are zero-filled every backward (atomics / += land there); C (conv weights) and D are fully overwritten by their
@@ -101,7 +103,14 @@ def _run_backward(path, p, names, upstream, use_graphs, dp=None):
         bounds = [0]
         for g_ in groups:
             bounds.append(bounds[-1] + sum(pad(p[n].numel()) for n in g_))
-        flat = torch.zeros(bounds[-1], device=upstream.device, dtype=torch.float32)
+        fkey = (key[1], key[2], tuple(bounds))
+        flat = flat_cache.get(fkey) if flat_cache is not None else None
+        if flat is None:
+            flat = torch.zeros(bounds[-1], device=upstream.device, dtype=torch.float32)
+            if flat_cache is not None:
+                flat_cache[fkey] = flat
+            if dp is not None and hasattr(dp, "register"):
+                dp.register(flat)  # collective: peers map this buffer for the peer-memory all-reduce (drn_b200/parallel.py)
         if not hasattr(path, "flat_storages"):
             path.flat_storages = set()
         path.flat_storages.add(flat.untyped_storage().data_ptr())
@@ -257,12 +266,14 @@ class _DenseFn(torch.autograd.Function):
         # data parallel: model._dp (drn_b200/parallel.py) all-reduces the flat gradient buffer, overlapped with the tail
         views = os.environ.get("DRN_GRAD_VIEWS", "1") == "1"
         if views:
-            owned = getattr(path, "flat_storages", ())
+            owned = set(getattr(path, "flat_storages", ()))
+            owned.update(f.untyped_storage().data_ptr() for f in model.__dict__.get("_flat_cache", {}).values())
             for n in names:
                 old = p[n].grad
                 if old is not None and old.untyped_storage().data_ptr() in owned:
                     p[n].grad = old.clone()
-        flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs, dp=model._dp)
+        flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs, dp=model._dp,
+                                    flat_cache=model.__dict__.setdefault("_flat_cache", {}))
         if not views:
             return (None,) * 8 + tuple(grads[n] for n in names)
         for n in names:

@@ -76,7 +76,12 @@ for it in range(3):  # eager first call, then the graph replay path twice
         worst = max(worst, float((g_dp[k] - e).norm()) / n)
 t = torch.tensor([worst], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
+red = dp_module._dp
+want = os.environ.get("DRN_EXPECT_TRANSPORT")
+if want:
+    assert red.transport_used[want] > 0 and red.transport_used["p2p" if want == "nccl" else "nccl"] == 0, red.transport_used
 if rank == 0:
+    print("transport", red.transport_used)
     print("dp_check%s order=%s world=%d max rel-L2 deviation of DP gradients from the mean of single-rank gradients: %.3e" % (" (auto hook)" if AUTO else "", os.environ.get("DRN_DP_ORDER", "tail_first"), world, float(t)))
     assert float(t) < 1e-3
 dist.destroy_process_group()

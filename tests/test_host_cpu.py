@@ -209,7 +209,7 @@ def test_gradients_are_attached_as_views_and_still_accumulate(monkeypatch):
     def fake_forward(path_, p, training, use_graphs, *inputs):
         path_.losses[:3] = torch.tensor([1.0, 2.0, 3.0])
 
-    def fake_backward(path_, p, names, upstream, use_graphs, dp=None):
+    def fake_backward(path_, p, names, upstream, use_graphs, dp=None, flat_cache=None):
         flat.zero_()                       # what every real backward does: the buffer is rewritten
         grads["w"].copy_(scale["k"] * upstream[0] * torch.ones(2, 3))
         grads["v"].copy_(scale["k"] * upstream[1] * torch.full((4,), 2.0))
@@ -251,7 +251,7 @@ def test_backward_after_another_forward_of_the_same_shape_raises(monkeypatch):
     flat = torch.zeros(8)
     path = types.SimpleNamespace(losses=torch.zeros(8), poison=torch.zeros(1), flat_storages=set())
     monkeypatch.setattr(MM, "_run_forward", lambda path_, p, *a: path_.losses.__setitem__(slice(0, 3), torch.ones(3)))
-    monkeypatch.setattr(MM, "_run_backward", lambda path_, p, names, up, ug, dp=None: (flat, {"w": flat[:3]}))
+    monkeypatch.setattr(MM, "_run_backward", lambda path_, p, names, up, ug, dp=None, flat_cache=None: (flat, {"w": flat[:3]}))
     dummy = torch.zeros(1)
     l1 = MM._DenseFn.apply(model, path, True, dummy, dummy, dummy, dummy, dummy, w)
     l2 = MM._DenseFn.apply(model, path, True, dummy, dummy, dummy, dummy, dummy, w)
