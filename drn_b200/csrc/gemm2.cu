@@ -29,10 +29,12 @@ namespace drn {
 constexpr int P2_STAGES = 3;
 constexpr uint32_t P2_HALF = 128 * 128;                 // one plane of one operand half: 128 rows x 128 B
 constexpr uint32_t P2_STAGE = 4 * P2_HALF;              // A hi, A lo, B hi, B lo
-constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + 1024;
 constexpr int P2_EPI_WARPS = 8;                         // 2 warps per TMEM lane quarter, each drains half of the 256 columns
+constexpr uint32_t P2_EPI_STAGE = 4096;                 // per epilogue warp: one 32 x 32 fp32 chunk (transposed epilogue)
+constexpr uint32_t P2_SMEM = P2_STAGES * P2_STAGE + P2_EPI_WARPS * P2_EPI_STAGE + 1024;
 constexpr int P2_THREADS = 64 + 32 * P2_EPI_WARPS;
 constexpr int P2_TILE = 256;
+constexpr int TRACE_CTAS = 160;
 
 struct PairTile {
   int prob;       // problem of the group
@@ -99,15 +101,17 @@ __device__ __forceinline__ PairTile decode_tile(const GroupParams& gp, int tile,
 // Per-role cursor over the work of one SM pair: whole tiles (static round-robin) or the segments of its stream-K range.
 struct PairSched {
   int tile, stride, num_tiles;  // static
+  int pair;                     // static, host-balanced (gp.lpt): this pair's row of gp.lpt_tiles
   int it, it_end;               // stream-K: global k-iteration cursor / end of this pair's range
   int seg_it;                   // stream-K: global iteration at which the current segment starts
 };
 
 __device__ __forceinline__ PairSched sched_init(const GroupParams& gp, int cluster_id, int num_clusters, int num_tiles) {
   PairSched s{};
-  s.tile = cluster_id;
+  s.tile = gp.lpt ? 0 : cluster_id;
   s.stride = num_clusters;
   s.num_tiles = num_tiles;
+  s.pair = cluster_id;
   if (gp.sk_quota > 0) {
     const int total = gp.it_start[gp.nprob];
     s.it = min(total, cluster_id * gp.sk_quota);
@@ -119,9 +123,15 @@ __device__ __forceinline__ PairSched sched_init(const GroupParams& gp, int clust
 // Next segment of this pair: tile `t`, k-iterations [k0, k0 + kn) of the tile's t.nk.  False when the pair is done.
 __device__ __forceinline__ bool next_seg(const GroupParams& gp, PairSched& s, int rank, PairTile& t, int& k0, int& kn) {
   if (gp.sk_quota <= 0) {
-    if (s.tile >= s.num_tiles) return false;
-    t = decode_tile(gp, s.tile, rank);
-    s.tile += s.stride;
+    if (gp.lpt) {  // host-balanced tile list of this pair (s.tile = cursor into it)
+      if (s.tile >= gp.lpt_count[s.pair]) return false;
+      t = decode_tile(gp, gp.lpt_tiles[s.pair][s.tile], rank);
+      ++s.tile;
+    } else {
+      if (s.tile >= s.num_tiles) return false;
+      t = decode_tile(gp, s.tile, rank);
+      s.tile += s.stride;
+    }
     k0 = 0;
     kn = t.nk;
     return true;
@@ -151,9 +161,20 @@ __device__ __forceinline__ void st_release_gpu(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Diagnostic stamps (drn_gemm_trace): where a launch spends its time -- entry, prologue done, first operands landed, last MMA
+// issued, first / last accumulator drained, exit -- per CTA, from the GPU's nanosecond timer.
+__device__ __forceinline__ void trace_stamp(const GroupParams& gp, int slot) {
+  if (gp.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    gp.trace[blockIdx.x * 8 + slot] = t;
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__ GroupMaps gm, int num_tiles) {
   pdl_trigger();
+  if (threadIdx.x == 0) trace_stamp(gp, 0);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[P2_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[P2_STAGES];
@@ -193,6 +214,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
   pdl_wait();  // prologue done (barriers, TMEM, descriptor prefetch): wait here for the kernel that produces our operands
+  if (threadIdx.x == 0) trace_stamp(gp, 1);
 
   if (warp == 0) {
     // ===== TMA producer (one thread per CTA; completion is signalled on the LEADER's full barrier) =====
@@ -288,6 +310,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
           const uint32_t ph = (g / P2_STAGES) & 1;
           mbar_wait(smem_u32(&full_bar[s]), ph);
           tc_fence_after();
+          if (g == 0) trace_stamp(gp, 2);
           const uint32_t sa = smem_base + s * P2_STAGE;
           const uint32_t sb = sa + 2 * P2_HALF;
           for (int prod = 0; prod < nprod; ++prod) {
@@ -303,6 +326,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
           umma_commit_pair(smem_u32(&empty_bar[s]));  // frees this stage in BOTH CTAs
         }
         umma_commit_pair(smem_u32(&tmem_full_bar[as]));
+        trace_stamp(gp, 3);  // overwritten tile after tile: the last one stays
       }
     }
     __syncwarp();
@@ -314,6 +338,8 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
     const int row = q * 32 + lane;
     constexpr int COLS_PER_WARP = P2_TILE / (P2_EPI_WARPS / 4);
     const int cbeg = ((warp - 2) >> 2) * COLS_PER_WARP, cend = cbeg + COLS_PER_WARP;
+    const uint32_t epi_stage = smem_base + P2_STAGES * P2_STAGE + (warp - 2) * P2_EPI_STAGE;
+    const bool epi_transposed = gp.epi_t != 0;
     int lt = 0;
     PairSched sc = sched_init(gp, cluster_id, num_clusters, num_tiles);
     PairTile t;
@@ -346,6 +372,7 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       }
       mbar_wait(smem_u32(&tmem_full_bar[as]), aph);
       tc_fence_after();
+      if (warp == 2 && lane == 0) trace_stamp(gp, lt == 1 ? 4 : 5);  // first / last accumulator complete
       if (k0 > 0) {
         // not the owner: this pair's range starts inside the tile -> partial accumulator to the workspace slot + flag
         float* slot = gp.sk_ws + static_cast<size_t>(cluster_id) * SK_SLOT_FLOATS + ws_off;
@@ -384,6 +411,22 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         if (out_base) out_base += p.tap_w[t.tap] * p.out_tap_stride + t.split * p.out_split_stride;
       }
       const int stats_blk = (!wgrad && p.stats) ? t.ms * 4 + q : -1;  // 32-row block of the output (BatchNorm partial sums)
+      // transposed epilogue (gemm_common.cuh): this lane's 8 rows of the block, fetched from the lanes that own them
+      // (plain stores -- weight-gradient slices, K-split slices -- stay row-per-thread: nothing to load, and the final drain of
+      // a launch, bound by the ~4 TB/s at which 148 SMs can write, measured 5 us that way against 8 us through shared memory)
+      const bool fast = (p.vec_ok != 0) && (p.out_mode != DRN_OUT_ATOMIC) && epi_transposed &&
+                        (p.bias || p.stats || p.out2 || p.rowscale || p.outp || p.out_mode == DRN_OUT_ADD);
+      EpiRows er;
+      er.valid = 0u;
+      if (fast) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = 4 * i + (lane >> 3);
+          er.orow[i] = __shfl_sync(0xffffffffu, static_cast<int>(orow), src);
+          er.bb[i] = __shfl_sync(0xffffffffu, bb, src);
+          er.valid |= (__shfl_sync(0xffffffffu, valid ? 1u : 0u, src) & 1u) << i;
+        }
+      }
 #pragma unroll 1
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
         if (t.n0 + c0 >= p.N) break;
@@ -399,7 +442,8 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
             v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
           }
         }
-        epilogue_chunk(p, v, valid, orow, bb, t.n0 + c0, out_base, stats_blk);
+        if (fast && t.n0 + c0 + 32 <= p.N) epilogue_chunk_t(p, v, epi_stage, er, t.n0 + c0, out_base, stats_blk, lane);
+        else epilogue_chunk(p, v, valid, orow, bb, t.n0 + c0, out_base, stats_blk);
       }
       tc_fence_before();
       __syncwarp();
@@ -407,17 +451,37 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[as]), 0));
         for (int j = 0; j < ncontrib; ++j) gp.sk_flags[(cluster_id + 1 + j) * 16 + rank * 8 + (warp - 2)] = 0u;  // re-armed for the next launch
       }
+      if (warp == 2 && lane == 0) trace_stamp(gp, 6);  // accumulator drained (the last one stays)
     }
   }
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+  if (threadIdx.x == 0) trace_stamp(gp, 7);
 }
 
 // Process-wide cap on the SM pairs the persistent kernel occupies (0 = none), set by the caller around individual launches:
 // the data-parallel schedule leaves 4 of the 74 pairs to NCCL while the prop_fc weight gradient runs (drn_b200/dense.py).
 static int g_pair_clusters = 0;
 void set_pair_clusters(int n) { g_pair_clusters = n > 0 ? n : 0; }
+
+// drn_gemm_trace(buf, launches): the next `launches` launches of the pair kernel (eager or captured into a CUDA graph: the slot
+// is baked into the captured launch) write their stamps to buf[launch][TRACE_CTAS][8]; each returns its CTA count in info.
+static unsigned long long* g_trace = nullptr;
+static int g_trace_left = 0, g_trace_next = 0;
+static int g_trace_info[256][3];
+void gemm_trace(unsigned long long* buf, int launches) {
+  g_trace = buf;
+  g_trace_left = buf ? (launches > 256 ? 256 : launches) : 0;
+  g_trace_next = 0;
+}
+int gemm_trace_info(int launch, int* ctas, int* tiles, int* lpt) {
+  if (launch < 0 || launch >= g_trace_next) return -1;
+  *ctas = g_trace_info[launch][0];
+  *tiles = g_trace_info[launch][1];
+  *lpt = g_trace_info[launch][2];
+  return 0;
+}
 
 // Stream-K runs when the caller passes a workspace (drn_gemm_group_ws).  DRN_SK_MIN (environment, read once) = fewest
 // k-iterations worth giving an SM pair (a range shorter than that costs more in the fold than it saves).
@@ -472,6 +536,59 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
     clusters = num_tiles;
   }
   if (clusters < 1) clusters = 1;
+  // ---- host-balanced static schedule (longest tiles first onto the least-loaded pair) --------------------------------------
+  gp.lpt = 0;
+  static int lpt_on = -1;
+  if (lpt_on < 0) lpt_on = sk_env("DRN_LPT", 1);
+  if (lpt_on && uniform && gp.sk_quota == 0 && gp.nprob > 1 && clusters <= LPT_MAX_PAIRS && num_tiles < 65536 && num_tiles > clusters) {
+    int load[LPT_MAX_PAIRS] = {0};
+    static thread_local unsigned short cnt[GROUP_MAX][LPT_MAX_PAIRS];
+    bool differ = false, fits = true;
+    for (int k = 0; k < gp.nprob; ++k) {
+      if (gp.nk_tile[k] != gp.nk_tile[0]) differ = true;
+      for (int c = 0; c < clusters; ++c) cnt[k][c] = 0;
+    }
+    if (differ) {  // uniform tile lengths: round-robin is already the balanced assignment
+      int total_cnt[LPT_MAX_PAIRS] = {0};
+      for (int k = 0; k < gp.nprob && fits; ++k) {  // problems arrive sorted by decreasing tile length (drn_gemm_group_ws)
+        const int nt = gp.tile_start[k + 1] - gp.tile_start[k];
+        int next = 0;  // ties go round-robin from the pair after the previous pick
+        for (int i = 0; i < nt; ++i) {
+          int best = -1;
+          for (int j = 0; j < clusters; ++j) {
+            const int c = (next + j) % clusters;
+            if (best < 0 || load[c] < load[best]) best = c;
+          }
+          load[best] += gp.nk_tile[k];
+          ++cnt[k][best];
+          if (++total_cnt[best] > LPT_MAX_TILES) { fits = false; break; }
+          next = (best + 1) % clusters;
+        }
+      }
+      if (fits) {
+        for (int c = 0; c < clusters; ++c) gp.lpt_count[c] = 0;
+        for (int k = 0; k < gp.nprob; ++k) {
+          int tile = gp.tile_start[k];
+          for (int round = 0; tile < gp.tile_start[k + 1]; ++round)
+            for (int c = 0; c < clusters; ++c)
+              if (cnt[k][c] > round) gp.lpt_tiles[c][gp.lpt_count[c]++] = static_cast<unsigned short>(tile++);
+        }
+        gp.lpt = 1;
+      }
+    }
+  }
+  static int epi_t = -1;  // DRN_EPI_T=0: row-per-thread epilogue stores (A/B)
+  if (epi_t < 0) epi_t = sk_env("DRN_EPI_T", 1);
+  gp.epi_t = epi_t;
+  gp.trace = nullptr;
+  if (g_trace_left > 0) {
+    gp.trace = g_trace + static_cast<size_t>(g_trace_next) * TRACE_CTAS * 8;
+    g_trace_info[g_trace_next][0] = 2 * clusters;
+    g_trace_info[g_trace_next][1] = num_tiles;
+    g_trace_info[g_trace_next][2] = gp.lpt;
+    ++g_trace_next;
+    --g_trace_left;
+  }
   launch_k(gemm_pair_kernel, 2 * clusters, P2_THREADS, P2_SMEM, st, gp, gm, num_tiles);
   return check_launch("gemm_pair_kernel");
 }

@@ -46,6 +46,7 @@ struct GemmKParams {
 
 // A group of independent problems walked by ONE persistent launch of the CTA-pair kernel (gemm2.cu)
 constexpr int GROUP_MAX = 6;
+constexpr int LPT_MAX_PAIRS = 80, LPT_MAX_TILES = 16;
 struct GroupParams {
   int nprob;
   int raster_gm;                  // tile-rows per rasterisation group (1 = plain row-major tile order)
@@ -60,6 +61,15 @@ struct GroupParams {
   int nk_tile[GROUP_MAX];         // k-iterations of one tile (uniform inside a problem)
   float* sk_ws;                   // [pairs][2 CTAs][8 column chunks][128 rows][32] fp32
   unsigned* sk_flags;             // [pairs][2 CTAs][8 epilogue warps], zero between launches
+  // Static schedule balanced on the host (launch_group): the problems of a group have tiles of different lengths (a weight
+  // gradient tile runs 32 k-iterations, a lateral 1x1 conv tile 4), and plain round-robin piles the long ones onto the same
+  // pairs.  lpt != 0: SM pair c walks lpt_tiles[c][0 .. lpt_count[c]) -- longest-processing-time-first assignment, tiles of
+  // one problem handed out in rounds so that concurrently running pairs still work on neighbouring tiles (L2 sharing).
+  int epi_t;                      // transposed epilogue (epilogue_chunk_t) for full, vector-aligned chunks
+  unsigned long long* trace;      // diagnostic (drn_gemm_trace): [CTA][8] %globaltimer stamps of this launch, or null
+  int lpt;
+  unsigned char lpt_count[LPT_MAX_PAIRS];
+  unsigned short lpt_tiles[LPT_MAX_PAIRS][LPT_MAX_TILES];
   GemmKParams p[GROUP_MAX];
 };
 constexpr size_t SK_SLOT_FLOATS = 2 * 128 * 256;  // one 256 x 256 fp32 partial tile per SM pair
@@ -222,6 +232,118 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, float* v, b
         }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Transposed epilogue of one FULL 32 x 32 chunk (persistent pair kernel).  tcgen05.ld hands every lane one ROW of the chunk, so
+// a row-per-thread store instruction touches 32 different 128-byte lines (32 LSU wavefronts for 1 KB) -- measured 4-25 us of
+// exposed drain at the end of every launch (scripts/gemm_trace.py) and the bound of the short-K layers.  Here the warp passes
+// the chunk through a 4 KB XOR-swizzled shared-memory tile and comes back with lane = (row l/8 of a group of 4, columns
+// 4 (l%8) ..+3): a store instruction then writes four complete 128-byte lines (4 wavefronts for 512 B), bias / gate values
+// are one 16-byte quantity per lane, and the BatchNorm column sums fall out of 8 adds + 2 shuffles instead of 62 shuffles.
+// Arithmetic and its order per element are those of epilogue_chunk (bit-identical outputs; only the order of the fp32 partial
+// sums inside a 32-row statistics block differs).  Requires p.vec_ok, a full chunk and a non-atomic output mode.
+struct EpiRows {      // the 8 rows of its 32-row block a lane serves: row 4 i + lane / 8
+  int orow[8];        // output row (< 2^31: rows of one problem)
+  int bb[8];          // sample (row gate)
+  unsigned valid;     // bit i
+};
+
+__device__ __forceinline__ void epilogue_chunk_t(const GemmKParams& p, const float* v, uint32_t stage, const EpiRows& er, int ncol0,
+                                                 float* out_base, int stats_blk, int lane) {
+  const int cg = lane & 7, rsub = lane >> 3;
+  const int col = ncol0 + 4 * cg;
+  const bool add = out_base && p.out_mode == DRN_OUT_ADD;
+  // Everything that comes from global memory is requested up front (bias, row gate; accumulate mode: the old values of all 8
+  // rows, once this lane's accumulator row has left its registers), so that the loads overlap the shared-memory transposition
+  // instead of forming a load -> add -> store chain per row.
+  float b4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (p.bias) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b4[k] = __ldg(p.bias + col + k);
+  }
+  float rs4[4] = {1.f, 1.f, 1.f, 1.f};
+  int rs_bb = -1;
+  if (p.rowscale) {
+    rs_bb = er.bb[0];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) rs4[k] = __ldg(p.rowscale + static_cast<long long>(rs_bb) * p.rowscale_ld + col + k);
+  }
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const uint32_t a = stage + lane * 128 + ((j4 ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j4]), "f"(v[4 * j4 + 1]), "f"(v[4 * j4 + 2]),
+                 "f"(v[4 * j4 + 3])
+                 : "memory");
+  }
+  float4 old[8];
+  if (add) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      old[i] = ((er.valid >> i) & 1u) ? __ldcg(reinterpret_cast<const float4*>(out_base + static_cast<long long>(er.orow[i]) * p.out_ld + p.out_col0 + col))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncwarp();
+  float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rl = 4 * i + rsub;
+    float x[4];
+    const uint32_t a = stage + rl * 128 + ((cg ^ (rl & 7)) << 4);
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[0]), "=f"(x[1]), "=f"(x[2]), "=f"(x[3]) : "r"(a));
+    if (!((er.valid >> i) & 1u)) continue;  // padding rows: no output, no statistics
+#pragma unroll
+    for (int k = 0; k < 4; ++k) x[k] += b4[k];
+    if (stats_blk >= 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        s1[k] += x[k];
+        s2[k] += x[k] * x[k];
+      }
+    }
+    const long long orow = er.orow[i];
+    if (p.out2) *reinterpret_cast<float4*>(p.out2 + orow * p.out2_ld + col) = make_float4(x[0], x[1], x[2], x[3]);
+    if (p.rowscale) {
+      if (er.bb[i] != rs_bb) {  // the block straddles two samples (short sequences only)
+        rs_bb = er.bb[i];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rs4[k] = __ldg(p.rowscale + static_cast<long long>(rs_bb) * p.rowscale_ld + col + k);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] *= rs4[k];
+    }
+    if (out_base) {
+      float4* o = reinterpret_cast<float4*>(out_base + orow * p.out_ld + p.out_col0 + col);
+      if (add) *o = make_float4(old[i].x + x[0], old[i].y + x[1], old[i].z + x[2], old[i].w + x[3]);
+      else *o = make_float4(x[0], x[1], x[2], x[3]);
+    }
+    if (p.outp) {
+      __nv_bfloat16* oh = p.outp + orow * p.outp_ld + p.outp_col0 + col;
+      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split_bf16(x[k], h[k], l[k]);
+      *reinterpret_cast<uint2*>(oh) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+      *reinterpret_cast<uint2*>(oh + p.outp_plane_stride) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    }
+  }
+  if (stats_blk >= 0) {  // warp-uniform
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 8);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 8);
+      s1[k] += __shfl_xor_sync(0xffffffffu, s1[k], 16);
+      s2[k] += __shfl_xor_sync(0xffffffffu, s2[k], 16);
+    }
+    if (rsub == 0) {
+      float* st = p.stats + static_cast<long long>(stats_blk) * 2 * p.N + col;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        st[k] = s1[k];
+        st[p.N + k] = s2[k];
+      }
+    }
+  }
+  __syncwarp();  // the staging tile is free for the next chunk
 }
 
 }  // namespace drn

@@ -675,6 +675,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Arrival at a step barrier: fire-and-forget add with release semantics (orders this thread's earlier writes and, through the
+// __syncthreads() before it, those of the whole CTA) -- no round trip for the returned value, no separate fence.
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ float fold16(float (&a)[16], int lane) {
 #pragma unroll
   for (int s = 8; s >= 1; s >>= 1) {
@@ -714,10 +719,8 @@ __global__ void __launch_bounds__(LSTM2_THREADS, 1) lstm_fwd2_kernel(QeDev q) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) pre[g] = inb ? q.xg[((r * 2 + dir) * 4 + g) * H + unit] : 0.f;  // issued before the barrier wait
     if (s > 0) {
-      if (tid == 0) {  // per-direction barrier: every CTA of this direction has published its h of step s - 1
+      if (tid == 0) {  // per-direction barrier: every CTA of this direction has published its h of step s - 1 (arrival below)
         unsigned* cnt = q.bar + dir * QE_MAX_L + (s - 1);
-        __threadfence();
-        atomicAdd(cnt, 1u);
         const long long t0 = clock64();
         while (ld_acquire_u32(cnt) < gridDim.x) {
           if (clock64() - t0 > 4000000000LL) __trap();
@@ -771,13 +774,30 @@ __global__ void __launch_bounds__(LSTM2_THREADS, 1) lstm_fwd2_kernel(QeDev q) {
     }
     c_carry = c;
     q.HT[(s & 1) * ht_sz + (static_cast<long long>(dir) * 32 + b) * H + unit] = h;
+    __syncthreads();  // all of this CTA's h values are written (and hs is free): arrive at the barrier of this step at once,
+    if (tid == 0 && s + 1 < L) red_release_add(q.bar + dir * QE_MAX_L + s, 1u);  // the stores nobody waits for come after
     if (inb) {
       float* G = q.G + ((r * 2 + dir) * 4) * H + unit;
       G[0] = gi; G[H] = gf; G[2 * H] = gg; G[3 * H] = go;
       q.Cst[(r * 2 + dir) * H + unit] = c;
       q.Hout[r * 2 * H + dir * H + unit] = h;
+      // Hprev planes [dir][b][t][unit] = the hidden state the recurrence consumes at time t (operand of the W_hh weight
+      // gradient): this step's h is the input of the next one, the first step consumed zeros (was a separate kernel)
+      const long long ps = 2LL * q.B * L * H;
+      const long long row0 = (static_cast<long long>(dir) * q.B + b) * L;
+      if (s == 0) {
+        const __nv_bfloat16 z = __float2bfloat16(0.f);
+        q.Hprev_pl[(row0 + t) * H + unit] = z;
+        q.Hprev_pl[ps + (row0 + t) * H + unit] = z;
+      }
+      if (s + 1 < L) {
+        const int tn = dir == 0 ? t + 1 : t - 1;
+        __nv_bfloat16 hh, ll;
+        split_bf16(h, hh, ll);
+        q.Hprev_pl[(row0 + tn) * H + unit] = hh;
+        q.Hprev_pl[ps + (row0 + tn) * H + unit] = ll;
+      }
     }
-    __syncthreads();  // all of this CTA's h values are written (and hs is free) before thread 0 arrives at the next barrier
   }
 }
 
@@ -816,8 +836,7 @@ __global__ void __launch_bounds__(256) qe_hprev_kernel(QeDev q) {
 __device__ __forceinline__ void dir_barrier(unsigned* cnt, unsigned expected) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(cnt, 1u);
+    red_release_add(cnt, 1u);
     const long long t0 = clock64();
     while (ld_acquire_u32(cnt) < expected) {
       if (clock64() - t0 > 4000000000LL) __trap();
@@ -917,7 +936,7 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
         for (int ww = 0; ww < NW; ++ww) sum += red[(ww * 32 + bb) * 33 + u];
         part[jq * 1024 + idx] = sum;
       }
-      __threadfence();
+      if (!PERSIST) __threadfence();  // PERSIST: the barrier's release (after its __syncthreads) publishes the CTA's writes
       if (PERSIST) {
         dir_barrier(q.bar + 2 * QE_MAX_L + dir * 2 * QE_MAX_L + 2 * s, gridDim.x * gridDim.y * q.BC);
       } else {
@@ -986,7 +1005,6 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
       if (!PERSIST && tid == 0 && nq > 1) q.cnt[slot] = 0u;
     }
     if (PERSIST && s + 1 < s1) {
-      __threadfence();
       dir_barrier(q.bar + 2 * QE_MAX_L + dir * 2 * QE_MAX_L + 2 * s + 1, gridDim.x * gridDim.y * q.BC);
     }
   }
@@ -1308,9 +1326,24 @@ extern "C" int drn_linear_fwd_batch(int n, const drn_linear_job_t* jobs, void* s
 
 // Kernels one drn_qe_forward / drn_qe_backward call launches (gpu_launches accounting of bench.py): the recurrence is ONE
 // cooperative launch when its grid fits the GPU, else one launch per time step.
+// The register-resident recurrence (lstm_fwd2_kernel, which also writes the Hprev planes) runs when the whole batch is one
+// 32-sample chunk, H is a multiple of 128 and its cooperative grid fits the GPU.  DRN_QE_FWD2=0: shared-memory form (A/B).
+static bool use_fwd2(int BC, int H, int L) {
+  static int fwd2 = -1;
+  if (fwd2 < 0) {
+    const char* e = getenv("DRN_QE_FWD2");
+    fwd2 = e ? atoi(e) : 1;
+  }
+  const size_t smem_f2 = static_cast<size_t>(32) * H * sizeof(float);
+  return fwd2 && BC == 1 && H % 128 == 0 && L <= QE_MAX_L &&
+         set_smem(reinterpret_cast<const void*>(lstm_fwd2_kernel), smem_f2, "lstm_fwd2") == 0 &&
+         fits_cooperative(reinterpret_cast<const void*>(lstm_fwd2_kernel), dim3(H / 8, 2, 1), smem_f2, LSTM2_THREADS);
+}
+
 extern "C" int drn_qe_launch_count(int B, int L, int H, int backward) {
   const int BC = (B + 31) / 32;
   if (!backward) {
+    if (use_fwd2(BC, H, L)) return 8;  // embed, pack_wih, xg contraction, recurrence (+ Hprev), vgather, qInput, qInput0-2, attention
     const size_t smem_f = (32 * H + H * 32 + 8 * 4 * 32) * sizeof(float);
     set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), smem_f, "lstm_fwd");
     const bool coop = fits_cooperative(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), dim3(H / 8, 2, BC), smem_f);
@@ -1359,15 +1392,9 @@ static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<true>), smem_f, "lstm_fwd"));
   TRY(set_smem(reinterpret_cast<const void*>(lstm_fwd_kernel<false>), smem_f, "lstm_fwd"));
   const dim3 grid_f(H / 8, 2, q.BC);
-  static int fwd2 = -1;  // DRN_QE_FWD2=0: the shared-memory form of the recurrence (A/B)
-  if (fwd2 < 0) {
-    const char* e = getenv("DRN_QE_FWD2");
-    fwd2 = e ? atoi(e) : 1;
-  }
   const size_t smem_f2 = static_cast<size_t>(32) * H * sizeof(float);
-  if (fwd2 && q.BC == 1 && H % 128 == 0 && L <= QE_MAX_L &&
-      set_smem(reinterpret_cast<const void*>(lstm_fwd2_kernel), smem_f2, "lstm_fwd2") == 0 &&
-      fits_cooperative(reinterpret_cast<const void*>(lstm_fwd2_kernel), dim3(H / 8, 2, 1), smem_f2, LSTM2_THREADS)) {
+  const bool fwd2 = use_fwd2(q.BC, H, L);
+  if (fwd2) {
     void* args[] = {&q};
     cudaError_t ce = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(lstm_fwd2_kernel), dim3(H / 8, 2, 1), dim3(LSTM2_THREADS), args, smem_f2, st);
     if (ce != cudaSuccess) return fail(static_cast<int>(ce), "lstm_fwd2 (cooperative): %s", cudaGetErrorString(ce));
@@ -1382,8 +1409,10 @@ static int qe_forward_parts(const drn_qe_t* a, int parts, void* stream) {
       TRY(check_launch("lstm_fwd_step"));
     }
   }
-  launch_k(qe_hprev_kernel, 148, 256, 0, st, q);
-  TRY(check_launch("qe_hprev"));
+  if (!fwd2) {
+    launch_k(qe_hprev_kernel, 148, 256, 0, st, q);
+    TRY(check_launch("qe_hprev"));
+  }
   launch_k(qe_vgather_kernel, B, 256, 0, st, q);
   TRY(check_launch("qe_vgather"));
   TRY(linear_small(st, q.v, 4 * H, a->w1, 4 * H, a->b1, q.hid, H, B, H, 4 * H, 1));

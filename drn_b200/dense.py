@@ -538,8 +538,20 @@ class DensePath:
     @staticmethod
     def _wgrad_split(blk):
         """K-splits of a weight gradient: ~2048 contraction rows (32 K-blocks) per 256 x 256 tile, so the tiles of the three
-        pyramid levels (8192 / 4096 / 2048 rows at B=32, T=256) cost the same and fill the 74 SM pairs evenly."""
-        return max(1, min(8, blk.rows // 2048))
+        pyramid levels (8192 / 4096 / 2048 rows at B=32, T=256) cost the same and fill the 74 SM pairs evenly.  The layers
+        with few output tiles (conv1: 6, FPN laterals: 2-8 before the split) are cut twice as fine: their launch is then no
+        longer bound by one 32-iteration tile per busy pair (makespan 32 -> 16 and 40 -> 24 k-iterations on 74 pairs)."""
+        s = max(1, min(8, blk.rows // 2048))
+        if blk.prefix.startswith("fpn.fpn_inner") or blk.prefix.endswith("forward_conv1"):
+            # never more slices than 64-row K-blocks (drn_gemm rejects a slice that would stay unwritten)
+            t, b = blk.t_out, blk.rows // blk.t_out
+            if t >= 64:
+                kblocks = b * ((t + 63) // 64)
+            else:
+                rk = 1 << max(0, (t - 1).bit_length())
+                kblocks = (b + 64 // rk - 1) // (64 // rk)
+            s = max(1, min(16, 2 * s, kblocks))
+        return s
 
     def _wgrad_desc(self, blk, x_pl, name, idx=0):
         """Weight gradient of `blk` into its slices of the workspace `name` (idx = pyramid level for shared head convs)."""

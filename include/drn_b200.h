@@ -405,6 +405,14 @@ int drn_nms_recall(const float* det, const float* score, const int32_t* count, c
                    int nms, double overlap, double iou_thr, const int32_t* topk, int ntopk, int empty_fallback, int32_t* picks,
                    int32_t* npicks, int32_t* hits, int32_t* correct, void* stream);
 
+/* Diagnostic: the next `launches` launches of the persistent contraction kernel (eager, or captured into a CUDA graph -- the
+ * slot is part of the captured launch) write %globaltimer stamps to buf[launch][160 CTAs][8]: 0 entry, 1 prologue done, 2 first
+ * operands landed, 3 last MMA issued, 4 / 5 first / last accumulator complete, 6 last accumulator drained, 7 exit.  buf = null
+ * switches it off.  drn_gemm_trace_info returns the CTA count, tile count and schedule kind of a traced launch
+ * (scripts/gemm_trace.py). */
+void drn_gemm_trace(uint64_t* buf, int launches);
+int drn_gemm_trace_info(int launch, int* ctas, int* tiles, int* lpt);
+
 /* ------------------------------------------------------------------------------------------------
  * Gradient exchange over NVLink peer memory (drn_b200/csrc/p2p.cu): the ONE collective of the data-parallel path
  * (all-reduce of the fp32 gradients, main.py:99 nn.DataParallel semantics), written as a kernel that

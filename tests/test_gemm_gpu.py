@@ -49,6 +49,7 @@ def run_rows(B, T, Cin, N, taps, P=1, b_mn=0, engine=0, nprod=3, seed=0, a_c0=0,
     return err, out, ref
 
 
+K1 = ((0, 0, 0),)
 K3 = ((-1, 0, 0), (0, 0, 1), (1, 0, 2))
 K3S2 = ((-1, 1, 0), (0, 0, 1), (0, 1, 2))  # input viewed [T/2][2]: row 2t+r-1
 
@@ -283,6 +284,38 @@ def test_fused_batchnorm_partial_sums(B, T, N):
     d3 = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=out, engine=3)
     d3.stats = stats.data_ptr()
     assert lib.drn_gemm(C.byref(d3), L.stream_ptr()) == -1
+
+
+def test_group_balanced_schedule_is_bit_identical_to_single_launches():
+    """A group whose problems have tiles of different lengths and more tiles than SM pairs is walked on the host-balanced
+    (longest-first) schedule; which pair computes a tile must not change a bit of it: every problem equals its own launch."""
+    descs, outs, keep = [], [], []
+    # weight gradient with 32-iteration tiles (2 x 2 tiles x 3 taps x 4 slices = 48 tiles)
+    B, T, Co, Ci = 32, 256, 512, 512
+    dy, x = Planes.from_float(_rand(B, T, Co, seed=301)), Planes.from_float(_rand(B, T, Ci, seed=302))
+    ws = torch.full((4, 3, Co, Ci), float("nan"), device=DEV)
+    descs.append(ops.desc(L.GEMM_WGRAD, dy.desc(), x.desc(), B, T, Ci, M=Co, taps=K3, out=ws[0], out_ld=Ci,
+                          out_tap_stride=Co * Ci, out_split_stride=ws.stride(0), split_k=4, engine=2))
+    outs.append(ws)
+    # 1 x 1 convs with 4- and 16-iteration tiles on ragged rows (64 + 36 tiles), a 3-tap conv with 24-iteration tiles (32 tiles)
+    for i, (b, t, cin, n, taps) in enumerate(((32, 250, 256, 512, K1), (17, 130, 1024, 1000, K1), (16, 256, 512, 512, K3))):
+        a = Planes.from_float(_rand(b, t, cin, seed=310 + i))
+        w = Planes.from_float(_rand(len(taps), n, cin, seed=320 + i, scale=(len(taps) * cin) ** -0.5))
+        keep += [a, w]
+        o = torch.full((b, t, n), float("nan"), device=DEV)
+        descs.append(ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), b, t, n, K=cin, taps=taps, out=o, engine=2))
+        outs.append(o)
+    assert ops.gemm_group(descs) == 1
+    torch.cuda.synchronize()
+    grouped = [o.clone() for o in outs]
+    for o in outs:
+        o.fill_(float("nan"))
+    for d in descs:  # one problem per launch: plain round-robin
+        arr = (L.GemmDesc * 1)(d)
+        L.check(L.load().drn_gemm_group(1, arr, L.stream_ptr()), "drn_gemm_group (single)")
+    torch.cuda.synchronize()
+    for g, o in zip(grouped, outs):
+        assert not torch.isnan(g).any() and torch.equal(g, o)
 
 
 # ---- stream-K schedule (drn_gemm_group_ws; opt-in, DRN_STREAMK=1 in the product path): many partial tiles per owner, every
