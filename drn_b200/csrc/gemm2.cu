@@ -114,7 +114,7 @@ __device__ __forceinline__ PairSched sched_init(const GroupParams& gp, int clust
   s.pair = cluster_id;
   if (gp.sk_quota > 0) {
     const int total = gp.it_start[gp.nprob];
-    s.it = min(total, cluster_id * gp.sk_quota);
+    s.it = min(total, gp.sk_it0 + cluster_id * gp.sk_quota);
     s.it_end = min(total, s.it + gp.sk_quota);
   }
   return s;
@@ -132,6 +132,13 @@ __device__ __forceinline__ bool next_seg(const GroupParams& gp, PairSched& s, in
       t = decode_tile(gp, s.tile, rank);
       s.tile += s.stride;
     }
+    k0 = 0;
+    kn = t.nk;
+    return true;
+  }
+  if (s.tile < gp.sk_static_tiles) {  // hybrid: the full waves first, whole tiles
+    t = decode_tile(gp, s.tile, rank);
+    s.tile += s.stride;
     k0 = 0;
     kn = t.nk;
     return true;
@@ -352,13 +359,15 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
       const uint32_t aph = (lt >> 1) & 1;
       ++lt;
       const uint32_t taddr = tmem_base + as * P2_TILE + (static_cast<uint32_t>(q * 32) << 16);
-      // stream-K: partial tiles of this warp's 32 rows live at [pair][rank][chunk][row][32] of the workspace
-      const size_t ws_off = static_cast<size_t>(rank) * (128 * 256) + static_cast<size_t>(row) * 32;
+      // stream-K / hybrid: partial tiles live at [pair][rank][32-column chunk][float4 j of the chunk][128 rows][4] of the
+      // workspace -- rows innermost, so that the 32 lanes (= rows) of a store or load instruction touch 512 contiguous bytes
+      // (row-major chunks made every instruction touch 32 lines: the fold of 5 partial tiles took ~40 us)
+      const size_t ws_off = static_cast<size_t>(rank) * (128 * 256) + static_cast<size_t>(row) * 4;
       int ncontrib = 0;
       if (k0 == 0 && kn < t.nk) {
         // owner of a tile other pairs finish: pairs cluster_id+1 ... whose ranges start before the end of this tile
         const int tile_end = sc.seg_it + t.nk;
-        while ((cluster_id + 1 + ncontrib) * gp.sk_quota < tile_end) ++ncontrib;
+        while (gp.sk_it0 + (cluster_id + 1 + ncontrib) * gp.sk_quota < tile_end) ++ncontrib;
         if (lane == 0) {
           for (int j = 0; j < ncontrib; ++j) {
             const unsigned* f = gp.sk_flags + (cluster_id + 1 + j) * 16 + rank * 8 + (warp - 2);
@@ -384,7 +393,8 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
           tmem_ld_wait();
           float* d = slot + (c0 >> 5) * (128 * 32);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) st_global_v8(d + j, v + j);
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(d + j4 * 512) = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
         }
         tc_fence_before();
         __syncwarp();
@@ -434,12 +444,13 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
         tmem_ld_32x32(taddr + c0, v);
         tmem_ld_wait();
         for (int j = 0; j < ncontrib; ++j) {  // fold the partial tiles, in pair order
-          const float4* src = reinterpret_cast<const float4*>(gp.sk_ws + static_cast<size_t>(cluster_id + 1 + j) * SK_SLOT_FLOATS +
-                                                              ws_off + (c0 >> 5) * (128 * 32));
+          const float* src = gp.sk_ws + static_cast<size_t>(cluster_id + 1 + j) * SK_SLOT_FLOATS + ws_off + (c0 >> 5) * (128 * 32);
+          float4 x[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = __ldcg(reinterpret_cast<const float4*>(src + i * 512));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 x = __ldcg(src + i);
-            v[4 * i] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
+            v[4 * i] += x[i].x; v[4 * i + 1] += x[i].y; v[4 * i + 2] += x[i].z; v[4 * i + 3] += x[i].w;
           }
         }
         if (fast && t.n0 + c0 + 32 <= p.N) epilogue_chunk_t(p, v, epi_stage, er, t.n0 + c0, out_base, stats_blk, lane);
@@ -464,6 +475,10 @@ gemm_pair_kernel(const __grid_constant__ GroupParams gp, const __grid_constant__
 // the data-parallel schedule leaves 4 of the 74 pairs to NCCL while the prop_fc weight gradient runs (drn_b200/dense.py).
 static int g_pair_clusters = 0;
 void set_pair_clusters(int n) { g_pair_clusters = n > 0 ? n : 0; }
+// Schedule of launches that are given a workspace: 0 = static only, 1 = hybrid (static full waves + k-split last wave; default),
+// 2 = full stream-K (every tile boundary ignored; measured slower on the DRN layers, kept for tests and A/B).
+static int g_schedule = -1;
+void set_schedule(int mode) { g_schedule = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 // drn_gemm_trace(buf, launches): the next `launches` launches of the pair kernel (eager or captured into a CUDA graph: the slot
 // is baked into the captured launch) write their stamps to buf[launch][TRACE_CTAS][8]; each returns its CTA count in info.
@@ -497,20 +512,29 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
     if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(gemm_pair): %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  if (g_schedule < 0) {
+    const char* e = getenv("DRN_SCHEDULE");  // static | hybrid | streamk
+    g_schedule = (e && e[0] == 's' && e[1] == 't' && e[2] == 'a') ? 0 : ((e && e[0] == 's' && e[1] == 't' && e[2] == 'r') ? 2 : 1);
+  }
   const int num_tiles = gp.tile_start[gp.nprob];
   int clusters = sm_count / 2;
   static int cap = -1;  // DRN_PAIR_CLUSTERS: leave SM pairs free for kernels of other streams (tuning / probing knob)
-  static int sk_min = 4;
+  static int sk_min = 4, hybrid_min_saved = 8, hybrid_min_quota = 8;
   if (cap < 0) {
     cap = sk_env("DRN_PAIR_CLUSTERS", 0);
     sk_min = sk_env("DRN_SK_MIN", 4);
     if (sk_min < 1) sk_min = 1;
+    hybrid_min_saved = sk_env("DRN_HYBRID_MIN_SAVED", 8);
+    hybrid_min_quota = sk_env("DRN_HYBRID_MIN_QUOTA", 8);
+    if (hybrid_min_quota < 1) hybrid_min_quota = 1;
   }
   if (cap > 0 && clusters > cap) clusters = cap;
   if (g_pair_clusters > 0 && clusters > g_pair_clusters) clusters = g_pair_clusters;
   if (clusters < 1) clusters = 1;
   // ---- stream-K: equal contiguous ranges of k-iterations per SM pair (needs uniform tiles inside every problem) ------------
   gp.sk_quota = 0;
+  gp.sk_static_tiles = 0;
+  gp.sk_it0 = 0;
   gp.sk_ws = nullptr;
   gp.sk_flags = nullptr;
   bool uniform = true;
@@ -523,18 +547,39 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
     gp.it_start[k + 1] = static_cast<int>(total);
   }
   for (int k = gp.nprob; k < GROUP_MAX; ++k) gp.it_start[k + 1] = gp.it_start[gp.nprob];
-  if (ws && uniform && total > 0 && total < (1ll << 30) &&
-      ws_bytes >= SK_FLAG_BYTES + static_cast<size_t>(clusters) * SK_SLOT_FLOATS * sizeof(float) &&
-      static_cast<size_t>(clusters) * 16 * sizeof(unsigned) <= SK_FLAG_BYTES) {
+  const bool ws_ok = ws && uniform && total > 0 && total < (1ll << 30) &&
+                     ws_bytes >= SK_FLAG_BYTES + static_cast<size_t>(clusters) * SK_SLOT_FLOATS * sizeof(float) &&
+                     static_cast<size_t>(clusters) * 16 * sizeof(unsigned) <= SK_FLAG_BYTES;
+  bool same_nk = true;
+  for (int k = 1; k < gp.nprob; ++k) same_nk = same_nk && gp.nk_tile[k] == gp.nk_tile[0];
+  if (ws_ok && g_schedule == 2) {  // full stream-K
     int quota = static_cast<int>((total + clusters - 1) / clusters);
     if (quota < sk_min) quota = sk_min;
     gp.sk_quota = quota;
     gp.sk_flags = static_cast<unsigned*>(ws);
     gp.sk_ws = reinterpret_cast<float*>(static_cast<char*>(ws) + SK_FLAG_BYTES);
     clusters = static_cast<int>((total + quota - 1) / quota);
+  } else if (ws_ok && g_schedule == 1 && same_nk && num_tiles > 0) {
+    // Hybrid: the full waves stay on the static round-robin (neighbouring pairs on neighbouring tiles: L2 sharing, one epilogue
+    // per tile); only the LAST, partial wave -- R < pairs tiles that would keep R pairs busy for a whole tile while the others
+    // idle -- is cut into equal k-ranges over all pairs.  Worth it when it saves more than the fold costs (~3 iterations).
+    const int nk = gp.nk_tile[0];
+    const int full = (num_tiles / clusters) * clusters, R = num_tiles - full;
+    if (R > 0) {
+      int quota = static_cast<int>((static_cast<long long>(R) * nk + clusters - 1) / clusters);
+      if (quota < hybrid_min_quota) quota = hybrid_min_quota;  // every extra segment is one more partial tile to write and fold
+      if (nk - quota >= hybrid_min_saved) {
+        gp.sk_quota = quota;
+        gp.sk_static_tiles = full;
+        gp.sk_it0 = full * nk;
+        gp.sk_flags = static_cast<unsigned*>(ws);
+        gp.sk_ws = reinterpret_cast<float*>(static_cast<char*>(ws) + SK_FLAG_BYTES);
+      }
+    }
   } else if (clusters > num_tiles) {
     clusters = num_tiles;
   }
+  if (gp.sk_quota == 0 && clusters > num_tiles) clusters = num_tiles;
   if (clusters < 1) clusters = 1;
   // ---- host-balanced static schedule (longest tiles first onto the least-loaded pair) --------------------------------------
   gp.lpt = 0;

@@ -57,6 +57,9 @@ struct GroupParams {
   // slot; the pair that ran the tile's first iterations folds the partial tiles in (in pair order: deterministic) and runs
   // the epilogue.  sk_quota == 0: static round-robin over whole tiles.
   int sk_quota;
+  // hybrid schedule: tiles [0, sk_static_tiles) -- the full waves -- are walked whole, round-robin; only the k-iterations of
+  // the remaining tiles (from iteration sk_it0 on) are cut into per-pair ranges.  Full stream-K: both zero.
+  int sk_static_tiles, sk_it0;
   int it_start[GROUP_MAX + 1];    // prefix sums of tiles x k-iterations per problem
   int nk_tile[GROUP_MAX];         // k-iterations of one tile (uniform inside a problem)
   float* sk_ws;                   // [pairs][2 CTAs][8 column chunks][128 rows][32] fp32
@@ -264,7 +267,7 @@ __device__ __forceinline__ void epilogue_chunk_t(const GemmKParams& p, const flo
   }
   float rs4[4] = {1.f, 1.f, 1.f, 1.f};
   int rs_bb = -1;
-  if (p.rowscale) {
+  if (p.rowscale && (er.valid & 1u)) {  // (a padding row's sample index lies outside the gate tensor)
     rs_bb = er.bb[0];
 #pragma unroll
     for (int k = 0; k < 4; ++k) rs4[k] = __ldg(p.rowscale + static_cast<long long>(rs_bb) * p.rowscale_ld + col + k);

@@ -146,8 +146,8 @@ class DensePath:
         self.post_loc = z(B, 3, self.top_n)
         self.post_count = torch.zeros(B, 3, dtype=torch.int32, device=dev)
         self.graphs = {}
-        if ops.STREAMK:
-            ops.workspace(dev)  # stream-K workspace of the contraction kernel: allocated here, not inside a graph capture
+        if ops.SCHEDULE != "static":
+            ops.workspace(dev)  # workspace of the contraction kernel (hybrid / stream-K folds): allocated here, not inside a graph capture
         self.launches_stage = 0
         self.Tl_c = (C.c_int * 3)(*self.Tl)
         self.strides_c = (C.c_float * 3)(*self.strides)
@@ -703,8 +703,9 @@ class DensePath:
                 i, n = chunk
                 rows = self.D // n
                 assert rows * n == self.D and rows % 8 == 0
+                # static schedule (no workspace): a chunk must stay on 64 SM pairs, the other 10 TPCs belong to the exchange kernel
                 self._gemm(L.GEMM_WGRAD, self.dP_pl.desc(), self.f_pl.desc(), B, self.T, self.D, M=rows, a_c0=i * rows,
-                           out=gw[i * rows:(i + 1) * rows], out_ld=self.D, out_tap_stride=0, engine=2)
+                           out=gw[i * rows:(i + 1) * rows], out_ld=self.D, out_tap_stride=0, engine=2, streamk=False)
         finally:
             if pair_clusters:
                 _lib().drn_set_pair_clusters(0)

@@ -59,18 +59,25 @@ def desc(form, a, b, B, T, N, K=0, M=0, taps=((0, 0, 0),), b_mn=0, a_c0=0, b_c0=
     return g
 
 
-# Stream-K schedule of the persistent contraction kernel (drn_gemm_group_ws): OPT-IN.  Measured on B200 (r02,
-# profiles/r02_ab_streamk.log, profiles/r02_insitu_{static,streamk}.json): 3.86 ms per step against 3.45 ms with the static
-# tile round-robin -- contiguous per-pair tile ranges lose the L2 sharing of operand tiles between neighbouring SM pairs
-# (prop_fc forward 514 -> 624 us) and every extra segment pays a full TMEM -> global epilogue (conv1 backward 48 -> 79 us).
-STREAMK = os.environ.get("DRN_STREAMK", "0") == "1"
+# Schedule of the persistent contraction kernel for the launches that get a workspace (include/drn_b200.h:
+# drn_gemm_set_schedule).  DRN_SCHEDULE = hybrid (default) | static | streamk.
+#   hybrid : full waves on the static tile round-robin, the k-iterations of the last, partial wave cut into equal ranges over
+#            all SM pairs and folded through the workspace (prop_fc weight gradient: 256 tiles = 3.46 waves on 74 pairs).
+#   streamk: every tile boundary ignored.  Measured on B200 (r02, profiles/r02_ab_streamk.log): 3.86 ms per step against 3.45 ms
+#            static -- contiguous per-pair tile ranges lose the L2 sharing of operand tiles between neighbouring SM pairs (prop_fc
+#            forward 514 -> 624 us) and every extra segment pays a full TMEM -> global epilogue (conv1 backward 48 -> 79 us).
+SCHEDULE = os.environ.get("DRN_SCHEDULE", "streamk" if os.environ.get("DRN_STREAMK", "0") == "1" else "hybrid")
+if SCHEDULE not in ("static", "hybrid", "streamk"):
+    raise ValueError("DRN_SCHEDULE must be static, hybrid or streamk")
+_MODE = {"static": 0, "hybrid": 1, "streamk": 2}
+STREAMK = SCHEDULE == "streamk"
 _WS = {}
 
 
 def workspace(device=None):
-    """Stream-K workspace of the persistent contraction kernel (drn_gemm_workspace_bytes, include/drn_b200.h): one per device,
+    """Workspace of the persistent contraction kernel (drn_gemm_workspace_bytes, include/drn_b200.h): one per device,
     zero-filled once, owned by the caller as every other buffer.  All contractions of a process run on one stream at a time
-    (model/main_model.py), so one workspace per device is enough; DRN_STREAMK=0 in the environment disables the schedule."""
+    (model/main_model.py), so one workspace per device is enough."""
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     ws = _WS.get(key)
@@ -81,17 +88,35 @@ def workspace(device=None):
 
 
 def _ws_args(streamk):
-    if not (STREAMK if streamk is None else streamk):
+    """streamk: None = the process schedule (DRN_SCHEDULE), False = static for this call (no workspace), True = full stream-K
+    for this call (set by `_schedule`)."""
+    if streamk is False or (streamk is None and SCHEDULE == "static"):
         return None, C.c_size_t(0)
     ws = workspace()
     return C.c_void_p(ws.data_ptr()), C.c_size_t(ws.numel())
+
+
+class _schedule:
+    """Context: full stream-K for the launches inside (tests, A/B), the process default restored afterwards."""
+
+    def __init__(self, streamk):
+        self.on = streamk is True
+
+    def __enter__(self):
+        if self.on:
+            L.load().drn_gemm_set_schedule(2)
+
+    def __exit__(self, *a):
+        if self.on:
+            L.load().drn_gemm_set_schedule(_MODE[SCHEDULE])
 
 
 def gemm(*a, streamk=None, **k):
     """One contraction, one launch (engine chosen by the library)."""
     g = desc(*a, **k)
     ws, nb = _ws_args(streamk)
-    L.check(L.load().drn_gemm_ws(C.byref(g), ws, nb, L.stream_ptr()), "drn_gemm")
+    with _schedule(streamk):
+        L.check(L.load().drn_gemm_ws(C.byref(g), ws, nb, L.stream_ptr()), "drn_gemm")
 
 
 GROUP_MAX = 6
@@ -104,6 +129,7 @@ def gemm_group(descs, streamk=None):
     for i in range(0, len(descs), GROUP_MAX):
         chunk = descs[i:i + GROUP_MAX]
         arr = (L.GemmDesc * len(chunk))(*chunk)
-        L.check(L.load().drn_gemm_group_ws(len(chunk), arr, ws, nb, L.stream_ptr()), "drn_gemm_group")
+        with _schedule(streamk):
+            L.check(L.load().drn_gemm_group_ws(len(chunk), arr, ws, nb, L.stream_ptr()), "drn_gemm_group")
         n += 1
     return n

@@ -405,6 +405,13 @@ int drn_nms_recall(const float* det, const float* score, const int32_t* count, c
                    int nms, double overlap, double iou_thr, const int32_t* topk, int ntopk, int empty_fallback, int32_t* picks,
                    int32_t* npicks, int32_t* hits, int32_t* correct, void* stream);
 
+/* Schedule of the persistent contraction kernel for launches that are given a workspace (drn_gemm_ws / drn_gemm_group_ws):
+ * 0 = static tile round-robin only; 1 = hybrid (default; environment DRN_SCHEDULE=static|hybrid|streamk): full waves static, the
+ * k-iterations of the last, partial wave cut into equal ranges over all SM pairs and folded through the workspace in pair order
+ * (deterministic); 2 = full stream-K.  Groups whose problems have tiles of different lengths use the host-balanced static
+ * schedule instead. */
+void drn_gemm_set_schedule(int mode);
+
 /* Diagnostic: the next `launches` launches of the persistent contraction kernel (eager, or captured into a CUDA graph -- the
  * slot is part of the captured launch) write %globaltimer stamps to buf[launch][160 CTAs][8]: 0 entry, 1 prologue done, 2 first
  * operands landed, 3 last MMA issued, 4 / 5 first / last accumulator complete, 6 last accumulator drained, 7 exit.  buf = null

@@ -1,0 +1,19 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gemm_gpu.py tests/test_model_gpu.py -q -x 2>&1 | tail -3
+for cfg in "DRN_SCHEDULE=hybrid"; do
+echo "---- [$cfg]"
+env $cfg timeout 300 python scripts/gemm_trace.py > gpurun_out/r02_gemm_trace_c_$cfg.json 2> gpurun_out/r02_gemm_trace.err
+tail -3 gpurun_out/r02_gemm_trace.err
+python - gpurun_out/r02_gemm_trace_c_$cfg.json <<'PY'
+import json,sys
+d=json.load(open(sys.argv[1]))
+keys=["ctas","tiles","first_operands_landed_median","last_mma_issued_median","last_mma_issued_max","last_accumulator_complete_max","drained_median","drained_max","exit_max"]
+print("%-26s"%"launch"+" ".join("%8s"%k[:8] for k in keys))
+for r in d["launches"]:
+    print("%-26s"%r["launch"]+" ".join("%8s"%r[k] for k in keys))
+print("sum of exit_max", sum(r["exit_max"] for r in d["launches"]))
+PY
+done
+bash scripts/ab_bench.sh "DRN_SCHEDULE=hybrid" "DRN_SCHEDULE=static" 2>&1 | tee gpurun_out/r02_ab_hybrid.log

@@ -286,6 +286,58 @@ def test_fused_batchnorm_partial_sums(B, T, N):
     assert lib.drn_gemm(C.byref(d3), L.stream_ptr()) == -1
 
 
+def test_hybrid_schedule_splits_only_the_last_wave():
+    """80 tiles of 24 k-iterations on 74 SM pairs: the first 74 run whole (bit-identical to the static schedule), the k-iterations
+    of the last 6 are cut into ranges over all pairs and folded through the workspace -- against fp64, with bias and BatchNorm
+    partial sums behind the fold, flags re-armed, bit-exact on a repeat; and a weight gradient with K-split slices (120 tiles)."""
+    import ctypes as C
+    assert ops.SCHEDULE == "hybrid"
+    B, T, Cin, N = 20, 256, 512, 1024
+    a = Planes.from_float(_rand(B, T, Cin, seed=401))
+    w = Planes.from_float(_rand(3, N, Cin, seed=402, scale=(3 * Cin) ** -0.5))
+    bias = _rand(N, seed=403)
+    y = torch.full((B, T, N), float("nan"), device=DEV)
+    d = ops.desc(L.GEMM_ROWS, a.desc(), w.desc(), B, T, N, K=Cin, taps=K3, out=y, bias=bias, engine=2)
+    rows = L.load().drn_gemm_stats_rows(C.byref(d))
+    stats = torch.full((rows, 2, N), float("nan"), device=DEV)
+    d.stats = stats.data_ptr()
+    ops.gemm_group([d])
+    assert _flags_clear()
+    ref = ref_rows(a, w, K3, 1, B, T, N, Cin, 0) + bias.double()
+    assert (y.double() - ref).abs().max().item() / ref.abs().max().item() < 2e-5
+    yy = y.double().view(-1, N)
+    st = stats.double().sum(0)
+    assert (st[0] - yy.sum(0)).abs().max().item() <= 1e-5 * yy.abs().sum(0).max().item()
+    assert (st[1] - (yy * yy).sum(0)).abs().max().item() <= 1e-5 * (yy * yy).sum(0).max().item()
+    first, first_stats = y.clone(), stats.clone()
+    ops.gemm_group([d])
+    assert _flags_clear() and torch.equal(first, y) and torch.equal(first_stats, stats)
+    ys = torch.full_like(y, float("nan"))
+    d.out, d.stats = ys.data_ptr(), None
+    _group_static([d])
+    torch.cuda.synchronize()
+    sm_pairs = L.load().drn_sm_count() // 2
+    if sm_pairs == 74:  # tiles 0 .. 73 (row-major over 4 column tiles) never met the workspace
+        whole = 74 // 4  # complete 256-row tile rows inside the first wave
+        assert torch.equal(ys.view(-1, N)[:whole * 256], first.view(-1, N)[:whole * 256])
+    assert (ys - first).abs().max().item() / ref.abs().max().item() < 2e-5
+    # weight gradient: 4 x 5 tiles x 3 taps x 2 slices = 120 tiles of 32 iterations
+    B, T, Co, Ci = 16, 256, 1024, 1280
+    dy, x = Planes.from_float(_rand(B, T, Co, seed=411)), Planes.from_float(_rand(B, T, Ci, seed=412))
+    ws = torch.full((2, 3, Co, Ci), float("nan"), device=DEV)
+    dw = ops.desc(L.GEMM_WGRAD, dy.desc(), x.desc(), B, T, Ci, M=Co, taps=K3, out=ws[0], out_ld=Ci,
+                  out_tap_stride=Co * Ci, out_split_stride=ws.stride(0), split_k=2, engine=2)
+    ops.gemm_group([dw])
+    assert _flags_clear() and not torch.isnan(ws).any()
+    DY, X = dy.to_float().double(), x.to_float().double()
+    for (sh, par, wt) in K3:
+        src = torch.zeros(B, T, Ci, dtype=torch.float64, device=DEV)
+        lo, hi = max(0, -sh), min(T, T - sh)
+        src[:, lo:hi] = X[:, lo + sh:hi + sh]
+        ref_w = torch.einsum("bto,btc->oc", DY, src)
+        assert (ws[:, wt].double().sum(0) - ref_w).abs().max().item() / ref_w.abs().max().item() < 2e-5
+
+
 def test_group_balanced_schedule_is_bit_identical_to_single_launches():
     """A group whose problems have tiles of different lengths and more tiles than SM pairs is walked on the host-balanced
     (longest-first) schedule; which pair computes a tile must not change a bit of it: every problem equals its own launch."""
