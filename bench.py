@@ -402,7 +402,9 @@ def run_ours(args):
     k_ms, k_flops = time_dominant_kernel(path, core._tensor_dict())
     achieved = k_flops / (k_ms * 1e-3) / 1e12
     traffic = None  # DRAM bytes of one prop_fc forward launch from the committed `ncu --set full` capture (profiles/)
-    tp = os.path.join(REPO, "profiles", "r01_prop_fc_fwd_traffic.json")
+    import glob
+    cands = sorted(glob.glob(os.path.join(REPO, "profiles", "r*_prop_fc_fwd_traffic.json")))  # the latest round's capture
+    tp = cands[-1] if cands else ""
     if os.path.isfile(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
     value = world * B_PER_GPU / (ms * 1e-3)

@@ -693,6 +693,20 @@ __device__ __forceinline__ float fold16(float (&a)[16], int lane) {
   }
   return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 16);  // lane l: sum over all lanes of entry (l & 15)
 }
+__device__ __forceinline__ float fold8(float (&a)[8], int lane) {
+#pragma unroll
+  for (int s = 4; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? a[i] : a[i + s];
+      const float keep = up ? a[i + s] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  float v = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 8);
+  return v + __shfl_xor_sync(0xffffffffu, v, 16);  // lane l: sum over all lanes of entry (l & 7)
+}
 __global__ void __launch_bounds__(LSTM2_THREADS, 1) lstm_fwd2_kernel(QeDev q) {
   pdl_sync();
   extern __shared__ __align__(16) float hs[];  // [32 samples][H]: hidden state of the previous step
@@ -731,34 +745,37 @@ __global__ void __launch_bounds__(LSTM2_THREADS, 1) lstm_fwd2_kernel(QeDev q) {
       for (int idx = tid; idx < 8 * H; idx += LSTM2_THREADS) cp_async16(hs + idx * 4, hprev + idx * 4);
       cp_async_wait_all();
       __syncthreads();
+      // 8 samples a pass; the dot products run as packed FFMA2 (two k-lanes per instruction: 1024 instead of 2048 issue slots
+      // per lane and step), the two halves of every accumulator pair are added before the fold
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float acc[4][16];
+      for (int pass = 0; pass < 4; ++pass) {
+        float2 acc[4][8];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[g][i] = 0.f;
+          for (int i = 0; i < 8; ++i) acc[g][i] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float* hrow = hs + (half * 16 + i) * H + 4 * lane;
+        for (int i = 0; i < 8; ++i) {
+          const float* hrow = hs + (pass * 8 + i) * H + 4 * lane;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (j < NJ) {
               const float4 h4 = *reinterpret_cast<const float4*>(hrow + 128 * j);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                acc[g][i] = fmaf(wr[g][j].x, h4.x, acc[g][i]);
-                acc[g][i] = fmaf(wr[g][j].y, h4.y, acc[g][i]);
-                acc[g][i] = fmaf(wr[g][j].z, h4.z, acc[g][i]);
-                acc[g][i] = fmaf(wr[g][j].w, h4.w, acc[g][i]);
+                acc[g][i] = __ffma2_rn(make_float2(wr[g][j].x, wr[g][j].y), make_float2(h4.x, h4.y), acc[g][i]);
+                acc[g][i] = __ffma2_rn(make_float2(wr[g][j].z, wr[g][j].w), make_float2(h4.z, h4.w), acc[g][i]);
               }
             }
           }
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const float v = fold16(acc[g], lane);
-          if ((lane >> 4) == half) pre[g] += v;  // lane l keeps sample l
+          float a8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a8[i] = acc[g][i].x + acc[g][i].y;
+          const float v = fold8(a8, lane);
+          if ((lane >> 3) == pass) pre[g] += v;  // lane l keeps sample l
         }
       }
     }
@@ -916,14 +933,14 @@ __global__ void __launch_bounds__(LSTM_THREADS) lstm_bwd_kernel(QeDev q, int s0,
 #pragma unroll 2
       for (int j = w * jw; j < (w + 1) * jw; ++j) {
         const float wv = wsm[j * 32 + lane];
+        const float2 wv2 = make_float2(wv, wv);
         const float4* d4 = reinterpret_cast<const float4*>(dgs + j * 32);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i) {  // packed FFMA2: two samples per instruction (same products, same order per sample)
           const float4 d = d4[i];
-          acc[4 * i + 0] = fmaf(d.x, wv, acc[4 * i + 0]);
-          acc[4 * i + 1] = fmaf(d.y, wv, acc[4 * i + 1]);
-          acc[4 * i + 2] = fmaf(d.z, wv, acc[4 * i + 2]);
-          acc[4 * i + 3] = fmaf(d.w, wv, acc[4 * i + 3]);
+          const float2 r0 = __ffma2_rn(make_float2(d.x, d.y), wv2, make_float2(acc[4 * i + 0], acc[4 * i + 1]));
+          const float2 r1 = __ffma2_rn(make_float2(d.z, d.w), wv2, make_float2(acc[4 * i + 2], acc[4 * i + 3]));
+          acc[4 * i + 0] = r0.x; acc[4 * i + 1] = r0.y; acc[4 * i + 2] = r1.x; acc[4 * i + 3] = r1.y;
         }
       }
 #pragma unroll

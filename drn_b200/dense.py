@@ -22,7 +22,6 @@ K3S2 = ((-1, 1, 0), (0, 0, 1), (0, 1, 2))           # k3/s2/p1 on the [T/2][2] p
 K3_DGRAD = ((1, 0, 0), (0, 0, 1), (-1, 0, 2))       # dX[u] = sum_r dY[u+1-r] W_r
 S2_DGRAD = (((0, 0, 1),), ((1, 0, 0), (0, 0, 2)))   # per output parity u = 2j+p
 BN_MOMENTUM, BN_EPS = 0.1, 1e-5
-SM_COUNT = 148
 
 
 def _lib():
