@@ -537,11 +537,17 @@ extern "C" int drn_gemm_group_ws(int n, const drn_gemm_t* descs, void* workspace
 namespace drn {
 void set_pair_clusters(int n);
 void set_schedule(int mode);
+int schedule_probe(int nprob, const int* tiles, const int* nk, int pairs, int has_ws, int mode, int* kind, int* quota,
+                   int* static_tiles, unsigned char* counts, unsigned short* lists);
 void gemm_trace(unsigned long long* buf, int launches);
 int gemm_trace_info(int launch, int* ctas, int* tiles, int* lpt);
 }
 extern "C" void drn_set_pair_clusters(int n) { drn::set_pair_clusters(n); }
 extern "C" void drn_gemm_set_schedule(int mode) { drn::set_schedule(mode); }
+extern "C" int drn_gemm_schedule_probe(int nprob, const int* tiles, const int* nk, int pairs, int has_ws, int mode, int* kind,
+                                       int* quota, int* static_tiles, unsigned char* counts, unsigned short* lists) {
+  return drn::schedule_probe(nprob, tiles, nk, pairs, has_ws, mode, kind, quota, static_tiles, counts, lists);
+}
 extern "C" void drn_gemm_trace(uint64_t* buf, int launches) { drn::gemm_trace(reinterpret_cast<unsigned long long*>(buf), launches); }
 extern "C" int drn_gemm_trace_info(int launch, int* ctas, int* tiles, int* lpt) { return drn::gemm_trace_info(launch, ctas, tiles, lpt); }
 

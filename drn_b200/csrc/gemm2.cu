@@ -505,13 +505,10 @@ static int sk_env(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int sm_count, void* ws, size_t ws_bytes, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
-    if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(gemm_pair): %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+// Host-side planning of one launch (pure: no CUDA call): fills the schedule fields of `gp` (static round-robin, host-balanced
+// tile lists, hybrid or full stream-K ranges) and returns the number of SM pairs (clusters) to launch.  Shared by launch_group and
+// by drn_gemm_schedule_probe, which lets the CPU tests check the planner without a GPU.
+int plan_group(GroupParams& gp, const int* nk_tile, int sm_count, void* ws, size_t ws_bytes) {
   if (g_schedule < 0) {
     const char* e = getenv("DRN_SCHEDULE");  // static | hybrid | streamk
     g_schedule = (e && e[0] == 's' && e[1] == 't' && e[2] == 'a') ? 0 : ((e && e[0] == 's' && e[1] == 't' && e[2] == 'r') ? 2 : 1);
@@ -519,12 +516,12 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
   const int num_tiles = gp.tile_start[gp.nprob];
   int clusters = sm_count / 2;
   static int cap = -1;  // DRN_PAIR_CLUSTERS: leave SM pairs free for kernels of other streams (tuning / probing knob)
-  static int sk_min = 4, hybrid_min_saved = 8, hybrid_min_quota = 8;
+  static int sk_min = 4, hybrid_min_saved = 24, hybrid_min_quota = 8;
   if (cap < 0) {
     cap = sk_env("DRN_PAIR_CLUSTERS", 0);
     sk_min = sk_env("DRN_SK_MIN", 4);
     if (sk_min < 1) sk_min = 1;
-    hybrid_min_saved = sk_env("DRN_HYBRID_MIN_SAVED", 8);
+    hybrid_min_saved = sk_env("DRN_HYBRID_MIN_SAVED", 24);
     hybrid_min_quota = sk_env("DRN_HYBRID_MIN_QUOTA", 8);
     if (hybrid_min_quota < 1) hybrid_min_quota = 1;
   }
@@ -562,7 +559,9 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
   } else if (ws_ok && g_schedule == 1 && same_nk && num_tiles > 0) {
     // Hybrid: the full waves stay on the static round-robin (neighbouring pairs on neighbouring tiles: L2 sharing, one epilogue
     // per tile); only the LAST, partial wave -- R < pairs tiles that would keep R pairs busy for a whole tile while the others
-    // idle -- is cut into equal k-ranges over all pairs.  Worth it when it saves more than the fold costs (~3 iterations).
+    // idle -- is cut into equal k-ranges over all pairs.  Worth it only when it saves clearly more than a fold costs (partial
+    // tile written, flag, partial tile read back: ~10 us on the critical path, measured: FPN layer forward, 11 iterations saved,
+    // got 7 us slower; prop_fc weight gradient, 69 saved, 30 us faster) -> at least 24 iterations (DRN_HYBRID_MIN_SAVED).
     const int nk = gp.nk_tile[0];
     const int full = (num_tiles / clusters) * clusters, R = num_tiles - full;
     if (R > 0) {
@@ -622,6 +621,18 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
       }
     }
   }
+  return clusters;
+}
+
+int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int sm_count, void* ws, size_t ws_bytes, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "cudaFuncSetAttribute(gemm_pair): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int clusters = plan_group(gp, nk_tile, sm_count, ws, ws_bytes);
+  const int num_tiles = gp.tile_start[gp.nprob];
   static int epi_t = -1;  // DRN_EPI_T=0: row-per-thread epilogue stores (A/B)
   if (epi_t < 0) epi_t = sk_env("DRN_EPI_T", 1);
   gp.epi_t = epi_t;
@@ -636,6 +647,38 @@ int launch_group(GroupParams& gp, const GroupMaps& gm, const int* nk_tile, int s
   }
   launch_k(gemm_pair_kernel, 2 * clusters, P2_THREADS, P2_SMEM, st, gp, gm, num_tiles);
   return check_launch("gemm_pair_kernel");
+}
+
+
+// Planner probe (no GPU needed): `nprob` problems with tiles[k] tiles of nk[k] k-iterations each, in the order given (the
+// launcher sorts by decreasing nk), on `pairs` SM pairs, with (has_ws != 0) or without a workspace, under schedule `mode`
+// (0 static / 1 hybrid / 2 stream-K; < 0 = leave the process setting).  Returns the pairs to launch; kind = 0 round-robin,
+// 1 host-balanced lists, 2 hybrid, 3 stream-K; quota / static_tiles = range length and whole-tile prefix of the k-split
+// schedules; counts[pair] and lists[pair * 16 + i] = the tile list of a pair (kind 1).
+int schedule_probe(int nprob, const int* tiles, const int* nk, int pairs, int has_ws, int mode, int* kind, int* quota,
+                   int* static_tiles, unsigned char* counts, unsigned short* lists) {
+  if (nprob < 1 || nprob > GROUP_MAX || pairs < 1) return -1;
+  static thread_local GroupParams gp;
+  gp.nprob = nprob;
+  gp.tile_start[0] = 0;
+  for (int k = 0; k < nprob; ++k) gp.tile_start[k + 1] = gp.tile_start[k] + tiles[k];
+  for (int k = nprob; k < GROUP_MAX; ++k) gp.tile_start[k + 1] = gp.tile_start[nprob];
+  const int saved = g_schedule;
+  if (mode >= 0) set_schedule(mode);
+  static char fake_ws[64];
+  const int clusters = plan_group(gp, nk, 2 * pairs, has_ws ? fake_ws : nullptr, has_ws ? (static_cast<size_t>(1) << 40) : 0);
+  const int effective = g_schedule;  // (plan_group resolves the environment default on first use)
+  if (mode >= 0) g_schedule = saved;
+  if (kind) *kind = gp.lpt ? 1 : (gp.sk_quota > 0 ? (effective == 2 ? 3 : 2) : 0);
+  if (quota) *quota = gp.sk_quota;
+  if (static_tiles) *static_tiles = gp.sk_static_tiles;
+  if (gp.lpt && counts && lists) {
+    for (int c = 0; c < clusters && c < LPT_MAX_PAIRS; ++c) {
+      counts[c] = gp.lpt_count[c];
+      for (int i = 0; i < gp.lpt_count[c]; ++i) lists[c * LPT_MAX_TILES + i] = gp.lpt_tiles[c][i];
+    }
+  }
+  return clusters;
 }
 
 }  // namespace drn

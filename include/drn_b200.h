@@ -411,6 +411,13 @@ int drn_nms_recall(const float* det, const float* score, const int32_t* count, c
  * (deterministic); 2 = full stream-K.  Groups whose problems have tiles of different lengths use the host-balanced static
  * schedule instead. */
 void drn_gemm_set_schedule(int mode);
+/* The launch planner on its own (host arithmetic only, no GPU): `nprob` problems of tiles[k] tiles with nk[k] k-iterations each,
+ * sorted by decreasing nk as the launcher does, on `pairs` SM pairs, with or without a workspace, under schedule `mode` (< 0: the
+ * process setting).  Returns the SM pairs that would be launched; *kind = 0 round-robin, 1 host-balanced tile lists
+ * (counts[pair], lists[pair * 16 + i]), 2 hybrid, 3 stream-K; *quota, *static_tiles = k-range length per pair and number of
+ * whole tiles walked statically.  tests/test_host_cpu.py checks the planner through it. */
+int drn_gemm_schedule_probe(int nprob, const int* tiles, const int* nk, int pairs, int has_ws, int mode, int* kind, int* quota,
+                            int* static_tiles, unsigned char* counts, unsigned short* lists);
 
 /* Diagnostic: the next `launches` launches of the persistent contraction kernel (eager, or captured into a CUDA graph -- the
  * slot is part of the captured launch) write %globaltimer stamps to buf[launch][160 CTAs][8]: 0 entry, 1 prologue done, 2 first

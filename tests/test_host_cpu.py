@@ -258,3 +258,60 @@ def test_backward_after_another_forward_of_the_same_shape_raises(monkeypatch):
     l2.sum().backward()  # the latest forward: fine
     with pytest.raises(RuntimeError, match="another forward"):
         l1.sum().backward()
+
+
+# ---- launch planner of the persistent contraction kernel (drn_gemm_schedule_probe: host arithmetic only) ----------------------
+def _probe(tiles, nk, pairs=74, ws=1, mode=1):
+    import ctypes as C
+    from drn_b200 import lib as L
+    lib = L.load()
+    n = len(tiles)
+    kind, quota, static_tiles = C.c_int(), C.c_int(), C.c_int()
+    counts, lists = (C.c_ubyte * 80)(), (C.c_ushort * (80 * 16))()
+    cl = lib.drn_gemm_schedule_probe(n, (C.c_int * n)(*tiles), (C.c_int * n)(*nk), pairs, ws, mode, C.byref(kind), C.byref(quota),
+                                     C.byref(static_tiles), counts, lists)
+    per_pair = [list(lists)[c * 16:c * 16 + counts[c]] for c in range(max(cl, 0))]
+    return cl, kind.value, quota.value, static_tiles.value, per_pair
+
+
+def test_planner_balanced_lists_cover_every_tile_once_and_beat_round_robin():
+    """Groups whose problems have tiles of different lengths get host-balanced (longest-first) tile lists: every tile exactly
+    once, no pair above 16 tiles, makespan never above plain round-robin -- on the shapes of the DRN backward launches."""
+    cases = {"conv0 bwd": ([204, 544], [32, 12]), "FPN layer bwd": ([84, 112], [32, 24]), "FPN inner bwd": ([48, 96], [16, 8]),
+             "towers bwd": ([168, 112], [48, 32]), "FPN inner fwd": ([16, 32, 64], [16, 8, 4]), "conv1 bwd": ([24, 16, 16], [16, 16, 8])}
+    for name, (tiles, nk) in cases.items():
+        order = sorted(range(len(tiles)), key=lambda k: -nk[k])  # the launcher sorts problems by decreasing tile length
+        tiles, nk = [tiles[k] for k in order], [nk[k] for k in order]
+        cl, kind, quota, static_tiles, lists = _probe(tiles, nk)
+        total = sum(tiles)
+        assert cl == min(74, total)
+        if total <= cl:
+            continue
+        assert kind == 1, name
+        seen = sorted(t for lst in lists for t in lst)
+        assert seen == list(range(total)), name
+        assert max(len(lst) for lst in lists) <= 16
+        starts = [sum(tiles[:k]) for k in range(len(tiles) + 1)]
+        cost = lambda t: nk[max(k for k in range(len(tiles)) if t >= starts[k])]  # noqa: E731
+        balanced = max(sum(cost(t) for t in lst) for lst in lists)
+        rr = max(sum(cost(t) for t in range(c, total, cl)) for c in range(cl))
+        ideal = sum(n * w for n, w in zip(tiles, nk)) / cl
+        assert balanced <= rr and balanced < ideal + max(nk), (name, balanced, rr, ideal)
+
+
+def test_planner_hybrid_only_where_it_pays_and_static_without_workspace():
+    # prop_fc weight gradient: 256 tiles of 128 iterations = 3.46 waves -> 3 waves static, the last 34 tiles in ranges of 59
+    assert _probe([256], [128]) == (74, 2, 59, 222, [[]] * 74)
+    # towers / FPN layer forward (16 / 11 iterations to gain: less than a fold costs), conv0 forward: static
+    assert _probe([224], [24])[:4] == (74, 0, 0, 0)
+    assert _probe([112], [24])[:4] == (74, 0, 0, 0)
+    assert _probe([64], [102])[:4] == (64, 0, 0, 0)
+    # no workspace (data-parallel weight-gradient chunks: 64 tiles must stay on 64 pairs) or DRN_SCHEDULE=static: round-robin
+    assert _probe([64], [128], ws=0)[:4] == (64, 0, 0, 0)
+    assert _probe([256], [128], ws=0)[:4] == (74, 0, 0, 0)
+    assert _probe([256], [128], mode=0)[:4] == (74, 0, 0, 0)
+    # full stream-K: every pair gets ceil(total / pairs) iterations
+    cl, kind, quota, static_tiles, _ = _probe([256], [128], mode=2)
+    assert (cl, kind, static_tiles) == (74, 3, 0) and quota == -(-256 * 128 // 74)
+    # uniform tiles in several problems: round-robin is already balanced -> no lists
+    assert _probe([64, 32, 16], [24, 24, 24], ws=0)[:2] == (74, 0)

@@ -52,6 +52,9 @@ def _worker(rank, world, port, q):
     dp.reduce_regions([flat[4:], flat[:0]])
     dp.wait(work)
     ok = ok and torch.allclose(flat, torch.arange(6, dtype=torch.float32) * 1.5)
+    # the peer-memory transport needs CUDA buffers and NCCL for the handle exchange: on CPU / gloo registration declines on every
+    # rank and the regions keep going through the process group
+    ok = ok and dp.reducer.register(flat) is False and dp.reducer.transport_used == {"p2p": 0, "nccl": 2}
     for p in toy.query_encoder.parameters():
         p.grad = torch.full_like(p, float(rank))
     toy.prop_fc.weight.grad = torch.full_like(toy.prop_fc.weight, 7.0)  # dense grads are NOT touched by finish_gradient_sync
