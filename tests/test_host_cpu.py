@@ -49,7 +49,8 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(drn_planes_t), sizeof(drn_gemm_t), offsetof(drn_gemm_t, b), offsetof(drn_gemm_t, tap_w),
          offsetof(drn_gemm_t, out_split_stride), offsetof(drn_gemm_t, outp_plane_stride), offsetof(drn_gemm_t, dbg_kadv),
          sizeof(drn_bn_part_t), offsetof(drn_bn_part_t, dbeta), sizeof(drn_pack_item_t), offsetof(drn_pack_item_t, slice_stride));
-  printf("%zu %zu %zu\n", offsetof(drn_gemm_t, stats), offsetof(drn_bn_job_t, partials), offsetof(drn_bn_job_t, partial_rows));
+  printf("%zu %zu %zu ", offsetof(drn_gemm_t, stats), offsetof(drn_bn_job_t, partials), offsetof(drn_bn_job_t, partial_rows));
+  printf("%zu %zu %zu %d %d\n", sizeof(drn_p2p_t), offsetof(drn_p2p_t, buf), offsetof(drn_p2p_t, flags), DRN_P2P_MAX_RANKS, DRN_P2P_FLAG_WORDS);
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -66,6 +67,8 @@ int main(void) {
             G.outp_plane_stride.offset, G.dbg_kadv.offset, ctypes.sizeof(L.BnPart), L.BnPart.dbeta.offset,
             ctypes.sizeof(L.PackItem), L.PackItem.slice_stride.offset,
             G.stats.offset, J.partials.offset, J.partial_rows.offset]
+    from drn_b200 import parallel as PAR
+    mine += [ctypes.sizeof(PAR.P2PComm), PAR.P2PComm.buf.offset, PAR.P2PComm.flags.offset, PAR.P2P_MAX_RANKS, PAR.P2P_FLAG_WORDS]
     assert [int(x) for x in out] == mine
 
 
