@@ -89,6 +89,7 @@ struct PackItem {
   long long plane_stride;
   int nslices;              // unpack only: partial sums to add up (K-splits x pyramid levels)
   long long slice_stride;
+  int vec;                  // every pointer / stride of the item allows the 16-byte forms below (set by fill_table)
 };
 struct PackTable {
   int n;
@@ -110,6 +111,30 @@ __global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const Pack
     }
     return;
   }
+  if (e.k == 3 && e.vec) {
+    // A thread owns 4 consecutive input channels of one output channel: its 12 consecutive fp32 weights [c..c+3][tap] are three
+    // 16-byte loads, the 4 hi + 4 lo bf16 of a tap two 8-byte stores (256 contiguous bytes per warp) -- the scalar form below
+    // issues 12 strided 4-byte loads and 24 2-byte stores for the same elements.  Same values.
+    const int C4 = e.C >> 2;
+    const long long total4 = static_cast<long long>(e.O) * C4;
+    for (long long i4 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i4 < total4;
+         i4 += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int o = static_cast<int>(i4 / C4), c = static_cast<int>(i4 % C4) * 4;
+      const float4* src = reinterpret_cast<const float4*>(e.w + (static_cast<long long>(o) * e.C + c) * 3);
+      const float4 a = __ldg(src), b = __ldg(src + 1), d = __ldg(src + 2);
+      const float w[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z, d.w};  // [channel][tap]
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int cl = 0; cl < 4; ++cl) split_bf16(w[cl * 3 + r], h[cl], l[cl]);
+        __nv_bfloat16* dst = e.dst + (static_cast<long long>(r) * e.Ototal + e.o0 + o) * e.C + c;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        *reinterpret_cast<uint2*>(dst + e.plane_stride) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      }
+    }
+    return;
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int o = static_cast<int>(i / e.C), c = static_cast<int>(i % e.C);
@@ -126,9 +151,38 @@ __global__ void __launch_bounds__(EW_THREADS) pack_conv_weight_kernel(const Pack
 // ---- weight-gradient workspaces [slice][k][Ototal][C] -> parameter gradients [O][C][k], summing the slices ------------------
 // (the K-splits of drn_gemm WGRAD and the three pyramid levels of a shared head conv store their partial sums side by side:
 // deterministic, no atomics, no zero-fill).  Reads are coalesced over C; gridDim.y = table item.
+// Vector form (k = 1 or 3, 16-byte aligned): a thread owns 4 consecutive input channels of one output channel -- 16-byte loads of
+// the slices (same slice order: bit-identical sums), K 16-byte stores of the 4 K contiguous gradient values.
+template <int K>
+__device__ __forceinline__ void unpack_vec(const PackItem& e) {
+  const int C4 = e.C >> 2;
+  const long long total4 = static_cast<long long>(e.O) * C4;
+  for (long long i4 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i4 < total4;
+       i4 += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i4 / C4), c = static_cast<int>(i4 % C4) * 4;
+    float out[4 * K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const float* src = e.w + (static_cast<long long>(r) * e.Ototal + e.o0 + o) * e.C + c;
+      float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int sl = 0; sl < e.nslices; ++sl) {
+        const float4 x = __ldcs(reinterpret_cast<const float4*>(src + sl * e.slice_stride));
+        s4.x += x.x; s4.y += x.y; s4.z += x.z; s4.w += x.w;
+      }
+      out[0 * K + r] = s4.x; out[1 * K + r] = s4.y; out[2 * K + r] = s4.z; out[3 * K + r] = s4.w;
+    }
+    float4* g = reinterpret_cast<float4*>(e.grad + (static_cast<long long>(o) * e.C + c) * K);
+#pragma unroll
+    for (int j = 0; j < K; ++j) g[j] = make_float4(out[4 * j], out[4 * j + 1], out[4 * j + 2], out[4 * j + 3]);
+  }
+}
+
 __global__ void __launch_bounds__(EW_THREADS) unpack_conv_wgrad_kernel(const PackTable tab) {
   pdl_sync();
   const PackItem& e = tab.it[blockIdx.y];
+  if (e.vec && e.k == 3) { unpack_vec<3>(e); return; }
+  if (e.vec && e.k == 1) { unpack_vec<1>(e); return; }
   const long long total = static_cast<long long>(e.O) * e.C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -807,7 +861,15 @@ static int fill_table(PackTable* t, int n, const drn_pack_item_t* items) {
     if (items[i].C % 8) return fail(DRN_EINVAL, "pack table: C %% 8 (item %d, C=%d)", i, items[i].C);
     t->it[i] = PackItem{items[i].src, static_cast<__nv_bfloat16*>(items[i].planes), items[i].grad, items[i].O, items[i].C,
                         items[i].k, items[i].Ototal, items[i].o0, items[i].plane_stride,
-                        items[i].nslices < 1 ? 1 : items[i].nslices, items[i].slice_stride};
+                        items[i].nslices < 1 ? 1 : items[i].nslices, items[i].slice_stride, 0};
+    static int v2 = -1;  // DRN_PACK_V2=0: scalar forms only (A/B)
+    if (v2 < 0) {
+      const char* e = getenv("DRN_PACK_V2");
+      v2 = e ? atoi(e) : 1;
+    }
+    auto al16 = [](const void* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % 16 == 0; };
+    t->it[i].vec = (v2 != 0 && al16(items[i].src) && al16(items[i].planes) && al16(items[i].grad) &&
+                    items[i].plane_stride % 8 == 0 && items[i].slice_stride % 4 == 0) ? 1 : 0;
   }
   return 0;
 }
