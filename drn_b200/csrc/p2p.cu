@@ -16,7 +16,7 @@
 //
 // Per GPU the NVLink traffic is (world-1)/world of the region in each direction -- what a ring moves in 2(world-1) dependent
 // steps moves here in one, which is what the NVSwitch topology is for (every peer at full bandwidth).  Spins are bounded
-// (~4 s) and trap, so a missing peer fails the step instead of hanging the GPU.
+// (~30 s) and trap, so a missing peer fails the step instead of hanging the GPU.
 #include <cuda.h>
 #include <string.h>
 
@@ -65,7 +65,7 @@ __device__ __forceinline__ bool reached(unsigned flag, unsigned epoch) { return 
 __device__ __forceinline__ void wait_flag(const unsigned* f, unsigned epoch) {
   const long long t0 = clock64();
   while (!reached(ld_acquire_sys(f), epoch)) {
-    if (clock64() - t0 > 8000000000LL) __trap();  // ~4 s: a peer never arrived
+    if (clock64() - t0 > 60000000000LL) __trap();  // ~30 s: a peer never arrived (ranks may be seconds apart at start-up)
   }
 }
 

@@ -442,7 +442,7 @@ int drn_gemm_trace_info(int launch, int* ctas, int* tiles, int* lpt);
  *     peers' flag blocks, an epoch counter in flags[rank][0]) order it: nobody reads before every rank has launched the call
  *     (its gradients are complete: stream order), nobody returns before every rank's stores have landed.  Every rank must
  *     issue the same sequence of calls.  `ctas` = CTAs of 512 threads (0 = default).  A peer that never arrives traps the
- *     kernel after ~4 s instead of hanging the GPU. */
+ *     kernel after ~30 s instead of hanging the GPU. */
 #define DRN_P2P_MAX_RANKS 8
 #define DRN_P2P_FLAG_WORDS 64
 typedef struct {
