@@ -318,3 +318,28 @@ def test_planner_hybrid_only_where_it_pays_and_static_without_workspace():
     assert (cl, kind, static_tiles) == (74, 3, 0) and quota == -(-256 * 128 // 74)
     # uniform tiles in several problems: round-robin is already balanced -> no lists
     assert _probe([64, 32, 16], [24, 24, 24], ws=0)[:2] == (74, 0)
+
+
+def test_weight_gradient_k_splits_never_exceed_the_k_blocks():
+    """DensePath._wgrad_split: ~2048 contraction rows per tile, twice as fine for conv1 / the FPN laterals, and never more slices
+    than 64-row K-blocks of the contraction (drn_gemm rejects a slice that would stay unwritten: gemm.cu prepare())."""
+    import types
+    from drn_b200.dense import DensePath
+
+    def kblocks(b, t):  # gemm.cu: Rk = 64 or pow2_ceil(T) < 64, Bbk samples per block
+        if t >= 64:
+            return b * ((t + 63) // 64)
+        rk = 1
+        while rk < t:
+            rk *= 2
+        return (b + 64 // rk - 1) // (64 // rk)
+
+    for b in (1, 3, 4, 32, 256):
+        for t in (8, 16, 32, 64, 128, 256, 512):
+            for prefix in ("backbone_net.forward_conv0", "backbone_net.forward_conv1", "fpn.fpn_inner2", "fpn.fpn_layer1", "fcos.head.towers"):
+                blk = types.SimpleNamespace(prefix=prefix, rows=b * t, t_out=t)
+                s = DensePath._wgrad_split(blk)
+                assert 1 <= s <= 16 and s <= max(1, kblocks(b, t)), (b, t, prefix, s)
+    full = lambda p: DensePath._wgrad_split(types.SimpleNamespace(prefix=p, rows=32 * 256, t_out=256))  # noqa: E731
+    assert full("backbone_net.forward_conv0") == 4 and full("fpn.fpn_inner1") == 8
+    assert DensePath._wgrad_split(types.SimpleNamespace(prefix="backbone_net.forward_conv1", rows=32 * 128, t_out=128)) == 4
