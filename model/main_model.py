@@ -31,6 +31,24 @@ def _mark(name):
         DP_TRACE.append((name, e))
 
 
+# NVTX ranges around the phases of a step (tracing row): DRN_NVTX=1.  Under CUDA-graph replay a range
+# brackets the host-side enqueue of the phase; with DRN_NO_GRAPHS=1 every kernel launch of the phase falls inside it.
+_NVTX = os.environ.get("DRN_NVTX", "0") == "1"
+
+
+class _nvtx:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
+
+
 def _sig(p):
     return hash(tuple(t.data_ptr() for t in p.values()))
 
@@ -55,12 +73,14 @@ def _replay(path, key, fn, use_graphs):
 def _run_forward(path, p, training, use_graphs, tokens, lengths, feats, pse, gt):
     """Forward schedule: the eager staging of the caller's tensors, then ONE replayable graph (query encoder + gates with the
     weight packing as a parallel branch under the recurrence, then prop_fc ... losses)."""
-    path.stage_inputs(p, tokens, lengths, feats, pse, gt)
+    with _nvtx("drn.stage_inputs"):
+        path.stage_inputs(p, tokens, lengths, feats, pse, gt)
 
     def core():
         path.forward_pre(p)
         path.forward_main(p, training)
-    _replay(path, ("fwd", training, _sig(p)), core, use_graphs)
+    with _nvtx("drn.forward"):
+        _replay(path, ("fwd", training, _sig(p)), core, use_graphs)
 
 
 def _run_backward(path, p, names, upstream, use_graphs, dp=None, flat_cache=None):
@@ -272,8 +292,9 @@ class _DenseFn(torch.autograd.Function):
                 old = p[n].grad
                 if old is not None and old.untyped_storage().data_ptr() in owned:
                     p[n].grad = old.clone()
-        flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs, dp=model._dp,
-                                    flat_cache=model.__dict__.setdefault("_flat_cache", {}))
+        with _nvtx("drn.backward"):
+            flat, grads = _run_backward(path, p, names, g.contiguous().float(), model.use_graphs, dp=model._dp,
+                                        flat_cache=model.__dict__.setdefault("_flat_cache", {}))
         if not views:
             return (None,) * 8 + tuple(grads[n] for n in names)
         for n in names:
